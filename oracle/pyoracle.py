@@ -1,0 +1,217 @@
+"""ctypes binding of the CPU ORACLE (oracle/libpacbot_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, `__graft_entry__.smoke()` and bench.py's
+`cpu_baseline` / `--impl reference` legs; never by the product package.  PARITY UNPINNED at the
+engine boundary -- see oracle/pacbot_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpacbot_oracle.so")
+
+OBS_SHAPE = (17, 28, 31)
+OBS_FLOATS = 17 * 28 * 31
+
+FLAT_DTYPE = np.dtype(
+    [
+        ("curr_ticks", "<u4"),
+        ("rng_ctr", "<u4"),
+        ("pellets", "<u4", (31,)),
+        ("level_steps", "<u2"),
+        ("curr_score", "<u2"),
+        ("num_pellets", "<u2"),
+        ("last_score", "<u2"),
+        ("update_period", "u1"),
+        ("mode", "u1"),
+        ("paused", "u1"),
+        ("pause_on_update", "u1"),
+        ("mode_steps", "u1"),
+        ("curr_level", "u1"),
+        ("curr_lives", "u1"),
+        ("ghost_combo", "u1"),
+        ("fruit_steps", "u1"),
+        ("last_action", "u1"),
+        ("ticks_per_step", "u1"),
+        ("random_start", "u1"),
+        ("random_ticks", "u1"),
+        ("randomize_ghosts", "u1"),
+        ("remove_super_pellets", "u1"),
+        ("pac_row", "i1"),
+        ("pac_col", "i1"),
+        ("pac_dir", "u1"),
+        ("g_row", "i1", (4,)),
+        ("g_col", "i1", (4,)),
+        ("g_dir", "u1", (4,)),
+        ("g_next_row", "i1", (4,)),
+        ("g_next_col", "i1", (4,)),
+        ("g_next_dir", "u1", (4,)),
+        ("g_fright", "u1", (4,)),
+        ("g_trapped", "u1", (4,)),
+        ("g_spawning", "u1", (4,)),
+        ("g_eaten", "u1", (4,)),
+    ],
+    align=True,
+)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with its Makefile (gcc); returns the .so path."""
+    src = os.path.join(_HERE, "pacbot_oracle.c")
+    hdr = os.path.join(_HERE, "pacbot_oracle.h")
+    stale = (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+    )
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        vp, i64, u8p, i32p, u32p, f32p = (
+            C.c_void_p,
+            C.c_int64,
+            C.POINTER(C.c_uint8),
+            C.POINTER(C.c_int32),
+            C.POINTER(C.c_uint32),
+            C.POINTER(C.c_float),
+        )
+        L.po_batch_create.restype = vp
+        L.po_batch_create.argtypes = [i64, vp, vp, i64]
+        L.po_batch_destroy.argtypes = [vp]
+        L.po_batch_reset.argtypes = [vp, vp]
+        L.po_batch_step.restype = i64
+        L.po_batch_step.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.po_batch_action_mask.argtypes = [vp, vp]
+        L.po_batch_obs.argtypes = [vp, vp]
+        L.po_batch_export.argtypes = [vp, vp]
+        L.po_batch_import.argtypes = [vp, vp]
+        L.po_batch_env.restype = vp
+        L.po_batch_env.argtypes = [vp, i64]
+        L.po_gym_first_ai_done.argtypes = [vp]
+        L.po_gym_first_ai_done.restype = C.c_int
+        L.po_gym_is_done.argtypes = [vp]
+        L.po_gym_is_done.restype = C.c_int
+        L.po_wall_at.argtypes = [C.c_int, C.c_int]
+        L.po_wall_at.restype = C.c_int
+        L.po_sizeof_flat.restype = C.c_size_t
+        L.po_sizeof_gym.restype = C.c_size_t
+        L.po_rollout.restype = C.c_double
+        L.po_rollout.argtypes = [
+            i64,
+            i64,
+            i64,
+            C.c_uint64,
+            C.c_int,
+            C.POINTER(C.c_uint64),
+            C.POINTER(C.c_int64),
+        ]
+        assert L.po_sizeof_flat() == FLAT_DTYPE.itemsize, (L.po_sizeof_flat(), FLAT_DTYPE.itemsize)
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+CFG_RANDOM_START = 1
+CFG_RANDOM_TICKS = 2
+CFG_RANDOMIZE_GHOSTS = 4
+CFG_REMOVE_SUPER_PELLETS = 8
+
+
+class OracleBatch:
+    """N independent scalar oracle envs with an injected raw-draw tape (uint32 [N, tape_len])."""
+
+    def __init__(self, n: int, cfg_flags=None, tape: np.ndarray | None = None):
+        self.n = int(n)
+        L = lib()
+        if cfg_flags is None:
+            cfg_flags = np.zeros(self.n, np.uint8)
+        self.cfg = np.ascontiguousarray(cfg_flags, dtype=np.uint8)
+        assert self.cfg.shape == (self.n,)
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.uint32)
+            assert tape.ndim == 2 and tape.shape[0] == self.n
+        self.tape = tape  # keep alive: the C side borrows the pointer
+        self._h = L.po_batch_create(
+            self.n, _ptr(self.cfg), _ptr(tape), 0 if tape is None else tape.shape[1]
+        )
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().po_batch_destroy(h)
+
+    def reset(self, mask: np.ndarray | None = None) -> None:
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().po_batch_reset(self._h, _ptr(mask))
+
+    def step(self, actions: np.ndarray, auto_reset: bool = False):
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        assert actions.shape == (self.n,)
+        reward = np.zeros(self.n, np.int32)
+        done = np.zeros(self.n, np.uint8)
+        bad = lib().po_batch_step(
+            self._h, _ptr(actions), _ptr(reward), _ptr(done), int(auto_reset)
+        )
+        if bad >= 0:
+            raise ValueError("Invalid action")
+        return reward, done.astype(bool)
+
+    def action_mask(self) -> np.ndarray:
+        out = np.zeros((self.n, 5), np.uint8)
+        lib().po_batch_action_mask(self._h, _ptr(out))
+        return out.astype(bool)
+
+    def obs(self) -> np.ndarray:
+        out = np.empty((self.n,) + OBS_SHAPE, np.float32)
+        lib().po_batch_obs(self._h, _ptr(out))
+        return out
+
+    def export_state(self) -> np.ndarray:
+        out = np.zeros(self.n, FLAT_DTYPE)
+        lib().po_batch_export(self._h, _ptr(out))
+        return out
+
+    def import_state(self, st: np.ndarray) -> None:
+        st = np.ascontiguousarray(st, dtype=FLAT_DTYPE)
+        assert st.shape == (self.n,)
+        lib().po_batch_import(self._h, _ptr(st))
+
+    def first_ai_done(self) -> np.ndarray:
+        L = lib()
+        return np.array(
+            [bool(L.po_gym_first_ai_done(L.po_batch_env(self._h, i))) for i in range(self.n)]
+        )
+
+    def is_done(self) -> np.ndarray:
+        L = lib()
+        return np.array([bool(L.po_gym_is_done(L.po_batch_env(self._h, i))) for i in range(self.n)])
+
+
+def rollout(n_envs: int, n_steps: int, warmup: int = 0, seed: int = 0, n_threads: int = 1):
+    """CPU baseline: returns (seconds, env_steps, checksum, episodes)."""
+    cs = C.c_uint64(0)
+    ep = C.c_int64(0)
+    secs = lib().po_rollout(
+        n_envs, n_steps, warmup, seed, n_threads, C.byref(cs), C.byref(ep)
+    )
+    return secs, n_envs * n_steps, cs.value, ep.value
