@@ -1,0 +1,213 @@
+/*
+ * pacbot_b200.h -- C ABI of the B200-native batched PacBot environment engine.
+ *
+ * Drop-in boundary for the one hot path of qxzcode/pacbot-rl: the pyo3 class `PacmanGym`
+ * (reference: pacbot_rs/src/lib.rs:17-25, pacbot_rs/src/env.rs:130-359, stub
+ * pacbot_rs/pacbot_rs.pyi:6-19).  Every entry point below names the reference method it
+ * replaces.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - `*_dev` pointers are device pointers on the engine's device, `*_host` are host pointers.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Calls that
+ *     take a stream are asynchronous on it unless stated otherwise.
+ *   - All functions return PB_OK (0) or a negative PB_ERR_* code and never throw.
+ *     `pb_last_error()` returns a thread-local human-readable message for the last failure.
+ *   - A handle is not thread-safe (the reference holds the GIL / a PyCell borrow for every call).
+ *   - Per-env config flags: bit0 random_start, bit1 random_ticks (the two ctor args,
+ *     env.rs:133), bit2 randomize_ghosts, bit3 remove_super_pellets (Rust-only config,
+ *     env.rs:14-21).
+ *   - Randomness is counter based: draw number `ctr` of env `g` (global env id = env_id_base + i)
+ *     is raw = pb_draw_raw(seed, g, ctr) and is mapped to [0, n) by (raw * n) >> 32.  The
+ *     per-env counter lives in the state (`rng_ctr`).  With a draw tape installed
+ *     (pb_set_draw_tape) raw = tape[i * tape_len + ctr % tape_len] instead: this is how parity
+ *     tests replay identical injected draws on the oracle and on the GPU.
+ */
+#ifndef PACBOT_B200_H
+#define PACBOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_VERSION 100 /* 0.1.0 */
+
+#define PB_OK 0
+#define PB_ERR_INVALID_ARG (-1)
+#define PB_ERR_CUDA (-2)
+#define PB_ERR_INVALID_ACTION (-3) /* reference: PyValueError("Invalid action"), env.rs:83-88 */
+#define PB_ERR_NO_DEVICE (-4)
+
+#define PB_ROWS 31
+#define PB_COLS 28
+#define PB_NUM_ACTIONS 5
+#define PB_OBS_CHANNELS 17
+#define PB_OBS_FLOATS (17 * 28 * 31) /* env.rs:23 OBS_SHAPE = (17, 28, 31); 59 024 bytes */
+
+#define PB_CFG_RANDOM_START 1u
+#define PB_CFG_RANDOM_TICKS 2u
+#define PB_CFG_RANDOMIZE_GHOSTS 4u
+#define PB_CFG_REMOVE_SUPER_PELLETS 8u
+
+/* pb_query selectors -- the scalar getters of PacmanGym */
+#define PB_Q_SCORE 0             /* score()             env.rs:269-271 */
+#define PB_Q_LIVES 1             /* lives()             env.rs:273-275 */
+#define PB_Q_IS_DONE 2           /* is_done()           env.rs:277-279 */
+#define PB_Q_FIRST_AI_DONE 3     /* first_ai_done()     env.rs:281-285 */
+#define PB_Q_REMAINING_PELLETS 4 /* remaining_pellets() env.rs:287-289 */
+#define PB_Q_TICKS_PER_STEP 5
+#define PB_Q_CURR_TICKS 6
+#define PB_Q_LEVEL 7
+#define PB_Q_UPDATE_PERIOD 8
+#define PB_Q_COUNT 9
+
+typedef struct pb_engine pb_engine; /* opaque: owns the device-resident SoA state of n envs */
+
+/* Host-side view of ONE env: the reference's `PacmanGym` fields (env.rs:96-110) plus the engine
+ * `GameState` fields its wrapper touches.  Directions: 0 up, 1 left,
+ * 2 down, 3 right, 4 none.  Modes: 1 scatter, 2 chase.  (32, 32) is the empty location. */
+typedef struct pb_env_state {
+    uint32_t curr_ticks;
+    uint32_t rng_ctr;
+    uint32_t pellets[PB_ROWS]; /* bit `col` of pellets[row], as GameState.pellets (env.rs:199) */
+    uint16_t level_steps;
+    uint16_t curr_score;
+    uint16_t num_pellets;
+    uint16_t last_score;
+    uint8_t update_period;
+    uint8_t mode;
+    uint8_t paused;
+    uint8_t pause_on_update;
+    uint8_t mode_steps;
+    uint8_t curr_level;
+    uint8_t curr_lives;
+    uint8_t ghost_combo;
+    uint8_t fruit_steps;
+    uint8_t last_action;
+    uint8_t ticks_per_step;
+    uint8_t cfg_flags;
+    int8_t pac_row, pac_col;
+    uint8_t pac_dir;
+    uint8_t reserved0;
+    int8_t g_row[4], g_col[4];
+    uint8_t g_dir[4];
+    int8_t g_next_row[4], g_next_col[4];
+    uint8_t g_next_dir[4];
+    uint8_t g_fright[4], g_trapped[4], g_spawning[4], g_eaten[4];
+} pb_env_state;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int pb_version(void);
+const char *pb_last_error(void);
+size_t pb_sizeof_env_state(void);
+/* packed device bytes per env (the S of SURVEY.md 8(d)): what one step reads and writes */
+int pb_state_bytes_per_env(void);
+/* raw draw of the counter RNG (host mirror of the device function; for tests and docs) */
+uint32_t pb_draw_raw(uint64_t seed, uint64_t env_gid, uint32_t ctr);
+/* raw draw used by pb_sample_actions */
+uint32_t pb_action_raw(uint64_t seed, uint64_t env_gid, uint64_t call_idx);
+
+/* maze tables the kernels use (host copies; derived from computed_data/node_coords.json):
+ * wall / initial-pellet row bitboards (bit `col` of row `row`), and NODE_COORDS[k]
+ * (pacbot_rs/src/grid.rs:13).  Return 0 / PB_ERR_INVALID_ARG. */
+uint32_t pb_maze_wall_row(int row);
+uint32_t pb_maze_pellet_row(int row);
+int pb_maze_node(int k, int *row, int *col);
+
+/* ---- lifetime --------------------------------------------------------------------------------
+ * pb_create replaces PacmanGym::new(random_start, random_ticks) (env.rs:133-138) for n envs:
+ * fresh unpaused game, ticks_per_step = 8, NOT randomised (call pb_reset for that).
+ * cfg_flags_host: n bytes or NULL (all zero). */
+int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_t env_id_base,
+              const uint8_t *cfg_flags_host);
+int pb_destroy(pb_engine *e);
+int64_t pb_num_envs(const pb_engine *e);
+int pb_device(const pb_engine *e);
+/* `random_start` property setter (env.rs:100-101) and friends; synchronous */
+int pb_set_cfg_flags(pb_engine *e, int64_t first, int64_t count, const uint8_t *cfg_flags_host);
+/* tape_dev: uint32 [n_envs][tape_len] on the device, borrowed; NULL restores the counter RNG */
+int pb_set_draw_tape(pb_engine *e, const uint32_t *tape_dev, int64_t tape_len);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* PacmanGym::reset (env.rs:140-212) for every env whose mask byte is non-zero (NULL = all). */
+int pb_reset(pb_engine *e, const uint8_t *mask_dev, void *stream);
+
+/* PacmanGym::step (env.rs:216-267) for all envs.
+ *   actions_dev  uint8 [n]  Action encoding env.rs:40-48 (0 stay, 1 down, 2 up, 3 left, 4 right)
+ *   reward_dev   int32 [n]
+ *   done_dev     uint8 [n]
+ *   mask_out_dev uint8 [n][5] or NULL: action_mask() (env.rs:293-302) of the state AFTER the step
+ *                (after the auto reset, if one happened)
+ *   auto_reset   non-zero: an env that finishes is reset in the same launch (reward/done still
+ *                describe the finished transition), so rollouts never leave the device.
+ * An action > 4 leaves that env untouched (reward 0, done 0) and records the lowest offending
+ * env index; see pb_check_actions.  Stepping an env that is already done is legal and does what
+ * the reference does (the engine keeps going). */
+int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8_t *done_dev,
+            uint8_t *mask_out_dev, int auto_reset, void *stream);
+
+/* PacmanGym::obs / obs_numpy (env.rs:305-307, 410-500) for all envs: float32 [17][28][31] per env
+ * written at out_dev + i * env_stride_floats (stride >= PB_OBS_FLOATS and a multiple of 4 floats;
+ * 0 means dense).  out_dev must be 16-byte aligned. */
+int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void *stream);
+
+/* Same for envs [first, first + count) only; env first + k is written at out_dev + k * stride.
+ * Lets a caller stream a large env population through a smaller observation ring. */
+int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_dev,
+                        int64_t env_stride_floats, void *stream);
+
+/* pb_step followed by pb_encode_obs of the resulting states, back to back on `stream`. */
+int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,
+                   uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev,
+                   int64_t env_stride_floats, void *stream);
+
+/* PacmanGym::action_mask (env.rs:293-302): uint8 [n][5]. */
+int pb_action_mask(pb_engine *e, uint8_t *mask_out_dev, void *stream);
+
+/* Scalar getters (PB_Q_*): int32 [n]. */
+int pb_query(pb_engine *e, int what, int32_t *out_dev, void *stream);
+
+/* Uniformly random VALID action per env from its current action mask (what EpsilonGreedy does
+ * at epsilon = 1, /root/reference/src/policies.py:29-32), drawn from the counter RNG's action
+ * stream keyed by (seed, env id, call_idx). */
+int pb_sample_actions(pb_engine *e, uint8_t *actions_dev, uint64_t call_idx, void *stream);
+
+/* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
+ * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */
+int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream);
+
+/* ---- state access (parity tests, MCTS-style cloning, checkpointing); synchronous ------------- */
+int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out_host);
+int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in_host);
+/* #[derive(Clone)] on PacmanGym (env.rs:96): copy env src_i of `src` over env dst_i of `dst` */
+int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t src_i, void *stream);
+
+/* ---- host-buffer entry point (what a per-call FFI binding would use) ------------------------- */
+/* Copies actions host->device, runs pb_step (+ pb_encode_obs when obs_out_dev != NULL), copies
+ * reward/done/mask device->host and synchronises `stream`.  Host pointers may be pageable or
+ * pinned; mask_host may be NULL.  Returns PB_ERR_INVALID_ACTION like pb_check_actions. */
+int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                 uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
+                 int64_t env_stride_floats, void *stream);
+/* obs of envs [first, first+count) straight to a host buffer (obs_numpy for a per-env view). */
+int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, void *stream);
+
+/* ---- on-device DQN helpers (reference: src/policies.py, src/replay_buffer.py) ---------------- */
+/* EpsilonGreedy(MaxQPolicy) (policies.py:16-59): with probability eps a uniformly random valid
+ * action, else argmax over valid actions of q (ties -> lowest index, like torch.argmax).
+ * q_dev float32 [n][5]; mask_dev uint8 [n][5] or NULL (= current action_mask()). */
+int pb_select_actions(pb_engine *e, const float *q_dev, const uint8_t *mask_dev, float epsilon,
+                      uint8_t *actions_dev, uint64_t call_idx, void *stream);
+/* Gather `count` observations (float32 [PB_OBS_FLOATS] each) from ring slots idx_dev[k]
+ * (int64 slot numbers) of ring_dev (slot stride in floats) into the dense out_dev, writing zeros
+ * where zero_mask_dev[k] != 0 (the `next_obs is None` case, train_dqn.py:154-159). */
+int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64_t *idx_dev,
+                  const uint8_t *zero_mask_dev, int64_t count, float *out_dev, int device,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACBOT_B200_H */

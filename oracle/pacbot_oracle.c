@@ -259,8 +259,12 @@ static void increment_level(po_game_state *g) {
     g->update_period = (uint8_t)(p < 1 ? 1 : p);
 }
 
-/* SURVEY B.5 [E10] */
+/* SURVEY B.5 [E10].  A collision needs Pac-Man on the board: right after a board clear or a death
+ * everything sits on the (32,32) sentinel and must not "collide" (otherwise clearing the board
+ * through set_pacman_location would immediately cost a life and env.rs:245-247 could never pay
+ * LAST_REWARD). */
 static void check_collisions(po_game_state *g) {
+    if (loc_is_empty(&g->pacman_loc)) return;
     uint8_t respawn_flag = 0;
     int n_respawn = 0;
     for (int i = 0; i < 4; i++) {

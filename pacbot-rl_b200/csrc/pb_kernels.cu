@@ -1,0 +1,980 @@
+// pb_kernels.cu -- sm_100a kernels and the C ABI (include/pacbot_b200.h) of the batched PacBot
+// environment engine.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (see build.py).
+//
+// Kernels
+//   k_step       one env per thread; packed state in, reward/done/mask out, optional auto reset
+//   k_reset      masked in-place PacmanGym::reset / constructor
+//   k_encode_obs one env per warp; the 59 024 B observation image is assembled in shared memory
+//                (constant wall channel + zero channels persist, only the dynamic cells are
+//                rewritten) and shipped to HBM by the TMA engine with cp.async.bulk (SASS UBLKCP)
+//   k_mask / k_query / k_sample_actions / k_select_actions / k_gather_obs / k_clone
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/pacbot_b200.h"
+#include "pb_engine.cuh"
+
+namespace pb {
+
+__constant__ MazeTables c_tab;
+
+// =============================================================================================
+// small PTX helpers (TMA bulk copy shared -> global)
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// =============================================================================================
+// state load / store for the one-env-per-thread kernels
+// =============================================================================================
+__device__ __forceinline__ void load_env(const StateView &st, long long i, EnvR &s) {
+    const uint4 c0 = st.core0[i], c1 = st.core1[i];
+    const uint4 ga = st.ghosts[i], gb = st.ghosts[st.npad + i];
+    unpack_env(c0, c1, ga, gb, s);
+}
+__device__ __forceinline__ void store_env(const StateView &st, long long i, const EnvR &s) {
+    uint4 c0, c1, ga, gb;
+    pack_env(s, c0, c1, ga, gb);
+    st.core0[i] = c0;
+    st.core1[i] = c1;
+    st.ghosts[i] = ga;
+    st.ghosts[st.npad + i] = gb;
+}
+
+struct RngParams {
+    uint64_t seed;
+    long long gid_base;
+    const uint32_t *tape;
+    long long tape_len;
+};
+__device__ __forceinline__ RngCtx make_rng(const RngParams &rp, long long i) {
+    RngCtx r;
+    r.seed = rp.seed;
+    r.gid = (uint64_t)(rp.gid_base + i);
+    r.tape = rp.tape ? rp.tape + i * rp.tape_len : nullptr;
+    r.tape_len = (uint32_t)rp.tape_len;
+    return r;
+}
+
+__device__ __forceinline__ void load_walls(uint32_t *s_walls) {
+    if (threadIdx.x < 32) s_walls[threadIdx.x] = c_tab.walls[threadIdx.x];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_mask(uint8_t *mask_out, long long i, uint32_t m) {
+    uint8_t *o = mask_out + i * 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) o[k] = (m >> k) & 1u;
+}
+
+// =============================================================================================
+// k_step
+// =============================================================================================
+constexpr int STEP_THREADS = 128;
+
+__global__ void __launch_bounds__(STEP_THREADS)
+k_step(StateView st, RngParams rp, const uint8_t *__restrict__ actions,
+       int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
+       uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    const int action = actions[i];
+    EnvR s;
+    load_env(st, i, s);
+    if (action > 4) {  // env.rs:83-88: "Invalid action" -- env untouched
+        atomicMin(bad_action, (unsigned long long)i);
+        reward[i] = 0;
+        done_out[i] = 0;
+        if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
+        return;
+    }
+    const PelRef pel{st.pel + i, st.npad};
+    const RngCtx rng = make_rng(rp, i);
+    int rew;
+    bool done;
+    gym_step(s, pel, c_tab, s_walls, rng, action, rew, done);
+    if (done && auto_reset) gym_reset(s, pel, c_tab, s_walls, rng, true);
+    store_env(st, i, s);
+    reward[i] = rew;
+    done_out[i] = done ? 1 : 0;
+    if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
+}
+
+// =============================================================================================
+// k_reset: mask == nullptr -> all envs; randomise == 0 -> constructor state (env.rs:133-138)
+// =============================================================================================
+__global__ void __launch_bounds__(STEP_THREADS)
+k_reset(StateView st, RngParams rp, const uint8_t *__restrict__ mask, int randomise) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    if (mask && !mask[i]) return;
+    EnvR s;
+    load_env(st, i, s);
+    const PelRef pel{st.pel + i, st.npad};
+    gym_reset(s, pel, c_tab, s_walls, make_rng(rp, i), randomise != 0);
+    store_env(st, i, s);
+}
+
+// =============================================================================================
+// k_mask / k_query
+// =============================================================================================
+__global__ void __launch_bounds__(STEP_THREADS) k_mask(StateView st, uint8_t *__restrict__ out) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    EnvR s;
+    load_env(st, i, s);
+    write_mask(out, i, action_mask_bits(s, s_walls));
+}
+
+__device__ __forceinline__ bool first_ai_done(const StateView &st, long long i, const EnvR &s) {
+    // env.rs:281-285: all four super pellets gone and no ghost frightened
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int b = fbit(k < 2 ? 3 : 23, (k & 1) ? 26 : 1);
+        any |= (st.pel[(long long)(b >> 5) * st.npad + i] >> (b & 31)) & 1u;
+    }
+    return !any && s.g[0].fright == 0 && s.g[1].fright == 0 && s.g[2].fright == 0 &&
+           s.g[3].fright == 0;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+k_query(StateView st, int what, int32_t *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    EnvR s;
+    load_env(st, i, s);
+    int v = 0;
+    switch (what) {
+    case PB_Q_SCORE: v = s.score; break;
+    case PB_Q_LIVES: v = s.lives; break;
+    case PB_Q_IS_DONE: v = is_done(s); break;
+    case PB_Q_FIRST_AI_DONE: v = first_ai_done(st, i, s); break;
+    case PB_Q_REMAINING_PELLETS: v = s.num_pellets; break;
+    case PB_Q_TICKS_PER_STEP: v = s.tps; break;
+    case PB_Q_CURR_TICKS: v = (int)s.ticks; break;
+    case PB_Q_LEVEL: v = s.level; break;
+    case PB_Q_UPDATE_PERIOD: v = s.period; break;
+    }
+    out[i] = v;
+}
+
+// =============================================================================================
+// k_sample_actions / k_select_actions (policies.py:16-59)
+// =============================================================================================
+__device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
+    while (k-- > 0) m &= m - 1;
+    return __ffs(m) - 1;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+k_sample_actions(StateView st, RngParams rp, uint8_t *__restrict__ actions,
+                 unsigned long long call_idx) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    const uint4 c1 = st.core1[i];
+    EnvR s;
+    s.prow = sx8(c1.x);
+    s.pcol = sx8(c1.x >> 8);
+    const uint32_t m = action_mask_bits(s, s_walls);
+    const uint32_t raw = action_raw(rp.seed, (uint64_t)(rp.gid_base + i), call_idx);
+    actions[i] = (uint8_t)kth_set_bit(m, (int)below(raw, (uint32_t)__popc(m)));
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+k_select_actions(StateView st, RngParams rp, const float *__restrict__ q,
+                 const uint8_t *__restrict__ mask_in, float epsilon,
+                 uint8_t *__restrict__ actions, unsigned long long call_idx) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    uint32_t m;
+    if (mask_in) {
+        m = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) m |= (mask_in[i * 5 + k] ? 1u : 0u) << k;
+    } else {
+        const uint4 c1 = st.core1[i];
+        EnvR s;
+        s.prow = sx8(c1.x);
+        s.pcol = sx8(c1.x >> 8);
+        m = action_mask_bits(s, s_walls);
+    }
+    const uint64_t gid = (uint64_t)(rp.gid_base + i);
+    // greedy iff rand > epsilon (policies.py:36), rand uniform in [0, 1) with 24 bits
+    const float u = (float)(action_raw(rp.seed, gid, 2ull * call_idx) >> 8) * (1.0f / 16777216.0f);
+    int a;
+    if (u > epsilon || m == 0u) {
+        float best = -INFINITY;
+        a = 0;
+        bool first = true;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float v = ((m >> k) & 1u) ? q[i * 5 + k] : -INFINITY;  // policies.py:57-58
+            if (first || v > best) {
+                best = v;
+                a = k;
+                first = false;
+            }
+        }
+    } else {
+        const uint32_t raw = action_raw(rp.seed, gid, 2ull * call_idx + 1ull);
+        a = kth_set_bit(m, (int)below(raw, (uint32_t)__popc(m)));
+    }
+    actions[i] = (uint8_t)a;
+}
+
+// =============================================================================================
+// k_encode_obs -- PacmanGym::obs (env.rs:410-500)
+//
+// One warp owns one 59 024 B image in shared memory.  The wall channel (ch 0) and the zeros of
+// the sparse channels are written once per kernel; per env the warp rewrites channel 1 (pellet
+// values: 4 pellet bits -> one 128-bit shared store), channel 15 (constant fill) and <= 18
+// single cells, then ONE lane hands the image to the TMA engine (cp.async.bulk shared->global,
+// 16 B granules, full-line HBM writes, no register staging).  While the TMA drains image k the
+// other warps of the SM build theirs; before a warp reuses its image it waits for the bulk
+// group's smem READ to finish and zeroes the cells it patched.
+// =============================================================================================
+constexpr int OBS_WARPS = 3;  // 3 x 59 024 B = 177 072 B of the 227 KB shared memory
+constexpr int OBS_THREADS = OBS_WARPS * 32;
+constexpr int OBS_SMEM = OBS_WARPS * OBS_BYTES;
+constexpr int CH_VEC = CH_FLOATS / 4;  // 217 float4 per channel
+
+__device__ __forceinline__ bool on_board(int row, int col) {
+    return (unsigned)row < (unsigned)ROWS && (unsigned)col < (unsigned)COLS;
+}
+__device__ __forceinline__ int obs_cell(int row, int col) {  // env.rs:124: [col][30 - row]
+    return col * ROWS + (ROWS - 1 - row);
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(OBS_THREADS, 1)
+k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
+             long long env_count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * OBS_BYTES);
+    float4 *img4 = reinterpret_cast<float4 *>(img);
+
+    // one-time image init: zeros + wall template (env.rs:426)
+    for (int q = lane; q < OBS_FLOATS / 4; q += 32) img4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    for (int c = lane; c < CH_FLOATS; c += 32) {
+        const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
+        img[c] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
+    }
+    __syncwarp();
+
+    const long long gw = (long long)blockIdx.x * OBS_WARPS + warp;
+    const long long nw = (long long)gridDim.x * OBS_WARPS;
+    int patched = -1;  // flat offset this lane set in the previous image (sparse channels only)
+
+    for (long long k = gw; k < env_count; k += nw) {
+        const long long i = env_first + k;
+        // ---- state loads (issued before the wait so their latency hides behind the drain) ----
+        const uint32_t F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
+        const uint4 c0 = st.core0[i], c1 = st.core1[i];
+        const uint4 ga = st.ghosts[i], gb = st.ghosts[st.npad + i];
+        EnvR s;
+        unpack_env(c0, c1, ga, gb, s);
+
+        // ---- image is free once the previous bulk store has finished READING it ----
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        if (patched >= 0) img[patched] = 0.0f;
+        patched = -1;
+        __syncwarp();  // un-patching must land before another lane patches the same cell
+
+        // ---- channel 1: pellet values (env.rs:427-441); bit order == float order ----
+        const float pv = (s.num_pellets == 1) ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
+                                              : (float)PELLET_POINTS / 200.0f;
+#pragma unroll
+        for (int it = 0; it < 7; it++) {
+            const int q = lane + 32 * it;  // float4 index inside the channel
+            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
+            if (q < CH_VEC) {
+                const uint32_t nib = w >> (4 * (lane & 7));
+                float4 v;
+                v.x = (nib & 1u) ? pv : 0.0f;
+                v.y = (nib & 2u) ? pv : 0.0f;
+                v.z = (nib & 4u) ? pv : 0.0f;
+                v.w = (nib & 8u) ? pv : 0.0f;
+                img4[CH_VEC * 1 + q] = v;
+            }
+        }
+        // ---- channel 15: ticks_per_step / update_period everywhere (env.rs:482-484) ----
+        {
+            const float sp = __fdiv_rn((float)s.tps, (float)s.period);
+            const float4 v = make_float4(sp, sp, sp, sp);
+#pragma unroll
+            for (int it = 0; it < 7; it++) {
+                const int q = lane + 32 * it;
+                if (q < CH_VEC) img4[CH_VEC * 15 + q] = v;
+            }
+        }
+        // ---- sparse cells: one lane each ----
+        // lanes 14..17 need the pellet word holding "their" super pellet (warp-wide shuffle)
+        const int sup_k = (lane - 14) & 3;
+        const int sup_bit = obs_cell(sup_k < 2 ? 3 : 23, (sup_k & 1) ? 26 : 1);
+        const uint32_t sup_word = __shfl_sync(0xffffffffu, F, sup_bit >> 5);
+        // env.rs:122-128: a location is drawn unless it is the (32, 32) sentinel; anything off
+        // the 31x28 board is treated the same way so a malformed state can never write outside
+        // its image
+        const bool pac_on = on_board(s.prow, s.pcol);
+        if (lane < 2) {  // ch 2, 3 (env.rs:452-457)
+            if (pac_on) {
+                patched = CH_FLOATS * (2 + lane) + obs_cell(s.prow, s.pcol);
+                img[patched] = 1.0f;
+            }
+        } else if (lane < 14) {
+            const int gi = (lane - 2) & 3, kind = (lane - 2) >> 2;  // kind 0: ch4+g, 1: ch8+g, 2: timer
+            int grow = 0, gcol = 0, gfr = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                if (g == gi) {
+                    grow = s.g[g].row;
+                    gcol = s.g[g].col;
+                    gfr = s.g[g].fright;
+                }
+            if (on_board(grow, gcol)) {
+                const int cell = obs_cell(grow, gcol);
+                if (kind < 2) {  // env.rs:461, 476-480
+                    patched = CH_FLOATS * (4 + 4 * kind + gi) + cell;
+                    img[patched] = 1.0f;
+                } else {  // env.rs:462-469; "last ghost wins" on a shared cell
+                    const int ch = gfr > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
+                    bool later_same = false;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const bool on = on_board(s.g[g].row, s.g[g].col);
+                        const int gch = s.g[g].fright > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
+                        if (g > gi && on && s.g[g].row == grow && s.g[g].col == gcol && gch == ch)
+                            later_same = true;
+                    }
+                    if (!later_same) {
+                        patched = CH_FLOATS * ch + cell;
+                        img[patched] = gfr > 0 ? __fdiv_rn((float)gfr, (float)GHOST_FRIGHT_STEPS)
+                                               : __fdiv_rn((float)s.mode_steps, (float)CHASE_DURATION);
+                    }
+                }
+            }
+        } else if (lane < 18) {  // ch 16: super pellets still present (env.rs:487-497)
+            if ((sup_word >> (sup_bit & 31)) & 1u) {
+                patched = CH_FLOATS * 16 + sup_bit;
+                img[patched] = 1.0f;
+            }
+        }
+        __syncwarp();
+        // ---- channel 1 fix-ups, in reference order: super value, fruit, then += ghost bonus ----
+        if (lane == 0) {
+            float *r1 = img + CH_FLOATS;
+            const float sv = (s.num_pellets == 1) ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
+                                                  : (float)SUPER_PELLET_POINTS / 200.0f;
+#pragma unroll
+            for (int kq = 0; kq < 4; kq++) {
+                const int b = obs_cell(kq < 2 ? 3 : 23, (kq & 1) ? 26 : 1);
+                if (r1[b] != 0.0f) r1[b] = sv;
+            }
+            if (s.fruit_steps > 0) {  // env.rs:433-437 (only where there is no pellet)
+                const int b = obs_cell(FRUIT_ROW, FRUIT_COL);
+                if (r1[b] == 0.0f) r1[b] = (float)FRUIT_POINTS / 200.0f;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {  // env.rs:464
+                if (s.g[g].fright > 0 && on_board(s.g[g].row, s.g[g].col)) {
+                    const int b = obs_cell(s.g[g].row, s.g[g].col);
+                    r1[b] = __fadd_rn(r1[b], (float)(1 << s.combo));
+                }
+            }
+        }
+        // ---- hand the image to the TMA engine ----
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            char *dst = reinterpret_cast<char *>(out + k * env_stride);
+            constexpr int CHUNK_BYTES = OBS_BYTES / CHUNKS;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; c++)
+                bulk_store_s2g(dst + c * CHUNK_BYTES, reinterpret_cast<char *>(img) + c * CHUNK_BYTES,
+                               CHUNK_BYTES);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+// =============================================================================================
+// k_gather_obs (train_dqn.py:153-159 collate) and k_clone
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_gather_obs(const float4 *__restrict__ ring, long long slot_stride4,
+             const long long *__restrict__ idx, const uint8_t *__restrict__ zero_mask,
+             float4 *__restrict__ out) {
+    const long long k = blockIdx.x;
+    const bool zero = zero_mask && zero_mask[k];
+    const float4 *src = ring + idx[k] * slot_stride4;
+    float4 *dst = out + k * (OBS_FLOATS / 4);
+    for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += 256)
+        dst[q] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(src + q);
+}
+
+__global__ void k_clone(StateView dst, long long di, StateView src, long long si) {
+    const int t = threadIdx.x;
+    if (t == 0) dst.core0[di] = src.core0[si];
+    if (t == 1) dst.core1[di] = src.core1[si];
+    if (t == 2) dst.ghosts[di] = src.ghosts[si];
+    if (t == 3) dst.ghosts[dst.npad + di] = src.ghosts[src.npad + si];
+    if (t >= 4 && t < 4 + PEL_WORDS)
+        dst.pel[(long long)(t - 4) * dst.npad + di] = src.pel[(long long)(t - 4) * src.npad + si];
+}
+
+}  // namespace pb
+
+// =============================================================================================
+// Host side: the C ABI
+// =============================================================================================
+using namespace pb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define PB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+struct pb_engine {
+    int device = 0;
+    long long n = 0, npad = 0;
+    uint64_t seed = 0;
+    long long gid_base = 0;
+    StateView st{};
+    const uint32_t *tape = nullptr;
+    long long tape_len = 0;
+    unsigned long long *bad_action = nullptr;  // device
+    // staging for the host-buffer entry points
+    uint8_t *stg_actions = nullptr;
+    int32_t *stg_reward = nullptr;
+    uint8_t *stg_done = nullptr;
+    uint8_t *stg_mask = nullptr;
+    float *stg_obs = nullptr;
+    long long stg_obs_envs = 0;
+    int num_sms = 148;
+};
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+RngParams rng_params(const pb_engine *e) {
+    return RngParams{e->seed, e->gid_base, e->tape, e->tape_len};
+}
+unsigned grid_for(long long n) { return (unsigned)((n + STEP_THREADS - 1) / STEP_THREADS); }
+
+void flat_to_rows(const uint32_t *f, uint32_t rows[PB_ROWS]) {
+    for (int r = 0; r < PB_ROWS; r++) rows[r] = 0;
+    for (int r = 0; r < ROWS; r++)
+        for (int c = 0; c < COLS; c++) {
+            const int i = fbit(r, c);
+            if ((f[i >> 5] >> (i & 31)) & 1u) rows[r] |= 1u << c;
+        }
+}
+void rows_to_flat(const uint32_t rows[PB_ROWS], uint32_t *f) {
+    for (int w = 0; w < PEL_WORDS; w++) f[w] = 0;
+    for (int r = 0; r < ROWS; r++)
+        for (int c = 0; c < COLS; c++)
+            if ((rows[r] >> c) & 1u) {
+                const int i = fbit(r, c);
+                f[i >> 5] |= 1u << (i & 31);
+            }
+}
+
+int launch_encode(pb_engine *e, float *out_dev, long long stride, long long first,
+                  long long count, cudaStream_t s) {
+    if (count <= 0) return PB_OK;
+    static thread_local int attr_set_for = -1;
+    auto kern = k_encode_obs<1>;
+    if (attr_set_for != e->device) {
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM));
+        attr_set_for = e->device;
+    }
+    long long blocks = (count + OBS_WARPS - 1) / OBS_WARPS;
+    if (blocks > e->num_sms) blocks = e->num_sms;
+    kern<<<(unsigned)blocks, OBS_THREADS, OBS_SMEM, s>>>(e->st, out_dev, stride, first, count);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pb_version(void) { return PB_VERSION; }
+const char *pb_last_error(void) { return g_err.c_str(); }
+size_t pb_sizeof_env_state(void) { return sizeof(pb_env_state); }
+int pb_state_bytes_per_env(void) { return STATE_BYTES_PER_ENV; }
+uint32_t pb_draw_raw(uint64_t seed, uint64_t env_gid, uint32_t ctr) {
+    return draw_raw(seed, env_gid, ctr);
+}
+uint32_t pb_action_raw(uint64_t seed, uint64_t env_gid, uint64_t call_idx) {
+    return action_raw(seed, env_gid, call_idx);
+}
+
+uint32_t pb_maze_wall_row(int row) { return (row >= 0 && row < ROWS) ? H_TABLES.walls[row] : 0u; }
+uint32_t pb_maze_pellet_row(int row) {
+    if (row < 0 || row >= ROWS) return 0u;
+    uint32_t rows[PB_ROWS];
+    flat_to_rows(H_TABLES.init_pel, rows);
+    return rows[row];
+}
+int pb_maze_node(int k, int *row, int *col) {
+    if (k < 0 || k >= NUM_NODES || !row || !col) return PB_ERR_INVALID_ARG;
+    *row = H_TABLES.node_rc[k] & 0xff;
+    *col = H_TABLES.node_rc[k] >> 8;
+    return PB_OK;
+}
+
+int pb_destroy(pb_engine *e) {
+    if (!e) return PB_OK;
+    DeviceGuard g(e->device);
+    cudaFree(e->st.core0);
+    cudaFree(e->st.core1);
+    cudaFree(e->st.ghosts);
+    cudaFree(e->st.pel);
+    cudaFree(e->bad_action);
+    cudaFree(e->stg_actions);
+    cudaFree(e->stg_reward);
+    cudaFree(e->stg_done);
+    cudaFree(e->stg_mask);
+    cudaFree(e->stg_obs);
+    delete e;
+    return PB_OK;
+}
+
+int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_t env_id_base,
+              const uint8_t *cfg_flags_host) {
+    if (!out || n_envs <= 0) return fail(PB_ERR_INVALID_ARG, "pb_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PB_ERR_NO_DEVICE, "pb_create: no CUDA device (this engine has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(PB_ERR_INVALID_ARG, "pb_create: bad device");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(PB_ERR_CUDA, "pb_create: cudaSetDevice failed");
+    pb_engine *e = new pb_engine();
+    e->device = device;
+    e->n = n_envs;
+    e->npad = (n_envs + 31) / 32 * 32;
+    e->seed = seed;
+    e->gid_base = env_id_base;
+    e->st.n = e->n;
+    e->st.npad = e->npad;
+#define PB_CUDA_OR_FREE(call)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            pb_destroy(e);                                                                     \
+            return fail(PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                      \
+    } while (0)
+    PB_CUDA_OR_FREE(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
+    PB_CUDA_OR_FREE(cudaMemcpyToSymbol(c_tab, &H_TABLES, sizeof(MazeTables)));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->st.core0, sizeof(uint4) * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->st.core1, sizeof(uint4) * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->st.ghosts, sizeof(uint4) * 2 * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->st.pel, sizeof(uint32_t) * PEL_WORDS * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->bad_action, sizeof(unsigned long long)));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->stg_actions, e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->stg_reward, sizeof(int32_t) * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->stg_done, e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->stg_mask, 5 * e->npad));
+    PB_CUDA_OR_FREE(cudaMemset(e->st.core0, 0, sizeof(uint4) * e->npad));
+    PB_CUDA_OR_FREE(cudaMemset(e->st.core1, 0, sizeof(uint4) * e->npad));
+    PB_CUDA_OR_FREE(cudaMemset(e->st.ghosts, 0, sizeof(uint4) * 2 * e->npad));
+    PB_CUDA_OR_FREE(cudaMemset(e->st.pel, 0, sizeof(uint32_t) * PEL_WORDS * e->npad));
+    PB_CUDA_OR_FREE(cudaMemset(e->bad_action, 0xff, sizeof(unsigned long long)));
+    // config flags live in core1.z bits 8..15; write them, then run the constructor path
+    {
+        std::vector<uint4> c1((size_t)e->npad, make_uint4(0, 0, 0, 0));
+        for (long long i = 0; i < e->n; i++)
+            c1[(size_t)i].z = (uint32_t)(cfg_flags_host ? (cfg_flags_host[i] & 0x0f) : 0) << 8;
+        PB_CUDA_OR_FREE(cudaMemcpy(e->st.core1, c1.data(), sizeof(uint4) * e->npad,
+                                   cudaMemcpyHostToDevice));
+    }
+    k_reset<<<grid_for(e->n), STEP_THREADS>>>(e->st, rng_params(e), nullptr, 0);
+    PB_CUDA_OR_FREE(cudaGetLastError());
+    PB_CUDA_OR_FREE(cudaDeviceSynchronize());
+#undef PB_CUDA_OR_FREE
+    *out = e;
+    return PB_OK;
+}
+
+int64_t pb_num_envs(const pb_engine *e) { return e ? e->n : 0; }
+int pb_device(const pb_engine *e) { return e ? e->device : -1; }
+
+int pb_set_cfg_flags(pb_engine *e, int64_t first, int64_t count, const uint8_t *cfg) {
+    if (!e || !cfg || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_set_cfg_flags: bad arguments");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(e->device);
+    std::vector<uint4> c1((size_t)count);
+    PB_CUDA(cudaMemcpy(c1.data(), e->st.core1 + first, sizeof(uint4) * count,
+                       cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < count; i++)
+        c1[(size_t)i].z = (c1[(size_t)i].z & ~0xff00u) | ((uint32_t)(cfg[i] & 0x0f) << 8);
+    PB_CUDA(cudaMemcpy(e->st.core1 + first, c1.data(), sizeof(uint4) * count,
+                       cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+int pb_set_draw_tape(pb_engine *e, const uint32_t *tape_dev, int64_t tape_len) {
+    if (!e || (tape_dev && tape_len <= 0) || tape_len > 0x7fffffffLL)
+        return fail(PB_ERR_INVALID_ARG, "pb_set_draw_tape: bad arguments");
+    e->tape = tape_dev;
+    e->tape_len = tape_dev ? tape_len : 0;
+    return PB_OK;
+}
+
+int pb_reset(pb_engine *e, const uint8_t *mask_dev, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_reset: null engine");
+    DeviceGuard g(e->device);
+    k_reset<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(e->st, rng_params(e),
+                                                                       mask_dev, 1);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8_t *done_dev,
+            uint8_t *mask_out_dev, int auto_reset, void *stream) {
+    if (!e || !actions_dev || !reward_dev || !done_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_step: null argument");
+    DeviceGuard g(e->device);
+    k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->bad_action);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_dev,
+                        int64_t env_stride_floats, void *stream) {
+    if (!e || !out_dev || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_encode_obs: bad arguments");
+    if (env_stride_floats == 0) env_stride_floats = OBS_FLOATS;
+    if (env_stride_floats < OBS_FLOATS || (env_stride_floats & 3) ||
+        (reinterpret_cast<uintptr_t>(out_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG,
+                    "pb_encode_obs: stride must be >= 14756 and a multiple of 4 floats, "
+                    "out must be 16-byte aligned");
+    DeviceGuard g(e->device);
+    return launch_encode(e, out_dev, env_stride_floats, first, count, (cudaStream_t)stream);
+}
+
+int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_encode_obs: null engine");
+    return pb_encode_obs_range(e, 0, e->n, out_dev, env_stride_floats, stream);
+}
+
+int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,
+                   uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev,
+                   int64_t env_stride_floats, void *stream) {
+    int rc = pb_step(e, actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset, stream);
+    if (rc != PB_OK) return rc;
+    return pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
+}
+
+int pb_action_mask(pb_engine *e, uint8_t *mask_out_dev, void *stream) {
+    if (!e || !mask_out_dev) return fail(PB_ERR_INVALID_ARG, "pb_action_mask: null argument");
+    DeviceGuard g(e->device);
+    k_mask<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(e->st, mask_out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_query(pb_engine *e, int what, int32_t *out_dev, void *stream) {
+    if (!e || !out_dev || what < 0 || what >= PB_Q_COUNT)
+        return fail(PB_ERR_INVALID_ARG, "pb_query: bad arguments");
+    DeviceGuard g(e->device);
+    k_query<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(e->st, what, out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_sample_actions(pb_engine *e, uint8_t *actions_dev, uint64_t call_idx, void *stream) {
+    if (!e || !actions_dev) return fail(PB_ERR_INVALID_ARG, "pb_sample_actions: null argument");
+    DeviceGuard g(e->device);
+    k_sample_actions<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), actions_dev, call_idx);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_select_actions(pb_engine *e, const float *q_dev, const uint8_t *mask_dev, float epsilon,
+                      uint8_t *actions_dev, uint64_t call_idx, void *stream) {
+    if (!e || !q_dev || !actions_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_select_actions: null argument");
+    DeviceGuard g(e->device);
+    k_select_actions<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), q_dev, mask_dev, epsilon, actions_dev, call_idx);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_check_actions: null engine");
+    DeviceGuard g(e->device);
+    unsigned long long bad = ~0ull;
+    cudaStream_t s = (cudaStream_t)stream;
+    PB_CUDA(cudaMemcpyAsync(&bad, e->bad_action, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    if (bad == ~0ull) return PB_OK;
+    PB_CUDA(cudaMemsetAsync(e->bad_action, 0xff, sizeof(bad), s));
+    if (first_bad_env) *first_bad_env = (int64_t)bad;
+    return fail(PB_ERR_INVALID_ACTION, "Invalid action");
+}
+
+int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out) {
+    if (!e || !out || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_get_state: bad arguments");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(e->device);
+    PB_CUDA(cudaDeviceSynchronize());
+    const size_t c = (size_t)count;
+    std::vector<uint4> c0(c), c1(c), ga(c), gb(c);
+    std::vector<uint32_t> pel(c * PEL_WORDS);
+    PB_CUDA(cudaMemcpy(c0.data(), e->st.core0 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(c1.data(), e->st.core1 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(ga.data(), e->st.ghosts + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy(gb.data(), e->st.ghosts + e->npad + first, sizeof(uint4) * c,
+                       cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpy2D(pel.data(), sizeof(uint32_t) * c, e->st.pel + first,
+                         sizeof(uint32_t) * e->npad, sizeof(uint32_t) * c, PEL_WORDS,
+                         cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < c; i++) {
+        EnvR s;
+        unpack_env(c0[i], c1[i], ga[i], gb[i], s);
+        pb_env_state &o = out[i];
+        memset(&o, 0, sizeof(o));
+        o.curr_ticks = s.ticks;
+        o.rng_ctr = s.rng_ctr;
+        uint32_t f[PEL_WORDS];
+        for (int w = 0; w < PEL_WORDS; w++) f[w] = pel[(size_t)w * c + i];
+        flat_to_rows(f, o.pellets);
+        o.level_steps = (uint16_t)s.level_steps;
+        o.curr_score = (uint16_t)s.score;
+        o.num_pellets = (uint16_t)s.num_pellets;
+        o.last_score = (uint16_t)s.last_score;
+        o.update_period = (uint8_t)s.period;
+        o.mode = (uint8_t)s.mode;
+        o.paused = (s.flags & F_PAUSED) ? 1 : 0;
+        o.pause_on_update = (s.flags & F_PAUSE_ON_UPDATE) ? 1 : 0;
+        o.mode_steps = (uint8_t)s.mode_steps;
+        o.curr_level = (uint8_t)s.level;
+        o.curr_lives = (uint8_t)s.lives;
+        o.ghost_combo = (uint8_t)s.combo;
+        o.fruit_steps = (uint8_t)s.fruit_steps;
+        o.last_action = (uint8_t)s.last_action;
+        o.ticks_per_step = (uint8_t)s.tps;
+        o.cfg_flags = (uint8_t)s.cfg;
+        o.pac_row = (int8_t)s.prow;
+        o.pac_col = (int8_t)s.pcol;
+        o.pac_dir = (uint8_t)s.pdir;
+        for (int k = 0; k < 4; k++) {
+            o.g_row[k] = (int8_t)s.g[k].row;
+            o.g_col[k] = (int8_t)s.g[k].col;
+            o.g_dir[k] = (uint8_t)s.g[k].dir;
+            o.g_next_row[k] = (int8_t)s.g[k].nrow;
+            o.g_next_col[k] = (int8_t)s.g[k].ncol;
+            o.g_next_dir[k] = (uint8_t)s.g[k].ndir;
+            o.g_fright[k] = (uint8_t)s.g[k].fright;
+            o.g_trapped[k] = (uint8_t)s.g[k].trapped;
+            o.g_spawning[k] = (s.gflags >> k) & 1;
+            o.g_eaten[k] = (s.gflags >> (4 + k)) & 1;
+        }
+    }
+    return PB_OK;
+}
+
+int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in) {
+    if (!e || !in || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_set_state: bad arguments");
+    if (count == 0) return PB_OK;
+    const size_t c = (size_t)count;
+    std::vector<uint4> c0(c), c1(c), ga(c), gb(c);
+    std::vector<uint32_t> pel(c * PEL_WORDS);
+    for (size_t i = 0; i < c; i++) {
+        const pb_env_state &o = in[i];
+        if (o.update_period == 0)
+            return fail(PB_ERR_INVALID_ARG, "pb_set_state: update_period must be >= 1");
+        EnvR s;
+        s.ticks = o.curr_ticks;
+        s.rng_ctr = o.rng_ctr;
+        s.level_steps = o.level_steps;
+        s.score = o.curr_score;
+        s.num_pellets = o.num_pellets;
+        s.last_score = o.last_score;
+        s.period = o.update_period;
+        s.mode = o.mode;
+        s.flags = (o.paused ? F_PAUSED : 0) | (o.pause_on_update ? F_PAUSE_ON_UPDATE : 0);
+        s.mode_steps = o.mode_steps;
+        s.level = o.curr_level;
+        s.lives = o.curr_lives;
+        s.combo = o.ghost_combo;
+        s.fruit_steps = o.fruit_steps;
+        s.last_action = o.last_action;
+        s.tps = o.ticks_per_step;
+        s.cfg = o.cfg_flags & 0x0f;
+        s.prow = o.pac_row;
+        s.pcol = o.pac_col;
+        s.pdir = o.pac_dir;
+        s.gflags = 0;
+        for (int k = 0; k < 4; k++) {
+            s.g[k].row = o.g_row[k];
+            s.g[k].col = o.g_col[k];
+            s.g[k].dir = o.g_dir[k];
+            s.g[k].nrow = o.g_next_row[k];
+            s.g[k].ncol = o.g_next_col[k];
+            s.g[k].ndir = o.g_next_dir[k];
+            s.g[k].fright = o.g_fright[k];
+            s.g[k].trapped = o.g_trapped[k];
+            s.gflags |= (o.g_spawning[k] ? 1 : 0) << k;
+            s.gflags |= (o.g_eaten[k] ? 1 : 0) << (4 + k);
+        }
+        pack_env(s, c0[i], c1[i], ga[i], gb[i]);
+        uint32_t f[PEL_WORDS];
+        rows_to_flat(o.pellets, f);
+        for (int w = 0; w < PEL_WORDS; w++) pel[(size_t)w * c + i] = f[w];
+    }
+    DeviceGuard g(e->device);
+    PB_CUDA(cudaDeviceSynchronize());
+    PB_CUDA(cudaMemcpy(e->st.core0 + first, c0.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(e->st.core1 + first, c1.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(e->st.ghosts + first, ga.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(e->st.ghosts + e->npad + first, gb.data(), sizeof(uint4) * c,
+                       cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy2D(e->st.pel + first, sizeof(uint32_t) * e->npad, pel.data(),
+                         sizeof(uint32_t) * c, sizeof(uint32_t) * c, PEL_WORDS,
+                         cudaMemcpyHostToDevice));
+    return PB_OK;
+}
+
+int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t src_i,
+                 void *stream) {
+    if (!dst || !src || dst_i < 0 || dst_i >= dst->n || src_i < 0 || src_i >= src->n ||
+        dst->device != src->device)
+        return fail(PB_ERR_INVALID_ARG, "pb_clone_env: bad arguments");
+    DeviceGuard g(dst->device);
+    k_clone<<<1, 32, 0, (cudaStream_t)stream>>>(dst->st, dst_i, src->st, src_i);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                 uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
+                 int64_t env_stride_floats, void *stream) {
+    if (!e || !actions_host || !reward_host || !done_host)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_host: null argument");
+    DeviceGuard g(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PB_CUDA(cudaMemcpyAsync(e->stg_actions, actions_host, (size_t)e->n, cudaMemcpyHostToDevice, s));
+    int rc = pb_step(e, e->stg_actions, e->stg_reward, e->stg_done, mask_host ? e->stg_mask : nullptr,
+                     auto_reset, stream);
+    if (rc != PB_OK) return rc;
+    if (obs_out_dev) {
+        rc = pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
+        if (rc != PB_OK) return rc;
+    }
+    PB_CUDA(cudaMemcpyAsync(reward_host, e->stg_reward, sizeof(int32_t) * (size_t)e->n,
+                            cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(done_host, e->stg_done, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    if (mask_host)
+        PB_CUDA(cudaMemcpyAsync(mask_host, e->stg_mask, 5 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    return pb_check_actions(e, nullptr, stream);
+}
+
+int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, void *stream) {
+    if (!e || !obs_host || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_obs_host: bad arguments");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->stg_obs_envs < count) {
+        PB_CUDA(cudaStreamSynchronize(s));
+        cudaFree(e->stg_obs);
+        e->stg_obs = nullptr;
+        e->stg_obs_envs = 0;
+        PB_CUDA(cudaMalloc(&e->stg_obs, sizeof(float) * OBS_FLOATS * (size_t)count));
+        e->stg_obs_envs = count;
+    }
+    int rc = launch_encode(e, e->stg_obs, OBS_FLOATS, first, count, s);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(cudaMemcpyAsync(obs_host, e->stg_obs, sizeof(float) * OBS_FLOATS * (size_t)count,
+                            cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    return PB_OK;
+}
+
+int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64_t *idx_dev,
+                  const uint8_t *zero_mask_dev, int64_t count, float *out_dev, int device,
+                  void *stream) {
+    if (!ring_dev || !idx_dev || !out_dev || count < 0 || (slot_stride_floats & 3) ||
+        slot_stride_floats < OBS_FLOATS || (reinterpret_cast<uintptr_t>(ring_dev) & 15) ||
+        (reinterpret_cast<uintptr_t>(out_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG, "pb_gather_obs: bad arguments");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(device);
+    k_gather_obs<<<(unsigned)count, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(ring_dev), slot_stride_floats / 4,
+        reinterpret_cast<const long long *>(idx_dev), zero_mask_dev,
+        reinterpret_cast<float4 *>(out_dev));
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+"""Batched, GPU-resident PacBot environments: the host-side mirror of the reference's
+`PacmanGym` (pacbot_rs/src/env.rs:130-359, pacbot_rs/pacbot_rs.pyi:6-19) over N envs at once.
+
+All tensors live on the engine's CUDA device and every call is enqueued on the caller's current
+torch stream.  PyTorch is plumbing here (memory + streams); the work is done by the sm_100a
+kernels behind the C ABI in include/pacbot_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (
+    CFG_RANDOM_START,
+    CFG_RANDOM_TICKS,
+    CFG_RANDOMIZE_GHOSTS,
+    CFG_REMOVE_SUPER_PELLETS,
+    ENV_STATE_DTYPE,
+    NUM_ACTIONS,
+    OBS_FLOATS,
+    OBS_SHAPE,
+    check,
+)
+
+BoolOrSeq = Union[bool, Sequence[bool], np.ndarray]
+
+
+def _per_env_flags(n: int, random_start, random_ticks, randomize_ghosts, remove_super_pellets):
+    def expand(v):
+        a = np.asarray(v, dtype=bool)
+        if a.ndim == 0:
+            a = np.full(n, bool(a))
+        if a.shape != (n,):
+            raise ValueError(f"per-env flag must be a bool or have shape ({n},)")
+        return a
+
+    f = np.zeros(n, np.uint8)
+    f |= expand(random_start).astype(np.uint8) * CFG_RANDOM_START
+    f |= expand(random_ticks).astype(np.uint8) * CFG_RANDOM_TICKS
+    f |= expand(randomize_ghosts).astype(np.uint8) * CFG_RANDOMIZE_GHOSTS
+    f |= expand(remove_super_pellets).astype(np.uint8) * CFG_REMOVE_SUPER_PELLETS
+    return f
+
+
+class BatchedPacmanGym:
+    """N independent `PacmanGym`s stepped by one kernel launch.
+
+    Same semantics per env as the reference class; batched signatures:
+      reset(mask=None), step(actions) -> (reward int32[N], done bool[N]),
+      action_mask() -> bool[N,5], obs(out=None) -> float32[N,17,28,31], scalar getters -> [N].
+    """
+
+    def __init__(
+        self,
+        num_envs: int,
+        random_start: BoolOrSeq = False,
+        random_ticks: BoolOrSeq = False,
+        *,
+        device: Union[None, int, str, torch.device] = None,
+        seed: int = 0,
+        env_id_base: int = 0,
+        randomize_ghosts: BoolOrSeq = False,
+        remove_super_pellets: BoolOrSeq = False,
+        auto_reset: bool = False,
+    ) -> None:
+        L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.PacbotB200Error(
+                "no CUDA device: the pacbot_b200 engine has no CPU path (use a B200)"
+            )
+        dev = torch.device("cuda" if device is None else device)
+        if dev.type != "cuda":
+            raise ValueError("BatchedPacmanGym needs a CUDA device")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self._cfg = _per_env_flags(
+            self.num_envs, random_start, random_ticks, randomize_ghosts, remove_super_pellets
+        )
+        self._L = L
+        self._h = C.c_void_p()
+        self._tape = None
+        self._sample_calls = 0
+        self._select_calls = 0
+        check(
+            L.pb_create(
+                C.byref(self._h),
+                self.num_envs,
+                dev.index,
+                self.seed & 0xFFFFFFFFFFFFFFFF,
+                self.env_id_base,
+                self._cfg.ctypes.data_as(C.c_void_p),
+            )
+        )
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.pb_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return self.num_envs
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _check_tensor(self, t: torch.Tensor, shape, dtype, name: str) -> torch.Tensor:
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape):
+            raise ValueError(
+                f"{name}: expected {dtype} tensor of shape {tuple(shape)} on {self.device}, "
+                f"got {t.dtype} {tuple(t.shape)} on {t.device}"
+            )
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: must be contiguous")
+        return t
+
+    def _actions_u8(self, actions) -> torch.Tensor:
+        if not isinstance(actions, torch.Tensor):
+            a = np.asarray(actions)
+            if a.shape != (self.num_envs,):
+                raise ValueError(f"actions: expected shape ({self.num_envs},)")
+            if a.dtype.kind not in "iu":
+                raise TypeError("actions must be integers")
+            if ((a < 0) | (a > 255)).any():
+                # pyo3 `u8` extraction failure (env.rs:85)
+                raise OverflowError("out of range integral type conversion attempted")
+            return torch.from_numpy(a.astype(np.uint8)).to(self.device, non_blocking=True)
+        if tuple(actions.shape) != (self.num_envs,):
+            raise ValueError(f"actions: expected shape ({self.num_envs},)")
+        if actions.dtype.is_floating_point or actions.dtype == torch.bool:
+            raise TypeError("actions must be an integer tensor")
+        a = actions.to(self.device)
+        if a.dtype != torch.uint8:
+            # values outside 0..4 map to 255 so the kernel reports them as invalid
+            a = torch.where((a < 0) | (a > 4), torch.full_like(a, 255), a).to(torch.uint8)
+        return a.contiguous()
+
+    # ------------------------------------------------------------------ configuration
+    @property
+    def random_start(self) -> np.ndarray:
+        """Per-env `random_start` flag (the reference exposes it get+set, env.rs:100-101)."""
+        return (self._cfg & CFG_RANDOM_START).astype(bool)
+
+    @random_start.setter
+    def random_start(self, value: BoolOrSeq) -> None:
+        v = np.asarray(value, dtype=bool)
+        if v.ndim == 0:
+            v = np.full(self.num_envs, bool(v))
+        self._cfg = (self._cfg & ~np.uint8(CFG_RANDOM_START)) | v.astype(np.uint8)
+        check(
+            self._L.pb_set_cfg_flags(
+                self._h, 0, self.num_envs, self._cfg.ctypes.data_as(C.c_void_p)
+            )
+        )
+
+    def set_draw_tape(self, tape: Optional[torch.Tensor]) -> None:
+        """Install (or remove) a tape of injected raw draws: uint32-valued [N, L] tensor.
+        Draw number c of env i becomes tape[i, c % L] (parity tests replay the oracle's draws)."""
+        if tape is None:
+            self._tape = None
+            check(self._L.pb_set_draw_tape(self._h, None, 0))
+            return
+        if tape.dtype not in (torch.int32, torch.uint32) or tape.ndim != 2:
+            raise ValueError("tape must be a 2-D int32/uint32 tensor holding the raw u32 bits")
+        if tape.shape[0] != self.num_envs:
+            raise ValueError("tape must have one row per env")
+        self._tape = tape.to(self.device).contiguous()
+        check(self._L.pb_set_draw_tape(self._h, C.c_void_p(self._tape.data_ptr()), tape.shape[1]))
+
+    # ------------------------------------------------------------------ hot path
+    def reset(self, mask: Optional[torch.Tensor] = None) -> None:
+        """PacmanGym.reset() for every env (or those where `mask` is True)."""
+        m = None
+        if mask is not None:
+            m = mask.to(self.device)
+            if m.dtype == torch.bool:
+                m = m.view(torch.uint8)
+            m = self._check_tensor(m.contiguous(), (self.num_envs,), torch.uint8, "mask")
+        check(self._L.pb_reset(self._h, None if m is None else C.c_void_p(m.data_ptr()), self._stream()))
+
+    def step(self, actions, *, check_actions: bool = True, mask_out: Optional[torch.Tensor] = None,
+             reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None):
+        """PacmanGym.step for all envs -> (reward int32[N], done bool[N]).
+
+        check_actions=True synchronises and raises ValueError("Invalid action") like the
+        reference; pass False inside device-resident loops."""
+        a = self._actions_u8(actions)
+        n = self.num_envs
+        reward = self._new((n,), torch.int32) if reward_out is None else self._check_tensor(
+            reward_out, (n,), torch.int32, "reward_out")
+        done = self._new((n,), torch.uint8) if done_out is None else self._check_tensor(
+            done_out.view(torch.uint8), (n,), torch.uint8, "done_out")
+        mptr = None
+        if mask_out is not None:
+            mptr = C.c_void_p(self._check_tensor(
+                mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        check(self._L.pb_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(reward.data_ptr()),
+                              C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
+                              self._stream()))
+        if check_actions:
+            self.check_actions()
+        return reward, done.view(torch.bool)
+
+    def check_actions(self) -> None:
+        bad = C.c_int64(-1)
+        check(self._L.pb_check_actions(self._h, C.byref(bad), self._stream()))
+
+    def obs(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """PacmanGym.obs() for all envs: float32 [N, 17, 28, 31] (written in place if `out`)."""
+        n = self.num_envs
+        if out is None:
+            out = self._new((n,) + OBS_SHAPE, torch.float32)
+        else:
+            self._check_tensor(out, (n,) + OBS_SHAPE, torch.float32, "out")
+        check(self._L.pb_encode_obs(self._h, C.c_void_p(out.data_ptr()), OBS_FLOATS, self._stream()))
+        return out
+
+    def obs_range(self, first: int, count: int, out: torch.Tensor) -> torch.Tensor:
+        """obs() of envs [first, first+count) into `out` (float32 [count, 17, 28, 31])."""
+        self._check_tensor(out, (count,) + OBS_SHAPE, torch.float32, "out")
+        check(self._L.pb_encode_obs_range(self._h, first, count, C.c_void_p(out.data_ptr()),
+                                          OBS_FLOATS, self._stream()))
+        return out
+
+    def step_obs(self, actions, obs_out: torch.Tensor, *, check_actions: bool = False,
+                 mask_out: Optional[torch.Tensor] = None):
+        """step() then obs() of the resulting states, back to back (one C-ABI call)."""
+        a = self._actions_u8(actions)
+        n = self.num_envs
+        self._check_tensor(obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out")
+        reward = self._new((n,), torch.int32)
+        done = self._new((n,), torch.uint8)
+        mptr = None
+        if mask_out is not None:
+            mptr = C.c_void_p(self._check_tensor(
+                mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        check(self._L.pb_step_encode(self._h, C.c_void_p(a.data_ptr()),
+                                     C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()),
+                                     mptr, int(self.auto_reset), C.c_void_p(obs_out.data_ptr()),
+                                     OBS_FLOATS, self._stream()))
+        if check_actions:
+            self.check_actions()
+        return reward, done.view(torch.bool)
+
+    def action_mask(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """PacmanGym.action_mask() for all envs: bool [N, 5]."""
+        n = self.num_envs
+        m = self._new((n, NUM_ACTIONS), torch.uint8) if out is None else self._check_tensor(
+            out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "out")
+        check(self._L.pb_action_mask(self._h, C.c_void_p(m.data_ptr()), self._stream()))
+        return m.view(torch.bool)
+
+    def _query(self, what: int) -> torch.Tensor:
+        out = self._new((self.num_envs,), torch.int32)
+        check(self._L.pb_query(self._h, what, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def score(self) -> torch.Tensor:
+        return self._query(_lib.Q_SCORE)
+
+    def lives(self) -> torch.Tensor:
+        return self._query(_lib.Q_LIVES)
+
+    def is_done(self) -> torch.Tensor:
+        return self._query(_lib.Q_IS_DONE).bool()
+
+    def first_ai_done(self) -> torch.Tensor:
+        return self._query(_lib.Q_FIRST_AI_DONE).bool()
+
+    def remaining_pellets(self) -> torch.Tensor:
+        return self._query(_lib.Q_REMAINING_PELLETS)
+
+    def ticks_per_step(self) -> torch.Tensor:
+        return self._query(_lib.Q_TICKS_PER_STEP)
+
+    def sample_actions(self, out: Optional[torch.Tensor] = None,
+                       call_idx: Optional[int] = None) -> torch.Tensor:
+        """Uniformly random valid action per env (EpsilonGreedy at epsilon = 1)."""
+        a = self._new((self.num_envs,), torch.uint8) if out is None else self._check_tensor(
+            out, (self.num_envs,), torch.uint8, "out")
+        if call_idx is None:
+            call_idx = self._sample_calls
+            self._sample_calls += 1
+        check(self._L.pb_sample_actions(self._h, C.c_void_p(a.data_ptr()), int(call_idx),
+                                        self._stream()))
+        return a
+
+    def select_actions(self, q_values: torch.Tensor, epsilon: float,
+                       mask: Optional[torch.Tensor] = None,
+                       call_idx: Optional[int] = None) -> torch.Tensor:
+        """EpsilonGreedy(MaxQPolicy) on device (src/policies.py:16-59): uint8 [N]."""
+        n = self.num_envs
+        q = self._check_tensor(q_values.contiguous(), (n, NUM_ACTIONS), torch.float32, "q_values")
+        mptr = None
+        if mask is not None:
+            mptr = C.c_void_p(self._check_tensor(
+                mask.contiguous().view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask").data_ptr())
+        a = self._new((n,), torch.uint8)
+        if call_idx is None:
+            call_idx = self._select_calls
+            self._select_calls += 1
+        check(self._L.pb_select_actions(self._h, C.c_void_p(q.data_ptr()), mptr, float(epsilon),
+                                        C.c_void_p(a.data_ptr()), int(call_idx), self._stream()))
+        return a
+
+    # ------------------------------------------------------------------ host-buffer entry
+    def step_host(self, actions: np.ndarray, obs_out: Optional[torch.Tensor] = None,
+                  want_mask: bool = True):
+        """The per-call FFI shape: numpy actions in, numpy (reward, done, mask) out, with the
+        host<->device copies inside the call.  The observation, if requested, is written to the
+        DEVICE tensor `obs_out` (it feeds the Q-network / replay ring there)."""
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        n = self.num_envs
+        if a.shape != (n,):
+            raise ValueError(f"actions: expected shape ({n},)")
+        reward = np.empty(n, np.int32)
+        done = np.empty(n, np.uint8)
+        mask = np.empty((n, NUM_ACTIONS), np.uint8) if want_mask else None
+        optr = None
+        if obs_out is not None:
+            optr = C.c_void_p(self._check_tensor(
+                obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
+        check(self._L.pb_step_host(
+            self._h, a.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
+            done.ctypes.data_as(C.c_void_p),
+            None if mask is None else mask.ctypes.data_as(C.c_void_p),
+            int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
+        return reward, done.astype(bool), (None if mask is None else mask.astype(bool))
+
+    def obs_numpy(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """obs_numpy() of envs [first, first+count): float32 [count, 17, 28, 31] on the host."""
+        if count is None:
+            count = self.num_envs - first
+        out = np.empty((count,) + OBS_SHAPE, np.float32)
+        check(self._L.pb_obs_host(self._h, first, count, out.ctypes.data_as(C.c_void_p),
+                                  self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Structured array (dtype `ENV_STATE_DTYPE` == C `pb_env_state`) of envs [first, +count)."""
+        if count is None:
+            count = self.num_envs - first
+        torch.cuda.synchronize(self.device)
+        out = np.zeros(count, ENV_STATE_DTYPE)
+        check(self._L.pb_get_state(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_state(self, state: np.ndarray, first: int = 0) -> None:
+        st = np.ascontiguousarray(state, dtype=ENV_STATE_DTYPE)
+        torch.cuda.synchronize(self.device)
+        check(self._L.pb_set_state(self._h, first, st.shape[0], st.ctypes.data_as(C.c_void_p)))
+        self._cfg[first:first + st.shape[0]] = st["cfg_flags"] & 0x0F
+
+    def clone_env_from(self, dst_index: int, src: "BatchedPacmanGym", src_index: int) -> None:
+        """`PacmanGym.clone()` (env.rs:96 derive(Clone)): copy one env between engines."""
+        check(self._L.pb_clone_env(self._h, dst_index, src._h, src_index, self._stream()))
+        self._cfg[dst_index] = src._cfg[src_index]
+
+    def view(self, index: int) -> "PacmanGymView":
+        from .gym import PacmanGymView
+
+        return PacmanGymView(self, index)

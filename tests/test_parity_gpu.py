@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical action
+tapes and identical injected draw tapes.  Bit-exact: integer state, reward, done, mask, and the
+float32 observation compared as raw uint32 bits (tolerance: none)."""
+import numpy as np
+import pytest
+
+from conftest import assert_states_equal, oracle_to_gpu_state
+
+pytestmark = pytest.mark.gpu
+
+STAY, DOWN, UP, LEFT, RIGHT = 0, 1, 2, 3, 4
+
+
+def torch_mod():
+    import torch
+
+    return torch
+
+
+def make_pair(pb, oracle, n, cfg, tape, auto_reset=False, seed=0):
+    torch = torch_mod()
+    cfg = np.asarray(cfg, np.uint8)
+    ob = oracle.OracleBatch(n, cfg, tape)
+    env = pb.BatchedPacmanGym(
+        n, (cfg & 1).astype(bool), (cfg & 2).astype(bool), device="cuda:0", seed=seed,
+        randomize_ghosts=(cfg & 4).astype(bool), remove_super_pellets=(cfg & 8).astype(bool),
+        auto_reset=auto_reset)
+    if tape is not None:
+        env.set_draw_tape(torch.from_numpy(np.ascontiguousarray(tape).view(np.int32)).cuda())
+    return ob, env
+
+
+def random_valid_actions(rng, mask, p_invalid_move=0.1):
+    """mostly valid actions, sometimes a blocked move (a legal no-op, env.rs:404)"""
+    n = mask.shape[0]
+    u = rng.random((n, 5)) * mask
+    a = u.argmax(1).astype(np.uint8)
+    wild = rng.random(n) < p_invalid_move
+    a[wild] = rng.integers(0, 5, wild.sum(), dtype=np.uint8)
+    return a
+
+
+def compare_step(ob, env, actions, t, auto_reset, check_obs):
+    torch = torch_mod()
+    r_o, d_o = ob.step(actions, auto_reset=auto_reset)
+    r_g, d_g = env.step(torch.from_numpy(actions).cuda())
+    assert np.array_equal(r_o, r_g.cpu().numpy()), f"reward differs at step {t}"
+    assert np.array_equal(d_o, d_g.cpu().numpy()), f"done differs at step {t}"
+    assert np.array_equal(ob.action_mask(), env.action_mask().cpu().numpy()), f"mask differs at step {t}"
+    assert_states_equal(ob.export_state(), env.get_state(), f"step {t}")
+    if check_obs:
+        o_o = ob.obs().view(np.uint32)
+        o_g = env.obs().cpu().numpy().view(np.uint32)
+        if not np.array_equal(o_o, o_g):
+            bad = np.argwhere(o_o != o_g)
+            raise AssertionError(f"obs differs at step {t}: {len(bad)} cells, first {bad[0]}")
+    return d_o
+
+
+def test_fresh_and_reset_states_match(pb, oracle):
+    n = 1024
+    rng = np.random.default_rng(1)
+    tape = rng.integers(0, 2**32, size=(n, 16), dtype=np.uint32)
+    cfg = (np.arange(n) % 16).astype(np.uint8)
+    ob, env = make_pair(pb, oracle, n, cfg, tape)
+    assert_states_equal(ob.export_state(), env.get_state(), "constructor")
+    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    ob.reset()
+    env.reset()
+    assert_states_equal(ob.export_state(), env.get_state(), "reset")
+    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    assert np.array_equal(ob.action_mask(), env.action_mask().cpu().numpy())
+    # masked reset
+    torch = torch_mod()
+    m = rng.random(n) < 0.3
+    ob.reset(m)
+    env.reset(torch.from_numpy(m).cuda())
+    assert_states_equal(ob.export_state(), env.get_state(), "masked reset")
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_random_rollout_parity(pb, oracle, auto_reset):
+    """>= 10^6 env-steps of random play incl. deaths, frightened phases, resets / done envs."""
+    n, steps = 4096, 260
+    rng = np.random.default_rng(7 + auto_reset)
+    tape = rng.integers(0, 2**32, size=(n, 509), dtype=np.uint32)
+    cfg = (np.arange(n) % 4).astype(np.uint8)
+    cfg[n // 2:] |= (np.arange(n - n // 2) % 4 << 2).astype(np.uint8)
+    ob, env = make_pair(pb, oracle, n, cfg, tape, auto_reset=auto_reset)
+    ob.reset()
+    env.reset()
+    episodes = 0
+    for t in range(steps):
+        a = random_valid_actions(rng, ob.action_mask())
+        d = compare_step(ob, env, a, t, auto_reset, check_obs=(t % 20 == 0 or t == steps - 1))
+        episodes += int(d.sum())
+    assert episodes > 200, episodes
+
+
+def test_counter_rng_mode_matches_oracle_fed_with_same_draws(pb, oracle):
+    """No tape on the GPU (counter RNG keyed by seed/env/ctr); the oracle gets the same raw
+    draws through its tape, computed with the host mirror pb_draw_raw."""
+    n, steps, L, seed, base = 512, 200, 1024, 1234, 77000
+    lib = pb._lib.load()
+    tape = np.array([[lib.pb_draw_raw(seed, base + i, c) for c in range(L)] for i in range(n)], np.uint32)
+    cfg = np.full(n, 3, np.uint8)
+    torch = torch_mod()
+    ob = oracle.OracleBatch(n, cfg, tape)
+    env = pb.BatchedPacmanGym(n, True, True, device="cuda:0", seed=seed, env_id_base=base, auto_reset=True)
+    ob.reset()
+    env.reset()
+    rng = np.random.default_rng(3)
+    for t in range(steps):
+        a = random_valid_actions(rng, ob.action_mask())
+        compare_step(ob, env, a, t, True, check_obs=(t % 50 == 0))
+    assert ob.export_state()["rng_ctr"].max() < L  # the tape never wrapped
+
+
+def fuzz_states(rng, pb, n):
+    """Random but well-formed env states that sit close to every rare branch."""
+    maze = pb.maze
+    nodes = np.array(maze.NODE_COORDS)
+    st = np.zeros(n, pb.ENV_STATE_DTYPE)
+    pel_rows = np.array(maze.PELLET_ROWS, np.uint32)
+    keep = rng.integers(0, 2**28, size=(n, 31), dtype=np.uint32)
+    dens = rng.random(n)
+    for k in range(3):  # thin the board for some envs
+        thin = dens < 0.25 * (k + 1)
+        keep[thin] &= rng.integers(0, 2**28, size=(int(thin.sum()), 31), dtype=np.uint32)
+    pellets = pel_rows[None, :] & keep
+    few = rng.random(n) < 0.3   # almost-empty boards: anger thresholds, last pellet
+    for i in np.flatnonzero(few):
+        target = rng.integers(1, 24)
+        cells = [(r, c) for r in range(31) for c in range(28) if (pellets[i, r] >> c) & 1]
+        rng.shuffle(cells)
+        pellets[i] = 0
+        for r, c in cells[:target]:
+            pellets[i, r] |= np.uint32(1 << c)
+    st["pellets"] = pellets
+    st["num_pellets"] = [sum(bin(int(w)).count("1") for w in p) for p in pellets]
+    near = rng.random(n) < 0.2   # counter lags the board by design (reset's wipe keeps them equal; fuzz both)
+    st["num_pellets"][near] = rng.choice([175, 174, 75, 74, 21, 20, 11, 10, 2, 1], near.sum())
+    st["curr_ticks"] = rng.integers(0, 5000, n)
+    st["curr_ticks"][rng.random(n) < 0.5] //= 12
+    st["curr_ticks"][rng.random(n) < 0.3] *= 12
+    st["update_period"] = rng.choice([12, 12, 12, 10, 8, 6, 4, 2, 1], n)
+    st["mode"] = rng.choice([1, 2], n)
+    st["mode_steps"] = rng.choice([0, 0, 1, 2, 30, 59, 179, 180], n)
+    st["level_steps"] = rng.choice([0, 0, 1, 5, 240, 959, 960], n)
+    st["curr_score"] = rng.integers(0, 5000, n)
+    st["last_score"] = st["curr_score"]
+    st["curr_level"] = 1
+    st["curr_lives"] = 3
+    st["ghost_combo"] = rng.integers(0, 4, n)
+    st["fruit_steps"] = rng.choice([0, 0, 1, 2, 30], n)
+    st["last_action"] = rng.integers(0, 5, n)
+    st["ticks_per_step"] = rng.integers(4, 14, n)
+    st["cfg_flags"] = rng.integers(0, 16, n)
+    pn = nodes[rng.integers(0, 288, n)]
+    st["pac_row"], st["pac_col"] = pn[:, 0], pn[:, 1]
+    st["pac_dir"] = rng.integers(0, 4, n)
+    for g in range(4):
+        # ghosts near Pac-Man half of the time so collisions happen
+        gn = nodes[rng.integers(0, 288, n)]
+        close = rng.random(n) < 0.5
+        for i in np.flatnonzero(close):
+            d = np.abs(nodes - pn[i]).sum(1)
+            cand = np.flatnonzero(d <= 3)
+            gn[i] = nodes[rng.choice(cand)]
+        st["g_row"][:, g], st["g_col"][:, g] = gn[:, 0], gn[:, 1]
+        # heading: a direction whose next cell is walkable (what plan() would have produced)
+        for i in range(n):
+            r, c = int(gn[i, 0]), int(gn[i, 1])
+            dirs = [d for d, (dr, dc) in enumerate([(-1, 0), (0, -1), (1, 0), (0, 1)])
+                    if not maze.wall_at(r + dr, c + dc)]
+            d = int(rng.choice(dirs))
+            st["g_dir"][i, g] = d
+            dr, dc = [(-1, 0), (0, -1), (1, 0), (0, 1)][d]
+            # next heading: walkable from the next cell and not a reversal (as plan() guarantees)
+            dirs2 = [d2 for d2, (er, ec) in enumerate([(-1, 0), (0, -1), (1, 0), (0, 1)])
+                     if not maze.wall_at(r + dr + er, c + dc + ec) and d2 != (d ^ 2)]
+            st["g_next_row"][i, g], st["g_next_col"][i, g] = r + dr, c + dc
+            st["g_next_dir"][i, g] = rng.choice(dirs2)
+        st["g_fright"][:, g] = rng.choice([0, 0, 0, 1, 2, 3, 40], n)
+        st["g_trapped"][:, g] = rng.choice([0, 0, 0, 1, 2], n)
+        st["g_spawning"][:, g] = rng.random(n) < 0.1
+        eaten = rng.random(n) < 0.05
+        st["g_eaten"][:, g] = eaten
+        st["g_row"][eaten, g] = 32
+        st["g_col"][eaten, g] = 32
+        st["g_dir"][eaten, g] = 4
+        st["g_next_row"][eaten, g], st["g_next_col"][eaten, g], st["g_next_dir"][eaten, g] = 13, 13, 0
+    return st
+
+
+def gpu_to_oracle_state(oracle, st):
+    out = np.zeros(len(st), oracle.FLAT_DTYPE)
+    for f in out.dtype.names:
+        if f in st.dtype.names:
+            out[f] = st[f]
+    out["random_start"] = st["cfg_flags"] & 1
+    out["random_ticks"] = (st["cfg_flags"] >> 1) & 1
+    out["randomize_ghosts"] = (st["cfg_flags"] >> 2) & 1
+    out["remove_super_pellets"] = (st["cfg_flags"] >> 3) & 1
+    return out
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fuzzed_states_parity(pb, oracle, seed):
+    """Random well-formed states near every rare branch (anger thresholds, fruit spawn/expiry, last
+    pellet, mode flip, level-time penalty, fright expiry, ghost eating combos, every ticks_per_step
+    and update period), then a few random steps; full state + obs compared every step."""
+    n, steps = 2048, 12
+    rng = np.random.default_rng(100 + seed)
+    tape = rng.integers(0, 2**32, size=(n, 211), dtype=np.uint32)
+    st = fuzz_states(rng, pb, n)
+    ob, env = make_pair(pb, oracle, n, st["cfg_flags"], tape, auto_reset=False)
+    env.set_state(st)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    assert_states_equal(ob.export_state(), env.get_state(), "import")
+    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    seen_done = 0
+    for t in range(steps):
+        a = random_valid_actions(rng, ob.action_mask(), p_invalid_move=0.2)
+        d = compare_step(ob, env, a, t, False, check_obs=True)
+        seen_done += int(d.sum())
+    final = ob.export_state()
+    assert seen_done > 0 and (final["curr_level"] > 1).any() and (final["curr_lives"] < 3).any()
+    assert (final["update_period"] < 12).any()
+
+
+def test_scripted_scenarios(pb, oracle):
+    """Targeted scenarios: each row is one env."""
+    maze = pb.maze
+    rng = np.random.default_rng(11)
+    base = fuzz_states(rng, pb, 1)
+    base["pellets"][:] = 0
+    base["num_pellets"] = 100
+    base["curr_ticks"], base["update_period"] = 12, 12     # next tick is an update tick
+    base["mode"], base["mode_steps"], base["level_steps"] = 1, 30, 500
+    base["fruit_steps"], base["ghost_combo"] = 0, 0
+    base["g_fright"][:] = 0
+    base["g_trapped"][:] = 0
+    base["g_spawning"][:] = 0
+    base["g_eaten"][:] = 0
+    base["ticks_per_step"], base["cfg_flags"], base["last_action"] = 8, 0, 0
+    base["pac_row"], base["pac_col"], base["pac_dir"] = 5, 6, 1
+    far = [(29, 1), (29, 26), (1, 1), (1, 26)]
+    for g, (r, c) in enumerate(far):
+        base["g_row"][0, g], base["g_col"][0, g], base["g_dir"][0, g] = r, c, 3 if c == 1 else 1
+        base["g_next_row"][0, g], base["g_next_col"][0, g] = r, c + (1 if c == 1 else -1)
+        base["g_next_dir"][0, g] = 3 if c == 1 else 1
+    scen, acts = [], []
+
+    def add(action, **mods):
+        s = base.copy()
+        for k, v in mods.items():
+            if isinstance(v, tuple) and isinstance(v[0], tuple):
+                for idx, val in v:
+                    s[k][0, idx] = val
+            else:
+                s[k] = v
+        scen.append(s)
+        acts.append(action)
+
+    # death by moving into a ghost / ghost moving into Pac-Man on the update tick
+    add(RIGHT, g_row=((0, 5),), g_col=((0, 7),))
+    add(STAY, g_next_row=((0, 5),), g_next_col=((0, 6),))
+    # eat 1..4 frightened ghosts in one move (combo 200/400/800/1600)
+    for k in range(1, 5):
+        add(RIGHT, curr_ticks=13, g_row=tuple((g, 5) for g in range(k)), g_col=tuple((g, 7) for g in range(k)),
+            g_fright=tuple((g, 20) for g in range(k)))
+    # fright expiry (1 -> 0) and the `fright_steps > 1` random-turn boundary (2)
+    add(STAY, g_fright=((0, 1), (1, 2), (2, 3)))
+    # mode flips with reversal, both directions
+    add(STAY, mode=1, mode_steps=0)
+    add(STAY, mode=2, mode_steps=0)
+    # level-time penalty
+    add(STAY, level_steps=0)
+    # super pellet: frighten all
+    sp = base["pellets"].copy()
+    sp[0, 3] = 1 << 1
+    add(UP, pac_row=4, pac_col=1, pellets=sp, num_pellets=50)
+    # fruit spawn at 174 / 74 and fruit pickup, anger at 20 / 10, last pellet
+    one = base["pellets"].copy()
+    one[0, 5] = 1 << 7
+    for np_before in (175, 75, 21, 11, 1):
+        add(RIGHT, pellets=one, num_pellets=np_before, curr_ticks=13)
+    add(RIGHT, pac_row=17, pac_col=12, fruit_steps=5, curr_ticks=13)
+    # every ticks_per_step with an update in the middle
+    for tps in range(4, 14):
+        add(LEFT, ticks_per_step=tps, curr_ticks=7)
+    st = np.concatenate(scen)
+    n = len(st)
+    tape = rng.integers(0, 2**32, size=(n, 64), dtype=np.uint32)
+    ob, env = make_pair(pb, oracle, n, st["cfg_flags"], tape)
+    env.set_state(st)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    a = np.array(acts, np.uint8)
+    for t in range(4):
+        compare_step(ob, env, a if t == 0 else random_valid_actions(rng, ob.action_mask()), t, False, True)
+    # spot-check the oracle did what the scenario intends (guards against vacuous scenarios)
+    ob2, _ = make_pair(pb, oracle, n, st["cfg_flags"], tape)
+    ob2.import_state(gpu_to_oracle_state(oracle, st))
+    r, d = ob2.step(a)
+    f = ob2.export_state()
+    assert d[0] and d[1] and r[0] <= -200 and r[1] <= -200
+    assert [int(f["curr_score"][i] - st["curr_score"][i]) for i in range(2, 6)] == [200, 600, 1400, 3000]
+    assert f["g_fright"][6].tolist()[:3] == [0, 1, 2]
+    assert (f["mode"][7], f["mode"][8]) == (2, 1)
+    assert f["update_period"][9] == 10
+    assert (f["g_fright"][10] == 39).all() or (f["g_fright"][10] == 40).all()
+    assert f["fruit_steps"][11] > 0 and f["fruit_steps"][12] > 0
+    assert f["update_period"][13] == 10 and f["update_period"][14] == 10 and f["mode"][13] == 2
+    assert d[15] and r[15] >= 3000
+
+
+def test_invalid_action_reporting(pb, oracle):
+    torch = torch_mod()
+    n = 300
+    ob, env = make_pair(pb, oracle, n, np.zeros(n, np.uint8), None)
+    before = env.get_state()
+    a = np.zeros(n, np.uint8)
+    a[[37, 200]] = [9, 5]
+    with pytest.raises(ValueError, match="Invalid action"):
+        env.step(torch.from_numpy(a).cuda())
+    after = env.get_state()
+    assert np.array_equal(before[[37, 200]], after[[37, 200]])   # offending envs untouched
+    assert after["curr_ticks"][0] == 8                            # the others stepped
+    env.step(torch.zeros(n, dtype=torch.uint8, device="cuda"))    # error record was cleared
+    with pytest.raises(ValueError):
+        env.step(torch.full((n,), 7, dtype=torch.int64, device="cuda"))
+
+
+def test_obs_stride_and_ring_slot(pb, oracle):
+    """pb_encode_obs writes each env at out + i*stride; untouched gaps stay untouched."""
+    import ctypes as C
+
+    torch = torch_mod()
+    n = 257
+    rng = np.random.default_rng(5)
+    tape = rng.integers(0, 2**32, size=(n, 8), dtype=np.uint32)
+    ob, env = make_pair(pb, oracle, n, np.full(n, 3, np.uint8), tape)
+    ob.reset()
+    env.reset()
+    stride = pb.OBS_FLOATS + 12
+    buf = torch.full((n * stride,), -7.0, dtype=torch.float32, device="cuda")
+    L = pb._lib.load()
+    pb._lib.check(L.pb_encode_obs(env._h, C.c_void_p(buf.data_ptr()), stride, None))
+    torch.cuda.synchronize()
+    got = buf.view(n, stride).cpu().numpy()
+    assert np.array_equal(got[:, :pb.OBS_FLOATS].view(np.uint32), ob.obs().reshape(n, -1).view(np.uint32))
+    assert (got[:, pb.OBS_FLOATS:] == -7.0).all()
+    with pytest.raises(ValueError):
+        pb._lib.check(L.pb_encode_obs(env._h, C.c_void_p(buf.data_ptr()), pb.OBS_FLOATS + 2, None))
+    with pytest.raises(ValueError):
+        pb._lib.check(L.pb_encode_obs(env._h, C.c_void_p(buf.data_ptr() + 4), stride, None))
+
+
+def test_repeated_encode_is_idempotent_and_unpatches(pb, oracle):
+    """The encoder reuses shared-memory images across envs: every env's image must be clean."""
+    torch = torch_mod()
+    n = 8192
+    rng = np.random.default_rng(9)
+    st = fuzz_states(rng, pb, n)
+    ob, env = make_pair(pb, oracle, n, st["cfg_flags"], None)
+    env.set_state(st)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    a = env.obs()
+    b = env.obs()
+    assert torch.equal(a, b)
+    ref = ob.obs()
+    assert np.array_equal(a.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_full_size_properties_65536(pb):
+    """BASELINE config 2 size (65 536 envs): size-independent properties of step + encode."""
+    torch = torch_mod()
+    n = 65536
+    env = pb.BatchedPacmanGym(n, np.arange(n) < n // 2, True, device="cuda:0", seed=3, auto_reset=True)
+    env.reset()
+    obs = torch.empty((n,) + pb.OBS_SHAPE, dtype=torch.float32, device="cuda")
+    total_done = 0
+    for t in range(40):
+        a = env.sample_actions()
+        r, d = env.step_obs(a, obs)
+        total_done += int(d.sum())
+    wall = torch.tensor(pb.maze.WALL_ROWS, device="cuda", dtype=torch.int64)
+    assert torch.equal(obs[:, 0].sum((1, 2)), torch.full((n,), 580.0, device="cuda"))
+    assert torch.equal(obs[:, 2], obs[:, 3]) and torch.equal(obs[:, 4:8], obs[:, 8:12])
+    tps = env.ticks_per_step().float()
+    st_period = env._query(pb._lib.Q_UPDATE_PERIOD).float()
+    assert torch.equal(obs[:, 15, 0, 0], tps / st_period)
+    assert torch.equal(obs[:, 15].amin((1, 2)), obs[:, 15].amax((1, 2)))
+    # pellet channel: #nonzero pellet-valued cells == remaining_pellets (no fruit/fright bonus cells counted)
+    pel_cells = ((obs[:, 1] == 0.05) | (obs[:, 1] == 0.25)).sum((1, 2))
+    rem = env.remaining_pellets()
+    fright_any = obs[:, 14].amax((1, 2)) > 0
+    ok = (pel_cells == rem) | fright_any | (rem == 1)
+    assert bool(ok.all())
+    assert total_done > 100
+    # determinism: same seed, same actions -> same trajectory digest
+    env2 = pb.BatchedPacmanGym(n, np.arange(n) < n // 2, True, device="cuda:0", seed=3, auto_reset=True)
+    env2.reset()
+    obs2 = torch.empty_like(obs)
+    for t in range(40):
+        r2, d2 = env2.step_obs(env2.sample_actions(), obs2)
+    assert torch.equal(obs, obs2) and torch.equal(r, r2)
+    del wall
