@@ -15,6 +15,7 @@ from ._lib import (
 )
 from .engine import BatchedPacmanGym
 from .gym import PacmanGym, PacmanGymView
+from . import dist_utils, models, policies, replay_buffer
 
 __all__ = [
     "BatchedPacmanGym",

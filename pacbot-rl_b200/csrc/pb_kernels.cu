@@ -282,7 +282,7 @@ __device__ __forceinline__ int obs_cell(int row, int col) {  // env.rs:124: [col
 template <int CHUNKS>
 __global__ void __launch_bounds__(OBS_THREADS, 1)
 k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
-             long long env_count) {
+             long long env_count, unsigned int *__restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * OBS_BYTES);
@@ -297,12 +297,19 @@ k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long l
     }
     __syncwarp();
 
-    const long long gw = (long long)blockIdx.x * OBS_WARPS + warp;
-    const long long nw = (long long)gridDim.x * OBS_WARPS;
     int patched = -1;  // flat offset this lane set in the previous image (sparse channels only)
 
-    for (long long k = gw; k < env_count; k += nw) {
+    // Dynamic work distribution: SMs do not drain to HBM at the same rate (two dies, shared
+    // memory partitions), so a static env->warp map leaves the fast SMs idle at the end (ncu:
+    // sm__cycles_active min/max = 0.65).  Each warp takes envs from a global ticket counter; the
+    // next ticket is requested before the current env is processed so its latency is hidden.
+    unsigned int next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
+    next = __shfl_sync(0xffffffffu, next, 0);
+    while ((long long)next < env_count) {
+        const long long k = next;
         const long long i = env_first + k;
+        if (lane == 0) next = atomicAdd(ticket, 1u);
         // ---- state loads (issued before the wait so their latency hides behind the drain) ----
         const uint32_t F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
         const uint4 c0 = st.core0[i], c1 = st.core1[i];
@@ -431,6 +438,7 @@ k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long l
                                CHUNK_BYTES);
             bulk_commit();
         }
+        next = __shfl_sync(0xffffffffu, next, 0);
     }
     if (lane == 0) bulk_wait_all();
 }
@@ -496,7 +504,10 @@ struct pb_engine {
     float *stg_obs = nullptr;
     long long stg_obs_envs = 0;
     int num_sms = 148;
+    unsigned int *tickets = nullptr;  // ring of work counters for k_encode_obs launches
+    unsigned int ticket_next = 0;
 };
+constexpr unsigned int TICKET_RING = 64;
 
 namespace {
 struct DeviceGuard {
@@ -546,7 +557,10 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     }
     long long blocks = (count + OBS_WARPS - 1) / OBS_WARPS;
     if (blocks > e->num_sms) blocks = e->num_sms;
-    kern<<<(unsigned)blocks, OBS_THREADS, OBS_SMEM, s>>>(e->st, out_dev, stride, first, count);
+    unsigned int *ticket = e->tickets + (e->ticket_next++ % TICKET_RING);
+    PB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+    kern<<<(unsigned)blocks, OBS_THREADS, OBS_SMEM, s>>>(e->st, out_dev, stride, first, count,
+                                                         ticket);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -592,6 +606,7 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->stg_done);
     cudaFree(e->stg_mask);
     cudaFree(e->stg_obs);
+    cudaFree(e->tickets);
     delete e;
     return PB_OK;
 }
@@ -634,6 +649,7 @@ int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_reward, sizeof(int32_t) * e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_done, e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_mask, 5 * e->npad));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->tickets, sizeof(unsigned int) * TICKET_RING));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core0, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core1, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.ghosts, 0, sizeof(uint4) * 2 * e->npad));

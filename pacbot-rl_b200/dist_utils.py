@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), envs sharded by contiguous global env-id
+ranges with no data-path collective; the only collective is the DQN gradient all-reduce
+(SURVEY.md 8e).  Pure torch.distributed: works with NCCL on GPUs and with gloo on CPU (tests)."""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1 process if absent)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def shard_env_ids(total_envs: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous global env-id range [first, first + count) owned by `rank`.  The per-env RNG is
+    keyed by the GLOBAL id, so a trajectory does not depend on how many GPUs share the work."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, rem = divmod(total_envs, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int) -> None:
+    """Average gradients across ranks with ONE all-reduce of the flattened gradient
+    (156 934 floats = 628 KB for QNetV2: latency-bound, so a single bucket)."""
+    if world <= 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def max_over_ranks(value: float, device: torch.device, world: int) -> float:
+    """Timing reduction of bench.py: the slowest rank defines the step time."""
+    if world <= 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,53 @@
+"""Q-network of the DQN loop.  Stays PyTorch/cuDNN (north star): tensor cores are used only here.
+
+`QNetV2` reproduces the architecture, initialisation and state-dict key names of the reference
+(/root/reference/src/models.py:66-110; keys `backbone.{0,2,5,8,11,15}`, `value_head.0`,
+`advantage_head.0` as consumed by pacbot_rs/src/candle_qnet.rs:18-44) so checkpoints written by
+either side load in the other (`q_net-latest.pt` / `.safetensors`, train_dqn.py:239-253)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+
+def init_orthogonal(module: nn.Module) -> None:
+    """Orthogonal init of every weight with >= 2 dims (reference models.py:6-14)."""
+    with torch.no_grad():
+        for p in module.parameters():
+            if p.dim() >= 2:
+                nn.init.orthogonal_(p)
+
+
+class QNetV2(nn.Module):
+    """conv5x5(C->16) SiLU, 3 x [conv3x3, maxpool2(ceil), SiLU] (32, 64, 128), grouped conv3x3
+    (128, 8 groups), global max, SiLU, Linear 128->256, SiLU, dueling heads V(1) / A(actions);
+    Q = V - mean(A) + A.  156 934 parameters for the (17, 28, 31) observation and 5 actions."""
+
+    def __init__(self, obs_shape, action_count: int) -> None:
+        super().__init__()
+        in_ch = int(obs_shape[0])
+        layers: list[nn.Module] = [nn.Conv2d(in_ch, 16, 5, padding="same"), nn.SiLU()]
+        for cin, cout in ((16, 32), (32, 64), (64, 128)):
+            layers += [nn.Conv2d(cin, cout, 3, padding="same"), nn.MaxPool2d(2, ceil_mode=True), nn.SiLU()]
+        layers += [
+            nn.Conv2d(128, 128, 3, groups=8, padding="same"),
+            nn.AdaptiveMaxPool2d((1, 1)),
+            nn.Flatten(),
+            nn.SiLU(),
+            nn.Linear(128, 256),
+            nn.SiLU(),
+        ]
+        self.backbone = nn.Sequential(*layers)
+        self.value_head = nn.Sequential(nn.Linear(256, 1))
+        self.advantage_head = nn.Sequential(nn.Linear(256, action_count))
+        init_orthogonal(self)
+        with torch.no_grad():  # both heads start at zero => Q == 0 at init
+            for head in (self.value_head[-1], self.advantage_head[-1]):
+                head.weight.zero_()
+                head.bias.zero_()
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        feat = self.backbone(obs)
+        value = self.value_head(feat)
+        adv = self.advantage_head(feat)
+        return value - adv.mean(dim=1, keepdim=True) + adv
