@@ -53,7 +53,7 @@ def test_replay_ring_matches_oracle_rollout(pb, oracle):
         exp_mask = ob.action_mask() & ~d[:, None]
         assert np.array_equal(buf._next_mask[slot].cpu().numpy(), exp_mask), t
         assert np.array_equal(buf._obs[nxt].cpu().numpy().view(np.uint32), ob.obs().view(np.uint32)), t
-    assert len(buf) == steps * n == int(buf._weight.sum().item())
+    assert len(buf) == min(steps, buf._slots) * n == int(buf._weight.sum().item())
 
 
 def _to_gpu_state(pb, st):
