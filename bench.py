@@ -41,7 +41,7 @@ ENCODE_BYTES_PER_ENV = STATE_BYTES + OBS_BYTES
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dqn", action="store_true")
+    ap.add_argument("--dqn-iters", type=int, default=200)
     return ap.parse_args()
 
 
@@ -62,6 +64,44 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def encode_traffic(envs_per_launch: int):
+    """DRAM bytes per k_encode_obs launch from the committed ncu capture (scaled per env)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "encode_traffic.json")) as f:
+            d = json.load(f)
+        per_env = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["envs_per_launch"]
+        return per_env * envs_per_launch
+    except Exception:
+        return None
+
+
+def dqn_throughput(dev, seed: int, iters: int):
+    """BASELINE.json configs[3]: train_dqn defaults with GPU-resident envs, iterations/s."""
+    import torch
+
+    from pacbot_rl_b200 import train_dqn
+
+    cfg = train_dqn.build_parser().parse_args(
+        ["--device", str(dev), "--seed", str(seed), "--no-checkpoints", "--log_every", "1000000"])
+    trainer = train_dqn.DQNTrainer(cfg, dev)
+    trainer.replay.fill()
+    trainer.policy.epsilon = cfg.initial_epsilon
+    for _ in range(10):
+        trainer.train_iteration()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        trainer.train_iteration()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    m = trainer.pop_metrics()
+    return {"iters_per_sec": iters / dt, "iters": iters,
+            "env_steps_per_sec": iters * cfg.experience_steps * cfg.num_parallel_envs / dt,
+            "config": "train_dqn defaults: batch 512, 32 envs, 4 experience steps/iter, buffer "
+                      "10k, QNetV2 fp32 (cuDNN), double DQN, Adam",
+            "loss": m["loss"]}
 
 
 class ClockSampler:
@@ -280,21 +320,28 @@ def main():
     e2e_full = None
     if not args.no_e2e:
         k_e2e = max(3, min(args.steps, 50))
-        host_actions = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        # actions are produced on the host here (as a host-side policy would): precompute valid
-        # ones from the current masks is impossible without a round trip, so use action 0..4
-        # uniformly (invalid moves are legal no-ops, env.rs:404)
+        # The host side owns the actions here (as a host-side policy would): a pool of pinned
+        # action buffers, uniform over 0..4 (a blocked move is a legal no-op, env.rs:404), and
+        # pinned result buffers; every step copies its actions H2D and its results D2H.
         rng = np.random.default_rng(args.seed + rank)
-        for i in range(2):
-            host_actions[i].numpy()[:] = rng.integers(0, 5, n, dtype=np.uint8)
+        pool = 8
+        host_actions = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(pool)]
+        for buf in host_actions:
+            buf.numpy()[:] = rng.integers(0, 5, n, dtype=np.uint8)
+        h_reward = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+        h_done = torch.empty(n, dtype=torch.bool).pin_memory().numpy()
+        h_mask = torch.empty((n, 5), dtype=torch.bool).pin_memory().numpy()
+        outs = (h_reward, h_done, h_mask)
+        checksum = 0
 
         def e2e_step(i: int):
+            a = host_actions[i % pool].numpy()
             if n <= chunk:  # one C-ABI call: H2D actions, step, encode, D2H reward/done/mask
                 slot = ring[slot_ctr[0] % n_slots]
                 slot_ctr[0] += 1
-                env.step_host(host_actions[i & 1].numpy(), obs_out=slot[:n])
+                env.step_host(a, obs_out=slot[:n], out=outs)
             else:  # env population larger than a ring slot: encode chunk by chunk
-                env.step_host(host_actions[i & 1].numpy(), obs_out=None)
+                env.step_host(a, obs_out=None, out=outs)
                 for first, cnt in chunks:
                     slot = ring[slot_ctr[0] % n_slots]
                     slot_ctr[0] += 1
@@ -305,8 +352,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for i in range(k_e2e):
-            host_actions[i & 1].numpy()[:] = rng.integers(0, 5, n, dtype=np.uint8)
             e2e_step(i)
+            checksum += int(h_reward[0]) + int(h_done[-1])   # the host reads the step's result
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -368,7 +415,9 @@ def main():
             "peak": peak,
             "unit": "GB/s",
             "frac": enc_gbs / peak,
-            "traffic": None,
+            "traffic": encode_traffic(chunk),
+            "traffic_source": "profiles/encode_traffic.json (dram__bytes_read.sum + "
+                              "dram__bytes_write.sum of one ncu --set full capture, per launch)",
             "peak_source": peak_src,
             "bytes_per_launch": chunk * ENCODE_BYTES_PER_ENV,
             "avg_launch_ms": enc_ms,
@@ -381,6 +430,8 @@ def main():
         line["e2e"] = e2e
     if e2e_full is not None:
         line["e2e_obs_to_host"] = e2e_full
+    if world == 1 and not args.no_dqn:
+        line["dqn"] = dqn_throughput(dev, args.seed, args.dqn_iters)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_envs, args.cpu_sample_steps,
                                             os.cpu_count() or 1, args.seed)

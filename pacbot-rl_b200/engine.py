@@ -323,17 +323,30 @@ class BatchedPacmanGym:
 
     # ------------------------------------------------------------------ host-buffer entry
     def step_host(self, actions: np.ndarray, obs_out: Optional[torch.Tensor] = None,
-                  want_mask: bool = True):
+                  want_mask: bool = True, out: Optional[tuple] = None):
         """The per-call FFI shape: numpy actions in, numpy (reward, done, mask) out, with the
         host<->device copies inside the call.  The observation, if requested, is written to the
-        DEVICE tensor `obs_out` (it feeds the Q-network / replay ring there)."""
+        DEVICE tensor `obs_out` (it feeds the Q-network / replay ring there).
+
+        `out=(reward int32[N], done bool|uint8[N], mask bool|uint8[N,5] or None)` reuses caller
+        buffers (pin them for full-speed D2H); otherwise fresh pageable arrays are returned."""
         a = np.ascontiguousarray(actions, dtype=np.uint8)
         n = self.num_envs
         if a.shape != (n,):
             raise ValueError(f"actions: expected shape ({n},)")
-        reward = np.empty(n, np.int32)
-        done = np.empty(n, np.uint8)
-        mask = np.empty((n, NUM_ACTIONS), np.uint8) if want_mask else None
+        if out is None:
+            reward = np.empty(n, np.int32)
+            done = np.empty(n, np.bool_)
+            mask = np.empty((n, NUM_ACTIONS), np.bool_) if want_mask else None
+        else:
+            reward, done, mask = out
+            if (reward.dtype != np.int32 or reward.shape != (n,) or done.itemsize != 1
+                    or done.shape != (n,) or not reward.flags.c_contiguous
+                    or not done.flags.c_contiguous):
+                raise ValueError("out: expected (int32[N], 1-byte[N], 1-byte[N,5] or None)")
+            if mask is not None and (mask.itemsize != 1 or mask.shape != (n, NUM_ACTIONS)
+                                     or not mask.flags.c_contiguous):
+                raise ValueError("out: mask must be a contiguous 1-byte [N,5] array")
         optr = None
         if obs_out is not None:
             optr = C.c_void_p(self._check_tensor(
@@ -343,7 +356,7 @@ class BatchedPacmanGym:
             done.ctypes.data_as(C.c_void_p),
             None if mask is None else mask.ctypes.data_as(C.c_void_p),
             int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
-        return reward, done.astype(bool), (None if mask is None else mask.astype(bool))
+        return reward, done, mask
 
     def obs_numpy(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         """obs_numpy() of envs [first, first+count): float32 [count, 17, 28, 31] on the host."""
