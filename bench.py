@@ -77,7 +77,7 @@ def encode_traffic(envs_per_launch: int):
         return None
 
 
-def dqn_throughput(dev, seed: int, iters: int):
+def dqn_throughput(dev, seed: int, iters: int, graph: bool = True):
     """BASELINE.json configs[3]: train_dqn defaults with GPU-resident envs, iterations/s."""
     import torch
 
@@ -87,7 +87,9 @@ def dqn_throughput(dev, seed: int, iters: int):
         ["--device", str(dev), "--seed", str(seed), "--no-checkpoints", "--log_every", "1000000"])
     trainer = train_dqn.DQNTrainer(cfg, dev)
     trainer.replay.fill()
-    trainer.policy.epsilon = cfg.initial_epsilon
+    trainer.epsilon = cfg.initial_epsilon
+    if graph:
+        trainer.capture_graph()
     for _ in range(10):
         trainer.train_iteration()
     torch.cuda.synchronize(dev)
@@ -97,7 +99,7 @@ def dqn_throughput(dev, seed: int, iters: int):
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     m = trainer.pop_metrics()
-    return {"iters_per_sec": iters / dt, "iters": iters,
+    return {"iters_per_sec": iters / dt, "iters": iters, "cuda_graph": graph,
             "env_steps_per_sec": iters * cfg.experience_steps * cfg.num_parallel_envs / dt,
             "config": "train_dqn defaults: batch 512, 32 envs, 4 experience steps/iter, buffer "
                       "10k, QNetV2 fp32 (cuDNN), double DQN, Adam",
@@ -227,11 +229,29 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
     }
     del per_step
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's
+    version banner, torchrun notices) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,6 +270,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs_per_gpu
@@ -422,7 +444,7 @@ def main():
             "bytes_per_launch": chunk * ENCODE_BYTES_PER_ENV,
             "avg_launch_ms": enc_ms,
         },
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "episodes_finished_last_step": episodes,
     }
@@ -431,11 +453,12 @@ def main():
     if e2e_full is not None:
         line["e2e_obs_to_host"] = e2e_full
     if world == 1 and not args.no_dqn:
-        line["dqn"] = dqn_throughput(dev, args.seed, args.dqn_iters)
+        line["dqn"] = dqn_throughput(dev, args.seed, args.dqn_iters, graph=True)
+        line["dqn_eager"] = dqn_throughput(dev, args.seed, args.dqn_iters, graph=False)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_envs, args.cpu_sample_steps,
                                             os.cpu_count() or 1, args.seed)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

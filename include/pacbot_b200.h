@@ -158,6 +158,13 @@ int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void 
 int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_dev,
                         int64_t env_stride_floats, void *stream);
 
+/* Observation of all envs into slot *slot_index_dev of a ring: env i is written at
+ * ring_dev + (*slot_index_dev) * slot_stride_floats + i * PB_OBS_FLOATS.  The slot number is
+ * read on the DEVICE at kernel time, so a captured CUDA graph keeps working while the replay
+ * ring advances (src/replay_buffer.py's deque append, done in place). */
+int pb_encode_obs_ring(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,
+                       const int64_t *slot_index_dev, void *stream);
+
 /* pb_step followed by pb_encode_obs of the resulting states, back to back on `stream`. */
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,
                    uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev,

@@ -282,7 +282,11 @@ __device__ __forceinline__ int obs_cell(int row, int col) {  // env.rs:124: [col
 template <int CHUNKS>
 __global__ void __launch_bounds__(OBS_THREADS, 1)
 k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
-             long long env_count, unsigned int *__restrict__ ticket) {
+             long long env_count, unsigned int *__restrict__ ticket,
+             const long long *__restrict__ slot_index, long long slot_stride) {
+    // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
+    // replayed while the replay ring advances
+    if (slot_index) out += *slot_index * slot_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * OBS_BYTES);
@@ -547,7 +551,8 @@ void rows_to_flat(const uint32_t rows[PB_ROWS], uint32_t *f) {
 }
 
 int launch_encode(pb_engine *e, float *out_dev, long long stride, long long first,
-                  long long count, cudaStream_t s) {
+                  long long count, cudaStream_t s, const long long *slot_index = nullptr,
+                  long long slot_stride = 0) {
     if (count <= 0) return PB_OK;
     static thread_local int attr_set_for = -1;
     auto kern = k_encode_obs<1>;
@@ -560,7 +565,7 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     unsigned int *ticket = e->tickets + (e->ticket_next++ % TICKET_RING);
     PB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
     kern<<<(unsigned)blocks, OBS_THREADS, OBS_SMEM, s>>>(e->st, out_dev, stride, first, count,
-                                                         ticket);
+                                                         ticket, slot_index, slot_stride);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -735,6 +740,16 @@ int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_d
 int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void *stream) {
     if (!e) return fail(PB_ERR_INVALID_ARG, "pb_encode_obs: null engine");
     return pb_encode_obs_range(e, 0, e->n, out_dev, env_stride_floats, stream);
+}
+
+int pb_encode_obs_ring(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,
+                       const int64_t *slot_index_dev, void *stream) {
+    if (!e || !ring_dev || !slot_index_dev || (slot_stride_floats & 3) ||
+        slot_stride_floats < (int64_t)OBS_FLOATS * e->n || (reinterpret_cast<uintptr_t>(ring_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG, "pb_encode_obs_ring: bad arguments");
+    DeviceGuard g(e->device);
+    return launch_encode(e, ring_dev, OBS_FLOATS, 0, e->n, (cudaStream_t)stream,
+                         reinterpret_cast<const long long *>(slot_index_dev), slot_stride_floats);
 }
 
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,

@@ -240,6 +240,18 @@ class BatchedPacmanGym:
                                           OBS_FLOATS, self._stream()))
         return out
 
+    def obs_ring(self, ring: torch.Tensor, slot_index: torch.Tensor) -> None:
+        """obs() of all envs into ring[slot_index] where `slot_index` is a 1-element int64 DEVICE
+        tensor read at kernel time (CUDA-graph friendly).  ring: float32 [R, N, 17, 28, 31]."""
+        if (ring.dtype != torch.float32 or ring.device != self.device or not ring.is_contiguous()
+                or tuple(ring.shape[1:]) != (self.num_envs,) + OBS_SHAPE):
+            raise ValueError("ring: expected contiguous float32 [R, N, 17, 28, 31] on the engine device")
+        if slot_index.dtype != torch.int64 or slot_index.device != self.device or slot_index.numel() != 1:
+            raise ValueError("slot_index: expected a 1-element int64 tensor on the engine device")
+        check(self._L.pb_encode_obs_ring(self._h, C.c_void_p(ring.data_ptr()),
+                                         self.num_envs * OBS_FLOATS,
+                                         C.c_void_p(slot_index.data_ptr()), self._stream()))
+
     def step_obs(self, actions, obs_out: torch.Tensor, *, check_actions: bool = False,
                  mask_out: Optional[torch.Tensor] = None):
         """step() then obs() of the resulting states, back to back (one C-ABI call)."""

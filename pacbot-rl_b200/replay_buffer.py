@@ -3,13 +3,17 @@
 
 Layout: a time ring of R = ceil(maxlen / N) + 1 slots; slot t % R holds, for all N envs, the
 observation BEFORE action t plus (action, reward, done, next_action_mask) of transition t.  The
-observation encoder writes straight into the ring (`BatchedPacmanGym.step_obs(..., ring[slot])`),
-so `next_obs` of transition t is simply slot (t+1) % R and is never copied; a finished episode's
-`next_obs` is "None" in the reference (zeros at collate time, train_dqn.py:154-159) and the
-slot then already holds the first observation of the next episode (the env was reset in the same
-kernel launch).  One slot is always "current observation only" which is why R has the +1.
-Sampling is uniform without replacement over the valid transitions (`random.sample`,
-replay_buffer.py:141-143) and the collate is two `pb_gather_obs` launches."""
+observation encoder writes straight into the ring (`pb_encode_obs_ring`), so `next_obs` of
+transition t is simply slot (t+1) % R and is never copied; a finished episode's `next_obs` is
+"None" in the reference (zeros at collate time, train_dqn.py:154-159) and the slot then already
+holds the first observation of the next episode (the env was reset in the same kernel launch).
+One slot is always "current observation only", which is why R has the +1.  Sampling is uniform
+without replacement over the valid transitions (`random.sample`, replay_buffer.py:141-143) and
+the collate is two `pb_gather_obs` launches.
+
+Everything that depends on the ring position uses a DEVICE-side step counter (`_t_dev`), never
+a Python int, so `generate_experience_step` + `sample_batch` can be captured in a CUDA graph
+and replayed while the ring advances."""
 from __future__ import annotations
 
 import ctypes as C
@@ -50,7 +54,6 @@ class ReplayBuffer:
     ) -> None:
         self.policy = policy
         self.phase1_policy = phase1_policy
-        self.device = torch.device(device)
         n = int(num_parallel_envs)
         self.num_envs = n
         self.maxlen = int(maxlen)
@@ -58,8 +61,8 @@ class ReplayBuffer:
         self._ring = self._slots + 1
         # replay_buffer.py:75-80: random_start for the first N * proportion envs, random_ticks all
         self.envs = BatchedPacmanGym(
-            n, np.arange(n) < n * random_start_proportion, True, device=self.device, seed=seed,
-            env_id_base=env_id_base, auto_reset=True)
+            n, np.arange(n) < n * random_start_proportion, True, device=torch.device(device),
+            seed=seed, env_id_base=env_id_base, auto_reset=True)
         dev = self.envs.device
         self.device = dev
         r = self._ring
@@ -71,7 +74,8 @@ class ReplayBuffer:
         self._weight = torch.zeros((r, n), dtype=torch.float32, device=dev)  # 1 = sampleable
         self._mask = torch.zeros((n, NUM_ACTIONS), dtype=torch.bool, device=dev)
         self._in_phase1 = torch.zeros(n, dtype=torch.bool, device=dev)
-        self._t = 0
+        self._t = 0                                                  # host mirror (len, fill)
+        self._t_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # the counter kernels use
         self.envs.reset()
         self.envs.obs(out=self._obs[0])
         self.envs.action_mask(out=self._mask)
@@ -102,25 +106,31 @@ class ReplayBuffer:
             self.generate_experience_step()
 
     @torch.no_grad()
-    def generate_experience_step(self) -> None:
-        """One env-step for each parallel env, appended to the ring (replay_buffer.py:102-139)."""
-        r = self._ring
-        slot, nxt = self._t % r, (self._t + 1) % r
-        last_obs = self._obs[slot]
+    def generate_experience_step(self, count_on_host: bool = True) -> None:
+        """One env-step for each parallel env, appended to the ring (replay_buffer.py:102-139).
+        `count_on_host=False` is for CUDA-graph replay: the caller advances `_t` itself."""
+        r, n = self._ring, self.num_envs
+        slot = self._t_dev % r
+        nxt = (self._t_dev + 1) % r
+        last_obs = self._obs.view(r, -1).index_select(0, slot).view((n,) + OBS_SHAPE)
         actions = self.policy(last_obs, self._mask)
         if self.phase1_policy is not None:
             actions = torch.where(self._in_phase1, self.phase1_policy(last_obs, self._mask), actions)
-        self._actions[slot] = actions
-        # step + auto reset + observation of the resulting state straight into ring slot t+1
-        reward, done = self.envs.step_obs(actions, self._obs[nxt], mask_out=self._mask)
-        self._rewards[slot] = reward
-        self._done[slot] = done
-        self._next_mask[slot] = self._mask & ~done.unsqueeze(1)   # [False]*5 when done (:115-117)
-        self._weight[slot] = (~self._in_phase1).to(torch.float32)
-        self._weight[nxt] = 0.0                                   # slot t+1 is "current obs" only
+        # step + auto reset, then the observation of the resulting state straight into slot t+1
+        reward, done = self.envs.step(actions, check_actions=False, mask_out=self._mask)
+        self.envs.obs_ring(self._obs, nxt)
+        self._actions.index_copy_(0, slot, actions.to(torch.int64).unsqueeze(0))
+        self._rewards.index_copy_(0, slot, reward.unsqueeze(0))
+        self._done.index_copy_(0, slot, done.unsqueeze(0))
+        # next_action_mask is [False]*5 when done (replay_buffer.py:115-117)
+        self._next_mask.index_copy_(0, slot, (self._mask & ~done.unsqueeze(1)).unsqueeze(0))
+        self._weight.index_copy_(0, slot, (~self._in_phase1).to(torch.float32).unsqueeze(0))
+        self._weight.index_fill_(0, nxt, 0.0)                     # slot t+1 is "current obs" only
         if self.phase1_policy is not None:
             self._in_phase1 = (self._in_phase1 | done) & ~self.envs.first_ai_done()
-        self._t += 1
+        self._t_dev += 1
+        if count_on_host:
+            self._t += 1
 
     @torch.no_grad()
     def sample_batch(self, batch_size: int) -> ReplayBatch:

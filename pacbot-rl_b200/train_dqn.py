@@ -71,6 +71,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--metrics-file", default=None)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--no-checkpoints", action="store_true")
+    p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", default=True,
+                   help="run the iteration eagerly instead of replaying one captured CUDA graph")
     for name, default in hyperparam_defaults.items():
         p.add_argument(f"--{name}", type=type(default), default=default, help="Default: %(default)s")
     return p
@@ -97,12 +99,17 @@ class DQNTrainer:
             old = model_cls((17, 28, 31), 5).to(device)
             old.load_state_dict(safetensors.torch.load_file(cfg.old_policy))
             phase1 = MaxQPolicy(old.eval())
-        self.policy = EpsilonGreedy(MaxQPolicy(self.q_net), 5, cfg.initial_epsilon if cfg.finetune else 1.0)
+        # epsilon lives in a 0-dim device tensor so that changing it needs no re-capture
+        self._eps_t = torch.tensor(cfg.initial_epsilon if cfg.finetune else 1.0, device=device)
+        self._eps_host = float(self._eps_t)
+        self._graph = None
+        self.policy = EpsilonGreedy(MaxQPolicy(self.q_net), 5, self._eps_t)
         self.replay = ReplayBuffer(
             maxlen=cfg.replay_buffer_size, policy=self.policy, num_parallel_envs=cfg.num_parallel_envs,
             random_start_proportion=cfg.random_start_proportion, device=device, seed=cfg.seed,
             env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1)
-        self.optimizer = torch.optim.Adam(self.q_net.parameters(), lr=cfg.learning_rate)
+        self.optimizer = torch.optim.Adam(self.q_net.parameters(), lr=cfg.learning_rate,
+                                          capturable=True)
         self.params = [p for p in self.q_net.parameters()]
         self.iter_num = 0
         # streaming metrics (device side)
@@ -110,13 +117,24 @@ class DQNTrainer:
         self._acc_n = 0
 
     # ------------------------------------------------------------------ one iteration
-    def update_target(self) -> None:
-        self.target_q_net.load_state_dict(self.q_net.state_dict())
+    @property
+    def epsilon(self) -> float:
+        return self._eps_host
 
-    def train_iteration(self) -> None:
+    @epsilon.setter
+    def epsilon(self, value: float) -> None:
+        self._eps_host = float(value)
+        self._eps_t.fill_(float(value))
+
+    @torch.no_grad()
+    def update_target(self) -> None:
+        torch._foreach_copy_(list(self.target_q_net.parameters()), list(self.q_net.parameters()))
+
+    def _iteration_body(self) -> None:
+        """Everything of one iteration that runs on the device: sample + collate, double-DQN
+        target, loss, backward, (all-reduce,) clip, Adam, metrics, experience collection.  No
+        host synchronisation and no host-dependent indexing, so it can be CUDA-graph captured."""
         cfg = self.cfg
-        if self.iter_num % cfg.target_network_update_steps == 0:
-            self.update_target()
         batch = self.replay.sample_batch(cfg.batch_size)
         with torch.no_grad():  # double DQN target (train_dqn.py:167-183)
             masks = batch.next_action_masks
@@ -126,7 +144,6 @@ class DQNTrainer:
             returns = next_q.gather(1, next_actions.unsqueeze(1)).squeeze(1)
             discounted = torch.where(batch.done, torch.zeros_like(returns), cfg.discount_factor * returns)
             target_q = batch.rewards * cfg.reward_scale + discounted
-        self.q_net.train()
         self.optimizer.zero_grad(set_to_none=False)
         all_q = self.q_net(batch.obs)
         predicted = all_q.gather(1, batch.actions.unsqueeze(1)).squeeze(1)
@@ -140,12 +157,43 @@ class DQNTrainer:
             self._acc += torch.stack([
                 loss.detach(), grad_norm.detach(), all_q.detach().amax(dim=1).mean() / cfg.reward_scale,
                 target_q.mean() / cfg.reward_scale, torch.isfinite(loss.detach()).float()])
-            self._acc_n += 1
-        # anneal epsilon (train_dqn.py:256-260), then collect experience (:263-265)
-        self.policy.epsilon = lerp(cfg.initial_epsilon, cfg.final_epsilon,
-                                   self.iter_num / max(1, cfg.num_iters - 1))
+        # collect experience (train_dqn.py:263-265); epsilon was set by the host wrapper
         for _ in range(cfg.experience_steps):
-            self.replay.generate_experience_step()
+            self.replay.generate_experience_step(count_on_host=False)
+
+    def capture_graph(self) -> None:
+        """Capture `_iteration_body` into ONE CUDA graph (the reference iteration is hundreds of
+        tiny launches + Python; here a replay is a single launch).  Needs >= 3 eager warm-up
+        iterations on a side stream first (optimizer state, cuDNN autotune, allocator)."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._iteration_body()
+                self.replay._t += self.cfg.experience_steps
+                self._acc_n += 1
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._iteration_body()
+        # the capture pass does not execute anything; nothing to account for on the host
+
+    def train_iteration(self) -> None:
+        cfg = self.cfg
+        if self.iter_num % cfg.target_network_update_steps == 0:
+            self.update_target()
+        # anneal epsilon (train_dqn.py:256-260).  The reference assigns it after the update and
+        # before the experience steps of the same iteration; the update does not read epsilon, so
+        # assigning it before the (captured) body is equivalent.
+        self.epsilon = lerp(cfg.initial_epsilon, cfg.final_epsilon,
+                            self.iter_num / max(1, cfg.num_iters - 1))
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._iteration_body()
+        self.replay._t += cfg.experience_steps
+        self._acc_n += 1
         self.iter_num += 1
 
     def _allreduce_grads(self) -> None:
@@ -161,7 +209,7 @@ class DQNTrainer:
         if vals[4] < 1.0:
             raise FloatingPointError("non-finite loss")  # error_if_nonfinite tripwire (:200-204)
         return {"loss": vals[0], "grad_norm": vals[1], "avg_predicted_value": vals[2],
-                "avg_target_q_value": vals[3], "exploration_epsilon": float(self.policy.epsilon),
+                "avg_target_q_value": vals[3], "exploration_epsilon": self.epsilon,
                 "iters_averaged": n}
 
     # ------------------------------------------------------------------ evaluation (:88-113)
@@ -241,7 +289,9 @@ def train(cfg: argparse.Namespace, max_seconds: Optional[float] = None) -> DQNTr
     trainer = DQNTrainer(cfg, device, rank, world)
     print(f"q_net has {sum(p.numel() for p in trainer.q_net.parameters())} parameters", flush=True)
     trainer.replay.fill()
-    trainer.policy.epsilon = cfg.initial_epsilon
+    trainer.epsilon = cfg.initial_epsilon
+    if cfg.cuda_graph:
+        trainer.capture_graph()
     metrics_f = open(cfg.metrics_file, "a") if (cfg.metrics_file and rank == 0) else None
     t0 = time.time()
     last_t, last_it = t0, 0

@@ -135,7 +135,17 @@ def test_short_training_run(pb, tmp_path):
         "--log_every", "10", "--evaluate_steps", "2", "--device", "cuda:0",
         "--checkpoint-dir", str(tmp_path / "ckpt"), "--metrics-file", str(tmp_path / "m.jsonl")])
     trainer = train_dqn.train(cfg)
-    assert trainer.iter_num == 40
+    assert trainer.iter_num == 40 and trainer._graph is not None    # captured CUDA graph path
+    # host mirror of the ring position == the device-side counter the kernels used
+    assert int(trainer.replay._t_dev.item()) == trainer.replay._t
+    assert len(trainer.replay) == trainer.replay.capacity
+    # the eager path runs the same body
+    cfg2 = train_dqn.build_parser().parse_args([
+        "--num_iters", "6", "--replay_buffer_size", "1024", "--batch_size", "128", "--log_every", "3",
+        "--device", "cuda:0", "--no-checkpoints", "--no-cuda-graph"])
+    eager = train_dqn.train(cfg2)
+    assert eager._graph is None and eager.iter_num == 6
+    assert int(eager.replay._t_dev.item()) == eager.replay._t
     import json
 
     rows = [json.loads(l) for l in open(tmp_path / "m.jsonl")]
