@@ -4,9 +4,8 @@
 // Kernels
 //   k_step       one env per thread; packed state in, reward/done/mask out, optional auto reset
 //   k_reset      masked in-place PacmanGym::reset / constructor
-//   k_encode_obs one env per warp; the 59 024 B observation image is assembled in shared memory
-//                (constant wall channel + zero channels persist, only the dynamic cells are
-//                rewritten) and shipped to HBM by the TMA engine with cp.async.bulk (SASS UBLKCP)
+//   k_encode_obs (pb_encode.cuh) one env per warp; the observation image is assembled in shared
+//                memory and shipped to HBM by the TMA engine with cp.async.bulk (SASS UBLKCP)
 //   k_mask / k_query / k_sample_actions / k_select_actions / k_gather_obs / k_clone
 #include <cstdio>
 #include <cstdlib>
@@ -23,29 +22,11 @@ namespace pb {
 
 __constant__ MazeTables c_tab;
 
-// =============================================================================================
-// small PTX helpers (TMA bulk copy shared -> global)
-// =============================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"(smem_u32(ssrc)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_all() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() {
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
+}  // namespace pb
+
+#include "pb_encode.cuh"
+
+namespace pb {
 
 // =============================================================================================
 // state load / store for the one-env-per-thread kernels
@@ -257,197 +238,6 @@ k_select_actions(StateView st, RngParams rp, const float *__restrict__ q,
 }
 
 // =============================================================================================
-// k_encode_obs -- PacmanGym::obs (env.rs:410-500)
-//
-// One warp owns one 59 024 B image in shared memory.  The wall channel (ch 0) and the zeros of
-// the sparse channels are written once per kernel; per env the warp rewrites channel 1 (pellet
-// values: 4 pellet bits -> one 128-bit shared store), channel 15 (constant fill) and <= 18
-// single cells, then ONE lane hands the image to the TMA engine (cp.async.bulk shared->global,
-// 16 B granules, full-line HBM writes, no register staging).  While the TMA drains image k the
-// other warps of the SM build theirs; before a warp reuses its image it waits for the bulk
-// group's smem READ to finish and zeroes the cells it patched.
-// =============================================================================================
-constexpr int OBS_WARPS = 3;  // 3 x 59 024 B = 177 072 B of the 227 KB shared memory
-constexpr int OBS_THREADS = OBS_WARPS * 32;
-constexpr int OBS_SMEM = OBS_WARPS * OBS_BYTES;
-constexpr int CH_VEC = CH_FLOATS / 4;  // 217 float4 per channel
-
-__device__ __forceinline__ bool on_board(int row, int col) {
-    return (unsigned)row < (unsigned)ROWS && (unsigned)col < (unsigned)COLS;
-}
-__device__ __forceinline__ int obs_cell(int row, int col) {  // env.rs:124: [col][30 - row]
-    return col * ROWS + (ROWS - 1 - row);
-}
-
-template <int CHUNKS>
-__global__ void __launch_bounds__(OBS_THREADS, 1)
-k_encode_obs(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
-             long long env_count, unsigned int *__restrict__ ticket,
-             const long long *__restrict__ slot_index, long long slot_stride) {
-    // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
-    // replayed while the replay ring advances
-    if (slot_index) out += *slot_index * slot_stride;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * OBS_BYTES);
-    float4 *img4 = reinterpret_cast<float4 *>(img);
-
-    // one-time image init: zeros + wall template (env.rs:426)
-    for (int q = lane; q < OBS_FLOATS / 4; q += 32) img4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    for (int c = lane; c < CH_FLOATS; c += 32) {
-        const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
-        img[c] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
-    }
-    __syncwarp();
-
-    int patched = -1;  // flat offset this lane set in the previous image (sparse channels only)
-
-    // Dynamic work distribution: SMs do not drain to HBM at the same rate (two dies, shared
-    // memory partitions), so a static env->warp map leaves the fast SMs idle at the end (ncu:
-    // sm__cycles_active min/max = 0.65).  Each warp takes envs from a global ticket counter; the
-    // next ticket is requested before the current env is processed so its latency is hidden.
-    unsigned int next = 0;
-    if (lane == 0) next = atomicAdd(ticket, 1u);
-    next = __shfl_sync(0xffffffffu, next, 0);
-    while ((long long)next < env_count) {
-        const long long k = next;
-        const long long i = env_first + k;
-        if (lane == 0) next = atomicAdd(ticket, 1u);
-        // ---- state loads (issued before the wait so their latency hides behind the drain) ----
-        const uint32_t F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
-        const uint4 c0 = st.core0[i], c1 = st.core1[i];
-        const uint4 ga = st.ghosts[i], gb = st.ghosts[st.npad + i];
-        EnvR s;
-        unpack_env(c0, c1, ga, gb, s);
-
-        // ---- image is free once the previous bulk store has finished READING it ----
-        if (lane == 0) bulk_wait_read_all();
-        __syncwarp();
-        if (patched >= 0) img[patched] = 0.0f;
-        patched = -1;
-        __syncwarp();  // un-patching must land before another lane patches the same cell
-
-        // ---- channel 1: pellet values (env.rs:427-441); bit order == float order ----
-        const float pv = (s.num_pellets == 1) ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
-                                              : (float)PELLET_POINTS / 200.0f;
-#pragma unroll
-        for (int it = 0; it < 7; it++) {
-            const int q = lane + 32 * it;  // float4 index inside the channel
-            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
-            if (q < CH_VEC) {
-                const uint32_t nib = w >> (4 * (lane & 7));
-                float4 v;
-                v.x = (nib & 1u) ? pv : 0.0f;
-                v.y = (nib & 2u) ? pv : 0.0f;
-                v.z = (nib & 4u) ? pv : 0.0f;
-                v.w = (nib & 8u) ? pv : 0.0f;
-                img4[CH_VEC * 1 + q] = v;
-            }
-        }
-        // ---- channel 15: ticks_per_step / update_period everywhere (env.rs:482-484) ----
-        {
-            const float sp = __fdiv_rn((float)s.tps, (float)s.period);
-            const float4 v = make_float4(sp, sp, sp, sp);
-#pragma unroll
-            for (int it = 0; it < 7; it++) {
-                const int q = lane + 32 * it;
-                if (q < CH_VEC) img4[CH_VEC * 15 + q] = v;
-            }
-        }
-        // ---- sparse cells: one lane each ----
-        // lanes 14..17 need the pellet word holding "their" super pellet (warp-wide shuffle)
-        const int sup_k = (lane - 14) & 3;
-        const int sup_bit = obs_cell(sup_k < 2 ? 3 : 23, (sup_k & 1) ? 26 : 1);
-        const uint32_t sup_word = __shfl_sync(0xffffffffu, F, sup_bit >> 5);
-        // env.rs:122-128: a location is drawn unless it is the (32, 32) sentinel; anything off
-        // the 31x28 board is treated the same way so a malformed state can never write outside
-        // its image
-        const bool pac_on = on_board(s.prow, s.pcol);
-        if (lane < 2) {  // ch 2, 3 (env.rs:452-457)
-            if (pac_on) {
-                patched = CH_FLOATS * (2 + lane) + obs_cell(s.prow, s.pcol);
-                img[patched] = 1.0f;
-            }
-        } else if (lane < 14) {
-            const int gi = (lane - 2) & 3, kind = (lane - 2) >> 2;  // kind 0: ch4+g, 1: ch8+g, 2: timer
-            int grow = 0, gcol = 0, gfr = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-                if (g == gi) {
-                    grow = s.g[g].row;
-                    gcol = s.g[g].col;
-                    gfr = s.g[g].fright;
-                }
-            if (on_board(grow, gcol)) {
-                const int cell = obs_cell(grow, gcol);
-                if (kind < 2) {  // env.rs:461, 476-480
-                    patched = CH_FLOATS * (4 + 4 * kind + gi) + cell;
-                    img[patched] = 1.0f;
-                } else {  // env.rs:462-469; "last ghost wins" on a shared cell
-                    const int ch = gfr > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
-                    bool later_same = false;
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const bool on = on_board(s.g[g].row, s.g[g].col);
-                        const int gch = s.g[g].fright > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
-                        if (g > gi && on && s.g[g].row == grow && s.g[g].col == gcol && gch == ch)
-                            later_same = true;
-                    }
-                    if (!later_same) {
-                        patched = CH_FLOATS * ch + cell;
-                        img[patched] = gfr > 0 ? __fdiv_rn((float)gfr, (float)GHOST_FRIGHT_STEPS)
-                                               : __fdiv_rn((float)s.mode_steps, (float)CHASE_DURATION);
-                    }
-                }
-            }
-        } else if (lane < 18) {  // ch 16: super pellets still present (env.rs:487-497)
-            if ((sup_word >> (sup_bit & 31)) & 1u) {
-                patched = CH_FLOATS * 16 + sup_bit;
-                img[patched] = 1.0f;
-            }
-        }
-        __syncwarp();
-        // ---- channel 1 fix-ups, in reference order: super value, fruit, then += ghost bonus ----
-        if (lane == 0) {
-            float *r1 = img + CH_FLOATS;
-            const float sv = (s.num_pellets == 1) ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
-                                                  : (float)SUPER_PELLET_POINTS / 200.0f;
-#pragma unroll
-            for (int kq = 0; kq < 4; kq++) {
-                const int b = obs_cell(kq < 2 ? 3 : 23, (kq & 1) ? 26 : 1);
-                if (r1[b] != 0.0f) r1[b] = sv;
-            }
-            if (s.fruit_steps > 0) {  // env.rs:433-437 (only where there is no pellet)
-                const int b = obs_cell(FRUIT_ROW, FRUIT_COL);
-                if (r1[b] == 0.0f) r1[b] = (float)FRUIT_POINTS / 200.0f;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; g++) {  // env.rs:464
-                if (s.g[g].fright > 0 && on_board(s.g[g].row, s.g[g].col)) {
-                    const int b = obs_cell(s.g[g].row, s.g[g].col);
-                    r1[b] = __fadd_rn(r1[b], (float)(1 << s.combo));
-                }
-            }
-        }
-        // ---- hand the image to the TMA engine ----
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            char *dst = reinterpret_cast<char *>(out + k * env_stride);
-            constexpr int CHUNK_BYTES = OBS_BYTES / CHUNKS;
-#pragma unroll
-            for (int c = 0; c < CHUNKS; c++)
-                bulk_store_s2g(dst + c * CHUNK_BYTES, reinterpret_cast<char *>(img) + c * CHUNK_BYTES,
-                               CHUNK_BYTES);
-            bulk_commit();
-        }
-        next = __shfl_sync(0xffffffffu, next, 0);
-    }
-    if (lane == 0) bulk_wait_all();
-}
-
-// =============================================================================================
 // k_gather_obs (train_dqn.py:153-159 collate) and k_clone
 // =============================================================================================
 __global__ void __launch_bounds__(256)
@@ -555,17 +345,18 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
                   long long slot_stride = 0) {
     if (count <= 0) return PB_OK;
     static thread_local int attr_set_for = -1;
-    auto kern = k_encode_obs<1>;
+    auto kern = k_encode_obs;
     if (attr_set_for != e->device) {
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
         attr_set_for = e->device;
     }
-    long long blocks = (count + OBS_WARPS - 1) / OBS_WARPS;
+    const int warps = ENC_WARPS;
+    long long blocks = (count + warps - 1) / warps;
     if (blocks > e->num_sms) blocks = e->num_sms;
     unsigned int *ticket = e->tickets + (e->ticket_next++ % TICKET_RING);
     PB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
-    kern<<<(unsigned)blocks, OBS_THREADS, OBS_SMEM, s>>>(e->st, out_dev, stride, first, count,
-                                                         ticket, slot_index, slot_stride);
+    kern<<<(unsigned)blocks, warps * 32, warps * IMG_BYTES + CH_BYTES, s>>>(
+        e->st, out_dev, stride, first, count, ticket, slot_index, slot_stride);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -81,6 +81,11 @@ struct MazeTables {
     uint32_t super_mask[PEL_WORDS];       // the 4 super-pellet bits
     uint32_t wipe_keep[5][PEL_WORDS];     // env.rs:185-207: bits that SURVIVE wipe type k
     uint16_t node_rc[NUM_NODES];          // NODE_COORDS: row | col << 8 (row-major walkable cells)
+    // IEEE-rounded quotients of the observation's timer channels (env.rs:463,468): u8 / 40.0 and
+    // u8 / 180.0 for every possible u8 numerator.  Table lookups keep the divergent single-cell
+    // code of the encoder free of division slow paths (out-of-line calls).
+    float fright_q[256];
+    float mode_q[256];
 };
 
 constexpr MazeTables make_tables() {
@@ -105,6 +110,10 @@ constexpr MazeTables make_tables() {
     for (int k = 0; k < 4; k++) {
         const int i = fbit(SUPER_ROW[k], SUPER_COL[k]);
         t.super_mask[i >> 5] |= 1u << (i & 31);
+    }
+    for (int v = 0; v < 256; v++) {
+        t.fright_q[v] = (float)v / (float)GHOST_FRIGHT_STEPS;
+        t.mode_q[v] = (float)v / (float)CHASE_DURATION;
     }
     return t;
 }

@@ -92,3 +92,41 @@ def oracle_to_gpu_state(pbmod, st):
         out[f] = st[f]
     out["cfg_flags"] = oracle_cfg_flags(st)
     return out
+
+
+def assert_obs_equal(oracle_obs, gpu_obs, context="", state=None):
+    """Bit-exact float32 comparison with a compact report (a bare `assert np.array_equal(...)`
+    on multi-hundred-MB arrays makes pytest spend minutes building the failure repr)."""
+    a = np.ascontiguousarray(oracle_obs).view(np.uint32)
+    b = np.ascontiguousarray(gpu_obs).view(np.uint32)
+    if a.shape == b.shape and np.array_equal(a, b):
+        return
+    assert a.shape == b.shape, f"{context}: obs shape {a.shape} vs {b.shape}"
+    bad = np.argwhere(a != b)
+    lines = [f"{context}: observation differs in {len(bad)} cells of {len(np.unique(bad[:, 0]))} envs"]
+    for e, ch, x, y in bad[:12]:
+        lines.append(f"  env {e} ch {ch} cell (row {30 - y}, col {x}): oracle "
+                     f"{oracle_obs[e, ch, x, y]!r} gpu {gpu_obs[e, ch, x, y]!r}")
+    if state is not None:
+        e = int(bad[0][0])
+        s = state[e]
+        lines.append("  state of first env: " + ", ".join(
+            f"{k}={s[k].tolist() if hasattr(s[k], 'tolist') else s[k]}" for k in
+            ("pac_row", "pac_col", "g_row", "g_col", "g_fright", "ghost_combo", "fruit_steps",
+             "num_pellets", "mode", "mode_steps")))
+    raise AssertionError("\n".join(lines))
+
+
+@pytest.fixture(autouse=True)
+def _watchdog():
+    """PB_TEST_WATCHDOG=<seconds>: dump the Python stack and exit if a single test exceeds it (a
+    hung CUDA call cannot be interrupted by pytest-timeout's signal method)."""
+    secs = int(os.environ.get("PB_TEST_WATCHDOG", "0"))
+    if secs > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(secs, exit=True)
+        yield
+        faulthandler.cancel_dump_traceback_later()
+    else:
+        yield

@@ -160,3 +160,87 @@ def test_short_training_run(pb, tmp_path):
     assert (tmp_path / "ckpt" / "q_net-latest.safetensors").exists()
     loaded = torch.load(tmp_path / "ckpt" / "q_net-latest.pt", map_location="cuda:0", weights_only=False)
     assert sum(p.numel() for p in loaded.parameters()) == 156_934
+
+
+class LastValidPolicy:
+    """Deterministic 'old' policy for the two-stage reset test: highest-index valid action."""
+
+    def __call__(self, obs, masks):
+        idx = __import__("torch").arange(5, device=masks.device)
+        return (masks.long() * idx).argmax(1)
+
+
+def test_two_stage_reset_matches_reference_loop(pb, oracle):
+    """reset_env (replay_buffer.py:44-54): after every reset the OLD policy plays, unrecorded,
+    until first_ai_done(); only then are transitions recorded.  The batched buffer interleaves
+    envs, but each env's own trajectory must equal the reference's sequential per-env loop."""
+    import torch
+    from conftest import oracle_to_gpu_state
+    from pacbot_rl_b200.replay_buffer import ReplayBuffer
+
+    n, total_steps = 16, 150
+    rng = np.random.default_rng(4)
+    tape = rng.integers(0, 2**32, size=(n, 263), dtype=np.uint32)
+    main, old = FirstValidPolicy(), LastValidPolicy()
+    buf = ReplayBuffer(n * (total_steps + 2), main, n, 0.5, torch.device("cuda:0"), seed=0, phase1_policy=old)
+    buf.envs.set_draw_tape(torch.from_numpy(tape.view(np.int32)).cuda())
+    # start state: one super pellet left, directly above Pac-Man (the old policy walks into it),
+    # a few ordinary pellets, ghosts far away; half the envs have NO super pellet at all
+    proto = oracle.OracleBatch(n, (np.arange(n) < n * 0.5).astype(np.uint8) | 2, tape)
+    st = proto.export_state()
+    st["paused"] = 0
+    st["pellets"][:] = 0
+    st["pellets"][:, 5] = 0x7FFFFFE
+    st["num_pellets"] = 26
+    with_super = np.arange(n) % 2 == 0
+    st["pellets"][with_super, 3] = 1 << 1
+    st["num_pellets"][with_super] = 27
+    st["pac_row"], st["pac_col"], st["pac_dir"] = 4, 1, 0
+    st["curr_ticks"] = 1
+    buf.envs.set_state(oracle_to_gpu_state(pb, st))
+    buf.envs.obs(out=buf._obs[0])
+    buf.envs.action_mask(out=buf._mask)
+    buf._in_phase1 = ~buf.envs.first_ai_done()
+    assert buf._in_phase1.cpu().numpy().tolist() == with_super.tolist()
+
+    # ---- reference semantics, env by env, on the oracle ----
+    def t(x):
+        return torch.from_numpy(x)
+
+    expected = []   # per env: list of (obs_bits, action, reward, done)
+    for i in range(n):
+        ob = oracle.OracleBatch(1, ((np.arange(n) < n * 0.5).astype(np.uint8) | 2)[i:i + 1], tape[i:i + 1])
+        ob.import_state(st[i:i + 1])
+        rec, steps_left = [], total_steps
+        in_phase1 = not ob.first_ai_done()[0]
+        while steps_left > 0:
+            obs, mask = ob.obs(), ob.action_mask()
+            if in_phase1:    # reset_env's inner loop: old policy, not recorded, re-reset on death
+                a = old(t(obs), t(mask)).numpy().astype(np.uint8)
+                _, d = ob.step(a, auto_reset=True)
+                in_phase1 = not ob.first_ai_done()[0]
+            else:
+                a = main(t(obs), t(mask)).numpy().astype(np.uint8)
+                r, d = ob.step(a, auto_reset=True)
+                rec.append((obs.view(np.uint32).copy(), int(a[0]), int(r[0]), bool(d[0])))
+                if d[0]:     # reset_env(env) after a recorded terminal transition
+                    in_phase1 = not ob.first_ai_done()[0]
+            steps_left -= 1
+        expected.append(rec)
+
+    for _ in range(total_steps):
+        buf.generate_experience_step()
+    w = buf._weight.cpu().numpy()
+    obs_ring = buf._obs.cpu().numpy().view(np.uint32)
+    acts, rews, dones = buf._actions.cpu().numpy(), buf._rewards.cpu().numpy(), buf._done.cpu().numpy()
+    passed_through_phase1 = 0
+    for i in range(n):
+        got = [(obs_ring[s, i], int(acts[s, i]), int(rews[s, i]), bool(dones[s, i]))
+               for s in range(total_steps) if w[s, i] > 0]
+        assert len(got) == len(expected[i]), (i, len(got), len(expected[i]))
+        for k, (g, e) in enumerate(zip(got, expected[i])):
+            assert g[1:] == e[1:], (i, k, g[1:], e[1:])
+            assert np.array_equal(g[0], e[0][0]), (i, k)
+        if with_super[i] and len(got) > 0:
+            passed_through_phase1 += 1
+    assert passed_through_phase1 >= 1

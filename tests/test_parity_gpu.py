@@ -4,7 +4,7 @@ float32 observation compared as raw uint32 bits (tolerance: none)."""
 import numpy as np
 import pytest
 
-from conftest import assert_states_equal, oracle_to_gpu_state
+from conftest import assert_obs_equal, assert_states_equal, oracle_to_gpu_state
 
 pytestmark = pytest.mark.gpu
 
@@ -49,11 +49,7 @@ def compare_step(ob, env, actions, t, auto_reset, check_obs):
     assert np.array_equal(ob.action_mask(), env.action_mask().cpu().numpy()), f"mask differs at step {t}"
     assert_states_equal(ob.export_state(), env.get_state(), f"step {t}")
     if check_obs:
-        o_o = ob.obs().view(np.uint32)
-        o_g = env.obs().cpu().numpy().view(np.uint32)
-        if not np.array_equal(o_o, o_g):
-            bad = np.argwhere(o_o != o_g)
-            raise AssertionError(f"obs differs at step {t}: {len(bad)} cells, first {bad[0]}")
+        assert_obs_equal(ob.obs(), env.obs().cpu().numpy(), f"step {t}", ob.export_state())
     return d_o
 
 
@@ -64,11 +60,11 @@ def test_fresh_and_reset_states_match(pb, oracle):
     cfg = (np.arange(n) % 16).astype(np.uint8)
     ob, env = make_pair(pb, oracle, n, cfg, tape)
     assert_states_equal(ob.export_state(), env.get_state(), "constructor")
-    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    assert_obs_equal(ob.obs(), env.obs().cpu().numpy(), "constructor")
     ob.reset()
     env.reset()
     assert_states_equal(ob.export_state(), env.get_state(), "reset")
-    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    assert_obs_equal(ob.obs(), env.obs().cpu().numpy(), "reset")
     assert np.array_equal(ob.action_mask(), env.action_mask().cpu().numpy())
     # masked reset
     torch = torch_mod()
@@ -218,7 +214,7 @@ def test_fuzzed_states_parity(pb, oracle, seed):
     env.set_state(st)
     ob.import_state(gpu_to_oracle_state(oracle, st))
     assert_states_equal(ob.export_state(), env.get_state(), "import")
-    assert np.array_equal(ob.obs().view(np.uint32), env.obs().cpu().numpy().view(np.uint32))
+    assert_obs_equal(ob.obs(), env.obs().cpu().numpy(), "import", ob.export_state())
     seen_done = 0
     for t in range(steps):
         a = random_valid_actions(rng, ob.action_mask(), p_invalid_move=0.2)
@@ -349,7 +345,7 @@ def test_obs_stride_and_ring_slot(pb, oracle):
     pb._lib.check(L.pb_encode_obs(env._h, C.c_void_p(buf.data_ptr()), stride, None))
     torch.cuda.synchronize()
     got = buf.view(n, stride).cpu().numpy()
-    assert np.array_equal(got[:, :pb.OBS_FLOATS].view(np.uint32), ob.obs().reshape(n, -1).view(np.uint32))
+    assert_obs_equal(ob.obs().reshape(n, 1, 1, -1), got[:, :pb.OBS_FLOATS].reshape(n, 1, 1, -1), "strided")
     assert (got[:, pb.OBS_FLOATS:] == -7.0).all()
     with pytest.raises(ValueError):
         pb._lib.check(L.pb_encode_obs(env._h, C.c_void_p(buf.data_ptr()), pb.OBS_FLOATS + 2, None))
@@ -369,8 +365,7 @@ def test_repeated_encode_is_idempotent_and_unpatches(pb, oracle):
     a = env.obs()
     b = env.obs()
     assert torch.equal(a, b)
-    ref = ob.obs()
-    assert np.array_equal(a.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    assert_obs_equal(ob.obs(), a.cpu().numpy(), "fuzzed 8192", ob.export_state())
 
 
 def test_full_size_properties_65536(pb):
@@ -407,3 +402,16 @@ def test_full_size_properties_65536(pb):
         r2, d2 = env2.step_obs(env2.sample_actions(), obs2)
     assert torch.equal(obs, obs2) and torch.equal(r, r2)
     del wall
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 257])
+def test_odd_batch_sizes(pb, oracle, n):
+    """Env counts that are not multiples of the warp / CTA size (ragged tails)."""
+    rng = np.random.default_rng(n)
+    tape = rng.integers(0, 2**32, size=(n, 101), dtype=np.uint32)
+    ob, env = make_pair(pb, oracle, n, np.full(n, 3, np.uint8), tape, auto_reset=True)
+    ob.reset()
+    env.reset()
+    for t in range(40):
+        a = random_valid_actions(rng, ob.action_mask())
+        compare_step(ob, env, a, t, True, check_obs=True)

@@ -99,3 +99,14 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "pyoracle" not in src and "pacbot_oracle" not in src, fn
+
+
+def test_create_rejects_empty_batch(pb):
+    """Edge case: zero / negative env counts are argument errors, not crashes."""
+    L = pb._lib.load()
+    h = C.c_void_p()
+    assert L.pb_create(C.byref(h), 0, 0, 0, 0, None) == -1
+    assert L.pb_create(C.byref(h), -5, 0, 0, 0, None) == -1
+    assert L.pb_create(None, 4, 0, 0, 0, None) == -1
+    with pytest.raises(ValueError):
+        pb._lib.check(-1)

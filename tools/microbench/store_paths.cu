@@ -1,0 +1,94 @@
+// Microbenchmark (not product code): how fast can 65 536 x 59 024 B blocks be streamed to HBM
+// from one B200 by different store paths?  Build: nvcc -gencode arch=compute_100a,code=sm_100a
+//   A  TMA bulk store of a whole 59 024 B image per warp, W warps/CTA (W = 1..3), ticket
+//   B  TMA bulk store split in 17 channel copies
+//   C  direct st.global.v4 from registers, env per warp, many warps
+//   D  direct st.global.v4, grid-stride over the flat buffer (what torch.fill_ does)
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+constexpr int OBS_BYTES = 59024;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int CHUNKS>
+__global__ void k_bulk(float *out, long long n, unsigned *ticket, int warps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *img4 = reinterpret_cast<float4 *>(smem + (size_t)warp * OBS_BYTES);
+    for (int q = lane; q < OBS_BYTES / 16; q += 32) img4[q] = make_float4(1.f, 2.f, 3.f, 4.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
+    next = __shfl_sync(~0u, next, 0);
+    while ((long long)next < n) {
+        long long k = next;
+        if (lane == 0) {
+            next = atomicAdd(ticket, 1u);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            char *dst = reinterpret_cast<char *>(out) + k * OBS_BYTES;
+            constexpr int CB = OBS_BYTES / CHUNKS;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; c++)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + c * CB),
+                             "r"(smem_u32(reinterpret_cast<char *>(img4) + c * CB)), "r"(CB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        next = __shfl_sync(~0u, next, 0);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__global__ void k_direct_env(float4 *out, long long n, unsigned *ticket) {
+    const int lane = threadIdx.x & 31;
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
+    next = __shfl_sync(~0u, next, 0);
+    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+    while ((long long)next < n) {
+        float4 *dst = out + (long long)next * (OBS_BYTES / 16);
+        if (lane == 0) next = atomicAdd(ticket, 1u);
+#pragma unroll 8
+        for (int q = lane; q < OBS_BYTES / 16; q += 32) dst[q] = v;
+        next = __shfl_sync(~0u, next, 0);
+    }
+}
+__global__ void k_direct_flat(float4 *out, long long total4) {
+    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x)
+        out[i] = v;
+}
+template <typename F> float timeit(F f, int reps = 8) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e9f;
+    for (int r = 0; r < reps + 2; r++) {
+        cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); if (r >= 2 && ms < best) best = ms;
+    }
+    return best;
+}
+int main() {
+    const long long n = 65536; const size_t bytes = (size_t)n * OBS_BYTES;
+    float *buf[3]; for (auto &b : buf) cudaMalloc(&b, bytes);
+    unsigned *ticket; cudaMalloc(&ticket, 4);
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaFuncSetAttribute(k_bulk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * OBS_BYTES);
+    cudaFuncSetAttribute(k_bulk<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * OBS_BYTES);
+    int it = 0;
+    for (int w = 1; w <= 3; w++) {
+        float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk<1><<<sms, 32 * w, w * OBS_BYTES>>>(buf[it++ % 3], n, ticket, w); });
+        printf("A bulk 59024B x1   warps/SM=%d : %.3f ms  %.0f GB/s\n", w, ms, bytes / ms / 1e6);
+    }
+    { float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk<17><<<sms, 96, 3 * OBS_BYTES>>>(buf[it++ % 3], n, ticket, 3); });
+      printf("B bulk 3472B x17   warps/SM=3 : %.3f ms  %.0f GB/s\n", ms, bytes / ms / 1e6); }
+    for (int wps : {8, 16, 32, 64}) {
+        float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_direct_env<<<sms * wps / 8, 256>>>((float4 *)buf[it++ % 3], n, ticket); });
+        printf("C direct v4 env/warp warps/SM=%d : %.3f ms  %.0f GB/s\n", wps, ms, bytes / ms / 1e6);
+    }
+    for (int bps : {4, 8, 16}) {
+        float ms = timeit([&] { k_direct_flat<<<sms * bps, 256>>>((float4 *)buf[it++ % 3], (long long)(bytes / 16)); });
+        printf("D direct v4 flat  blocks/SM=%d : %.3f ms  %.0f GB/s\n", bps, ms, bytes / ms / 1e6);
+    }
+    { float ms = timeit([&] { cudaMemsetAsync(buf[it++ % 3], 0, bytes); });
+      printf("E cudaMemsetAsync              : %.3f ms  %.0f GB/s\n", ms, bytes / ms / 1e6); }
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
