@@ -1,9 +1,10 @@
 // pb_encode.cuh -- k_encode_obs: PacmanGym::obs (/root/reference/pacbot_rs/src/env.rs:410-500)
 // for a batch of envs, written to HBM by the TMA engine.
 //
-// Shape of the kernel (one CTA per SM, persistent, 4 warps, one env per warp at a time):
+// Shape of the kernel (one CTA per SM, persistent, ENC_WARPS = 4 warps, one env per warp at a
+// time, ENC_BUFS = 1 image per warp):
 //   * shared memory holds ONE wall-channel template (ch 0, constant for every env, 3 472 B) and
-//     FOUR private images of channels 1..16 (4 x 55 552 B): 225 680 B of the 227 KB;
+//     FOUR private images of channels 1..16 (55 552 B each): 225 680 B of the 227 KB;
 //   * per env a warp rewrites only what changes: channel 1 (pellet values: a nibble of the
 //     observation-ordered pellet bitboard becomes one 128-bit shared store), channel 15 (constant
 //     fill) and <= 19 single cells (Pac-Man x2, ghosts x8, mode/fright timers, super pellets,
@@ -11,16 +12,28 @@
 //     only the patched cells are cleared again;
 //   * ONE lane then issues two cp.async.bulk shared->global copies (SASS UBLKCP): wall template
 //     -> channel 0, private image -> channels 1..16.  No register staging, full-line HBM writes;
-//   * before reusing its image the warp waits for the bulk group's shared-memory READ only
+//   * before an image is rebuilt the warp waits for the bulk group's shared-memory READ only
 //     (cp.async.bulk.wait_group.read), so global-write latency is never on the critical path;
-//   * envs are handed out by a global atomic ticket requested one env ahead (SMs drain to HBM at
-//     different rates; a static map left fast SMs idle: ncu sm__cycles_active min/max 0.65).
+//   * envs are handed out by a global atomic ticket (SMs drain to HBM at different rates; a
+//     static map left fast SMs idle: ncu sm__cycles_active min/max 0.65, +22 % time); ticket and
+//     packed state are fetched one to two envs ahead of their use.
 //
-// Why TMA and why 4 images: tools/microbench/store_paths.cu measures, for this exact access
-// pattern (65 536 x 59 024 B), TMA bulk stores at 7.49 TB/s vs 7.15 TB/s for the best
-// st.global.v4 variant and 7.34 TB/s for cudaMemset, but only when >= 2 copies per SM are in
-// flight (1 in flight: 6.78 TB/s).  A warp has no copy in flight while it rebuilds its image, so
-// 4 images with a short rebuild keep the in-flight count above 2.
+// Why TMA: tools/microbench/store_paths.cu measures, for this exact access pattern (65 536 x
+// 59 024 B), bare TMA bulk stores at 7.48 TB/s (0.517 ms) vs 7.15 TB/s for the best
+// st.global.v4 variant and 7.34 TB/s for cudaMemset, provided >= 2 copies per SM are in flight
+// (1 in flight: 6.8 TB/s).  What the real encoder adds on top is the dependent chain
+// "image free -> state -> rebuild -> fence.proxy.async -> issue": the same microbenchmark with that
+// chain (loads + 434 dependent STS.128 + fence) drops to 7.2-7.25 TB/s, and this kernel reaches
+// 7.05-7.1 TB/s (0.547-0.551 ms).  Tried and measured equal within noise (0.547-0.561 ms):
+// 3 x 59 024 B images with channel 0 inside, 4 x 1 images, 2 warps x 2 double-buffered images,
+// with and without the two-deep software pipeline.
+//
+// Per-lane roles are written BRANCH FREE (selects + one predicated store per lane).  A first
+// version used an if/else chain per lane group with nested conditionals; for particular states
+// (tests/test_parity_gpu.py fuzz seed 2) lanes at the end of the chain did not get their store in
+// before lane 0 issued the copy, ptxas having dropped every __syncwarp() it considered redundant;
+// the mismatch vanished with printf in the kernel.  Hence also warp_arrived(): a vote whose result
+// is consumed, which cannot be dropped.
 //
 // Bit-exactness: every float is either an exactly representable constant computed with IEEE
 // division at compile time (10/200, 50/200, ...), or an IEEE division / addition done with
@@ -33,13 +46,14 @@ namespace pb {
 // defined in pb_kernels.cu before this header is included
 // (same translation unit): __constant__ MazeTables c_tab;
 
-constexpr int ENC_WARPS = 4;
+constexpr int ENC_WARPS = 4;   // warps per CTA
+constexpr int ENC_BUFS = 1;    // images per warp (2 = double buffering; measured no faster)
 constexpr int ENC_THREADS = ENC_WARPS * 32;
 constexpr int CH_BYTES = CH_FLOATS * 4;                 // 3 472
 constexpr int IMG_CH = OBS_CH - 1;                      // channels 1..16 live in the private image
 constexpr int IMG_FLOATS = IMG_CH * CH_FLOATS;          // 13 888
 constexpr int IMG_BYTES = IMG_FLOATS * 4;               // 55 552
-constexpr int ENC_SMEM = ENC_WARPS * IMG_BYTES + CH_BYTES;  // 225 680
+constexpr int ENC_SMEM = ENC_WARPS * ENC_BUFS * IMG_BYTES + CH_BYTES;  // 225 680
 constexpr int CH_VEC = CH_FLOATS / 4;                   // 217 float4 per channel
 static_assert(ENC_SMEM <= 227 * 1024, "encoder images must fit the 227 KB shared memory");
 static_assert(IMG_BYTES % 16 == 0 && CH_BYTES % 16 == 0, "bulk copies move 16 B granules");
@@ -55,8 +69,10 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
 __device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read_all() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+// wait until at most N of this thread's bulk groups are still reading shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -94,13 +110,12 @@ k_encode_obs(StateView st, float *__restrict__ out,
     if (slot_index) out += *slot_index * slot_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_warps = blockDim.x >> 5;
-    float *wall_ch = reinterpret_cast<float *>(smem_raw + (size_t)n_warps * IMG_BYTES);
-    float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * IMG_BYTES);
-    float4 *img4 = reinterpret_cast<float4 *>(img);
+    float *wall_ch = reinterpret_cast<float *>(smem_raw + (size_t)ENC_WARPS * ENC_BUFS * IMG_BYTES);
+    float *img_base = reinterpret_cast<float *>(smem_raw + (size_t)warp * ENC_BUFS * IMG_BYTES);
 
-    // ---- one-time init: wall template (env.rs:426) by warp 0, zeroed private images ----
-    for (int q = lane; q < IMG_FLOATS / 4; q += 32) img4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- one-time init: wall template (env.rs:426), zeroed private images ----
+    for (int q = lane; q < ENC_BUFS * IMG_FLOATS / 4; q += 32)
+        reinterpret_cast<float4 *>(img_base)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = threadIdx.x; c < CH_FLOATS; c += blockDim.x) {
         const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
         wall_ch[c] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
@@ -108,19 +123,50 @@ k_encode_obs(StateView st, float *__restrict__ out,
     fence_proxy_async_smem();
     __syncthreads();  // the template is read by every warp's bulk copies
 
-    int patched = -1;  // image offset this lane set for the previous env (sparse channels only)
+    // image offset this lane patched in buffer 0 / 1 for an earlier env (sparse channels only)
+    int patched0 = -1, patched1 = -1;
+    int buf = 0;
 
-    unsigned int next = 0;
-    if (lane == 0) next = atomicAdd(ticket, 1u);
-    next = __shfl_sync(0xffffffffu, next, 0);
-    while ((long long)next < env_count) {
-        const long long k = next;
-        const long long i = env_first + k;
-        if (lane == 0) next = atomicAdd(ticket, 1u);  // consumed at the bottom of the loop
-        // ---- state loads (issued before the wait so their latency hides behind the drain) ----
-        const uint32_t F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
-        const uint4 c0 = st.core0[i], c1 = st.core1[i];
-        const uint4 ga = st.ghosts[i], gb = st.ghosts[st.npad + i];
+    // Software pipeline, two envs deep: while env `cur` is encoded, the packed state of env `nxt`
+    // is already being loaded and the ticket after that is being fetched, so neither the atomic's
+    // nor the loads' latency sits on the per-env critical path of the warp.
+    // `pend` (lane 0 only) is a ticket whose atomic is still in flight: it is requested right
+    // AFTER a bulk copy is issued and first read one whole env later, because fence.proxy.async
+    // (MEMBAR.ALL.CTA in SASS) makes a lane wait for all of its outstanding memory operations --
+    // an atomic requested before the fence would put its L2 round trip on the critical path.
+    unsigned int cur = 0, nxt = 0, pend = 0;
+    if (lane == 0) {
+        cur = atomicAdd(ticket, 1u);
+        nxt = atomicAdd(ticket, 1u);
+        pend = atomicAdd(ticket, 1u);
+    }
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    uint32_t F = 0u;
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, ga = c0, gb = c0;
+    if ((long long)cur < env_count) {
+        const long long i = env_first + cur;
+        F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
+        c0 = st.core0[i];
+        c1 = st.core1[i];
+        ga = st.ghosts[i];
+        gb = st.ghosts[st.npad + i];
+    }
+    while ((long long)cur < env_count) {
+        const long long k = cur;
+        float *img = img_base + buf * IMG_FLOATS;
+        float4 *img4 = reinterpret_cast<float4 *>(img);
+        // ---- prefetch the state of the next env ----
+        uint32_t F_n = 0u;
+        uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = c0_n, ga_n = c0_n, gb_n = c0_n;
+        if ((long long)nxt < env_count) {
+            const long long i = env_first + nxt;
+            F_n = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
+            c0_n = st.core0[i];
+            c1_n = st.core1[i];
+            ga_n = st.ghosts[i];
+            gb_n = st.ghosts[st.npad + i];
+        }
         EnvR s;
         unpack_env(c0, c1, ga, gb, s);
 
@@ -213,10 +259,14 @@ k_encode_obs(StateView st, float *__restrict__ out,
         }
 
         // ---- the image is free once the previous bulk copies have finished READING it ----
-        if (lane == 0) bulk_wait_read_all();
+        // (the copy of the OTHER buffer, issued for the previous env, stays in flight: this is what
+        // keeps the TMA engine busy while this warp rebuilds an image)
+        if (lane == 0) bulk_wait_read<ENC_BUFS - 1>();
         if (!warp_arrived((unsigned int)k)) __trap();  // nobody touches the image before lane 0's wait is over
-        if (patched >= 0) img[patched] = 0.0f;
-        patched = -1;
+        {
+            const int patched = buf ? patched1 : patched0;
+            if (patched >= 0) img[patched] = 0.0f;
+        }
 
         // ---- channel 1 base values and channel 15 fill: 2 x 7 128-bit stores per lane ----
 #pragma unroll
@@ -239,7 +289,11 @@ k_encode_obs(StateView st, float *__restrict__ out,
 
         // ---- single cells: one predicated store per lane (disjoint cells by construction) ----
         if (do_store) img[off] = val;
-        if (do_store && unpatch) patched = off;
+        {
+            const int patched = (do_store && unpatch) ? off : -1;
+            patched0 = buf ? patched0 : patched;
+            patched1 = buf ? patched : patched1;
+        }
 
         // ---- hand channel 0 (template) + channels 1..16 (image) to the TMA engine ----
         fence_proxy_async_smem();
@@ -250,7 +304,15 @@ k_encode_obs(StateView st, float *__restrict__ out,
             bulk_store_s2g(dst + CH_BYTES, img, IMG_BYTES);
             bulk_commit();
         }
-        next = __shfl_sync(0xffffffffu, next, 0);
+        buf = (buf + 1) % ENC_BUFS;
+        cur = nxt;
+        nxt = __shfl_sync(0xffffffffu, pend, 0);          // requested one env ago: long since back
+        if (lane == 0) pend = atomicAdd(ticket, 1u);     // in flight during the next env
+        F = F_n;
+        c0 = c0_n;
+        c1 = c1_n;
+        ga = ga_n;
+        gb = gb_n;
     }
     if (lane == 0) bulk_wait_all();
 }

@@ -355,7 +355,7 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     if (blocks > e->num_sms) blocks = e->num_sms;
     unsigned int *ticket = e->tickets + (e->ticket_next++ % TICKET_RING);
     PB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
-    kern<<<(unsigned)blocks, warps * 32, warps * IMG_BYTES + CH_BYTES, s>>>(
+    kern<<<(unsigned)blocks, ENC_THREADS, ENC_SMEM, s>>>(
         e->st, out_dev, stride, first, count, ticket, slot_index, slot_stride);
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -37,6 +37,55 @@ __global__ void k_bulk(float *out, long long n, unsigned *ticket, int warps) {
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+// A + the ingredients of the real encoder, one flag each:
+//   1: fence.proxy.async + __syncwarp before every issue   2: rewrite 2 channels (434 STS.128)
+//   4: 176 B of global loads per env (the packed state)     8: 4 warps x 55 552 B + shared 3 472 B
+template <int FLAGS>
+__global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 *state) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int IMG = (FLAGS & 8) ? 55552 : OBS_BYTES;
+    float4 *img4 = reinterpret_cast<float4 *>(smem + (size_t)warp * IMG);
+    unsigned char *shared_ch = smem + (size_t)(blockDim.x >> 5) * IMG;
+    for (int q = lane; q < IMG / 16; q += 32) img4[q] = make_float4(1.f, 2.f, 3.f, 4.f);
+    if (FLAGS & 8) for (int q = threadIdx.x; q < 3472 / 16; q += blockDim.x) reinterpret_cast<float4 *>(shared_ch)[q] = make_float4(1.f, 1.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
+    next = __shfl_sync(~0u, next, 0);
+    float acc = 0.f;
+    while ((long long)next < n) {
+        long long k = next;
+        if (lane == 0) next = atomicAdd(ticket, 1u);
+        uint4 s0 = make_uint4(0, 0, 0, 0);
+        if (FLAGS & 4) { s0 = state[k * 4 + (lane & 3)]; uint4 s1 = state[(n + k) * 4 + (lane & 3)]; s0.x ^= s1.y; }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (FLAGS & 2) {
+            const float v = (float)(s0.x & 1) + acc;
+#pragma unroll
+            for (int it = 0; it < 7; it++) {
+                const int q = lane + 32 * it;
+                if (q < 217) { img4[q] = make_float4(v, v, v, v); img4[217 * 14 + q] = make_float4(v, 1.f, v, 2.f); }
+            }
+        }
+        if (FLAGS & 1) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); }
+        if (lane == 0) {
+            char *dst = reinterpret_cast<char *>(out) + k * OBS_BYTES;
+            if (FLAGS & 8) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(shared_ch)), "r"(3472) : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + 3472), "r"(smem_u32(img4)), "r"(55552) : "memory");
+            } else {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(img4)), "r"(OBS_BYTES) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        acc += (float)(s0.y & 1);
+        next = __shfl_sync(~0u, next, 0);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __global__ void k_direct_env(float4 *out, long long n, unsigned *ticket) {
     const int lane = threadIdx.x & 31;
     unsigned next = 0;
@@ -79,6 +128,21 @@ int main() {
     }
     { float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk<17><<<sms, 96, 3 * OBS_BYTES>>>(buf[it++ % 3], n, ticket, 3); });
       printf("B bulk 3472B x17   warps/SM=3 : %.3f ms  %.0f GB/s\n", ms, bytes / ms / 1e6); }
+    uint4 *state; cudaMalloc(&state, (size_t)n * 8 * 16); cudaMemset(state, 1, (size_t)n * 8 * 16);
+#define RUNX(F, W, label) { cudaFuncSetAttribute(k_bulk_x<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+        int smem = ((F) & 8) ? (W) * 55552 + 3472 : (W) * OBS_BYTES; \
+        float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk_x<F><<<sms, 32 * (W), smem>>>(buf[it++ % 3], n, ticket, state); }); \
+        printf("X %-44s warps/SM=%d : %.3f ms  %.0f GB/s\n", label, W, ms, bytes / ms / 1e6); }
+    RUNX(0, 3, "baseline (same as A)");
+    RUNX(1, 3, "+fence.proxy.async per env");
+    RUNX(2, 3, "+rewrite 2 channels");
+    RUNX(3, 3, "+fence +rewrite");
+    RUNX(4, 3, "+state loads");
+    RUNX(7, 3, "+fence +rewrite +loads");
+    RUNX(8, 4, "split 3472+55552, 4 warps");
+    RUNX(15, 4, "split, 4 warps, +fence +rewrite +loads");
+    RUNX(15, 3, "split, 3 warps, +fence +rewrite +loads");
+    RUNX(15, 2, "split, 2 warps, +fence +rewrite +loads");
     for (int wps : {8, 16, 32, 64}) {
         float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_direct_env<<<sms * wps / 8, 256>>>((float4 *)buf[it++ % 3], n, ticket); });
         printf("C direct v4 env/warp warps/SM=%d : %.3f ms  %.0f GB/s\n", wps, ms, bytes / ms / 1e6);
