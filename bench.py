@@ -287,13 +287,14 @@ def main():
     done = torch.empty(n, dtype=torch.bool, device=dev)
     mask = torch.empty((n, 5), dtype=torch.bool, device=dev)
     chunks = [(f, min(chunk, n - f)) for f in range(0, n, chunk)]
-    launches_per_step = 2 + len(chunks)
+    launches_per_step = 1 + len(chunks)
     slot_ctr = [0]
     enc_events = []
 
     def hot_step(call_idx: int, time_encode: bool):
-        env.sample_actions(out=actions, call_idx=call_idx)
-        env.step(actions, check_actions=False, mask_out=mask, reward_out=reward, done_out=done)
+        # random valid action per env + PacmanGym.step, one launch (pb_step_random)
+        env.step_random(call_idx=call_idx, actions_out=actions, mask_out=mask, reward_out=reward,
+                        done_out=done)
         if time_encode:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -321,8 +322,11 @@ def main():
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        hot_step(call, True)
+    for it in range(args.steps):
+        # the encoder launches are bracketed by CUDA events on every 8th step only: an event
+        # record between k_step and k_encode_obs breaks their programmatic-dependent-launch
+        # adjacency, which the other 7 steps keep (as real callers of step_obs do)
+        hot_step(call, it % 8 == 0)
         call += 1
     ev1.record()
     barrier()

@@ -181,6 +181,12 @@ int pb_query(pb_engine *e, int what, int32_t *out_dev, void *stream);
  * stream keyed by (seed, env id, call_idx). */
 int pb_sample_actions(pb_engine *e, uint8_t *actions_dev, uint64_t call_idx, void *stream);
 
+/* pb_sample_actions(call_idx) + pb_step in ONE launch (random-policy rollouts: the policy is
+ * EpsilonGreedy at epsilon = 1).  The action each env took is written to actions_out_dev
+ * (uint8 [n], may be NULL).  Bit-identical to calling the two entry points in sequence. */
+int pb_step_random(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev, int32_t *reward_dev,
+                   uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, void *stream);
+
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */
 int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream);

@@ -122,6 +122,9 @@ k_encode_obs(StateView st, float *__restrict__ out,
     }
     fence_proxy_async_smem();
     __syncthreads();  // the template is read by every warp's bulk copies
+    // everything above overlapped the previous kernel (programmatic dependent launch); from here
+    // on the env state and the ticket are read, so wait for the preceding grid to finish
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // image offset this lane patched in buffer 0 / 1 for an earlier env (sparse channels only)
     int patched0 = -1, patched1 = -1;
@@ -314,7 +317,15 @@ k_encode_obs(StateView st, float *__restrict__ out,
         ga = ga_n;
         gb = gb_n;
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) {
+        bulk_wait_all();
+        // ticket[1] counts finished warps; the last one re-arms {ticket, count} for the next launch
+        const unsigned int finished = atomicAdd(ticket + 1, 1u);
+        if (finished == gridDim.x * ENC_WARPS - 1) {
+            atomicExch(ticket, 0u);
+            atomicExch(ticket + 1, 0u);
+        }
+    }
 }
 
 }  // namespace pb

@@ -76,17 +76,37 @@ __device__ __forceinline__ void write_mask(uint8_t *mask_out, long long i, uint3
 // =============================================================================================
 constexpr int STEP_THREADS = 128;
 
+__device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
+    while (k-- > 0) m &= m - 1;
+    return __ffs(m) - 1;
+}
+
+// actions == nullptr: every env draws a uniformly random VALID action from its own mask (the
+// action stream of the counter RNG, keyed by call_idx), i.e. k_sample_actions fused in; the
+// chosen action is reported through actions_out (may be nullptr).
 __global__ void __launch_bounds__(STEP_THREADS)
 k_step(StateView st, RngParams rp, const uint8_t *__restrict__ actions,
        int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
-       uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action) {
+       uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action,
+       uint8_t *__restrict__ actions_out, unsigned long long call_idx) {
+    // let a programmatically-dependent kernel (the observation encoder) start its prologue now;
+    // it still waits for this whole grid (griddepcontrol.wait) before reading the state
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
     const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
     if (i >= st.n) return;
-    const int action = actions[i];
     EnvR s;
     load_env(st, i, s);
+    int action;
+    if (actions) {
+        action = actions[i];
+    } else {
+        const uint32_t m = action_mask_bits(s, s_walls);
+        const uint32_t raw = action_raw(rp.seed, (uint64_t)(rp.gid_base + i), call_idx);
+        action = kth_set_bit(m, (int)below(raw, (uint32_t)__popc(m)));
+    }
+    if (actions_out) actions_out[i] = (uint8_t)action;
     if (action > 4) {  // env.rs:83-88: "Invalid action" -- env untouched
         atomicMin(bad_action, (unsigned long long)i);
         reward[i] = 0;
@@ -172,11 +192,6 @@ k_query(StateView st, int what, int32_t *__restrict__ out) {
 // =============================================================================================
 // k_sample_actions / k_select_actions (policies.py:16-59)
 // =============================================================================================
-__device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
-    while (k-- > 0) m &= m - 1;
-    return __ffs(m) - 1;
-}
-
 __global__ void __launch_bounds__(STEP_THREADS)
 k_sample_actions(StateView st, RngParams rp, uint8_t *__restrict__ actions,
                  unsigned long long call_idx) {
@@ -353,11 +368,24 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     const int warps = ENC_WARPS;
     long long blocks = (count + warps - 1) / warps;
     if (blocks > e->num_sms) blocks = e->num_sms;
-    unsigned int *ticket = e->tickets + (e->ticket_next++ % TICKET_RING);
-    PB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
-    kern<<<(unsigned)blocks, ENC_THREADS, ENC_SMEM, s>>>(
-        e->st, out_dev, stride, first, count, ticket, slot_index, slot_stride);
-    PB_CUDA(cudaGetLastError());
+    // {ticket, finished-warp count} pair; the last warp of a launch zeroes both again, so no
+    // memset node is needed per launch (the ring only matters for launches on different streams)
+    unsigned int *ticket = e->tickets + 2 * (e->ticket_next++ % TICKET_RING);
+    // Programmatic dependent launch: the encoder's prologue (zeroing 222 KB of shared memory,
+    // wall template) overlaps the tail of the preceding kernel in the stream (k_step); the
+    // kernel executes griddepcontrol.wait before it touches the env state or the ticket.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(ENC_THREADS);
+    cfg.dynamicSmemBytes = ENC_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, kern, e->st, out_dev, stride, first, count, ticket,
+                               slot_index, slot_stride));
     return PB_OK;
 }
 }  // namespace
@@ -445,7 +473,8 @@ int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_reward, sizeof(int32_t) * e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_done, e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_mask, 5 * e->npad));
-    PB_CUDA_OR_FREE(cudaMalloc(&e->tickets, sizeof(unsigned int) * TICKET_RING));
+    PB_CUDA_OR_FREE(cudaMalloc(&e->tickets, sizeof(unsigned int) * 2 * TICKET_RING));
+    PB_CUDA_OR_FREE(cudaMemset(e->tickets, 0, sizeof(unsigned int) * 2 * TICKET_RING));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core0, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core1, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.ghosts, 0, sizeof(uint4) * 2 * e->npad));
@@ -509,7 +538,19 @@ int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8
     DeviceGuard g(e->device);
     k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
         e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action);
+        e->bad_action, nullptr, 0ull);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_step_random(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev, int32_t *reward_dev,
+                   uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, void *stream) {
+    if (!e || !reward_dev || !done_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_random: null argument");
+    DeviceGuard g(e->device);
+    k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->bad_action, actions_out_dev, call_idx);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

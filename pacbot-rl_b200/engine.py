@@ -219,6 +219,28 @@ class BatchedPacmanGym:
             self.check_actions()
         return reward, done.view(torch.bool)
 
+    def step_random(self, *, call_idx: Optional[int] = None, actions_out: Optional[torch.Tensor] = None,
+                    mask_out: Optional[torch.Tensor] = None, reward_out: Optional[torch.Tensor] = None,
+                    done_out: Optional[torch.Tensor] = None):
+        """sample_actions() + step() fused into one launch (random-policy rollouts).  Returns
+        (reward, done); the actions taken land in `actions_out` (uint8 [N]) if given."""
+        n = self.num_envs
+        reward = self._new((n,), torch.int32) if reward_out is None else self._check_tensor(
+            reward_out, (n,), torch.int32, "reward_out")
+        done = self._new((n,), torch.uint8) if done_out is None else self._check_tensor(
+            done_out.view(torch.uint8), (n,), torch.uint8, "done_out")
+        aptr = None if actions_out is None else C.c_void_p(self._check_tensor(
+            actions_out, (n,), torch.uint8, "actions_out").data_ptr())
+        mptr = None if mask_out is None else C.c_void_p(self._check_tensor(
+            mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        if call_idx is None:
+            call_idx = self._sample_calls
+            self._sample_calls += 1
+        check(self._L.pb_step_random(self._h, int(call_idx), aptr, C.c_void_p(reward.data_ptr()),
+                                     C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
+                                     self._stream()))
+        return reward, done.view(torch.bool)
+
     def check_actions(self) -> None:
         bad = C.c_int64(-1)
         check(self._L.pb_check_actions(self._h, C.byref(bad), self._stream()))

@@ -195,3 +195,21 @@ def test_gather_obs_matches_torch_indexing(pb):
     ref = ring[idx]
     ref[zero] = 0
     assert torch.equal(out, ref)
+
+
+def test_step_random_equals_sample_then_step(pb):
+    """pb_step_random == pb_sample_actions(call_idx) followed by pb_step, bit for bit."""
+    import torch
+
+    n = 5000
+    a_env = pb.BatchedPacmanGym(n, True, True, seed=21, auto_reset=True)
+    b_env = pb.BatchedPacmanGym(n, True, True, seed=21, auto_reset=True)
+    a_env.reset()
+    b_env.reset()
+    acts = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for t in range(60):
+        r_a, d_a = a_env.step_random(call_idx=t, actions_out=acts)
+        sampled = b_env.sample_actions(call_idx=t)
+        r_b, d_b = b_env.step(sampled)
+        assert torch.equal(acts, sampled) and torch.equal(r_a, r_b) and torch.equal(d_a, d_b)
+    assert np.array_equal(a_env.get_state(), b_env.get_state())
