@@ -71,6 +71,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--metrics-file", default=None)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--no-checkpoints", action="store_true")
+    p.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
+                   help="keep the Q-network in NCHW (default: NHWC weights/activations for cuDNN)")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", default=True,
                    help="run the iteration eagerly instead of replaying one captured CUDA graph")
     for name, default in hyperparam_defaults.items():
@@ -90,6 +92,8 @@ class DQNTrainer:
         self.q_net = model_cls((17, 28, 31), 5).to(device)
         if cfg.finetune:
             self.q_net = torch.load(cfg.finetune, map_location=device, weights_only=False)
+        if cfg.channels_last and hasattr(self.q_net, "use_channels_last"):
+            self.q_net.use_channels_last()
         torch.manual_seed(cfg.seed * 1000003 + rank)
         self.target_q_net = copy.deepcopy(self.q_net).eval()
         phase1 = None
@@ -261,7 +265,10 @@ class DQNTrainer:
             try:
                 import safetensors.torch
 
-                safetensors.torch.save_file(self.q_net.state_dict(), d / "q_net-latest.safetensors")
+                # plain row-major tensors under the reference's key names (candle_qnet.rs:18-44),
+                # whatever memory format the live network uses
+                sd = {k: v.detach().contiguous() for k, v in self.q_net.state_dict().items()}
+                safetensors.torch.save_file(sd, d / "q_net-latest.safetensors")
             except ImportError:
                 pass
 
