@@ -261,6 +261,21 @@ k_encode_obs(StateView st, float *__restrict__ out,
             unpatch = false; off = cell; val = (float)FRUIT_POINTS / 200.0f;
         }
 
+        // ---- channel-1 vectors in registers: everything that can be computed without touching
+        // the image happens BEFORE the wait, so that the chain "image free -> stores -> fence ->
+        // issue" is as short as possible (that chain is what keeps the encoder below the bare
+        // TMA store rate, see the header) ----
+        float4 ch1_v[7];
+#pragma unroll
+        for (int it = 0; it < 7; it++) {
+            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
+            const uint32_t nib = w >> (4 * (lane & 7));
+            ch1_v[it].x = (nib & 1u) ? pv : 0.0f;
+            ch1_v[it].y = (nib & 2u) ? pv : 0.0f;
+            ch1_v[it].z = (nib & 4u) ? pv : 0.0f;
+            ch1_v[it].w = (nib & 8u) ? pv : 0.0f;
+        }
+
         // ---- the image is free once the previous bulk copies have finished READING it ----
         // (the copy of the OTHER buffer, issued for the previous env, stays in flight: this is what
         // keeps the TMA engine busy while this warp rebuilds an image)
@@ -271,19 +286,13 @@ k_encode_obs(StateView st, float *__restrict__ out,
             if (patched >= 0) img[patched] = 0.0f;
         }
 
-        // ---- channel 1 base values and channel 15 fill: 2 x 7 128-bit stores per lane ----
+        // ---- channel 1 base values and channel 15 fill: 2 x 7 128-bit stores per lane (the
+        // values were prepared in registers before the wait) ----
 #pragma unroll
         for (int it = 0; it < 7; it++) {
             const int q = lane + 32 * it;  // float4 index inside a channel
-            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
             if (q < CH_VEC) {
-                const uint32_t nib = w >> (4 * (lane & 7));
-                float4 v;
-                v.x = (nib & 1u) ? pv : 0.0f;
-                v.y = (nib & 2u) ? pv : 0.0f;
-                v.z = (nib & 4u) ? pv : 0.0f;
-                v.w = (nib & 8u) ? pv : 0.0f;
-                img4[q] = v;                                             // channel 1
+                img4[q] = ch1_v[it];                                     // channel 1
                 img4[CH_VEC * 14 + q] = make_float4(sp, sp, sp, sp);     // channel 15
             }
         }

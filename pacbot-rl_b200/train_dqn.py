@@ -70,6 +70,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--log_every", type=int, default=50)
     p.add_argument("--metrics-file", default=None)
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--eval_envs", type=int, default=1,
+                   help="greedy evaluation episodes run in parallel (the reference runs 1)")
     p.add_argument("--no-checkpoints", action="store_true")
     p.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
                    help="keep the Q-network in NCHW (default: NHWC weights/activations for cuDNN)")
@@ -307,7 +309,7 @@ def train(cfg: argparse.Namespace, max_seconds: Optional[float] = None) -> DQNTr
         if (it + 1) % cfg.log_every == 0 or it == cfg.num_iters - 1:
             m = trainer.pop_metrics()
             if (it + 1) % (cfg.log_every * cfg.evaluate_steps) == 0:
-                m.update(trainer.evaluate_episode())
+                m.update(trainer.evaluate_episode(num_envs=cfg.eval_envs))
             now = time.time()
             m["iter"] = it + 1
             m["iters_per_sec"] = (it + 1 - last_it) / max(1e-9, now - last_t)
@@ -337,7 +339,7 @@ def main(argv=None) -> None:
         device = torch.device(cfg.device or "cuda")
         trainer = DQNTrainer(cfg, device)
         trainer.q_net = torch.load(cfg.eval, map_location=device, weights_only=False)
-        print(json.dumps(trainer.evaluate_episode()))
+        print(json.dumps(trainer.evaluate_episode(num_envs=cfg.eval_envs)))
         return
     train(cfg)
 

@@ -415,3 +415,46 @@ def test_odd_batch_sizes(pb, oracle, n):
     for t in range(40):
         a = random_valid_actions(rng, ob.action_mask())
         compare_step(ob, env, a, t, True, check_obs=True)
+
+
+def test_full_size_properties_2m_envs(pb):
+    """BASELINE config 3 shard size (2 097 152 envs on one GPU): the observation of the whole
+    population cannot be resident at once (118 GB), so it is streamed through a small ring with
+    pb_encode_obs_range; size-independent properties are checked on every chunk."""
+    torch = torch_mod()
+    n, chunk = 2 * 1024 * 1024, 32768
+    env = pb.BatchedPacmanGym(n, np.arange(n) < n // 2, True, device="cuda:0", seed=11, auto_reset=True)
+    env.reset()
+    finished = 0
+    for t in range(6):
+        _, d = env.step_random(call_idx=t)
+        finished += int(d.sum())
+    assert finished > 1000
+    tps = env.ticks_per_step().float()
+    period = env._query(pb._lib.Q_UPDATE_PERIOD).float()
+    rem = env.remaining_pellets()
+    ring = torch.empty((2, chunk) + pb.OBS_SHAPE, dtype=torch.float32, device="cuda")
+    wall_sum = torch.full((chunk,), 580.0, device="cuda")
+    digest = torch.zeros((), dtype=torch.float64, device="cuda")
+    for ci, first in enumerate(range(0, n, chunk)):
+        if ci % 8 and ci != n // chunk - 1:
+            continue                                  # every 8th chunk plus the last one
+        o = env.obs_range(first, chunk, ring[ci & 1])
+        assert torch.equal(o[:, 0].sum((1, 2)), wall_sum)
+        assert torch.equal(o[:, 2], o[:, 3]) and torch.equal(o[:, 4:8], o[:, 8:12])
+        sl = slice(first, first + chunk)
+        assert torch.equal(o[:, 15, 0, 0], tps[sl] / period[sl])
+        assert torch.equal(o[:, 15].amin((1, 2)), o[:, 15].amax((1, 2)))
+        pel_cells = ((o[:, 1] == 0.05) | (o[:, 1] == 0.25)).sum((1, 2))
+        ok = (pel_cells == rem[sl]) | (o[:, 14].amax((1, 2)) > 0) | (rem[sl] == 1)
+        assert bool(ok.all())
+        digest += o.double().sum()
+    assert float(digest) > 0
+    # env-id sharding: the second half of this population == an engine created on that shard
+    half = pb.BatchedPacmanGym(n // 2, False, True, device="cuda:0", seed=11, env_id_base=n // 2, auto_reset=True)
+    half.reset()
+    for t in range(6):
+        half.step_random(call_idx=t)
+    a = env.get_state(n - 4096, 4096)
+    b = half.get_state(n // 2 - 4096, 4096)
+    assert np.array_equal(a, b)
