@@ -102,7 +102,7 @@ def dqn_throughput(dev, seed: int, iters: int, graph: bool = True):
     return {"iters_per_sec": iters / dt, "iters": iters, "cuda_graph": graph,
             "env_steps_per_sec": iters * cfg.experience_steps * cfg.num_parallel_envs / dt,
             "config": "train_dqn defaults: batch 512, 32 envs, 4 experience steps/iter, buffer "
-                      "10k, QNetV2 fp32 (cuDNN), double DQN, Adam",
+                      "10k, QNetV2 fp32 (cuDNN, NHWC weights), double DQN, Adam",
             "loss": m["loss"]}
 
 
@@ -345,7 +345,7 @@ def main():
     e2e = None
     e2e_full = None
     if not args.no_e2e:
-        k_e2e = max(3, min(args.steps, 50))
+        k_e2e = max(3, min(args.steps, 500))
         # The host side owns the actions here (as a host-side policy would): a pool of pinned
         # action buffers, uniform over 0..4 (a blocked move is a legal no-op, env.rs:404), and
         # pinned result buffers; every step copies its actions H2D and its results D2H.
@@ -389,8 +389,9 @@ def main():
         e2e = {"value": n * world * k_e2e / dt, "unit": "env-steps/s",
                "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * (4 + 1 + 5), "steps": k_e2e,
                "what": "BatchedPacmanGym.step_host -> pb_step_host: host actions in, "
-                       "reward/done/mask back to the host, observation encoded into the "
-                       "device-resident ring (it is consumed on the GPU)"}
+                       "reward/done/mask back to the host (read by the host every step; the D2H "
+                       "copies ride a side stream while the encoder runs), observation encoded "
+                       "into the device-resident ring (it is consumed on the GPU)"}
         # variant that also drags the full observation back to the host (PCIe-bound by design)
         if rank == 0 and world == 1:
             n_small = min(n, 4096)

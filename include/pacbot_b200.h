@@ -198,9 +198,13 @@ int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state 
 int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t src_i, void *stream);
 
 /* ---- host-buffer entry point (what a per-call FFI binding would use) ------------------------- */
-/* Copies actions host->device, runs pb_step (+ pb_encode_obs when obs_out_dev != NULL), copies
- * reward/done/mask device->host and synchronises `stream`.  Host pointers may be pageable or
- * pinned; mask_host may be NULL.  Returns PB_ERR_INVALID_ACTION like pb_check_actions. */
+/* Copies actions host->device, runs pb_step (+ pb_encode_obs when obs_out_dev != NULL) on
+ * `stream` and copies reward/done/mask device->host.  Returns as soon as those RESULTS are on the
+ * host: they only depend on the step kernel and travel on an internal side stream while the
+ * observation encode is still running; the observation itself is ordered on `stream` like any
+ * other asynchronous call (work queued on `stream` afterwards sees it; a host reader must
+ * synchronise `stream`).  Host pointers may be pageable or pinned; mask_host may be NULL.
+ * Returns PB_ERR_INVALID_ACTION like pb_check_actions. */
 int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
                  uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
                  int64_t env_stride_floats, void *stream);

@@ -315,6 +315,9 @@ struct pb_engine {
     int num_sms = 148;
     unsigned int *tickets = nullptr;  // ring of work counters for k_encode_obs launches
     unsigned int ticket_next = 0;
+    // pb_step_host: results travel device->host on a side stream while the encoder runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_step = nullptr;
 };
 constexpr unsigned int TICKET_RING = 64;
 
@@ -431,6 +434,8 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->stg_mask);
     cudaFree(e->stg_obs);
     cudaFree(e->tickets);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_step) cudaEventDestroy(e->ev_step);
     delete e;
     return PB_OK;
 }
@@ -475,6 +480,8 @@ int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_
     PB_CUDA_OR_FREE(cudaMalloc(&e->stg_mask, 5 * e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->tickets, sizeof(unsigned int) * 2 * TICKET_RING));
     PB_CUDA_OR_FREE(cudaMemset(e->tickets, 0, sizeof(unsigned int) * 2 * TICKET_RING));
+    PB_CUDA_OR_FREE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    PB_CUDA_OR_FREE(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core0, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core1, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.ghosts, 0, sizeof(uint4) * 2 * e->npad));
@@ -789,16 +796,28 @@ int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host
     int rc = pb_step(e, e->stg_actions, e->stg_reward, e->stg_done, mask_host ? e->stg_mask : nullptr,
                      auto_reset, stream);
     if (rc != PB_OK) return rc;
+    // reward / done / mask only depend on k_step: ship them to the host on the side stream while
+    // the (much longer) observation encode runs on the caller's stream
+    PB_CUDA(cudaEventRecord(e->ev_step, s));
     if (obs_out_dev) {
         rc = pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
         if (rc != PB_OK) return rc;
     }
+    cudaStream_t c = e->copy_stream;
+    PB_CUDA(cudaStreamWaitEvent(c, e->ev_step, 0));
+    unsigned long long bad = ~0ull;
     PB_CUDA(cudaMemcpyAsync(reward_host, e->stg_reward, sizeof(int32_t) * (size_t)e->n,
-                            cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaMemcpyAsync(done_host, e->stg_done, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+                            cudaMemcpyDeviceToHost, c));
+    PB_CUDA(cudaMemcpyAsync(done_host, e->stg_done, (size_t)e->n, cudaMemcpyDeviceToHost, c));
     if (mask_host)
-        PB_CUDA(cudaMemcpyAsync(mask_host, e->stg_mask, 5 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
-    return pb_check_actions(e, nullptr, stream);
+        PB_CUDA(cudaMemcpyAsync(mask_host, e->stg_mask, 5 * (size_t)e->n, cudaMemcpyDeviceToHost, c));
+    PB_CUDA(cudaMemcpyAsync(&bad, e->bad_action, sizeof(bad), cudaMemcpyDeviceToHost, c));
+    PB_CUDA(cudaStreamSynchronize(c));
+    if (bad != ~0ull) {
+        PB_CUDA(cudaMemsetAsync(e->bad_action, 0xff, sizeof(bad), s));
+        return fail(PB_ERR_INVALID_ACTION, "Invalid action");
+    }
+    return PB_OK;
 }
 
 int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, void *stream) {
