@@ -25,6 +25,7 @@ __constant__ MazeTables c_tab;
 }  // namespace pb
 
 #include "pb_encode.cuh"
+#include "pb_encode2.cuh"
 
 namespace pb {
 
@@ -362,13 +363,20 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
                   long long count, cudaStream_t s, const long long *slot_index = nullptr,
                   long long slot_stride = 0) {
     if (count <= 0) return PB_OK;
+    // two encoders with identical output: image-per-warp (k_encode_obs) and shared-template
+    // (k_encode_obs_tpl); PB_ENCODER=img|tpl selects, default below
+    static const bool use_tpl = [] {
+        const char *v = getenv("PB_ENCODER");
+        return v ? (strcmp(v, "tpl") == 0) : false;
+    }();
     static thread_local int attr_set_for = -1;
-    auto kern = k_encode_obs;
     if (attr_set_for != e->device) {
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_encode_obs_tpl, cudaFuncAttributeMaxDynamicSharedMemorySize, E2_SMEM));
         attr_set_for = e->device;
     }
-    const int warps = ENC_WARPS;
+    auto kern = use_tpl ? k_encode_obs_tpl : k_encode_obs;
+    const int warps = use_tpl ? E2_WARPS : ENC_WARPS;
     long long blocks = (count + warps - 1) / warps;
     if (blocks > e->num_sms) blocks = e->num_sms;
     // {ticket, finished-warp count} pair; the last warp of a launch zeroes both again, so no
@@ -379,8 +387,8 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     // kernel executes griddepcontrol.wait before it touches the env state or the ticket.
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(ENC_THREADS);
-    cfg.dynamicSmemBytes = ENC_SMEM;
+    cfg.blockDim = dim3(use_tpl ? E2_THREADS : ENC_THREADS);
+    cfg.dynamicSmemBytes = use_tpl ? E2_SMEM : ENC_SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
