@@ -1,8 +1,8 @@
 // pb_encode.cuh -- k_encode_obs: PacmanGym::obs (/root/reference/pacbot_rs/src/env.rs:410-500)
 // for a batch of envs, written to HBM by the TMA engine.
 //
-// Shape of the kernel (one CTA per SM, persistent, ENC_WARPS = 4 warps, one env per warp at a
-// time, ENC_BUFS = 1 image per warp):
+// Shape of the kernel (one CTA per SM, persistent, ENC_WARPS = 4 warps, one env and one image per
+// warp at a time):
 //   * shared memory holds ONE wall-channel template (ch 0, constant for every env, 3 472 B) and
 //     FOUR private images of channels 1..16 (55 552 B each): 225 680 B of the 227 KB;
 //   * per env a warp rewrites only what changes: channel 1 (pellet values: a nibble of the
@@ -15,18 +15,29 @@
 //   * before an image is rebuilt the warp waits for the bulk group's shared-memory READ only
 //     (cp.async.bulk.wait_group.read), so global-write latency is never on the critical path;
 //   * envs are handed out by a global atomic ticket (SMs drain to HBM at different rates; a
-//     static map left fast SMs idle: ncu sm__cycles_active min/max 0.65, +22 % time); ticket and
-//     packed state are fetched one to two envs ahead of their use.
+//     static map left fast SMs idle: ncu sm__cycles_active min/max 0.65, +22 % time), and a warp
+//     takes its ticket AS LATE AS POSSIBLE: only once its image is free again (see below).
 //
 // Why TMA: tools/microbench/store_paths.cu measures, for this exact access pattern (65 536 x
 // 59 024 B), bare TMA bulk stores at 7.48 TB/s (0.517 ms) vs 7.15 TB/s for the best
 // st.global.v4 variant and 7.34 TB/s for cudaMemset, provided >= 2 copies per SM are in flight
-// (1 in flight: 6.8 TB/s).  What the real encoder adds on top is the dependent chain
-// "image free -> state -> rebuild -> fence.proxy.async -> issue": the same microbenchmark with that
-// chain (loads + 434 dependent STS.128 + fence) drops to 7.2-7.25 TB/s, and this kernel reaches
-// 7.05-7.1 TB/s (0.547-0.551 ms).  Tried and measured equal within noise (0.547-0.561 ms):
-// 3 x 59 024 B images with channel 0 inside, 4 x 1 images, 2 warps x 2 double-buffered images,
-// with and without the two-deep software pipeline.
+// (1 in flight: 6.8 TB/s).
+//
+// Why late tickets: HBM write efficiency depends on WHICH addresses are being written at the same
+// time.  The 592 warps of the grid each write one 59 KB block; the tighter the window of blocks in
+// flight, the better the DRAM pages/channels are used.  The same microbenchmark (variant G) with
+// tickets of 1 / 2 / 4 / 8 consecutive envs per warp takes 0.520 / 0.527 / 0.534 / 0.540 ms, and
+// in this kernel every scheme that holds a ticket ahead of its write widens the window:
+//     ticket + state prefetched two envs ahead (software pipeline)      0.547-0.551 ms
+//     tickets in batches of 4, state staged through cp.async            0.569 ms
+//     ticket taken when the previous image is handed to the TMA engine  0.542 ms
+//     ticket taken when the previous copy has finished reading (this)   0.539 ms  (7.20 TB/s)
+// although the late ticket puts the atomic's and the state fetch's latency back on the warp's
+// critical path: with 4 warps per SM the TMA engine still has >= 2 copies queued.  Also measured,
+// equal within noise or slower: 3 x 59 024 B images with channel 0 inside, 2 warps x 2
+// double-buffered images, channel-1 values prepared in registers before the wait or not, and the
+// shared-template encoder with 16 envs in flight per SM (pb_encode2.cuh, 0.602 ms: five copies
+// and <= 18 scattered 4-byte stores per env disturb the write stream more than they help).
 //
 // Per-lane roles are written BRANCH FREE (selects + one predicated store per lane).  A first
 // version used an if/else chain per lane group with nested conditionals; for particular states
@@ -47,13 +58,15 @@ namespace pb {
 // (same translation unit): __constant__ MazeTables c_tab;
 
 constexpr int ENC_WARPS = 4;   // warps per CTA
-constexpr int ENC_BUFS = 1;    // images per warp (2 = double buffering; measured no faster)
 constexpr int ENC_THREADS = ENC_WARPS * 32;
 constexpr int CH_BYTES = CH_FLOATS * 4;                 // 3 472
 constexpr int IMG_CH = OBS_CH - 1;                      // channels 1..16 live in the private image
 constexpr int IMG_FLOATS = IMG_CH * CH_FLOATS;          // 13 888
 constexpr int IMG_BYTES = IMG_FLOATS * 4;               // 55 552
-constexpr int ENC_SMEM = ENC_WARPS * ENC_BUFS * IMG_BYTES + CH_BYTES;  // 225 680
+// per-warp staging area for one env's packed state: core0, core1, ghosts x2 (4 x 16 B) followed
+// by the 28 pellet words
+constexpr int STAGE_WORDS = 48;
+constexpr int ENC_SMEM = ENC_WARPS * IMG_BYTES + CH_BYTES + ENC_WARPS * STAGE_WORDS * 4;
 constexpr int CH_VEC = CH_FLOATS / 4;                   // 217 float4 per channel
 static_assert(ENC_SMEM <= 227 * 1024, "encoder images must fit the 227 KB shared memory");
 static_assert(IMG_BYTES % 16 == 0 && CH_BYTES % 16 == 0, "bulk copies move 16 B granules");
@@ -80,6 +93,15 @@ __device__ __forceinline__ void bulk_wait_all() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+__device__ __forceinline__ void cp_async_4(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ bool on_board(int row, int col) {
     return (unsigned)row < (unsigned)ROWS && (unsigned)col < (unsigned)COLS;
@@ -110,12 +132,14 @@ k_encode_obs(StateView st, float *__restrict__ out,
     if (slot_index) out += *slot_index * slot_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *wall_ch = reinterpret_cast<float *>(smem_raw + (size_t)ENC_WARPS * ENC_BUFS * IMG_BYTES);
-    float *img_base = reinterpret_cast<float *>(smem_raw + (size_t)warp * ENC_BUFS * IMG_BYTES);
+    float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * IMG_BYTES);
+    float4 *img4 = reinterpret_cast<float4 *>(img);
+    float *wall_ch = reinterpret_cast<float *>(smem_raw + (size_t)ENC_WARPS * IMG_BYTES);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + (size_t)ENC_WARPS * IMG_BYTES + CH_BYTES) +
+                      warp * STAGE_WORDS;
 
-    // ---- one-time init: wall template (env.rs:426), zeroed private images ----
-    for (int q = lane; q < ENC_BUFS * IMG_FLOATS / 4; q += 32)
-        reinterpret_cast<float4 *>(img_base)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- one-time init: wall template (env.rs:426), zeroed private image ----
+    for (int q = lane; q < IMG_FLOATS / 4; q += 32) img4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = threadIdx.x; c < CH_FLOATS; c += blockDim.x) {
         const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
         wall_ch[c] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
@@ -126,55 +150,44 @@ k_encode_obs(StateView st, float *__restrict__ out,
     // on the env state and the ticket are read, so wait for the preceding grid to finish
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // image offset this lane patched in buffer 0 / 1 for an earlier env (sparse channels only)
-    int patched0 = -1, patched1 = -1;
-    int buf = 0;
+    // image offset this lane patched for the previous env (sparse channels only)
+    int patched = -1;
 
-    // Software pipeline, two envs deep: while env `cur` is encoded, the packed state of env `nxt`
-    // is already being loaded and the ticket after that is being fetched, so neither the atomic's
-    // nor the loads' latency sits on the per-env critical path of the warp.
-    // `pend` (lane 0 only) is a ticket whose atomic is still in flight: it is requested right
-    // AFTER a bulk copy is issued and first read one whole env later, because fence.proxy.async
-    // (MEMBAR.ALL.CTA in SASS) makes a lane wait for all of its outstanding memory operations --
-    // an atomic requested before the fence would put its L2 round trip on the critical path.
-    unsigned int cur = 0, nxt = 0, pend = 0;
-    if (lane == 0) {
-        cur = atomicAdd(ticket, 1u);
-        nxt = atomicAdd(ticket, 1u);
-        pend = atomicAdd(ticket, 1u);
-    }
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    nxt = __shfl_sync(0xffffffffu, nxt, 0);
-    uint32_t F = 0u;
-    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, ga = c0, gb = c0;
-    if ((long long)cur < env_count) {
-        const long long i = env_first + cur;
-        F = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
-        c0 = st.core0[i];
-        c1 = st.core1[i];
-        ga = st.ghosts[i];
-        gb = st.ghosts[st.npad + i];
-    }
+    auto next_ticket = [&]() -> unsigned int {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    unsigned int cur = next_ticket();
     while ((long long)cur < env_count) {
         const long long k = cur;
-        float *img = img_base + buf * IMG_FLOATS;
-        float4 *img4 = reinterpret_cast<float4 *>(img);
-        // ---- prefetch the state of the next env ----
-        uint32_t F_n = 0u;
-        uint4 c0_n = make_uint4(0, 0, 0, 0), c1_n = c0_n, ga_n = c0_n, gb_n = c0_n;
-        if ((long long)nxt < env_count) {
-            const long long i = env_first + nxt;
-            F_n = (lane < PEL_WORDS) ? st.pel[(long long)lane * st.npad + i] : 0u;
-            c0_n = st.core0[i];
-            c1_n = st.core1[i];
-            ga_n = st.ghosts[i];
-            gb_n = st.ghosts[st.npad + i];
+        // ---- this env's packed state (176 B): every lane fetches one piece straight into the
+        // warp's staging area (LDGSTS: 28 pellet words + 4 x 16 B), then all lanes read it back;
+        // one memory round trip, no shuffles to spread the 16-byte records ----
+        {
+            const long long env = env_first + k;
+            if (lane < PEL_WORDS) {
+                cp_async_4(stage + 16 + lane, st.pel + (long long)lane * st.npad + env);
+            } else {
+                const int w = lane - PEL_WORDS;
+                const uint4 *src = (w == 0) ? st.core0 + env : (w == 1) ? st.core1 + env
+                                   : (w == 2) ? st.ghosts + env : st.ghosts + st.npad + env;
+                cp_async_16(stage + 4 * w, src);
+            }
+            cp_async_commit();
+            cp_async_wait_all();
         }
+        if (!warp_arrived((unsigned int)k)) __trap();  // every lane's piece has landed
+        const uint32_t F = (lane < PEL_WORDS) ? stage[16 + lane] : 0u;
+        const uint4 c0 = *reinterpret_cast<const uint4 *>(stage);
+        const uint4 c1 = *reinterpret_cast<const uint4 *>(stage + 4);
+        const uint4 ga = *reinterpret_cast<const uint4 *>(stage + 8);
+        const uint4 gb = *reinterpret_cast<const uint4 *>(stage + 12);
         EnvR s;
         unpack_env(c0, c1, ga, gb, s);
 
-        // ---- per-lane role for the single cells: pure register work, branch free, done before
-        // the wait.  Every lane ends up with at most ONE store (offset, value, needs-un-patch):
+        // ---- per-lane role for the single cells: pure register work, branch free.
+        // Every lane ends up with at most ONE store (offset, value, needs-un-patch):
         //   lane 0,1    Pac-Man, ch 2 / 3                       (env.rs:452-457)
         //   lane 4..7   ghost g = lane & 3, ch 4+g              (env.rs:461)
         //   lane 8..11  ghost g, ch 8+g                         (env.rs:476-480)
@@ -261,38 +274,22 @@ k_encode_obs(StateView st, float *__restrict__ out,
             unpatch = false; off = cell; val = (float)FRUIT_POINTS / 200.0f;
         }
 
-        // ---- channel-1 vectors in registers: everything that can be computed without touching
-        // the image happens BEFORE the wait, so that the chain "image free -> stores -> fence ->
-        // issue" is as short as possible (that chain is what keeps the encoder below the bare
-        // TMA store rate, see the header) ----
-        float4 ch1_v[7];
-#pragma unroll
-        for (int it = 0; it < 7; it++) {
-            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
-            const uint32_t nib = w >> (4 * (lane & 7));
-            ch1_v[it].x = (nib & 1u) ? pv : 0.0f;
-            ch1_v[it].y = (nib & 2u) ? pv : 0.0f;
-            ch1_v[it].z = (nib & 4u) ? pv : 0.0f;
-            ch1_v[it].w = (nib & 8u) ? pv : 0.0f;
-        }
-
-        // ---- the image is free once the previous bulk copies have finished READING it ----
-        // (the copy of the OTHER buffer, issued for the previous env, stays in flight: this is what
-        // keeps the TMA engine busy while this warp rebuilds an image)
-        if (lane == 0) bulk_wait_read<ENC_BUFS - 1>();
-        if (!warp_arrived((unsigned int)k)) __trap();  // nobody touches the image before lane 0's wait is over
-        {
-            const int patched = buf ? patched1 : patched0;
-            if (patched >= 0) img[patched] = 0.0f;
-        }
-
-        // ---- channel 1 base values and channel 15 fill: 2 x 7 128-bit stores per lane (the
-        // values were prepared in registers before the wait) ----
+        // ---- rebuild the image (it is free: the ticket was only taken after the previous copy
+        // had finished reading it).  Clear last env's single cell, then channel 1 base values (a
+        // nibble of the pellet bitboard -> one 128-bit store) and the channel 15 fill ----
+        if (patched >= 0) img[patched] = 0.0f;
 #pragma unroll
         for (int it = 0; it < 7; it++) {
             const int q = lane + 32 * it;  // float4 index inside a channel
+            const uint32_t w = __shfl_sync(0xffffffffu, F, (lane >> 3) + 4 * it);
             if (q < CH_VEC) {
-                img4[q] = ch1_v[it];                                     // channel 1
+                const uint32_t nib = w >> (4 * (lane & 7));
+                float4 v;
+                v.x = (nib & 1u) ? pv : 0.0f;
+                v.y = (nib & 2u) ? pv : 0.0f;
+                v.z = (nib & 4u) ? pv : 0.0f;
+                v.w = (nib & 8u) ? pv : 0.0f;
+                img4[q] = v;                                             // channel 1
                 img4[CH_VEC * 14 + q] = make_float4(sp, sp, sp, sp);     // channel 15
             }
         }
@@ -301,11 +298,7 @@ k_encode_obs(StateView st, float *__restrict__ out,
 
         // ---- single cells: one predicated store per lane (disjoint cells by construction) ----
         if (do_store) img[off] = val;
-        {
-            const int patched = (do_store && unpatch) ? off : -1;
-            patched0 = buf ? patched0 : patched;
-            patched1 = buf ? patched : patched1;
-        }
+        patched = (do_store && unpatch) ? off : -1;
 
         // ---- hand channel 0 (template) + channels 1..16 (image) to the TMA engine ----
         fence_proxy_async_smem();
@@ -316,15 +309,11 @@ k_encode_obs(StateView st, float *__restrict__ out,
             bulk_store_s2g(dst + CH_BYTES, img, IMG_BYTES);
             bulk_commit();
         }
-        buf = (buf + 1) % ENC_BUFS;
-        cur = nxt;
-        nxt = __shfl_sync(0xffffffffu, pend, 0);          // requested one env ago: long since back
-        if (lane == 0) pend = atomicAdd(ticket, 1u);     // in flight during the next env
-        F = F_n;
-        c0 = c0_n;
-        c1 = c1_n;
-        ga = ga_n;
-        gb = gb_n;
+        // ---- the image is free once the bulk copies have finished READING it; only then take
+        // the next ticket, so that the blocks being written at any one time stay close together
+        // in memory (see the header: late tickets are worth 2 % of HBM write bandwidth) ----
+        if (lane == 0) bulk_wait_read<0>();
+        cur = next_ticket();
     }
     if (lane == 0) {
         bulk_wait_all();

@@ -86,6 +86,40 @@ __global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+// ticket granularity / copy size sensitivity of the bare TMA store stream:
+// BATCH envs per ticket, each env written as PIECES equal bulk copies (one ticket per piece
+// when PIECES > 1 and BATCH == 1)
+template <int BATCH, int PIECES>
+__global__ void k_bulk_gran(float *out, long long n, unsigned *ticket) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PB = OBS_BYTES / PIECES / 16 * 16;   // piece bytes (16 B granules)
+    float4 *img4 = reinterpret_cast<float4 *>(smem + (size_t)warp * OBS_BYTES);
+    for (int q = lane; q < OBS_BYTES / 16; q += 32) img4[q] = make_float4(1.f, 2.f, 3.f, 4.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long long units = n * PIECES;
+    unsigned next = 0;
+    if (lane == 0) next = atomicAdd(ticket, (unsigned)BATCH);
+    next = __shfl_sync(~0u, next, 0);
+    while ((long long)next < units) {
+        const long long u0 = next;
+        if (lane == 0) {
+            next = atomicAdd(ticket, (unsigned)BATCH);
+            for (int b = 0; b < BATCH && u0 + b < units; b++) {
+                const long long u = u0 + b, k = u / PIECES; const int piece = (int)(u % PIECES);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                char *dst = reinterpret_cast<char *>(out) + k * OBS_BYTES + (long long)piece * PB;
+                const int bytes = (piece == PIECES - 1) ? OBS_BYTES - piece * PB : PB;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                             "r"(smem_u32(reinterpret_cast<char *>(img4) + piece * PB)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        next = __shfl_sync(~0u, next, 0);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __global__ void k_direct_env(float4 *out, long long n, unsigned *ticket) {
     const int lane = threadIdx.x & 31;
     unsigned next = 0;
@@ -143,6 +177,15 @@ int main() {
     RUNX(15, 4, "split, 4 warps, +fence +rewrite +loads");
     RUNX(15, 3, "split, 3 warps, +fence +rewrite +loads");
     RUNX(15, 2, "split, 2 warps, +fence +rewrite +loads");
+#define RUNG(B, P, label) { cudaFuncSetAttribute(k_bulk_gran<B, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * OBS_BYTES); \
+        float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk_gran<B, P><<<sms, 96, 3 * OBS_BYTES>>>(buf[it++ % 3], n, ticket); }); \
+        printf("G %-44s : %.3f ms  %.0f GB/s\n", label, ms, bytes / ms / 1e6); }
+    RUNG(1, 1, "ticket = 1 env (same as A)");
+    RUNG(2, 1, "ticket = 2 envs");
+    RUNG(4, 1, "ticket = 4 envs");
+    RUNG(8, 1, "ticket = 8 envs");
+    RUNG(1, 2, "ticket = half env (2 x 29.5 KB)");
+    RUNG(1, 4, "ticket = quarter env (4 x 14.7 KB)");
     for (int wps : {8, 16, 32, 64}) {
         float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_direct_env<<<sms * wps / 8, 256>>>((float4 *)buf[it++ % 3], n, ticket); });
         printf("C direct v4 env/warp warps/SM=%d : %.3f ms  %.0f GB/s\n", wps, ms, bytes / ms / 1e6);
