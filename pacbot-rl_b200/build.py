@@ -45,7 +45,9 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *SOURCES]
+    # PB_NVCC_EXTRA: extra flags for A/B experiments (e.g. "-DPB_ENC_PREFETCH_DIST=512")
+    extra = os.environ.get("PB_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB, *SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

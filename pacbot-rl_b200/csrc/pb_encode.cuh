@@ -31,13 +31,22 @@
 //     ticket + state prefetched two envs ahead (software pipeline)      0.547-0.551 ms
 //     tickets in batches of 4, state staged through cp.async            0.569 ms
 //     ticket taken when the previous image is handed to the TMA engine  0.542 ms
-//     ticket taken when the previous copy has finished reading (this)   0.539 ms  (7.20 TB/s)
+//     ticket taken when the previous copy has finished reading          0.539 ms  (7.20 TB/s)
+//     ... plus the L2 evict_first hint on the bulk stores (this kernel) 0.532 ms  (7.29 TB/s)
 // although the late ticket puts the atomic's and the state fetch's latency back on the warp's
-// critical path: with 4 warps per SM the TMA engine still has >= 2 copies queued.  Also measured,
-// equal within noise or slower: 3 x 59 024 B images with channel 0 inside, 2 warps x 2
-// double-buffered images, channel-1 values prepared in registers before the wait or not, and the
-// shared-template encoder with 16 envs in flight per SM (pb_encode2.cuh, 0.602 ms: five copies
-// and <= 18 scattered 4-byte stores per env disturb the write stream more than they help).
+// critical path: with 4 warps per SM the TMA engine still has ~2 copies queued on average.
+// The evict_first cache hint (createpolicy + cp.async.bulk ... .L2::cache_hint) tells L2 that the
+// 3.9 GB write stream has no reuse, so it drains to DRAM in arrival order instead of displacing
+// other lines: +1.4 % here (A/B on one box: 0.5319 vs 0.5391 ms); with the hint an earlier ticket
+// is again slower (0.5351 ms).  Also measured, equal within noise or slower: 3 x 59 024 B images
+// with channel 0 inside, 2 warps x 2 double-buffered images, channel-1 values prepared in
+// registers before the wait or not, prefetch.global.L2 of the state of the env 256 / 1 024
+// tickets ahead (0.5413 / 0.5427 vs 0.5413 ms: the state fetch is not what the chain waits for),
+// and the shared-template encoder with 16 envs in flight per SM (pb_encode2.cuh, 0.602 ms: five
+// copies and <= 18 scattered 4-byte stores per env disturb the write stream more than they
+// help).  What is left to the bare-TMA ceiling (0.517 ms) is the per-env dependent chain "image
+// free -> ticket -> state -> rebuild -> fence -> issue", during which that warp's 55 KB are not
+// in flight; the microbenchmark with the same chain, hint and late ticket reaches 0.526 ms.
 //
 // Per-lane roles are written BRANCH FREE (selects + one predicated store per lane).  A first
 // version used an if/else chain per lane group with nested conditionals; for particular states
@@ -77,6 +86,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+// PB_ENC_STORE_HINT (default 1): the observation stream is written once and not read by this
+// kernel, so its lines are marked evict_first in L2; 0 = plain stores, for A/B runs
+// (tools/ab_encoder.sh)
+#ifndef PB_ENC_STORE_HINT
+#define PB_ENC_STORE_HINT 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() {
@@ -166,14 +191,14 @@ k_encode_obs(StateView st, float *__restrict__ out,
         // one memory round trip, no shuffles to spread the 16-byte records ----
         {
             const long long env = env_first + k;
-            if (lane < PEL_WORDS) {
-                cp_async_4(stage + 16 + lane, st.pel + (long long)lane * st.npad + env);
-            } else {
-                const int w = lane - PEL_WORDS;
-                const uint4 *src = (w == 0) ? st.core0 + env : (w == 1) ? st.core1 + env
-                                   : (w == 2) ? st.ghosts + env : st.ghosts + st.npad + env;
-                cp_async_16(stage + 4 * w, src);
-            }
+            const int w = lane - PEL_WORDS;
+            const void *src = (lane < PEL_WORDS) ? (const void *)(st.pel + (long long)lane * st.npad + env)
+                              : (w == 0) ? (const void *)(st.core0 + env)
+                              : (w == 1) ? (const void *)(st.core1 + env)
+                              : (w == 2) ? (const void *)(st.ghosts + env)
+                                         : (const void *)(st.ghosts + st.npad + env);
+            if (lane < PEL_WORDS) cp_async_4(stage + 16 + lane, src);
+            else cp_async_16(stage + 4 * w, src);
             cp_async_commit();
             cp_async_wait_all();
         }
@@ -305,8 +330,14 @@ k_encode_obs(StateView st, float *__restrict__ out,
         const bool all_written = warp_arrived((unsigned int)k);  // every lane's cells are in the image
         if (lane == 0 && all_written) {
             char *dst = reinterpret_cast<char *>(out + k * env_stride);
+#if PB_ENC_STORE_HINT
+            const uint64_t pol = l2_policy_evict_first();
+            bulk_store_s2g_hint(dst, wall_ch, CH_BYTES, pol);
+            bulk_store_s2g_hint(dst + CH_BYTES, img, IMG_BYTES, pol);
+#else
             bulk_store_s2g(dst, wall_ch, CH_BYTES);
             bulk_store_s2g(dst + CH_BYTES, img, IMG_BYTES);
+#endif
             bulk_commit();
         }
         // ---- the image is free once the bulk copies have finished READING it; only then take

@@ -40,6 +40,8 @@ __global__ void k_bulk(float *out, long long n, unsigned *ticket, int warps) {
 // A + the ingredients of the real encoder, one flag each:
 //   1: fence.proxy.async + __syncwarp before every issue   2: rewrite 2 channels (434 STS.128)
 //   4: 176 B of global loads per env (the packed state)     8: 4 warps x 55 552 B + shared 3 472 B
+//  16: L2 evict_first cache hint on the bulk stores         32: late ticket (taken after wait.read)
+//  64: L2 evict_last hint instead (negative control)
 template <int FLAGS>
 __global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 *state) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -55,9 +57,12 @@ __global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 
     if (lane == 0) next = atomicAdd(ticket, 1u);
     next = __shfl_sync(~0u, next, 0);
     float acc = 0.f;
+    uint64_t pol = 0;
+    if (FLAGS & 16) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (FLAGS & 64) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     while ((long long)next < n) {
         long long k = next;
-        if (lane == 0) next = atomicAdd(ticket, 1u);
+        if (!(FLAGS & 32) && lane == 0) next = atomicAdd(ticket, 1u);
         uint4 s0 = make_uint4(0, 0, 0, 0);
         if (FLAGS & 4) { s0 = state[k * 4 + (lane & 3)]; uint4 s1 = state[(n + k) * 4 + (lane & 3)]; s0.x ^= s1.y; }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -73,7 +78,14 @@ __global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 
         if (FLAGS & 1) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); }
         if (lane == 0) {
             char *dst = reinterpret_cast<char *>(out) + k * OBS_BYTES;
-            if (FLAGS & 8) {
+            if (FLAGS & (16 | 64)) {
+                if (FLAGS & 8) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(shared_ch)), "r"(3472), "l"(pol) : "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + 3472), "r"(smem_u32(img4)), "r"(55552), "l"(pol) : "memory");
+                } else {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(img4)), "r"(OBS_BYTES), "l"(pol) : "memory");
+                }
+            } else if (FLAGS & 8) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(shared_ch)), "r"(3472) : "memory");
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + 3472), "r"(smem_u32(img4)), "r"(55552) : "memory");
             } else {
@@ -82,6 +94,10 @@ __global__ void k_bulk_x(float *out, long long n, unsigned *ticket, const uint4 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         acc += (float)(s0.y & 1);
+        if ((FLAGS & 32) && lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            next = atomicAdd(ticket, 1u);
+        }
         next = __shfl_sync(~0u, next, 0);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -177,6 +193,13 @@ int main() {
     RUNX(15, 4, "split, 4 warps, +fence +rewrite +loads");
     RUNX(15, 3, "split, 3 warps, +fence +rewrite +loads");
     RUNX(15, 2, "split, 2 warps, +fence +rewrite +loads");
+    RUNX(16, 3, "baseline + L2 evict_first");
+    RUNX(64, 3, "baseline + L2 evict_last");
+    RUNX(8 + 16, 4, "split, 4 warps + evict_first");
+    RUNX(15 + 32, 4, "split, 4 warps, full chain, late ticket");
+    RUNX(15 + 16, 4, "split, 4 warps, full chain, evict_first");
+    RUNX(15 + 16 + 32, 4, "split, 4w, full chain, evict_first, late");
+    RUNX(15 + 16 + 32, 3, "split, 3w, full chain, evict_first, late");
 #define RUNG(B, P, label) { cudaFuncSetAttribute(k_bulk_gran<B, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * OBS_BYTES); \
         float ms = timeit([&] { cudaMemsetAsync(ticket, 0, 4); k_bulk_gran<B, P><<<sms, 96, 3 * OBS_BYTES>>>(buf[it++ % 3], n, ticket); }); \
         printf("G %-44s : %.3f ms  %.0f GB/s\n", label, ms, bytes / ms / 1e6); }
