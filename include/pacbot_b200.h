@@ -224,6 +224,68 @@ int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64
                   const uint8_t *zero_mask_dev, int64_t count, float *out_dev, int device,
                   void *stream);
 
+/* Batched #[derive(Clone)] (env.rs:96) between engines on one device: for k in [0, count) copy
+ * env src_idx_dev[k] of `src` over env dst_idx_dev[k] of `dst` (int64 device arrays; NULL =
+ * identity; negative or out-of-range entries are skipped).  Used for MCTS clones and for state
+ * snapshots (an experience buffer of 176-byte states instead of 59 KB observations). */
+int pb_copy_envs(pb_engine *dst, const int64_t *dst_idx_dev, const pb_engine *src,
+                 const int64_t *src_idx_dev, int64_t count, void *stream);
+
+/* ---- batched MCTS (reference: pacbot_rs/src/mcts.rs) --------------------- */
+/* One search tree per env of `root`, all trees advanced in lock step.  `sim` is a second engine
+ * of the same size on the same device: slot i receives the clone of env i that a simulation
+ * steps (select_trajectory's env.clone(), mcts.rs:293), so the leaf observation of tree i is
+ * pb_encode_obs(sim) row i.  Both engines are borrowed and must outlive the pb_mcts.
+ * max_nodes = node capacity per tree (2..32767); a search iteration adds at most one node.
+ * Simulated env steps draw from the counter RNG with seed sim_seed(seed, epoch) =
+ * mix64(seed ^ ((epoch + 1) * 0xd6e8feb86659fd93)), same gid and draw counter as the real env;
+ * epoch = number of pb_mcts_backprop calls so far.  All float arithmetic is single IEEE f32
+ * operations in the reference's order. */
+typedef struct pb_mcts pb_mcts;
+/* the seed simulations of search iteration `epoch` draw from (host helper, like pb_draw_raw) */
+uint64_t pb_sim_seed(uint64_t seed, uint64_t epoch);
+int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes);
+int pb_mcts_destroy(pb_mcts *m);
+int pb_mcts_max_nodes(const pb_mcts *m);
+/* reset_root without the noise (mcts.rs:252-255): root := new_visited(value, policy) for every
+ * env with mask_dev[i] != 0 (NULL = all); value_dev float32 [n], policy_dev float32 [n][5]. */
+int pb_mcts_reset_root(pb_mcts *m, const uint8_t *mask_dev, const float *value_dev,
+                       const float *policy_dev, void *stream);
+/* add_root_policy_noise (mcts.rs:259-281): prior = (1 - mix) * prior + mix * noise over the
+ * valid actions of the real env; the k-th valid action takes noise_dev[i][k] (float32 [n][5]). */
+int pb_mcts_root_noise(pb_mcts *m, const uint8_t *mask_dev, const float *noise_dev, float mix,
+                       void *stream);
+/* select_trajectory (mcts.rs:290-321) for every env with active_dev[i] != 0 (NULL = all).
+ * leaf_kind_dev uint8 [n] (may be NULL): 0 inactive, 1 trajectory ended in a terminal state,
+ * 2 unexpanded leaf (its state is slot i of `sim`: encode + evaluate it);
+ * leaf_mask_dev uint8 [n][5] (may be NULL): action mask of that state. */
+int pb_mcts_select(pb_mcts *m, const uint8_t *active_dev, uint8_t *leaf_kind_dev,
+                   uint8_t *leaf_mask_dev, void *stream);
+/* backprop_trajectory (mcts.rs:325-381) of the trajectories of the last pb_mcts_select;
+ * value_dev / policy_dev are read only for leaf_kind 2.  Increments the epoch. */
+int pb_mcts_backprop(pb_mcts *m, const float *value_dev, const float *policy_dev, void *stream);
+/* take_action (mcts.rs:153-170) for every env with mask_dev[i] != 0 (NULL = all): steps the real
+ * env (no auto reset), writes reward/done, and status_dev uint8 [n]: 0 untouched, 1 episode done,
+ * 2 re-rooted to the existing child (caller adds root noise), 3 child absent (caller evaluates
+ * the new root: pb_mcts_reset_root + noise), 4 env was already done (untouched; the reference
+ * panics), 5 action > 4 (untouched). */
+int pb_mcts_take_action(pb_mcts *m, const uint8_t *mask_dev, const uint8_t *actions_dev,
+                        int32_t *reward_dev, uint8_t *done_dev, uint8_t *status_dev, void *stream);
+/* Per-tree getters (mcts.rs:173-243) */
+#define PB_MCTS_Q_BEST_ACTION 0         /* int32 [n]: most visited valid child, ties -> last */
+#define PB_MCTS_Q_ACTION_DISTRIBUTION 1 /* float32 [n][5]: child visits / (root visits - 1) */
+#define PB_MCTS_Q_POLICY_PRIOR 2        /* float32 [n][5] */
+#define PB_MCTS_Q_ACTION_VALUES 3       /* float32 [n][5]: child value, root value where absent */
+#define PB_MCTS_Q_VALUE 4               /* float32 [n]: total_return / visit_count of the root */
+#define PB_MCTS_Q_MAX_DEPTH 5           /* int32 [n] */
+#define PB_MCTS_Q_NODE_COUNT 6          /* int32 [n] */
+#define PB_MCTS_Q_ROOT_VISITS 7         /* int32 [n] */
+int pb_mcts_query(pb_mcts *m, int what, void *out_dev, void *stream);
+/* Synchronises `stream`; returns PB_ERR_INVALID_ARG (text in pb_last_error) if any kernel since
+ * the last check hit a full node pool, a double expansion or a search from a finished env;
+ * *epoch_out (may be NULL) receives the epoch counter. */
+int pb_mcts_check(pb_mcts *m, uint64_t *epoch_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

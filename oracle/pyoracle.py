@@ -62,12 +62,14 @@ FLAT_DTYPE = np.dtype(
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc); returns the .so path."""
-    src = os.path.join(_HERE, "pacbot_oracle.c")
-    hdr = os.path.join(_HERE, "pacbot_oracle.h")
+    srcs = [
+        os.path.join(_HERE, f)
+        for f in ("pacbot_oracle.c", "pacbot_oracle.h", "mcts_oracle.c", "mcts_oracle.h", "Makefile")
+    ]
     stale = (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     )
     if stale:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)

@@ -16,6 +16,7 @@ from ._lib import (
 from .engine import BatchedPacmanGym
 from .gym import PacmanGym, PacmanGymView
 from . import dist_utils, models, policies, replay_buffer
+from . import mcts, alphazero
 
 __all__ = [
     "BatchedPacmanGym",

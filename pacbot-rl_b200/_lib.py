@@ -106,7 +106,22 @@ SIGNATURES = {
     "pb_obs_host": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "pb_select_actions": (_int, [_vp, _vp, _vp, C.c_float, _vp, _u64, _vp]),
     "pb_gather_obs": (_int, [_vp, _i64, _vp, _vp, _i64, _vp, _int, _vp]),
+    "pb_copy_envs": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "pb_mcts_create": (_int, [C.POINTER(_vp), _vp, _vp, _int]),
+    "pb_mcts_destroy": (_int, [_vp]),
+    "pb_sim_seed": (_u64, [_u64, _u64]),
+    "pb_mcts_max_nodes": (_int, [_vp]),
+    "pb_mcts_reset_root": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pb_mcts_root_noise": (_int, [_vp, _vp, _vp, C.c_float, _vp]),
+    "pb_mcts_select": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pb_mcts_backprop": (_int, [_vp, _vp, _vp, _vp]),
+    "pb_mcts_take_action": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pb_mcts_query": (_int, [_vp, _int, _vp, _vp]),
+    "pb_mcts_check": (_int, [_vp, C.POINTER(_u64), _vp]),
 }
+
+MCTS_Q_BEST_ACTION, MCTS_Q_ACTION_DISTRIBUTION, MCTS_Q_POLICY_PRIOR, MCTS_Q_ACTION_VALUES = 0, 1, 2, 3
+MCTS_Q_VALUE, MCTS_Q_MAX_DEPTH, MCTS_Q_NODE_COUNT, MCTS_Q_ROOT_VISITS = 4, 5, 6, 7
 
 _lib = None
 

@@ -280,6 +280,8 @@ __global__ void k_clone(StateView dst, long long di, StateView src, long long si
 
 }  // namespace pb
 
+#include "pb_mcts.cuh"
+
 // =============================================================================================
 // Host side: the C ABI
 // =============================================================================================
@@ -868,3 +870,5 @@ int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64
 }
 
 }  // extern "C"
+
+#include "pb_mcts_abi.inl"

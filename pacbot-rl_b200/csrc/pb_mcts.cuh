@@ -1,0 +1,447 @@
+// pb_mcts.cuh -- batched Monte-Carlo tree search on the device: one search tree per env, all trees
+// advanced in lock step by one kernel launch per phase.
+//
+// Reference semantics: /root/reference/pacbot_rs/src/mcts.rs
+//   SearchTreeNode {visit_count, total_return, policy_priors[5], children[5]}      :17-23
+//   pick_action (PUCT, exploration rate 100, ties -> LAST maximum)                 :49-68
+//   best_action / value / child_value / max_depth / node_count                     :71-110
+//   MCTSContext::take_action (step, re-root to the child or fresh root)            :153-170
+//   select_trajectory (clone env, walk until done or unexpanded)                   :290-321
+//   backprop_trajectory (expand leaf / terminal child, discounted returns, 0.99)   :325-381
+//   add_root_policy_noise (0.75 * prior + 0.25 * noise over the valid actions)     :259-281
+//
+// B200 shape: the reference keeps one Box-linked tree per MCTSContext on the host and calls a
+// Python evaluator per leaf (or per batch of leaves, alphazero.rs:106-133), copying every leaf
+// observation host->device.  Here the trees live in HBM as index pools (48-byte nodes, two pools
+// per tree so that re-rooting is a compacting copy), the env clone a simulation steps is a slot
+// of a second engine (`sim`), the leaf observation is written by k_encode_obs straight from that
+// slot, and the evaluator consumes it on the device.  One thread walks one tree: the walk is a
+// dependent chain of node loads and env steps, so trees -- not nodes -- are the parallel axis.
+//
+// Floating point: every operation is a single IEEE f32 op in the reference's order
+// (__fdiv_rn / __fmul_rn / __fadd_rn / __fsqrt_rn: no FMA contraction), so tree statistics are
+// bit-identical to the scalar oracle (oracle/mcts_oracle.c) given the same evaluations.
+#pragma once
+#include "pb_engine.cuh"
+
+namespace pb {
+
+struct MctsNode {
+    uint32_t visit;
+    float total;
+    float prior[5];
+    int32_t child[5];  // index into the same pool, -1 = None
+};
+static_assert(sizeof(MctsNode) == 48, "MctsNode is 48 bytes");
+
+constexpr float MCTS_DISCOUNT = 0.99f;          // mcts.rs:15
+constexpr float MCTS_EXPLORATION_RATE = 100.0f; // mcts.rs:59
+constexpr int MCTS_THREADS = 32;
+
+// leaf_kind values
+enum { MCTS_INACTIVE = 0, MCTS_TERMINAL = 1, MCTS_NEEDS_EVAL = 2 };
+// take_action status values
+enum {
+    MCTS_ST_UNTOUCHED = 0,
+    MCTS_ST_DONE = 1,         // episode ended, tree left as is
+    MCTS_ST_REROOTED = 2,     // root := existing child (caller adds root noise)
+    MCTS_ST_NEEDS_ROOT = 3,   // child did not exist: caller evaluates the new root state
+    MCTS_ST_WAS_DONE = 4,     // env was already done (reference panics): untouched
+    MCTS_ST_BAD_ACTION = 5,   // action > 4: untouched
+};
+// error bits (sticky, read by pb_mcts_check)
+enum { MCTS_ERR_POOL_FULL = 1u, MCTS_ERR_EXPAND_TWICE = 2u, MCTS_ERR_ROOT_DONE = 4u };
+
+struct MctsView {
+    MctsNode *pool;            // [2][n][M]
+    int32_t *cur;              // [n] pool in use
+    int32_t *n_nodes;          // [n]
+    int32_t *traj_len;         // [n]
+    int32_t *path;             // [n][M] node at depth k (parent of transition k)
+    uint8_t *traj_act;         // [n][M]
+    int32_t *traj_rew;         // [n][M]
+    uint8_t *leaf_kind;        // [n]
+    int32_t *stack;            // [n][M] scratch (re-root, max_depth)
+    unsigned long long *epoch; // number of completed search iterations
+    unsigned int *error;       // sticky error bits
+    long long n;
+    int M;
+    __device__ __forceinline__ MctsNode *nodes(long long i, int which) const {
+        return pool + ((long long)which * n + i) * M;
+    }
+};
+
+__device__ __forceinline__ void node_init(MctsNode &nd, uint32_t visit, float total, const float *prior) {
+    nd.visit = visit;
+    nd.total = total;
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        nd.prior[a] = prior ? prior[a] : 0.0f;
+        nd.child[a] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset_root (mcts.rs:252-257, without the noise): root := new_visited(evaluation)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_reset_root(MctsView v, const uint8_t *__restrict__ mask, const float *__restrict__ value,
+                  const float *__restrict__ policy) {
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n || (mask && !mask[i])) return;
+    MctsNode nd;
+    node_init(nd, 1u, value[i], policy + i * 5);
+    v.nodes(i, v.cur[i])[0] = nd;
+    v.n_nodes[i] = 1;
+}
+
+// add_root_policy_noise (mcts.rs:259-281): the k-th VALID action gets noise[i][k]
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_root_noise(MctsView v, StateView root, const uint8_t *__restrict__ mask,
+                  const float *__restrict__ noise, float keep, float mix) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n || (mask && !mask[i])) return;
+    EnvR s;
+    load_env(root, i, s);
+    const uint32_t m = action_mask_bits(s, s_walls);
+    MctsNode *nd = v.nodes(i, v.cur[i]);
+    int k = 0;
+    for (int a = 0; a < 5; a++) {
+        if (!((m >> a) & 1u)) continue;
+        nd->prior[a] = __fadd_rn(__fmul_rn(keep, nd->prior[a]), __fmul_rn(mix, noise[i * 5 + k]));
+        k++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select_trajectory (mcts.rs:290-321)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mcts_pick_action(const MctsNode &nd, const MctsNode *nodes, uint32_t m) {
+    const float parent_value = __fdiv_rn(nd.total, (float)nd.visit);   // mcts.rs:82-86
+    const float sqrt_visits = __fsqrt_rn((float)nd.visit);
+    // children's statistics: independent loads, issued together
+    uint32_t cvis[5];
+    float ctot[5];
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        const int c = nd.child[a];
+        cvis[a] = c >= 0 ? nodes[c].visit : 0u;
+        ctot[a] = c >= 0 ? nodes[c].total : 0.0f;
+    }
+    int best = -1;
+    float best_key = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+        if (!((m >> a) & 1u)) continue;
+        const float cv = nd.child[a] >= 0 ? __fdiv_rn(ctot[a], (float)cvis[a]) : parent_value;
+        const float exploration = __fdiv_rn(__fmul_rn(nd.prior[a], sqrt_visits), (float)(1u + cvis[a]));
+        const float key = __fadd_rn(cv, __fmul_rn(MCTS_EXPLORATION_RATE, exploration));
+        if (best < 0 || key >= best_key) {  // max_by_key: the LAST maximum wins
+            best = a;
+            best_key = key;
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long long gid_base,
+              const uint8_t *__restrict__ active, uint8_t *__restrict__ leaf_kind_out,
+              uint8_t *__restrict__ leaf_mask_out) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n) return;
+    EnvR s;
+    load_env(root, i, s);
+    int kind = MCTS_INACTIVE;
+    if (!active || active[i]) {
+        if (is_done(s)) {  // reference: assert!(!self.env.is_done())
+            atomicOr(v.error, MCTS_ERR_ROOT_DONE);
+        } else {
+            // env.clone(): the simulation steps slot i of the `sim` engine
+            for (int w = 0; w < PEL_WORDS; w++)
+                sim.pel[(long long)w * sim.npad + i] = root.pel[(long long)w * root.npad + i];
+            const PelRef pel{sim.pel + i, sim.npad};
+            RngCtx rng;
+            rng.seed = sim_seed(seed, *v.epoch);
+            rng.gid = (uint64_t)(gid_base + i);
+            rng.tape = nullptr;
+            rng.tape_len = 0;
+            const MctsNode *nodes = v.nodes(i, v.cur[i]);
+            int32_t *path = v.path + i * v.M;
+            uint8_t *act = v.traj_act + i * v.M;
+            int32_t *rew = v.traj_rew + i * v.M;
+            int node = 0, len = 0;
+            for (;;) {
+                const MctsNode nd = nodes[node];
+                const int a = mcts_pick_action(nd, nodes, action_mask_bits(s, s_walls));
+                int reward;
+                bool done;
+                gym_step(s, pel, c_tab, s_walls, rng, a, reward, done);
+                path[len] = node;
+                act[len] = (uint8_t)a;
+                rew[len] = reward;
+                len++;
+                if (done) {
+                    kind = MCTS_TERMINAL;
+                    break;
+                }
+                if (nd.child[a] < 0) {
+                    kind = MCTS_NEEDS_EVAL;
+                    break;
+                }
+                if (len >= v.M) {  // cannot happen with n_nodes <= M (depth < n_nodes)
+                    atomicOr(v.error, MCTS_ERR_POOL_FULL);
+                    kind = MCTS_INACTIVE;
+                    break;
+                }
+                node = nd.child[a];
+            }
+            v.traj_len[i] = len;
+            store_env(sim, i, s);
+        }
+    }
+    v.leaf_kind[i] = (uint8_t)kind;
+    if (leaf_kind_out) leaf_kind_out[i] = (uint8_t)kind;
+    if (leaf_mask_out) write_mask(leaf_mask_out, i, action_mask_bits(s, s_walls));
+}
+
+// ---------------------------------------------------------------------------------------------
+// backprop_trajectory (mcts.rs:325-381), iterative: expand the leaf, then walk the path upwards
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__restrict__ policy) {
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i == 0) *v.epoch += 1ull;  // one search iteration done (select of the next one sees it)
+    if (i >= v.n) return;
+    const int kind = v.leaf_kind[i];
+    if (kind == MCTS_INACTIVE) return;
+    v.leaf_kind[i] = MCTS_INACTIVE;  // a trajectory is consumed exactly once
+    MctsNode *nodes = v.nodes(i, v.cur[i]);
+    const int32_t *path = v.path + i * v.M;
+    const uint8_t *act = v.traj_act + i * v.M;
+    const int32_t *rew = v.traj_rew + i * v.M;
+    const int len = v.traj_len[i];
+    const int parent = path[len - 1], a_last = act[len - 1];
+    int c = nodes[parent].child[a_last];
+    float subsequent;
+    if (kind == MCTS_NEEDS_EVAL) {
+        if (c >= 0) {  // "tried to expand the same child twice"
+            atomicOr(v.error, MCTS_ERR_EXPAND_TWICE);
+            return;
+        }
+        subsequent = value[i];
+    } else {
+        subsequent = 0.0f;
+    }
+    if (c < 0) {
+        c = v.n_nodes[i];
+        if (c >= v.M) {
+            atomicOr(v.error, MCTS_ERR_POOL_FULL);
+            return;
+        }
+        v.n_nodes[i] = c + 1;
+        MctsNode nd;  // SearchTreeNode::new(policy) / new_terminal()
+        node_init(nd, 0u, 0.0f, kind == MCTS_NEEDS_EVAL ? policy + i * 5 : nullptr);
+        nodes[c] = nd;
+        nodes[parent].child[a_last] = c;
+    }
+    int child = c;
+    for (int k = len - 1; k >= 0; k--) {
+        const float this_return = __fadd_rn((float)rew[k], __fmul_rn(MCTS_DISCOUNT, subsequent));
+        nodes[child].visit += 1u;
+        nodes[child].total = __fadd_rn(nodes[child].total, this_return);
+        subsequent = this_return;
+        child = path[k];
+    }
+    // child == path[0] == root
+    nodes[0].visit += 1u;
+    nodes[0].total = __fadd_rn(nodes[0].total, __fmul_rn(MCTS_DISCOUNT, subsequent));
+}
+
+// ---------------------------------------------------------------------------------------------
+// take_action (mcts.rs:153-170): step the real env; keep the chosen child's subtree as the new
+// tree (compacting copy into the other pool) or ask for a fresh root
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__restrict__ mask,
+                   const uint8_t *__restrict__ actions, int32_t *__restrict__ reward,
+                   uint8_t *__restrict__ done_out, uint8_t *__restrict__ status) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n) return;
+    if (mask && !mask[i]) {
+        status[i] = MCTS_ST_UNTOUCHED;
+        return;
+    }
+    reward[i] = 0;
+    done_out[i] = 0;
+    EnvR s;
+    load_env(root, i, s);
+    if (is_done(s)) {
+        status[i] = MCTS_ST_WAS_DONE;
+        return;
+    }
+    const int a = actions[i];
+    if (a > 4) {
+        status[i] = MCTS_ST_BAD_ACTION;
+        return;
+    }
+    const PelRef pel{root.pel + i, root.npad};
+    const RngCtx rng = make_rng(rp, i);
+    int rew;
+    bool done;
+    gym_step(s, pel, c_tab, s_walls, rng, a, rew, done);
+    store_env(root, i, s);
+    reward[i] = rew;
+    done_out[i] = done ? 1 : 0;
+    if (done) {
+        status[i] = MCTS_ST_DONE;
+        return;
+    }
+    const int which = v.cur[i];
+    const MctsNode *old_nodes = v.nodes(i, which);
+    const int c = old_nodes[0].child[a];
+    if (c < 0) {
+        status[i] = MCTS_ST_NEEDS_ROOT;
+        return;
+    }
+    // self.root = *child: copy the subtree into the other pool, depth first, new root at index 0
+    MctsNode *new_nodes = v.nodes(i, which ^ 1);
+    int32_t *stack = v.stack + i * v.M;
+    new_nodes[0] = old_nodes[c];
+    int count = 1, sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack[--sp];
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+            const int oc = new_nodes[ni].child[b];  // still an index into the OLD pool
+            if (oc >= 0) {
+                const int nn = count++;
+                new_nodes[nn] = old_nodes[oc];
+                new_nodes[ni].child[b] = nn;
+                stack[sp++] = nn;
+            }
+        }
+    }
+    v.cur[i] = which ^ 1;
+    v.n_nodes[i] = count;
+    status[i] = MCTS_ST_REROOTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// queries (mcts.rs:173-243)
+// ---------------------------------------------------------------------------------------------
+enum {
+    MCTS_Q_BEST_ACTION = 0,          // int32 [n]
+    MCTS_Q_ACTION_DISTRIBUTION = 1,  // float32 [n][5]
+    MCTS_Q_POLICY_PRIOR = 2,         // float32 [n][5]
+    MCTS_Q_ACTION_VALUES = 3,        // float32 [n][5]
+    MCTS_Q_VALUE = 4,                // float32 [n]
+    MCTS_Q_MAX_DEPTH = 5,            // int32 [n]
+    MCTS_Q_NODE_COUNT = 6,           // int32 [n]
+    MCTS_Q_ROOT_VISITS = 7,          // int32 [n]
+};
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_query(MctsView v, StateView root, int what, void *__restrict__ out) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n) return;
+    const MctsNode *nodes = v.nodes(i, v.cur[i]);
+    const MctsNode r = nodes[0];
+    float *fo = reinterpret_cast<float *>(out);
+    int32_t *io = reinterpret_cast<int32_t *>(out);
+    switch (what) {
+    case MCTS_Q_BEST_ACTION: {  // mcts.rs:71-79 (ties -> last)
+        EnvR s;
+        load_env(root, i, s);
+        const uint32_t m = action_mask_bits(s, s_walls);
+        int best = -1;
+        uint32_t best_key = 0;
+        for (int a = 0; a < 5; a++) {
+            if (!((m >> a) & 1u)) continue;
+            const uint32_t vis = r.child[a] >= 0 ? nodes[r.child[a]].visit : 0u;
+            if (best < 0 || vis >= best_key) {
+                best = a;
+                best_key = vis;
+            }
+        }
+        io[i] = best;
+        break;
+    }
+    case MCTS_Q_ACTION_DISTRIBUTION: {  // mcts.rs:180-186
+        const float total_child_visits = (float)(r.visit - 1u);
+        for (int a = 0; a < 5; a++)
+            fo[i * 5 + a] = r.child[a] >= 0
+                                ? __fdiv_rn((float)nodes[r.child[a]].visit, total_child_visits)
+                                : 0.0f;
+        break;
+    }
+    case MCTS_Q_POLICY_PRIOR:
+        for (int a = 0; a < 5; a++) fo[i * 5 + a] = r.prior[a];
+        break;
+    case MCTS_Q_ACTION_VALUES: {  // mcts.rs:196-198
+        const float pv = __fdiv_rn(r.total, (float)r.visit);
+        for (int a = 0; a < 5; a++) {
+            const int c = r.child[a];
+            fo[i * 5 + a] = c >= 0 ? __fdiv_rn(nodes[c].total, (float)nodes[c].visit) : pv;
+        }
+        break;
+    }
+    case MCTS_Q_VALUE:
+        fo[i] = __fdiv_rn(r.total, (float)r.visit);
+        break;
+    case MCTS_Q_MAX_DEPTH: {  // mcts.rs:95-101; stack entries = node | depth << 16
+        int32_t *stack = v.stack + i * v.M;
+        int sp = 0, best = 0;
+        stack[sp++] = 0;
+        while (sp > 0) {
+            const int e = stack[--sp];
+            const int ni = e & 0xffff, d = e >> 16;
+            best = d > best ? d : best;
+            for (int a = 0; a < 5; a++) {
+                const int c = nodes[ni].child[a];
+                if (c >= 0) stack[sp++] = c | ((d + 1) << 16);
+            }
+        }
+        io[i] = best;
+        break;
+    }
+    case MCTS_Q_NODE_COUNT:
+        io[i] = v.n_nodes[i];
+        break;
+    case MCTS_Q_ROOT_VISITS:
+        io[i] = (int32_t)r.visit;
+        break;
+    default:
+        break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pb_copy_envs: batched #[derive(Clone)] between engines (one warp per copy)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_copy_envs(StateView dst, const long long *__restrict__ dst_idx, StateView src,
+            const long long *__restrict__ src_idx, long long count) {
+    const long long k = ((long long)blockIdx.x * 128 + threadIdx.x) >> 5;
+    const int t = threadIdx.x & 31;
+    if (k >= count) return;
+    const long long di = dst_idx ? dst_idx[k] : k, si = src_idx ? src_idx[k] : k;
+    if (di < 0 || si < 0 || di >= dst.n || si >= src.n) return;
+    if (t == 0) dst.core0[di] = src.core0[si];
+    if (t == 1) dst.core1[di] = src.core1[si];
+    if (t == 2) dst.ghosts[di] = src.ghosts[si];
+    if (t == 3) dst.ghosts[dst.npad + di] = src.ghosts[src.npad + si];
+    if (t >= 4 && t < 4 + PEL_WORDS)
+        dst.pel[(long long)(t - 4) * dst.npad + di] = src.pel[(long long)(t - 4) * src.npad + si];
+}
+
+}  // namespace pb

@@ -1,0 +1,182 @@
+// pb_mcts_abi.inl -- host side of the pb_mcts_* / pb_copy_envs entry points
+// (include/pacbot_b200.h); included at the end of pb_kernels.cu, after `struct pb_engine`.
+
+struct pb_mcts {
+    pb_engine *root = nullptr;  // borrowed
+    pb_engine *sim = nullptr;   // borrowed; slot i holds the env clone tree i simulates with
+    int device = 0;
+    MctsView v{};
+};
+
+namespace {
+unsigned mcts_grid(long long n) { return (unsigned)((n + MCTS_THREADS - 1) / MCTS_THREADS); }
+}  // namespace
+
+extern "C" {
+
+int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes) {
+    if (!out || !root || !sim || root == sim || root->n != sim->n || root->device != sim->device ||
+        max_nodes < 2 || max_nodes > 32767)
+        return fail(PB_ERR_INVALID_ARG,
+                    "pb_mcts_create: need two distinct engines of equal size on one device and "
+                    "2 <= max_nodes <= 32767");
+    DeviceGuard g(root->device);
+    if (!g.ok) return fail(PB_ERR_NO_DEVICE, "pb_mcts_create: cannot select the CUDA device");
+    pb_mcts *m = new pb_mcts();
+    m->root = root;
+    m->sim = sim;
+    m->device = root->device;
+    MctsView &v = m->v;
+    v.n = root->n;
+    v.M = max_nodes;
+    const size_t n = (size_t)v.n, M = (size_t)max_nodes;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](auto **p, size_t bytes, int fill) {
+        if (err != cudaSuccess) return;
+        err = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+        if (err == cudaSuccess) err = cudaMemset(*p, fill, bytes);
+    };
+    alloc(&v.pool, sizeof(MctsNode) * 2 * n * M, 0);
+    alloc(&v.cur, sizeof(int32_t) * n, 0);
+    alloc(&v.n_nodes, sizeof(int32_t) * n, 0);
+    alloc(&v.traj_len, sizeof(int32_t) * n, 0);
+    alloc(&v.path, sizeof(int32_t) * n * M, 0);
+    alloc(&v.traj_act, n * M, 0);
+    alloc(&v.traj_rew, sizeof(int32_t) * n * M, 0);
+    alloc(&v.leaf_kind, n, 0);
+    alloc(&v.stack, sizeof(int32_t) * n * M, 0);
+    alloc(&v.epoch, sizeof(unsigned long long), 0);
+    alloc(&v.error, sizeof(unsigned int), 0);
+    if (err != cudaSuccess) {
+        std::string msg = std::string("pb_mcts_create: ") + cudaGetErrorString(err);
+        pb_mcts_destroy(m);
+        return fail(PB_ERR_CUDA, msg);
+    }
+    *out = m;
+    return PB_OK;
+}
+
+int pb_mcts_destroy(pb_mcts *m) {
+    if (!m) return PB_OK;
+    DeviceGuard g(m->device);
+    MctsView &v = m->v;
+    cudaFree(v.pool);
+    cudaFree(v.cur);
+    cudaFree(v.n_nodes);
+    cudaFree(v.traj_len);
+    cudaFree(v.path);
+    cudaFree(v.traj_act);
+    cudaFree(v.traj_rew);
+    cudaFree(v.leaf_kind);
+    cudaFree(v.stack);
+    cudaFree(v.epoch);
+    cudaFree(v.error);
+    delete m;
+    return PB_OK;
+}
+
+int pb_mcts_max_nodes(const pb_mcts *m) { return m ? m->v.M : 0; }
+uint64_t pb_sim_seed(uint64_t seed, uint64_t epoch) { return sim_seed(seed, epoch); }
+
+int pb_mcts_reset_root(pb_mcts *m, const uint8_t *mask_dev, const float *value_dev,
+                       const float *policy_dev, void *stream) {
+    if (!m || !value_dev || !policy_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_mcts_reset_root: null argument");
+    DeviceGuard g(m->device);
+    k_mcts_reset_root<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, mask_dev, value_dev, policy_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_root_noise(pb_mcts *m, const uint8_t *mask_dev, const float *noise_dev, float mix,
+                       void *stream) {
+    if (!m || !noise_dev) return fail(PB_ERR_INVALID_ARG, "pb_mcts_root_noise: null argument");
+    DeviceGuard g(m->device);
+    k_mcts_root_noise<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, m->root->st, mask_dev, noise_dev, 1.0f - mix, mix);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_select(pb_mcts *m, const uint8_t *active_dev, uint8_t *leaf_kind_dev,
+                   uint8_t *leaf_mask_dev, void *stream) {
+    if (!m) return fail(PB_ERR_INVALID_ARG, "pb_mcts_select: null handle");
+    DeviceGuard g(m->device);
+    k_mcts_select<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, m->root->st, m->sim->st, m->root->seed, m->root->gid_base, active_dev, leaf_kind_dev,
+        leaf_mask_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_backprop(pb_mcts *m, const float *value_dev, const float *policy_dev, void *stream) {
+    if (!m || !value_dev || !policy_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_mcts_backprop: null argument");
+    DeviceGuard g(m->device);
+    k_mcts_backprop<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, value_dev,
+                                                                                  policy_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_take_action(pb_mcts *m, const uint8_t *mask_dev, const uint8_t *actions_dev,
+                        int32_t *reward_dev, uint8_t *done_dev, uint8_t *status_dev, void *stream) {
+    if (!m || !actions_dev || !reward_dev || !done_dev || !status_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_mcts_take_action: null argument");
+    DeviceGuard g(m->device);
+    k_mcts_take_action<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, m->root->st, rng_params(m->root), mask_dev, actions_dev, reward_dev, done_dev,
+        status_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_query(pb_mcts *m, int what, void *out_dev, void *stream) {
+    if (!m || !out_dev || what < 0 || what > MCTS_Q_ROOT_VISITS)
+        return fail(PB_ERR_INVALID_ARG, "pb_mcts_query: bad arguments");
+    DeviceGuard g(m->device);
+    k_mcts_query<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, m->root->st,
+                                                                               what, out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_check(pb_mcts *m, uint64_t *epoch_out, void *stream) {
+    if (!m) return fail(PB_ERR_INVALID_ARG, "pb_mcts_check: null handle");
+    DeviceGuard g(m->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int err = 0;
+    unsigned long long epoch = 0;
+    PB_CUDA(cudaMemcpyAsync(&err, m->v.error, sizeof(err), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(&epoch, m->v.epoch, sizeof(epoch), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    if (epoch_out) *epoch_out = epoch;
+    if (err) {
+        PB_CUDA(cudaMemsetAsync(m->v.error, 0, sizeof(err), s));
+        std::string msg = "pb_mcts:";
+        if (err & MCTS_ERR_POOL_FULL) msg += " node pool full (search beyond max_nodes);";
+        if (err & MCTS_ERR_EXPAND_TWICE) msg += " tried to expand the same child twice;";
+        if (err & MCTS_ERR_ROOT_DONE) msg += " search from a finished env;";
+        return fail(PB_ERR_INVALID_ARG, msg);
+    }
+    return PB_OK;
+}
+
+int pb_copy_envs(pb_engine *dst, const int64_t *dst_idx_dev, const pb_engine *src,
+                 const int64_t *src_idx_dev, int64_t count, void *stream) {
+    if (!dst || !src || count < 0 || dst->device != src->device)
+        return fail(PB_ERR_INVALID_ARG, "pb_copy_envs: bad arguments");
+    if ((!dst_idx_dev && count > dst->n) || (!src_idx_dev && count > src->n))
+        return fail(PB_ERR_INVALID_ARG, "pb_copy_envs: count exceeds the engine size");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(dst->device);
+    const unsigned blocks = (unsigned)((count * 32 + 127) / 128);
+    k_copy_envs<<<blocks, 128, 0, (cudaStream_t)stream>>>(
+        dst->st, reinterpret_cast<const long long *>(dst_idx_dev), src->st,
+        reinterpret_cast<const long long *>(src_idx_dev), count);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // extern "C"

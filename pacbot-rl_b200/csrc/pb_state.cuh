@@ -145,6 +145,12 @@ __host__ __device__ inline uint32_t action_raw(uint64_t seed, uint64_t gid, uint
     return (uint32_t)(mix64(env_key(seed, gid) + call * 0xd1342543de82ef95ull +
                             0xa0761d6478bd642full) >> 32);
 }
+// seed of the game-draw stream used by MCTS SIMULATIONS (pb_mcts.cuh): the cloned env of search
+// iteration `epoch` keeps its gid and rng_ctr but draws from a different seed, so a simulation
+// never sees the draws the real env is going to get
+__host__ __device__ inline uint64_t sim_seed(uint64_t seed, uint64_t epoch) {
+    return mix64(seed ^ ((epoch + 1ull) * 0xd6e8feb86659fd93ull));
+}
 __host__ __device__ inline uint32_t below(uint32_t raw, uint32_t n) {
     return (uint32_t)(((uint64_t)raw * (uint64_t)n) >> 32);
 }

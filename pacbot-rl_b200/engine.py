@@ -422,6 +422,27 @@ class BatchedPacmanGym:
         check(self._L.pb_clone_env(self._h, dst_index, src._h, src_index, self._stream()))
         self._cfg[dst_index] = src._cfg[src_index]
 
+    def copy_envs_from(self, src: "BatchedPacmanGym", src_index: Optional[torch.Tensor] = None,
+                       dst_index: Optional[torch.Tensor] = None, count: Optional[int] = None) -> None:
+        """Batched clone on the device (pb_copy_envs): env src_index[k] of `src` overwrites env
+        dst_index[k] of this engine; int64 device tensors, None = identity, negative = skip."""
+        def ptr(t, name):
+            if t is None:
+                return None
+            if t.dtype != torch.int64 or t.device != self.device or not t.is_contiguous() or t.ndim != 1:
+                raise ValueError(f"{name}: expected a contiguous 1-D int64 tensor on {self.device}")
+            return C.c_void_p(t.data_ptr())
+
+        if count is None:
+            if dst_index is not None:
+                count = dst_index.shape[0]
+            elif src_index is not None:
+                count = src_index.shape[0]
+            else:
+                count = min(self.num_envs, src.num_envs)
+        check(self._L.pb_copy_envs(self._h, ptr(dst_index, "dst_index"), src._h,
+                                   ptr(src_index, "src_index"), int(count), self._stream()))
+
     def view(self, index: int) -> "PacmanGymView":
         from .gym import PacmanGymView
 

@@ -1,0 +1,236 @@
+"""GPU parity of the batched MCTS / AlphaZero collector (pb_mcts_* behind BatchedMCTS) against
+the scalar oracle (oracle/mcts_oracle.c, a restatement of pacbot_rs/src/mcts.rs + alphazero.rs).
+Both sides get the same evaluator outputs, the same root noise and the same counter-RNG draws;
+tree statistics, rewards and experience items must agree BIT FOR BIT."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_obs_equal, assert_states_equal
+from mcts_common import NoiseSource, np_evaluator, uniform_evaluator
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pymcts(oracle):
+    from oracle import pymcts
+
+    pymcts.lib()
+    return pymcts
+
+
+def torch_eval(fn):
+    def run(obs, mask):
+        v, p = fn(obs.cpu().numpy(), mask.cpu().numpy())
+        return torch.from_numpy(v).to(obs.device), torch.from_numpy(p).to(obs.device)
+
+    return run
+
+
+def bits(x):
+    return np.ascontiguousarray(np.asarray(x, np.float32)).view(np.uint32)
+
+
+def compare_trees(om, gm, n, ctx):
+    gv = {
+        "root_visits": gm.root_visits().cpu().numpy(),
+        "node_count": gm.node_count().cpu().numpy(),
+        "max_depth": gm.max_depth().cpu().numpy(),
+        "best_action": gm.best_action().cpu().numpy(),
+        "value": gm.value().cpu().numpy(),
+        "action_distribution": gm.action_distribution().cpu().numpy(),
+        "policy_prior": gm.policy_prior().cpu().numpy(),
+        "action_values": gm.action_values().cpu().numpy(),
+    }
+    for i in range(n):
+        assert om.root_visits(i) == gv["root_visits"][i], f"{ctx} tree {i} root visits"
+        assert om.node_count(i) == gv["node_count"][i], f"{ctx} tree {i} node count"
+        assert om.max_depth(i) == gv["max_depth"][i], f"{ctx} tree {i} max depth"
+        assert np.array_equal(bits(om.policy_prior(i)), bits(gv["policy_prior"][i])), f"{ctx} tree {i} priors"
+        assert bits(om.value(i)) == bits(gv["value"][i]), f"{ctx} tree {i} value"
+        assert np.array_equal(bits(om.action_values(i)), bits(gv["action_values"][i])), f"{ctx} tree {i} Q"
+        if om.root_visits(i) > 1:
+            assert np.array_equal(bits(om.action_distribution(i)), bits(gv["action_distribution"][i])), \
+                f"{ctx} tree {i} visit distribution"
+        assert om.best_action(i) == gv["best_action"][i], f"{ctx} tree {i} best action"
+
+
+@pytest.mark.parametrize("evaluator", [np_evaluator, uniform_evaluator], ids=["hashed", "uniform"])
+def test_search_take_action_and_reset_match_oracle(pb, pymcts, evaluator):
+    n, seed, base, iters_per_move, moves = 24, 11, 3000, 30, 14
+    rs = (np.arange(n) % 3 != 0)
+    noise = NoiseSource(n)
+    om = pymcts.OracleMCTS(n, rs.astype(np.uint8), 0, seed, base, evaluator, noise.oracle)
+    env = pb.BatchedPacmanGym(n, rs, False, device="cuda:0", seed=seed, env_id_base=base)
+    gm = pb.mcts.BatchedMCTS(env, torch_eval(evaluator), moves * iters_per_move + 2, noise_fn=noise.torch_fn)
+    om.reset()
+    gm.reset()
+    assert_states_equal(om.export_state(), env.get_state(), "after reset")
+    compare_trees(om, gm, n, "fresh roots")
+    finished = 0
+    for move in range(moves):
+        for it in range(iters_per_move):
+            om.search_iteration()
+            gm.search_iteration()
+            if it % 10 == 3:
+                compare_trees(om, gm, n, f"move {move} iteration {it}")
+        compare_trees(om, gm, n, f"move {move} before acting")
+        actions = gm.best_action().to(torch.uint8)
+        # every third tree plays its LEAST likely legal action instead: exercises the
+        # "child absent -> fresh root" branch (mcts.rs:164-166)
+        mask = env.action_mask().cpu().numpy()
+        a = actions.cpu().numpy().copy()
+        for i in range(0, n, 3):
+            dist = gm.action_distribution()[i].cpu().numpy()
+            legal = np.nonzero(mask[i])[0]
+            a[i] = legal[np.argmin(dist[legal])]
+        o_rew, o_done = om.take_action(a)
+        g_rew, g_done, status = gm.take_action(torch.from_numpy(a))
+        assert np.array_equal(o_rew, g_rew.cpu().numpy()), f"move {move} rewards"
+        assert np.array_equal(o_done, g_done.cpu().numpy()), f"move {move} done"
+        assert_states_equal(om.export_state(), env.get_state(), f"move {move} after take_action")
+        if o_done.any():  # MCTSContext::reset for the finished games
+            finished += int(o_done.sum())
+            om.reset(o_done.astype(np.uint8))
+            gm.reset(torch.from_numpy(o_done).cuda())
+        compare_trees(om, gm, n, f"move {move} after acting")
+    assert gm.check() == om.epoch == moves * iters_per_move
+    assert np.array_equal(noise.calls_oracle, noise.calls_gpu)
+
+
+def test_ponder_grows_each_tree_to_the_requested_size(pb, pymcts):
+    n, seed, base, size = 9, 4, 10, 37
+    noise = NoiseSource(n)
+    om = pymcts.OracleMCTS(n, 1, 0, seed, base, np_evaluator, noise.oracle)
+    env = pb.BatchedPacmanGym(n, True, False, device="cuda:0", seed=seed, env_id_base=base)
+    gm = pb.mcts.BatchedMCTS(env, torch_eval(np_evaluator), size, noise_fn=noise.torch_fn)
+    om.reset()
+    gm.reset()
+    for _ in range(size - 1):   # ponder_and_choose: max_tree_size - node_count iterations
+        om.search_iteration()
+    best = gm.ponder(size)
+    compare_trees(om, gm, n, "after ponder")
+    assert (gm.node_count() <= size).all() and int(gm.root_visits().min()) == size
+    assert np.array_equal(best.cpu().numpy(), [om.best_action(i) for i in range(n)])
+    # a second ponder to the same size is a no-op (saturating_sub, mcts.rs:209)
+    gm.ponder(size)
+    compare_trees(om, gm, n, "after a no-op ponder")
+    with pytest.raises(ValueError):
+        gm.ponder(size + 1)
+
+
+def test_search_from_a_finished_env_is_reported(pb):
+    env = pb.BatchedPacmanGym(2, False, False, device="cuda:0")
+    gm = pb.mcts.BatchedMCTS(env, torch_eval(uniform_evaluator), 8)
+    gm.reset()
+    st = env.get_state()
+    st["curr_lives"][1] = 2          # is_done (env.rs:277-279)
+    env.set_state(st)
+    gm.search_iteration()
+    with pytest.raises(ValueError, match="finished env"):
+        gm.check()
+    with pytest.raises(RuntimeError):
+        gm.take_action(torch.zeros(2, dtype=torch.uint8))
+
+
+def test_copy_envs_batched_clone(pb):
+    src = pb.BatchedPacmanGym(64, True, True, device="cuda:0", seed=8)
+    src.reset()
+    for k in range(5):
+        src.step_random(call_idx=k)
+    dst = pb.BatchedPacmanGym(200, False, False, device="cuda:0", seed=1)
+    before = dst.get_state()
+    si = torch.tensor([3, 7, 63, 0, 5], device="cuda:0")
+    di = torch.tensor([199, 0, 17, -1, 100], device="cuda:0")   # -1: skipped
+    dst.copy_envs_from(src, src_index=si, dst_index=di)
+    after, s = dst.get_state(), src.get_state()
+    for a, b in [(199, 3), (0, 7), (17, 63), (100, 5)]:
+        assert after[a:a + 1].tobytes() == s[b:b + 1].tobytes()
+    untouched = np.setdiff1d(np.arange(200), [199, 0, 17, 100])
+    assert np.array_equal(after[untouched], before[untouched])
+    out = torch.empty((3, 17, 28, 31), device="cuda:0")
+    dst.obs_range(17, 1, out[:1])
+    assert torch.equal(out[0], src.obs()[63])
+
+
+def test_collector_matches_oracle(pb, pymcts):
+    P, tree, L, seed, base = 8, 16, 12, 23, 700
+    noise = NoiseSource(P)
+    oc = pymcts.OracleCollector(tree, L, 0.99, P, seed, base, np_evaluator, noise.oracle)
+    cfg = pb.alphazero.AlphaZeroConfig(tree, L, 0.99, P)
+    gc = pb.alphazero.BatchedExperienceCollector(torch_eval(np_evaluator), cfg, device="cuda:0", seed=seed,
+                                                 env_id_base=base, noise_fn=noise.torch_fn)
+    total = 0
+    for call in range(6):
+        items = oc.generate_experience()
+        batch = gc.generate_experience()
+        assert len(batch) == len(items), f"call {call}: number of items"
+        total += len(items)
+        assert np.array_equal(items["action_mask"].astype(bool), batch.action_mask.cpu().numpy()), f"call {call} masks"
+        assert np.array_equal(bits(items["value"]), bits(batch.value.cpu().numpy())), f"call {call} values"
+        assert np.array_equal(bits(items["action_distribution"]),
+                              bits(batch.action_distribution.cpu().numpy())), f"call {call} distributions"
+        assert_obs_equal(items["obs"], batch.obs.cpu().numpy(), f"call {call} observations")
+        # the compact replay form: the snapshot states re-encode to the same observations
+        out = torch.empty_like(batch.obs)
+        stage = pb.BatchedPacmanGym(len(batch), False, False, device="cuda:0")
+        stage.copy_envs_from(gc.snap, src_index=batch.state_slots)
+        assert torch.equal(stage.obs(out), batch.obs)
+    assert total >= 6
+    assert_states_equal(oc.export_state(), gc.env.get_state(), "collector envs at the end")
+    assert np.array_equal(noise.calls_oracle, noise.calls_gpu)
+
+
+def test_mcts_context_drop_in_surface(pb):
+    """MCTSContext with the reference's NumPy evaluator (pacbot_rs.pyi:26-41), as
+    train_alphazero.py:119-131 drives it."""
+    calls = []
+
+    def evaluator(obs, mask):
+        assert isinstance(obs, np.ndarray) and obs.dtype == np.float32 and obs.shape[1:] == (17, 28, 31)
+        assert isinstance(mask, np.ndarray) and mask.dtype == np.bool_ and mask.shape[1:] == (5,)
+        calls.append(obs.shape[0])
+        return uniform_evaluator(obs, mask)
+
+    gym = pb.PacmanGym(random_start=True, random_ticks=False, device="cuda:0", seed=2)
+    gym.reset()
+    mc = pb.mcts.MCTSContext(gym, evaluator)
+    assert mc.node_count() == 1 and mc.max_depth() == 0 and calls
+    with pytest.raises(RuntimeError):
+        mc.action_distribution()        # assert!(self.root.visit_count > 1)
+    mc.reset()
+    steps = 0
+    while steps < 5:
+        action = mc.ponder_and_choose(24)
+        assert mc.node_count() == 24 and isinstance(action, int) and mc.env.action_mask()[action]
+        assert abs(sum(mc.action_distribution()) - 1.0) < 1e-6
+        assert len(mc.policy_prior()) == 5 and len(mc.action_values()) == 5
+        assert isinstance(mc.value(), float) and mc.max_depth() >= 1
+        assert mc.root_obs_numpy().shape == (17, 28, 31)
+        score_before = mc.env.score()
+        reward, done = mc.take_action(action)
+        assert isinstance(reward, int) and isinstance(done, bool)
+        assert mc.env.score() >= score_before
+        steps += 1
+        if done:
+            break
+    # the caller's env object was copied, not captured (pyo3 extracts PacmanGym by value)
+    assert gym.score() == 0
+    with pytest.raises(ValueError):
+        mc.take_action(7)
+    mc.evaluator = uniform_evaluator    # #[pyo3(get, set)] evaluator
+    mc.ponder_and_choose(30)
+
+
+def test_experience_collector_drop_in_surface(pb):
+    cfg = pb.alphazero.AlphaZeroConfig(tree_size=10, max_episode_length=6, discount_factor=0.99,
+                                       num_parallel_envs=4)
+    assert "tree_size: 10" in repr(cfg)
+    col = pb.alphazero.ExperienceCollector(uniform_evaluator, cfg, device="cuda:0", seed=1)
+    items = col.generate_experience()
+    assert col.config is cfg and len(items) >= 1
+    it = items[0]
+    assert it.obs.shape == (17, 28, 31) and it.obs.dtype == np.float32
+    assert len(it.action_mask) == 5 and all(isinstance(b, bool) for b in it.action_mask)
+    assert isinstance(it.value, float) and len(it.action_distribution) == 5
