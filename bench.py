@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-dqn", action="store_true")
     ap.add_argument("--dqn-iters", type=int, default=200)
+    ap.add_argument("--no-mcts", action="store_true")
+    ap.add_argument("--mcts-steps", type=int, default=400, help="search iterations timed in the mcts leg")
     return ap.parse_args()
 
 
@@ -104,6 +106,59 @@ def dqn_throughput(dev, seed: int, iters: int, graph: bool = True):
             "config": "train_dqn defaults: batch 512, 32 envs, 4 experience steps/iter, buffer "
                       "10k, QNetV2 fp32 (cuDNN, NHWC weights), double DQN, Adam",
             "loss": m["loss"]}
+
+
+def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, graph: bool,
+                    cpu_steps: int = 0):
+    """the AlphaZero experience collector (alphazero.rs generate_experience_step:
+    one MCTS search iteration per tree -- select, leaf observation encode, NetV2 evaluation,
+    backprop -- plus the env steps / re-roots / resets that become due), simulations per second."""
+    import torch
+
+    from pacbot_rl_b200 import alphazero, models
+
+    model = models.NetV2((17, 28, 31), 6).to(dev).use_channels_last().eval()
+
+    @torch.no_grad()
+    def evaluator(obs, mask):  # train_alphazero.py:83-95 (reward_scale 1/100)
+        pred = model(obs)
+        return pred[:, -1] * 100.0, torch.softmax(pred[:, :-1].masked_fill(~mask, -torch.inf), dim=-1)
+
+    cfg = alphazero.AlphaZeroConfig(tree_size, 1000, 0.99, num_envs)
+    col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=seed)
+    if graph:
+        col.mcts.enable_cuda_graph()
+    finished: list = []
+    for _ in range(max(10, tree_size)):  # warm-up incl. the first round of env steps
+        col.generate_experience_step(finished)
+    torch.cuda.synchronize(dev)
+    items0 = int(col.ep_len.sum()) + sum(f[1] for f in finished)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        col.generate_experience_step(finished)
+    col.mcts.check()
+    dt = time.perf_counter() - t0
+    items = int(col.ep_len.sum()) + sum(f[1] for f in finished) - items0
+    out = {"sims_per_sec": steps * num_envs / dt, "env_steps_per_sec": items / dt,
+           "search_iterations": steps, "ms_per_iteration": 1e3 * dt / steps, "cuda_graph": graph,
+           "config": f"{num_envs} trees x tree_size {tree_size}, NetV2 fp32 evaluator (cuDNN, NHWC) on "
+                     "device-resident leaf observations, Dirichlet root noise, max_episode_length 1000"}
+    if cpu_steps:
+        import ctypes as C
+
+        from oracle import pymcts
+
+        L = pymcts.lib()
+        L.pm_collector_bench.restype = C.c_double
+        L.pm_collector_bench.argtypes = [pymcts._Config, C.c_uint64, C.c_int64, C.POINTER(C.c_int64)]
+        n_items = C.c_int64(0)
+        secs = L.pm_collector_bench(pymcts._Config(tree_size, 1000, 0.99, num_envs), seed, cpu_steps,
+                                    C.byref(n_items))
+        out["cpu_port_sims_per_sec"] = cpu_steps * num_envs / secs
+        out["cpu_port_note"] = ("C restatement of mcts.rs/alphazero.rs (oracle/), 1 thread, tree + env "
+                                "+ leaf observation encode only: its evaluator is the constant "
+                                "untrained-model branch, no network")
+    return out
 
 
 class ClockSampler:
@@ -460,6 +515,11 @@ def main():
     if world == 1 and not args.no_dqn:
         line["dqn"] = dqn_throughput(dev, args.seed, args.dqn_iters, graph=True)
         line["dqn_eager"] = dqn_throughput(dev, args.seed, args.dqn_iters, graph=False)
+    if world == 1 and not args.no_mcts:
+        cpu_steps = 0 if args.no_cpu_baseline else 400
+        line["mcts"] = mcts_throughput(dev, args.seed, 128, 100, args.mcts_steps, True, cpu_steps)
+        line["mcts_eager"] = mcts_throughput(dev, args.seed, 128, 100, max(50, args.mcts_steps // 4), False)
+        line["mcts_4096"] = mcts_throughput(dev, args.seed, 4096, 100, max(50, args.mcts_steps // 4), True)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_envs, args.cpu_sample_steps,
                                             os.cpu_count() or 1, args.seed)

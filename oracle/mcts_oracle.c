@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ---- counter RNG (include/pacbot_b200.h "Counter RNG") ------------------------------------ */
 static uint64_t mix64(uint64_t z) {
@@ -425,6 +426,39 @@ static void generate_experience_step(pm_collector *c) { /* alphazero.rs:97-196 *
         int64_t nodes = pm_node_count(b, i);
         e->num_search_iters_remaining = c->cfg.tree_size > nodes ? c->cfg.tree_size - nodes : 0;
     }
+}
+
+/* ---- CPU baseline (bench.py "mcts" leg): collector with the untrained-model evaluator --------- */
+/* train_alphazero.py:97-101: value 0, policy = mask / sum(mask) */
+void pm_eval_uniform(void *ctx, int64_t tree, const float *obs, const uint8_t *mask, float *value,
+                     float *policy) {
+    (void)ctx; (void)tree; (void)obs;
+    int k = 0;
+    for (int a = 0; a < 5; a++) k += mask[a] ? 1 : 0;
+    *value = 0.0f;
+    for (int a = 0; a < 5; a++) policy[a] = mask[a] ? 1.0f / (float)k : 0.0f;
+}
+void pm_noise_uniform(void *ctx, int64_t tree, int num_valid, float *noise) {
+    (void)ctx; (void)tree;
+    for (int k = 0; k < num_valid; k++) noise[k] = 1.0f / (float)num_valid;
+}
+/* runs `steps` generate_experience_steps (each = one search iteration of every tree, leaf
+ * observation encode included, plus the env steps that become due); returns seconds */
+double pm_collector_bench(pm_config cfg, uint64_t seed, int64_t steps, int64_t *env_steps) {
+    pm_collector *c = pm_collector_create(cfg, seed, 0, pm_eval_uniform, NULL, pm_noise_uniform, NULL);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int64_t items = 0;
+    for (int64_t s = 0; s < steps; s++) {
+        generate_experience_step(c);
+        items += c->final_len;
+        c->final_len = 0;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int64_t i = 0; i < cfg.num_parallel_envs; i++) items += c->envs[i].len;
+    if (env_steps) *env_steps = items;
+    pm_collector_destroy(c);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 int64_t pm_collector_generate(pm_collector *c, const pm_item **items) { /* alphazero.rs:86-92 */

@@ -99,6 +99,13 @@ void pm_collector_destroy(pm_collector *c);
 int64_t pm_collector_generate(pm_collector *c, const pm_item **items);
 pm_batch *pm_collector_batch(pm_collector *c);
 
+/* CPU baseline of bench.py's "mcts" leg: the collector with the untrained-model evaluator
+ * (train_alphazero.py:97-101) and uniform root noise, single thread */
+void pm_eval_uniform(void *ctx, int64_t tree, const float *obs, const uint8_t *mask, float *value,
+                     float *policy);
+void pm_noise_uniform(void *ctx, int64_t tree, int num_valid, float *noise);
+double pm_collector_bench(pm_config cfg, uint64_t seed, int64_t steps, int64_t *env_steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ class BatchedMCTS:
         check(self._L.pb_mcts_create(C.byref(self._h), env._h, self.sim._h, self.max_nodes))
         dev = self.device
         self._obs = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev)
+        self._leaf_obs = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev)
+        self._graph = None
         self._leaf_kind = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._leaf_mask = torch.zeros((n, NUM_ACTIONS), dtype=torch.uint8, device=dev)
         self._value = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -155,12 +157,33 @@ class BatchedMCTS:
     def search_iteration(self, active: Optional[torch.Tensor] = None) -> None:
         """One select -> evaluate -> backprop round for every active tree (the loop body of
         ponder_and_choose, mcts.rs:213-221; one generate_experience_step, alphazero.rs:106-145)."""
+        if active is None and self._graph is not None:
+            self._graph.replay()
+            return
         a = self._mask_u8(active)
         check(self._L.pb_mcts_select(self._h, self._p(a), self._p(self._leaf_kind),
                                      self._p(self._leaf_mask), self._stream()))
-        leaf_obs = self.sim.obs(out=self._obs)
+        leaf_obs = self.sim.obs(out=self._leaf_obs)
         value, policy = self._evaluate(leaf_obs, self._leaf_mask.view(torch.bool))
         check(self._L.pb_mcts_backprop(self._h, self._p(value), self._p(policy), self._stream()))
+
+    def enable_cuda_graph(self) -> None:
+        """Capture select -> encode -> evaluator -> backprop (all trees active) in ONE CUDA graph;
+        search_iteration() without a mask then replays it.  The evaluator must be capturable (no
+        host sync, static shapes) and must read its weights in place.  The warm-up runs with every
+        tree inactive: trees are untouched, only the epoch counter (simulation RNG stream)
+        advances."""
+        idle = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.search_iteration(idle)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.search_iteration(None)
+        self._graph = graph
 
     def ponder(self, max_tree_size: int) -> torch.Tensor:
         """ponder_and_choose (mcts.rs:208-224) for all trees: grow every tree to `max_tree_size`

@@ -61,3 +61,41 @@ class QNetV2(nn.Module):
         value = self.value_head(feat)
         adv = self.advantage_head(feat)
         return value - adv.mean(dim=1, keepdim=True) + adv
+
+
+class NetV2(nn.Module):
+    """The AlphaZero network (reference models.py:113-147): QNetV2's trunk with one linear head of
+    `output_dim` outputs (5 policy logits + 1 value, train_alphazero.py:75), last layer zero
+    initialised.  Same module indices as the reference (`network.{0,2,5,8,11,15,17}`) so that
+    `torch.save(model)` / state dicts interchange."""
+
+    def __init__(self, obs_shape, output_dim: int) -> None:
+        super().__init__()
+        in_ch = int(obs_shape[0])
+        layers: list[nn.Module] = [nn.Conv2d(in_ch, 16, 5, padding="same"), nn.SiLU()]
+        for cin, cout in ((16, 32), (32, 64), (64, 128)):
+            layers += [nn.Conv2d(cin, cout, 3, padding="same"), nn.MaxPool2d(2, ceil_mode=True), nn.SiLU()]
+        layers += [
+            nn.Conv2d(128, 128, 3, groups=128 // 16, padding="same"),
+            nn.AdaptiveMaxPool2d((1, 1)),
+            nn.Flatten(),
+            nn.SiLU(),
+            nn.Linear(128, 256),
+            nn.SiLU(),
+            nn.Linear(256, output_dim),
+        ]
+        self.network = nn.Sequential(*layers)
+        init_orthogonal(self)
+        with torch.no_grad():
+            self.network[-1].weight.zero_()
+            self.network[-1].bias.zero_()
+
+    def use_channels_last(self) -> "NetV2":
+        self.to(memory_format=torch.channels_last)
+        self._channels_last = True
+        return self
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_channels_last", False):
+            obs = obs.contiguous(memory_format=torch.channels_last)
+        return self.network(obs)

@@ -234,3 +234,31 @@ def test_experience_collector_drop_in_surface(pb):
     assert it.obs.shape == (17, 28, 31) and it.obs.dtype == np.float32
     assert len(it.action_mask) == 5 and all(isinstance(b, bool) for b in it.action_mask)
     assert isinstance(it.value, float) and len(it.action_distribution) == 5
+
+
+def test_alphazero_trainer_short_run(pb, tmp_path):
+    """train_alphazero mirror end to end: collect with MCTS, state-replay, encode-on-sample,
+    two optimiser iterations, greedy evaluation, checkpoint in the reference's format."""
+    from pacbot_rl_b200 import train_alphazero as ta
+
+    args = ta.build_parser().parse_args([
+        "--device", "cuda:0", "--num_iters", "2", "--batch_size", "32", "--train_instances_per_iter", "64",
+        "--num_parallel_envs", "8", "--experience_steps", "16", "--experience_buffer_size", "64",
+        "--tree_size", "8", "--max_episode_length", "10", "--eval_envs", "4",
+        "--checkpoint-dir", str(tmp_path / "ckpt"), "--metrics-file", str(tmp_path / "m.jsonl")])
+    tr = ta.AlphaZeroTrainer(args)
+    assert sum(p.numel() for p in tr.model.parameters()) == 156_934 - 256 - 1 - 5 * 256 - 5 + 6 * 256 + 6
+    w0 = tr.model.network[0].weight.detach().clone()
+    tr.train()
+    assert tr.has_model_updated and len(tr.buffer) == 64
+    assert not torch.equal(w0, tr.model.network[0].weight)
+    rows = [__import__("json").loads(l) for l in open(tmp_path / "m.jsonl")]
+    assert len(rows) == 2 and all(np.isfinite(r["avg_loss"]) for r in rows)
+    assert rows[0]["eval_episode_steps"] >= 1
+    model = torch.load(tmp_path / "ckpt" / "model-latest.pt", weights_only=False)
+    assert sorted(k for k in model.state_dict() if k.endswith("weight")) == [
+        f"network.{i}.weight" for i in (0, 11, 15, 17, 2, 5, 8)]
+    # sampled observations are exactly the encoder's output for the stored states
+    obs, mask, value, dist = tr.buffer.sample(32)
+    assert obs.shape == (32, 17, 28, 31) and torch.isfinite(obs).all()
+    assert (dist[~mask] == 0).all() and torch.allclose(dist.sum(1), torch.ones(32, device="cuda:0"), atol=1e-5)
