@@ -127,18 +127,18 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
     cfg = alphazero.AlphaZeroConfig(tree_size, 1000, 0.99, num_envs)
     col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=seed)
     if graph:
-        col.mcts.enable_cuda_graph()
+        col.enable_cuda_graph()
     finished: list = []
     for _ in range(max(10, tree_size)):  # warm-up incl. the first round of env steps
         col.generate_experience_step(finished)
     torch.cuda.synchronize(dev)
-    items0 = int(col.ep_len.sum()) + sum(f[1] for f in finished)
+    items0 = int(col.ep_len.sum()) + sum(int(f[0].numel()) for f in finished)
     t0 = time.perf_counter()
     for _ in range(steps):
         col.generate_experience_step(finished)
     col.mcts.check()
     dt = time.perf_counter() - t0
-    items = int(col.ep_len.sum()) + sum(f[1] for f in finished) - items0
+    items = int(col.ep_len.sum()) + sum(int(f[0].numel()) for f in finished) - items0
     out = {"sims_per_sec": steps * num_envs / dt, "env_steps_per_sec": items / dt,
            "search_iterations": steps, "ms_per_iteration": 1e3 * dt / steps, "cuda_graph": graph,
            "config": f"{num_envs} trees x tree_size {tree_size}, NetV2 fp32 evaluator (cuDNN, NHWC) on "

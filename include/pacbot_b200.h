@@ -271,6 +271,21 @@ int pb_mcts_backprop(pb_mcts *m, const float *value_dev, const float *policy_dev
  * panics), 5 action > 4 (untouched). */
 int pb_mcts_take_action(pb_mcts *m, const uint8_t *mask_dev, const uint8_t *actions_dev,
                         int32_t *reward_dev, uint8_t *done_dev, uint8_t *status_dev, void *stream);
+/* The env-step half of ExperienceCollector::generate_experience_step (alphazero.rs:141-195) for
+ * all trees in one launch.  remaining_dev int32 [n] (search iterations left before the tree
+ * acts) is decremented; a tree that reaches 0 stores its ExperienceItem at slot
+ * i * max_episode_length + ep_len_dev[i] -- the env STATE into engine `snap` (which needs
+ * n * max_episode_length envs; encode it later instead of keeping a 59 KB observation),
+ * ep_mask_dev uint8 [n][L][5], ep_dist_dev float32 [n][L][5] (visit distribution), ep_value_dev
+ * float32 [n][L] (the reward) -- then plays its most visited action like pb_mcts_take_action,
+ * increments ep_len_dev[i] and, if it was re-rooted, sets remaining_dev[i] = tree_size - nodes.
+ * status_dev uint8 [n]: the pb_mcts_take_action status, plus 8 if the episode hit
+ * max_episode_length without ending.  *flags_dev (uint32, or-ed): bit 0 an episode ended (done or
+ * truncated: the caller finalises it and resets the env), bit 1 a tree needs a fresh root. */
+int pb_mcts_collect_act(pb_mcts *m, pb_engine *snap, int max_episode_length, int tree_size,
+                        int32_t *remaining_dev, int32_t *ep_len_dev, uint8_t *ep_mask_dev,
+                        float *ep_dist_dev, float *ep_value_dev, uint8_t *status_dev,
+                        uint32_t *flags_dev, void *stream);
 /* Per-tree getters (mcts.rs:173-243) */
 #define PB_MCTS_Q_BEST_ACTION 0         /* int32 [n]: most visited valid child, ties -> last */
 #define PB_MCTS_Q_ACTION_DISTRIBUTION 1 /* float32 [n][5]: child visits / (root visits - 1) */

@@ -16,9 +16,9 @@ from typing import Callable, Optional
 import numpy as np
 import torch
 
-from ._lib import NUM_ACTIONS, OBS_SHAPE
+from ._lib import NUM_ACTIONS, OBS_SHAPE, check
 from .engine import BatchedPacmanGym
-from .mcts import BatchedMCTS, numpy_evaluator_adapter
+from .mcts import ST_DONE, ST_NEEDS_ROOT, ST_REROOTED, ST_WAS_DONE, BatchedMCTS, numpy_evaluator_adapter
 
 
 class AlphaZeroConfig:
@@ -61,14 +61,20 @@ class ExperienceBatch:
     action_mask: torch.Tensor              # bool [K,5]
     value: torch.Tensor                    # float32 [K]
     action_distribution: torch.Tensor      # float32 [K,5]
-    state_slots: torch.Tensor              # int64 [K]: slots of the snapshot engine holding the states
+    state_engine: BatchedPacmanGym         # engine holding the K env states ...
+    state_slots: torch.Tensor              # ... at these slots (int64 [K]); valid until the next call
 
     def __len__(self) -> int:
         return int(self.value.shape[0])
 
 
 class BatchedExperienceCollector:
-    """ExperienceCollector (alphazero.rs:58-197) with device-resident trees, envs and episodes."""
+    """ExperienceCollector (alphazero.rs:58-197) with device-resident trees, envs and episodes.
+
+    One generate_experience_step = one search iteration of every tree (BatchedMCTS) + ONE kernel
+    for the env steps that became due (pb_mcts_collect_act: experience record, take_action, next
+    search budget) + root noise for the re-rooted trees; the host reads one flag word per step
+    and only gets involved when an episode ended."""
 
     def __init__(self, evaluator: Callable, config: AlphaZeroConfig, *, device=None, seed: int = 0,
                  env_id_base: int = 0, noise_fn: Optional[Callable] = None) -> None:
@@ -82,85 +88,133 @@ class BatchedExperienceCollector:
         self.mcts.reset_root()  # MCTSContext::new -> reset_root
         dev = self.device
         self.remaining = torch.full((P,), config.tree_size - 1, dtype=torch.int32, device=dev)
-        # unfinished episodes: states in a snapshot engine (slot = env * L + t) + small tensors
+        # unfinished episodes: states in a snapshot engine (slot = env * L + t) + small tensors;
+        # finished ones move to the outbox engine until they are handed out
         self.snap = BatchedPacmanGym(P * L, False, False, device=dev, seed=seed, env_id_base=env_id_base)
+        self.outbox = BatchedPacmanGym(P * L, False, False, device=dev, seed=seed, env_id_base=env_id_base)
         self.ep_mask = torch.zeros((P, L, NUM_ACTIONS), dtype=torch.bool, device=dev)
         self.ep_dist = torch.zeros((P, L, NUM_ACTIONS), dtype=torch.float32, device=dev)
         self.ep_value = torch.zeros((P, L), dtype=torch.float32, device=dev)
-        self.ep_len = np.zeros(P, np.int64)  # host mirror (the step loop reads flags anyway)
+        self.ep_len = torch.zeros(P, dtype=torch.int32, device=dev)
+        self._status = torch.zeros(P, dtype=torch.uint8, device=dev)
+        self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._graph = None
+        self._pending: list = []   # finished episodes not handed out yet
+        self._out_count = 0
         self.search_iterations = 0
+
+    # ------------------------------------------------------------------ device part of a step
+    def _device_step(self) -> None:
+        cfg = self.config
+        p = BatchedMCTS._p
+        self.mcts.search_iteration()
+        check(self.mcts._L.pb_mcts_collect_act(
+            self.mcts._h, self.snap._h, cfg.max_episode_length, cfg.tree_size, p(self.remaining),
+            p(self.ep_len), p(self.ep_mask), p(self.ep_dist), p(self.ep_value), p(self._status),
+            p(self._flags), self.mcts._stream()))
+        # take_action re-rooted these trees: root noise (mcts.rs:160-163)
+        self.mcts.add_root_noise((self._status & 7) == ST_REROOTED)
+
+    def enable_cuda_graph(self) -> None:
+        """Capture the device part of a step (search iteration, env steps, root noise) in ONE CUDA
+        graph.  Needs a capturable evaluator and the built-in Dirichlet noise.  The warm-up
+        consists of three ordinary steps; episodes they finish are handed out by the next
+        generate_experience()."""
+        if self.mcts.noise_fn is not None:
+            raise ValueError("a host noise_fn cannot be captured in a CUDA graph")
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.generate_experience_step(self._pending)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._device_step()
+        self._graph = graph
+
+    # ------------------------------------------------------------------ host part of a step
+    def _finish(self, finished: list) -> None:
+        """Episodes that ended in this step (alphazero.rs:163-184) and trees that need a fresh
+        root (mcts.rs:164-166)."""
+        cfg, P, L = self.config, self.config.num_parallel_envs, self.config.max_episode_length
+        dev = self.device
+        status = self._status.cpu().numpy()
+        st = status & 7
+        if (st == ST_WAS_DONE).any():
+            raise RuntimeError("collector stepped a finished env (assert!(!is_done) in the reference)")
+        needs_root = st == ST_NEEDS_ROOT
+        if needs_root.any():
+            idx = torch.from_numpy(np.nonzero(needs_root)[0]).to(dev)
+            self.mcts.reset_root(torch.from_numpy(needs_root).to(dev), idx)
+            self.remaining[idx] = cfg.tree_size - 1
+        ended = np.nonzero((st == ST_DONE) | ((status & 8) != 0))[0]
+        if ended.size == 0:
+            return
+        ep_len = self.ep_len.cpu().numpy()
+        truncated = [int(i) for i in ended if status[i] & 8]
+        if truncated:  # bootstrap from the new root's value (:180-184): one mul, one add
+            ti = torch.tensor(truncated, device=dev)
+            tl = torch.from_numpy(ep_len[truncated].astype(np.int64) - 1).to(dev)
+            boot = self.mcts.value()[ti] * cfg.discount_factor
+            self.ep_value[ti, tl] = self.ep_value[ti, tl] + boot
+        for i in (int(i) for i in ended):  # end_episode (:163-176), env order
+            n = int(ep_len[i])
+            values = self.ep_value[i, :n].cpu().numpy()
+            nxt = np.float32(0.0)
+            disc = np.float32(cfg.discount_factor)
+            for k in range(n - 1, -1, -1):
+                values[k] = values[k] + disc * nxt
+                nxt = values[k]
+            # the snapshot slots are reused by this env's next episode: move the states out
+            src = torch.arange(i * L, i * L + n, device=dev)
+            dst = torch.arange(self._out_count, self._out_count + n, device=dev)
+            self.outbox.copy_envs_from(self.snap, src_index=src, dst_index=dst)
+            finished.append((dst, torch.from_numpy(values).to(dev), self.ep_mask[i, :n].clone(),
+                             self.ep_dist[i, :n].clone()))
+            self._out_count += n
+        ei = torch.from_numpy(ended).to(dev)
+        em = torch.zeros(P, dtype=torch.bool, device=dev)
+        em[ei] = True
+        self.ep_len[ei] = 0
+        self.mcts.reset(em, ei)  # mcts_context.reset(): env.reset + fresh root
+        self.remaining[ei] = cfg.tree_size - 1   # tree_size - node_count() of a fresh tree (:192-193)
 
     # one parallel search iteration + the env steps that became due (alphazero.rs:97-196)
     def generate_experience_step(self, finished: list) -> None:
-        cfg, P, L = self.config, self.config.num_parallel_envs, self.config.max_episode_length
-        self.mcts.search_iteration()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._device_step()
         self.search_iterations += 1
-        self.remaining -= 1
-        act_host = (self.remaining == 0).cpu().numpy()
-        if not act_host.any():
-            return
-        dev = self.device
-        idx_host = np.nonzero(act_host)[0]
-        idx = torch.from_numpy(idx_host).to(dev)
-        act = torch.from_numpy(act_host).to(dev)
-        t = torch.from_numpy(self.ep_len[idx_host]).to(dev)
-        # experience of the acting envs: state snapshot, mask, visit distribution (:147-161)
-        self.snap.copy_envs_from(self.env, src_index=idx, dst_index=idx * L + t)
-        self.ep_mask[idx, t] = self.env.action_mask()[idx]
-        self.ep_dist[idx, t] = self.mcts.action_distribution()[idx]
-        best = self.mcts.best_action()
-        reward, done, _ = self.mcts.take_action(best.to(torch.uint8), mask=act)
-        self.ep_value[idx, t] = reward[idx].to(torch.float32)
-        self.ep_len[idx_host] += 1
-        done_host = done.cpu().numpy()
-        ended = [int(i) for i in idx_host if done_host[i] or self.ep_len[i] >= L]
-        if ended:
-            truncated = [i for i in ended if not done_host[i]]
-            if truncated:  # bootstrap from the new root's value (:180-184): one mul, one add
-                ti = torch.tensor(truncated, device=dev)
-                tl = torch.from_numpy(self.ep_len[truncated] - 1).to(dev)
-                boot = self.mcts.value()[ti] * cfg.discount_factor
-                self.ep_value[ti, tl] = self.ep_value[ti, tl] + boot
-            for i in ended:  # end_episode (:163-176), env order
-                n = int(self.ep_len[i])
-                values = self.ep_value[i, :n].cpu().numpy()
-                nxt = np.float32(0.0)
-                disc = np.float32(cfg.discount_factor)
-                for k in range(n - 1, -1, -1):
-                    values[k] = values[k] + disc * nxt
-                    nxt = values[k]
-                finished.append((i, n, torch.from_numpy(values).to(dev), self.ep_mask[i, :n].clone(),
-                                 self.ep_dist[i, :n].clone()))
-                self.ep_len[i] = 0
-            em = torch.zeros(P, dtype=torch.bool, device=dev)
-            ei = torch.tensor(ended, device=dev)
-            em[ei] = True
-            self.mcts.reset(em, ei)  # mcts_context.reset(): env.reset + fresh root
-        counts = self.mcts.node_count()
-        self.remaining[idx] = (cfg.tree_size - counts[idx]).clamp(min=0)
+        if int(self._flags.item()):  # the one host read per step
+            self._flags.zero_()
+            self._finish(finished)
 
     def generate_experience(self, materialize_obs: bool = True) -> ExperienceBatch:
         """generate_experience (alphazero.rs:86-92): at least one finished episode."""
-        L = self.config.max_episode_length
-        finished: list = []
-        pending_obs = []
+        finished, self._pending = self._pending, []
+        if not finished:
+            self._out_count = 0
         while not finished:
             self.generate_experience_step(finished)
-            # the snapshot slots of an ended episode are reused by that env's next episode, so
-            # encode its observations before searching on
-            if materialize_obs:
-                for (i, n, *_rest) in finished[len(pending_obs):]:
-                    out = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=self.device)
-                    pending_obs.append(self.snap.obs_range(i * L, n, out))
-        dev = self.device
-        slots = torch.cat([torch.arange(i * L, i * L + n, device=dev) for (i, n, *_r) in finished])
-        return ExperienceBatch(
-            obs=torch.cat(pending_obs) if materialize_obs else None,
-            action_mask=torch.cat([f[3] for f in finished]),
-            value=torch.cat([f[2] for f in finished]),
-            action_distribution=torch.cat([f[4] for f in finished]),
+        self._pending = []
+        slots = torch.cat([f[0] for f in finished])
+        obs = None
+        if materialize_obs:  # the outbox is filled front to back: one encode launch
+            k = self._out_count
+            obs = torch.empty((k,) + OBS_SHAPE, dtype=torch.float32, device=self.device)
+            self.outbox.obs_range(0, k, obs)
+        batch = ExperienceBatch(
+            obs=obs,
+            action_mask=torch.cat([f[2] for f in finished]),
+            value=torch.cat([f[1] for f in finished]),
+            action_distribution=torch.cat([f[3] for f in finished]),
+            state_engine=self.outbox,
             state_slots=slots,
         )
+        self._out_count = 0  # the next call overwrites the outbox
+        return batch
 
 
 class ExperienceCollector:

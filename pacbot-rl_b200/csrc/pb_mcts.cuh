@@ -266,50 +266,24 @@ k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__rest
 // take_action (mcts.rs:153-170): step the real env; keep the chosen child's subtree as the new
 // tree (compacting copy into the other pool) or ask for a fresh root
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MCTS_THREADS)
-k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__restrict__ mask,
-                   const uint8_t *__restrict__ actions, int32_t *__restrict__ reward,
-                   uint8_t *__restrict__ done_out, uint8_t *__restrict__ status) {
-    __shared__ uint32_t s_walls[32];
-    load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
-    if (i >= v.n) return;
-    if (mask && !mask[i]) {
-        status[i] = MCTS_ST_UNTOUCHED;
-        return;
-    }
-    reward[i] = 0;
-    done_out[i] = 0;
+__device__ __forceinline__ int mcts_take_action(const MctsView &v, const StateView &root,
+                                                const RngParams &rp, const uint32_t *s_walls,
+                                                long long i, int a, int &rew, bool &done) {
+    rew = 0;
+    done = false;
     EnvR s;
     load_env(root, i, s);
-    if (is_done(s)) {
-        status[i] = MCTS_ST_WAS_DONE;
-        return;
-    }
-    const int a = actions[i];
-    if (a > 4) {
-        status[i] = MCTS_ST_BAD_ACTION;
-        return;
-    }
+    if (is_done(s)) return MCTS_ST_WAS_DONE;
+    if (a > 4) return MCTS_ST_BAD_ACTION;
     const PelRef pel{root.pel + i, root.npad};
     const RngCtx rng = make_rng(rp, i);
-    int rew;
-    bool done;
     gym_step(s, pel, c_tab, s_walls, rng, a, rew, done);
     store_env(root, i, s);
-    reward[i] = rew;
-    done_out[i] = done ? 1 : 0;
-    if (done) {
-        status[i] = MCTS_ST_DONE;
-        return;
-    }
+    if (done) return MCTS_ST_DONE;
     const int which = v.cur[i];
     const MctsNode *old_nodes = v.nodes(i, which);
     const int c = old_nodes[0].child[a];
-    if (c < 0) {
-        status[i] = MCTS_ST_NEEDS_ROOT;
-        return;
-    }
+    if (c < 0) return MCTS_ST_NEEDS_ROOT;
     // self.root = *child: copy the subtree into the other pool, depth first, new root at index 0
     MctsNode *new_nodes = v.nodes(i, which ^ 1);
     int32_t *stack = v.stack + i * v.M;
@@ -331,7 +305,99 @@ k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__re
     }
     v.cur[i] = which ^ 1;
     v.n_nodes[i] = count;
-    status[i] = MCTS_ST_REROOTED;
+    return MCTS_ST_REROOTED;
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__restrict__ mask,
+                   const uint8_t *__restrict__ actions, int32_t *__restrict__ reward,
+                   uint8_t *__restrict__ done_out, uint8_t *__restrict__ status) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n) return;
+    if (mask && !mask[i]) {
+        status[i] = MCTS_ST_UNTOUCHED;
+        return;
+    }
+    int rew;
+    bool done;
+    status[i] = (uint8_t)mcts_take_action(v, root, rp, s_walls, i, actions[i], rew, done);
+    reward[i] = rew;
+    done_out[i] = done ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The env-step half of ExperienceCollector::generate_experience_step (alphazero.rs:141-195) for
+// all trees in one launch: count the finished search iteration; a tree whose budget is used up
+// records its experience (state snapshot instead of the 59 KB observation, action mask, visit
+// distribution), plays its most visited action (take_action) and gets its next search budget.
+// Episodes that END here (done, or max_episode_length reached) are flagged for the host, which
+// finalises them (value recursion, hand-out, env reset + fresh root); so are trees that need a
+// fresh root.  Experience slot of (tree i, step t): i * max_len + t.
+// ---------------------------------------------------------------------------------------------
+enum { MCTS_ST_TRUNCATED_BIT = 8 };  // or-ed into the take_action status when the episode is cut
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int max_len,
+                   int tree_size, int32_t *__restrict__ remaining, int32_t *__restrict__ ep_len,
+                   uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
+                   float *__restrict__ ep_value, uint8_t *__restrict__ status,
+                   unsigned int *__restrict__ host_flags) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    if (i >= v.n) return;
+    const int left = remaining[i] - 1;  // alphazero.rs:142
+    remaining[i] = left;
+    if (left != 0) {
+        status[i] = MCTS_ST_UNTOUCHED;
+        return;
+    }
+    const int t = ep_len[i];
+    const long long slot = i * max_len + t;
+    // ExperienceItem (alphazero.rs:145-161): the state stands in for root_obs_numpy()
+    snap.core0[slot] = root.core0[i];
+    snap.core1[slot] = root.core1[i];
+    snap.ghosts[slot] = root.ghosts[i];
+    snap.ghosts[snap.npad + slot] = root.ghosts[root.npad + i];
+    for (int w = 0; w < PEL_WORDS; w++)
+        snap.pel[(long long)w * snap.npad + slot] = root.pel[(long long)w * root.npad + i];
+    EnvR s;
+    load_env(root, i, s);
+    const uint32_t m = action_mask_bits(s, s_walls);
+    const MctsNode *nodes = v.nodes(i, v.cur[i]);
+    const MctsNode r = nodes[0];
+    const float total_child_visits = (float)(r.visit - 1u);  // mcts.rs:180-186
+    int best = -1;
+    uint32_t best_key = 0;
+    for (int a = 0; a < 5; a++) {
+        const uint32_t vis = r.child[a] >= 0 ? nodes[r.child[a]].visit : 0u;
+        ep_mask[slot * 5 + a] = (m >> a) & 1u;
+        ep_dist[slot * 5 + a] = r.child[a] >= 0 ? __fdiv_rn((float)vis, total_child_visits) : 0.0f;
+        if (((m >> a) & 1u) && (best < 0 || vis >= best_key)) {  // best_action, mcts.rs:71-79
+            best = a;
+            best_key = vis;
+        }
+    }
+    int rew;
+    bool done;
+    int st = mcts_take_action(v, root, rp, s_walls, i, best, rew, done);
+    ep_value[slot] = (float)rew;  // alphazero.rs:157
+    ep_len[i] = t + 1;
+    unsigned int flags = 0;
+    if (st == MCTS_ST_DONE) flags |= 1u;
+    if (st != MCTS_ST_DONE && t + 1 >= max_len) {  // alphazero.rs:177-184
+        st |= MCTS_ST_TRUNCATED_BIT;
+        flags |= 1u;
+    }
+    if ((st & 7) == MCTS_ST_NEEDS_ROOT || (st & 7) == MCTS_ST_WAS_DONE) flags |= 2u;
+    if (st == MCTS_ST_REROOTED) {  // alphazero.rs:192-193
+        const int nodes_now = v.n_nodes[i];
+        remaining[i] = tree_size > nodes_now ? tree_size - nodes_now : 0;
+    }
+    status[i] = (uint8_t)st;
+    if (flags) atomicOr(host_flags, flags);
 }
 
 // ---------------------------------------------------------------------------------------------

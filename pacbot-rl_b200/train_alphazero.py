@@ -86,12 +86,12 @@ class ExperienceBuffer:
     def __len__(self) -> int:
         return self.size
 
-    def extend(self, batch, snapshot_engine: BatchedPacmanGym) -> None:
+    def extend(self, batch) -> None:
         k = len(batch)
         if k > self.capacity:  # a deque keeps the newest maxlen items
             raise ValueError("more new items than the buffer holds")
         slots = (self.head + torch.arange(k, device=self.device)) % self.capacity
-        self.states.copy_envs_from(snapshot_engine, src_index=batch.state_slots, dst_index=slots)
+        self.states.copy_envs_from(batch.state_engine, src_index=batch.state_slots, dst_index=slots)
         self.action_mask[slots] = batch.action_mask
         self.value[slots] = batch.value
         self.action_distribution[slots] = batch.action_distribution
@@ -169,7 +169,7 @@ class AlphaZeroTrainer:
         while self.num_exp_steps_needed > 0:
             batch = self.collector.generate_experience(materialize_obs=False)
             self.num_exp_steps_needed -= len(batch)
-            self.buffer.extend(batch, self.collector.snap)
+            self.buffer.extend(batch)
             collected += len(batch)
         return collected
 

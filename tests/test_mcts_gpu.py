@@ -175,7 +175,7 @@ def test_collector_matches_oracle(pb, pymcts):
         # the compact replay form: the snapshot states re-encode to the same observations
         out = torch.empty_like(batch.obs)
         stage = pb.BatchedPacmanGym(len(batch), False, False, device="cuda:0")
-        stage.copy_envs_from(gc.snap, src_index=batch.state_slots)
+        stage.copy_envs_from(batch.state_engine, src_index=batch.state_slots)
         assert torch.equal(stage.obs(out), batch.obs)
     assert total >= 6
     assert_states_equal(oc.export_state(), gc.env.get_state(), "collector envs at the end")

@@ -1,0 +1,48 @@
+"""Where does a collector step (one MCTS search iteration of every tree + due env steps) spend its
+GPU time?  torch.profiler kernel table for the eager step, wall time per step eager vs graph.
+Run on the GPU box: python tools/profile_mcts.py [num_trees]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from pacbot_rl_b200 import alphazero, models
+
+dev = torch.device("cuda:0")
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+model = models.NetV2((17, 28, 31), 6).to(dev).use_channels_last().eval()
+
+@torch.no_grad()
+def evaluator(obs, mask):
+    pred = model(obs)
+    return pred[:, -1] * 100.0, torch.softmax(pred[:, :-1].masked_fill(~mask, -torch.inf), dim=-1)
+
+def make():
+    return alphazero.BatchedExperienceCollector(evaluator, alphazero.AlphaZeroConfig(100, 1000, 0.99, P), device=dev)
+
+def wall(col, steps=300):
+    fin = []
+    for _ in range(120):
+        col.generate_experience_step(fin)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(steps):
+        col.generate_experience_step(fin)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps * 1e3
+
+col = make()
+print(f"{P} trees, eager step: {wall(col):.3f} ms")
+fin = []
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(50):
+        col.generate_experience_step(fin)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
+colg = make(); colg.enable_cuda_graph()
+print(f"{P} trees, graph step: {wall(colg):.3f} ms")
+# the search iteration alone (no env steps, no host read)
+m = colg.mcts
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(300):
+    m._graph.replay() if m._graph is not None else m.search_iteration()
+torch.cuda.synchronize()
+print(f"search iteration only (eager launches): {(time.perf_counter() - t0) / 300 * 1e3:.3f} ms")
