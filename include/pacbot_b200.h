@@ -236,7 +236,10 @@ int pb_copy_envs(pb_engine *dst, const int64_t *dst_idx_dev, const pb_engine *sr
  * of the same size on the same device: slot i receives the clone of env i that a simulation
  * steps (select_trajectory's env.clone(), mcts.rs:293), so the leaf observation of tree i is
  * pb_encode_obs(sim) row i.  Both engines are borrowed and must outlive the pb_mcts.
- * max_nodes = node capacity per tree (2..32767); a search iteration adds at most one node.
+ * max_nodes = LIVE node capacity per tree (2..32767); a search iteration adds at most one node.
+ * (Physically each tree has two pools of 8 x max_nodes 64-byte nodes: take_action moves the root
+ * index and compacts the kept subtree into the other pool only when the free tail runs short;
+ * env PB_MCTS_POOL_FACTOR overrides the 8.)
  * Simulated env steps draw from the counter RNG with seed sim_seed(seed, epoch) =
  * mix64(seed ^ ((epoch + 1) * 0xd6e8feb86659fd93)), same gid and draw counter as the real env;
  * epoch = number of pb_mcts_backprop calls so far.  All float arithmetic is single IEEE f32

@@ -12,8 +12,9 @@
 //
 // B200 shape: the reference keeps one Box-linked tree per MCTSContext on the host and calls a
 // Python evaluator per leaf (or per batch of leaves, alphazero.rs:106-133), copying every leaf
-// observation host->device.  Here the trees live in HBM as index pools (48-byte nodes, two pools
-// per tree so that re-rooting is a compacting copy), the env clone a simulation steps is a slot
+// observation host->device.  Here the trees live in HBM as index pools (64-byte nodes; re-rooting
+// moves the root index and only occasionally compacts the tree into a second pool, see
+// MctsView), the env clone a simulation steps is a slot
 // of a second engine (`sim`), the leaf observation is written by k_encode_obs straight from that
 // slot, and the evaluator consumes it on the device.  One thread walks one tree: the walk is a
 // dependent chain of node loads and env steps, so trees -- not nodes -- are the parallel axis.
@@ -26,13 +27,15 @@
 
 namespace pb {
 
-struct MctsNode {
+struct __align__(16) MctsNode {
     uint32_t visit;
     float total;
     float prior[5];
     int32_t child[5];  // index into the same pool, -1 = None
+    uint32_t size;     // nodes in this subtree, itself included (node_count(), mcts.rs:104-110)
+    uint32_t pad[3];
 };
-static_assert(sizeof(MctsNode) == 48, "MctsNode is 48 bytes");
+static_assert(sizeof(MctsNode) == 64, "MctsNode is 64 bytes");
 
 constexpr float MCTS_DISCOUNT = 0.99f;          // mcts.rs:15
 constexpr float MCTS_EXPLORATION_RATE = 100.0f; // mcts.rs:59
@@ -52,20 +55,27 @@ enum {
 // error bits (sticky, read by pb_mcts_check)
 enum { MCTS_ERR_POOL_FULL = 1u, MCTS_ERR_EXPAND_TWICE = 2u, MCTS_ERR_ROOT_DONE = 4u };
 
+// Node storage: M physical slots per tree and pool, of which at most L (= max_nodes) are LIVE
+// (reachable from the root).  take_action normally just moves the root index to the chosen child
+// and leaves the rest of the old tree behind as garbage; only when the free tail of the pool
+// could not hold the live-node budget any more is the kept subtree copied, compacted, into the
+// other pool (M = 8 L by default: about one compaction per ten moves instead of one per move).
 struct MctsView {
     MctsNode *pool;            // [2][n][M]
     int32_t *cur;              // [n] pool in use
-    int32_t *n_nodes;          // [n]
+    int32_t *root;             // [n] index of the root node in that pool
+    int32_t *n_alloc;          // [n] slots handed out in that pool (live + garbage)
     int32_t *traj_len;         // [n]
-    int32_t *path;             // [n][M] node at depth k (parent of transition k)
-    uint8_t *traj_act;         // [n][M]
-    int32_t *traj_rew;         // [n][M]
+    int32_t *path;             // [n][L] node at depth k (parent of transition k)
+    uint8_t *traj_act;         // [n][L]
+    int32_t *traj_rew;         // [n][L]
     uint8_t *leaf_kind;        // [n]
-    int32_t *stack;            // [n][M] scratch (re-root, max_depth)
+    int32_t *stack;            // [n][L] scratch (compaction, max_depth)
     unsigned long long *epoch; // number of completed search iterations
     unsigned int *error;       // sticky error bits
     long long n;
-    int M;
+    int M;                     // physical slots per tree and pool
+    int L;                     // live-node capacity (max_nodes)
     __device__ __forceinline__ MctsNode *nodes(long long i, int which) const {
         return pool + ((long long)which * n + i) * M;
     }
@@ -79,6 +89,8 @@ __device__ __forceinline__ void node_init(MctsNode &nd, uint32_t visit, float to
         nd.prior[a] = prior ? prior[a] : 0.0f;
         nd.child[a] = -1;
     }
+    nd.size = 1u;
+    nd.pad[0] = nd.pad[1] = nd.pad[2] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -91,8 +103,9 @@ k_mcts_reset_root(MctsView v, const uint8_t *__restrict__ mask, const float *__r
     if (i >= v.n || (mask && !mask[i])) return;
     MctsNode nd;
     node_init(nd, 1u, value[i], policy + i * 5);
-    v.nodes(i, v.cur[i])[0] = nd;
-    v.n_nodes[i] = 1;
+    v.nodes(i, v.cur[i])[0] = nd;  // the old tree, wherever it was, is dropped
+    v.root[i] = 0;
+    v.n_alloc[i] = 1;
 }
 
 // add_root_policy_noise (mcts.rs:259-281): the k-th VALID action gets noise[i][k]
@@ -106,7 +119,7 @@ k_mcts_root_noise(MctsView v, StateView root, const uint8_t *__restrict__ mask,
     EnvR s;
     load_env(root, i, s);
     const uint32_t m = action_mask_bits(s, s_walls);
-    MctsNode *nd = v.nodes(i, v.cur[i]);
+    MctsNode *nd = v.nodes(i, v.cur[i]) + v.root[i];
     int k = 0;
     for (int a = 0; a < 5; a++) {
         if (!((m >> a) & 1u)) continue;
@@ -171,10 +184,10 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
             rng.tape = nullptr;
             rng.tape_len = 0;
             const MctsNode *nodes = v.nodes(i, v.cur[i]);
-            int32_t *path = v.path + i * v.M;
-            uint8_t *act = v.traj_act + i * v.M;
-            int32_t *rew = v.traj_rew + i * v.M;
-            int node = 0, len = 0;
+            int32_t *path = v.path + i * v.L;
+            uint8_t *act = v.traj_act + i * v.L;
+            int32_t *rew = v.traj_rew + i * v.L;
+            int node = v.root[i], len = 0;
             for (;;) {
                 const MctsNode nd = nodes[node];
                 const int a = mcts_pick_action(nd, nodes, action_mask_bits(s, s_walls));
@@ -193,7 +206,7 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
                     kind = MCTS_NEEDS_EVAL;
                     break;
                 }
-                if (len >= v.M) {  // cannot happen with n_nodes <= M (depth < n_nodes)
+                if (len >= v.L) {  // cannot happen with <= L live nodes (depth < live nodes)
                     atomicOr(v.error, MCTS_ERR_POOL_FULL);
                     kind = MCTS_INACTIVE;
                     break;
@@ -221,9 +234,9 @@ k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__rest
     if (kind == MCTS_INACTIVE) return;
     v.leaf_kind[i] = MCTS_INACTIVE;  // a trajectory is consumed exactly once
     MctsNode *nodes = v.nodes(i, v.cur[i]);
-    const int32_t *path = v.path + i * v.M;
-    const uint8_t *act = v.traj_act + i * v.M;
-    const int32_t *rew = v.traj_rew + i * v.M;
+    const int32_t *path = v.path + i * v.L;
+    const uint8_t *act = v.traj_act + i * v.L;
+    const int32_t *rew = v.traj_rew + i * v.L;
     const int len = v.traj_len[i];
     const int parent = path[len - 1], a_last = act[len - 1];
     int c = nodes[parent].child[a_last];
@@ -237,17 +250,19 @@ k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__rest
     } else {
         subsequent = 0.0f;
     }
+    uint32_t grown = 0u;
     if (c < 0) {
-        c = v.n_nodes[i];
-        if (c >= v.M) {
+        c = v.n_alloc[i];
+        if (c >= v.M || nodes[path[0]].size >= (uint32_t)v.L) {  // physical / live capacity
             atomicOr(v.error, MCTS_ERR_POOL_FULL);
             return;
         }
-        v.n_nodes[i] = c + 1;
+        v.n_alloc[i] = c + 1;
         MctsNode nd;  // SearchTreeNode::new(policy) / new_terminal()
         node_init(nd, 0u, 0.0f, kind == MCTS_NEEDS_EVAL ? policy + i * 5 : nullptr);
         nodes[c] = nd;
         nodes[parent].child[a_last] = c;
+        grown = 1u;  // every node on the path has one more descendant
     }
     int child = c;
     for (int k = len - 1; k >= 0; k--) {
@@ -256,10 +271,11 @@ k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__rest
         nodes[child].total = __fadd_rn(nodes[child].total, this_return);
         subsequent = this_return;
         child = path[k];
+        nodes[child].size += grown;
     }
     // child == path[0] == root
-    nodes[0].visit += 1u;
-    nodes[0].total = __fadd_rn(nodes[0].total, __fmul_rn(MCTS_DISCOUNT, subsequent));
+    nodes[child].visit += 1u;
+    nodes[child].total = __fadd_rn(nodes[child].total, __fmul_rn(MCTS_DISCOUNT, subsequent));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,11 +298,19 @@ __device__ __forceinline__ int mcts_take_action(const MctsView &v, const StateVi
     if (done) return MCTS_ST_DONE;
     const int which = v.cur[i];
     const MctsNode *old_nodes = v.nodes(i, which);
-    const int c = old_nodes[0].child[a];
+    const int c = old_nodes[v.root[i]].child[a];
     if (c < 0) return MCTS_ST_NEEDS_ROOT;
-    // self.root = *child: copy the subtree into the other pool, depth first, new root at index 0
+    // self.root = *child.  Normally that is just a new root index (the old root and its other
+    // subtrees stay behind as garbage); the kept subtree can still grow to L live nodes, so when
+    // the free tail of the pool is shorter than that growth it is compacted into the other pool.
+    const int live = (int)old_nodes[c].size;
+    if (v.M - v.n_alloc[i] >= v.L - live) {
+        v.root[i] = c;
+        return MCTS_ST_REROOTED;
+    }
+    // compacting copy, depth first, new root at index 0
     MctsNode *new_nodes = v.nodes(i, which ^ 1);
-    int32_t *stack = v.stack + i * v.M;
+    int32_t *stack = v.stack + i * v.L;
     new_nodes[0] = old_nodes[c];
     int count = 1, sp = 0;
     stack[sp++] = 0;
@@ -304,7 +328,8 @@ __device__ __forceinline__ int mcts_take_action(const MctsView &v, const StateVi
         }
     }
     v.cur[i] = which ^ 1;
-    v.n_nodes[i] = count;
+    v.root[i] = 0;
+    v.n_alloc[i] = count;
     return MCTS_ST_REROOTED;
 }
 
@@ -367,7 +392,7 @@ k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int
     load_env(root, i, s);
     const uint32_t m = action_mask_bits(s, s_walls);
     const MctsNode *nodes = v.nodes(i, v.cur[i]);
-    const MctsNode r = nodes[0];
+    const MctsNode r = nodes[v.root[i]];
     const float total_child_visits = (float)(r.visit - 1u);  // mcts.rs:180-186
     int best = -1;
     uint32_t best_key = 0;
@@ -393,7 +418,7 @@ k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int
     }
     if ((st & 7) == MCTS_ST_NEEDS_ROOT || (st & 7) == MCTS_ST_WAS_DONE) flags |= 2u;
     if (st == MCTS_ST_REROOTED) {  // alphazero.rs:192-193
-        const int nodes_now = v.n_nodes[i];
+        const int nodes_now = (int)v.nodes(i, v.cur[i])[v.root[i]].size;
         remaining[i] = tree_size > nodes_now ? tree_size - nodes_now : 0;
     }
     status[i] = (uint8_t)st;
@@ -421,7 +446,8 @@ k_mcts_query(MctsView v, StateView root, int what, void *__restrict__ out) {
     const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
     if (i >= v.n) return;
     const MctsNode *nodes = v.nodes(i, v.cur[i]);
-    const MctsNode r = nodes[0];
+    const int root_idx = v.root[i];
+    const MctsNode r = nodes[root_idx];
     float *fo = reinterpret_cast<float *>(out);
     int32_t *io = reinterpret_cast<int32_t *>(out);
     switch (what) {
@@ -465,9 +491,9 @@ k_mcts_query(MctsView v, StateView root, int what, void *__restrict__ out) {
         fo[i] = __fdiv_rn(r.total, (float)r.visit);
         break;
     case MCTS_Q_MAX_DEPTH: {  // mcts.rs:95-101; stack entries = node | depth << 16
-        int32_t *stack = v.stack + i * v.M;
+        int32_t *stack = v.stack + i * v.L;
         int sp = 0, best = 0;
-        stack[sp++] = 0;
+        stack[sp++] = root_idx;
         while (sp > 0) {
             const int e = stack[--sp];
             const int ni = e & 0xffff, d = e >> 16;
@@ -481,7 +507,7 @@ k_mcts_query(MctsView v, StateView root, int what, void *__restrict__ out) {
         break;
     }
     case MCTS_Q_NODE_COUNT:
-        io[i] = v.n_nodes[i];
+        io[i] = (int32_t)r.size;
         break;
     case MCTS_Q_ROOT_VISITS:
         io[i] = (int32_t)r.visit;

@@ -28,8 +28,14 @@ int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes
     m->device = root->device;
     MctsView &v = m->v;
     v.n = root->n;
-    v.M = max_nodes;
-    const size_t n = (size_t)v.n, M = (size_t)max_nodes;
+    v.L = max_nodes;
+    // physical slots per tree and pool: 8x the live capacity (a compaction about every tenth
+    // move instead of every move), PB_MCTS_POOL_FACTOR overrides; node indices stay below 65536
+    int factor = 8;
+    if (const char *f = getenv("PB_MCTS_POOL_FACTOR")) factor = atoi(f) > 0 ? atoi(f) : 1;
+    long long phys = (long long)max_nodes * factor;
+    v.M = (int)(phys > 65535 ? 65535 : phys);
+    const size_t n = (size_t)v.n, L = (size_t)max_nodes, M = (size_t)v.M;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](auto **p, size_t bytes, int fill) {
         if (err != cudaSuccess) return;
@@ -38,13 +44,14 @@ int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes
     };
     alloc(&v.pool, sizeof(MctsNode) * 2 * n * M, 0);
     alloc(&v.cur, sizeof(int32_t) * n, 0);
-    alloc(&v.n_nodes, sizeof(int32_t) * n, 0);
+    alloc(&v.root, sizeof(int32_t) * n, 0);
+    alloc(&v.n_alloc, sizeof(int32_t) * n, 0);
     alloc(&v.traj_len, sizeof(int32_t) * n, 0);
-    alloc(&v.path, sizeof(int32_t) * n * M, 0);
-    alloc(&v.traj_act, n * M, 0);
-    alloc(&v.traj_rew, sizeof(int32_t) * n * M, 0);
+    alloc(&v.path, sizeof(int32_t) * n * L, 0);
+    alloc(&v.traj_act, n * L, 0);
+    alloc(&v.traj_rew, sizeof(int32_t) * n * L, 0);
     alloc(&v.leaf_kind, n, 0);
-    alloc(&v.stack, sizeof(int32_t) * n * M, 0);
+    alloc(&v.stack, sizeof(int32_t) * n * L, 0);
     alloc(&v.epoch, sizeof(unsigned long long), 0);
     alloc(&v.error, sizeof(unsigned int), 0);
     if (err != cudaSuccess) {
@@ -62,7 +69,8 @@ int pb_mcts_destroy(pb_mcts *m) {
     MctsView &v = m->v;
     cudaFree(v.pool);
     cudaFree(v.cur);
-    cudaFree(v.n_nodes);
+    cudaFree(v.root);
+    cudaFree(v.n_alloc);
     cudaFree(v.traj_len);
     cudaFree(v.path);
     cudaFree(v.traj_act);
@@ -75,7 +83,7 @@ int pb_mcts_destroy(pb_mcts *m) {
     return PB_OK;
 }
 
-int pb_mcts_max_nodes(const pb_mcts *m) { return m ? m->v.M : 0; }
+int pb_mcts_max_nodes(const pb_mcts *m) { return m ? m->v.L : 0; }
 uint64_t pb_sim_seed(uint64_t seed, uint64_t epoch) { return sim_seed(seed, epoch); }
 
 int pb_mcts_reset_root(pb_mcts *m, const uint8_t *mask_dev, const float *value_dev,

@@ -56,8 +56,12 @@ def compare_trees(om, gm, n, ctx):
         assert om.best_action(i) == gv["best_action"][i], f"{ctx} tree {i} best action"
 
 
+@pytest.mark.parametrize("pool_factor", ["8", "1"], ids=["pool8x", "pool1x"])
 @pytest.mark.parametrize("evaluator", [np_evaluator, uniform_evaluator], ids=["hashed", "uniform"])
-def test_search_take_action_and_reset_match_oracle(pb, pymcts, evaluator):
+def test_search_take_action_and_reset_match_oracle(pb, pymcts, evaluator, pool_factor, monkeypatch):
+    # pool1x: every re-root compacts the kept subtree into the other pool; pool8x: re-rooting only
+    # moves the root index and compaction is rare; the tree statistics must not care
+    monkeypatch.setenv("PB_MCTS_POOL_FACTOR", pool_factor)
     n, seed, base, iters_per_move, moves = 24, 11, 3000, 30, 14
     rs = (np.arange(n) % 3 != 0)
     noise = NoiseSource(n)
