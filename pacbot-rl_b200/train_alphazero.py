@@ -62,6 +62,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--eval_envs", type=int, default=1)
     p.add_argument("--metrics-file", default=None)
     p.add_argument("--no-checkpoints", action="store_true")
+    p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", default=True,
+                   help="run the collector step eagerly instead of replaying one captured CUDA graph")
     for name, default in hyperparam_defaults.items():
         p.add_argument(f"--{name}", type=type(default), default=default, help="Default: %(default)s")
     return p
@@ -164,6 +166,10 @@ class AlphaZeroTrainer:
     def collect(self) -> int:
         a = self.args
         self.model.eval()
+        if a.cuda_graph and self.has_model_updated and self.collector._graph is None:
+            # from the first update on the evaluator is the network: capture the collector step
+            # (search iteration + env steps + root noise) once; Adam updates the weights in place
+            self.collector.enable_cuda_graph()
         self.num_exp_steps_needed = min(self.num_exp_steps_needed + a.experience_steps, self.buffer.capacity)
         collected = 0
         while self.num_exp_steps_needed > 0:

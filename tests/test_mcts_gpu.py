@@ -240,6 +240,50 @@ def test_experience_collector_drop_in_surface(pb):
     assert isinstance(it.value, float) and len(it.action_distribution) == 5
 
 
+def test_collector_cuda_graph_matches_eager(pb, monkeypatch):
+    """The captured collector step (search iteration + env steps + root noise in one CUDA graph)
+    must leave envs, trees and episode buffers exactly where eager execution leaves them."""
+    from pacbot_rl_b200 import mcts as M
+
+    def flat_noise(num_valid, alpha=None):   # capturable, deterministic stand-in for the Dirichlet
+        k = num_valid.to(torch.float32)[:, None]
+        w = (torch.arange(5, device=k.device)[None, :] < k).to(torch.float32) * (
+            1.0 + torch.arange(5, device=k.device)[None, :].to(torch.float32))
+        return w / w.sum(dim=1, keepdim=True)
+
+    monkeypatch.setattr(M, "dirichlet_root_noise", flat_noise)
+
+    def evaluator(obs, mask):
+        value = (obs[:, 1] != 0).sum(dim=(1, 2)).to(torch.float32) * 0.25 - obs[:, 2].flatten(1).argmax(1) % 7
+        m = mask.to(torch.float32) * (1.0 + obs[:, 2].flatten(1).argmax(1)[:, None] % 3)
+        return value, m / m.sum(dim=1, keepdim=True)
+
+    cfg = pb.alphazero.AlphaZeroConfig(20, 15, 0.99, 32)
+    cols = [pb.alphazero.BatchedExperienceCollector(evaluator, cfg, device="cuda:0", seed=3, env_id_base=50)
+            for _ in range(2)]
+    cols[1].enable_cuda_graph()           # = 3 ordinary steps, then capture
+    fin = [[], cols[1]._pending]
+    for _ in range(3):
+        cols[0].generate_experience_step(fin[0])
+    for step in range(150):
+        for c, f in zip(cols, fin):
+            c.generate_experience_step(f)
+        if step % 30 == 29:
+            a, b = cols
+            assert_states_equal_gpu = a.env.get_state().tobytes() == b.env.get_state().tobytes()
+            assert assert_states_equal_gpu, f"env states differ at step {step}"
+            assert torch.equal(a.remaining, b.remaining) and torch.equal(a.ep_len, b.ep_len)
+            assert torch.equal(a.mcts.root_visits(), b.mcts.root_visits())
+            assert torch.equal(a.mcts.node_count(), b.mcts.node_count())
+            assert torch.equal(a.mcts.value(), b.mcts.value())
+            assert torch.equal(a.mcts.policy_prior(), b.mcts.policy_prior())
+            assert torch.equal(a.ep_value, b.ep_value) and torch.equal(a.ep_dist, b.ep_dist)
+    assert len(fin[0]) == len(fin[1]) and len(fin[0]) > 0
+    for x, y in zip(fin[0], fin[1]):
+        assert all(torch.equal(p, q) for p, q in zip(x, y))
+    assert cols[0].mcts.check() == cols[1].mcts.check()
+
+
 def test_alphazero_trainer_short_run(pb, tmp_path):
     """train_alphazero mirror end to end: collect with MCTS, state-replay, encode-on-sample,
     two optimiser iterations, greedy evaluation, checkpoint in the reference's format."""
