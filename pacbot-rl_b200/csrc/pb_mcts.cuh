@@ -76,10 +76,21 @@ struct MctsView {
     long long n;
     int M;                     // physical slots per tree and pool
     int L;                     // live-node capacity (max_nodes)
+    int tpw;                   // trees per warp (1..32), see mcts_tree_of_thread
     __device__ __forceinline__ MctsNode *nodes(long long i, int which) const {
         return pool + ((long long)which * n + i) * M;
     }
 };
+
+// Thread -> tree map of every MCTS kernel (blocks of one warp).  A tree walk is branchy (PUCT,
+// the env step, variable depth), so the 32 lanes of a warp that each walk their own tree execute
+// the UNION of 32 instruction streams one after the other: ncu showed ~9 700 warp instructions for
+// ~1 500 per tree.  While there are fewer trees than the GPU has warp slots, only the first `tpw`
+// lanes of a warp own a tree (tpw = 1 for the reference's 128 trees: one tree per warp, 128 SMs
+// busy instead of 4); idle lanes get index n and leave through the kernels' bounds check.
+__device__ __forceinline__ long long mcts_tree_of_thread(const MctsView &v) {
+    return (int)threadIdx.x < v.tpw ? (long long)blockIdx.x * v.tpw + threadIdx.x : v.n;
+}
 
 __device__ __forceinline__ void node_init(MctsNode &nd, uint32_t visit, float total, const float *prior) {
     nd.visit = visit;
@@ -99,7 +110,7 @@ __device__ __forceinline__ void node_init(MctsNode &nd, uint32_t visit, float to
 __global__ void __launch_bounds__(MCTS_THREADS)
 k_mcts_reset_root(MctsView v, const uint8_t *__restrict__ mask, const float *__restrict__ value,
                   const float *__restrict__ policy) {
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n || (mask && !mask[i])) return;
     MctsNode nd;
     node_init(nd, 1u, value[i], policy + i * 5);
@@ -114,7 +125,7 @@ k_mcts_root_noise(MctsView v, StateView root, const uint8_t *__restrict__ mask,
                   const float *__restrict__ noise, float keep, float mix) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n || (mask && !mask[i])) return;
     EnvR s;
     load_env(root, i, s);
@@ -165,7 +176,7 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
               uint8_t *__restrict__ leaf_mask_out) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n) return;
     EnvR s;
     load_env(root, i, s);
@@ -227,7 +238,7 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MCTS_THREADS)
 k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__restrict__ policy) {
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i == 0) *v.epoch += 1ull;  // one search iteration done (select of the next one sees it)
     if (i >= v.n) return;
     const int kind = v.leaf_kind[i];
@@ -339,7 +350,7 @@ k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__re
                    uint8_t *__restrict__ done_out, uint8_t *__restrict__ status) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n) return;
     if (mask && !mask[i]) {
         status[i] = MCTS_ST_UNTOUCHED;
@@ -371,7 +382,7 @@ k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int
                    unsigned int *__restrict__ host_flags) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n) return;
     const int left = remaining[i] - 1;  // alphazero.rs:142
     remaining[i] = left;
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(MCTS_THREADS)
 k_mcts_query(MctsView v, StateView root, int what, void *__restrict__ out) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * MCTS_THREADS + threadIdx.x;
+    const long long i = mcts_tree_of_thread(v);
     if (i >= v.n) return;
     const MctsNode *nodes = v.nodes(i, v.cur[i]);
     const int root_idx = v.root[i];

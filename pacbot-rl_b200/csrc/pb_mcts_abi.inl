@@ -9,7 +9,7 @@ struct pb_mcts {
 };
 
 namespace {
-unsigned mcts_grid(long long n) { return (unsigned)((n + MCTS_THREADS - 1) / MCTS_THREADS); }
+unsigned mcts_grid(const MctsView &v) { return (unsigned)((v.n + v.tpw - 1) / v.tpw); }
 }  // namespace
 
 extern "C" {
@@ -35,6 +35,16 @@ int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes
     if (const char *f = getenv("PB_MCTS_POOL_FACTOR")) factor = atoi(f) > 0 ? atoi(f) : 1;
     long long phys = (long long)max_nodes * factor;
     v.M = (int)(phys > 65535 ? 65535 : phys);
+    // trees per warp: 1 while every tree can have a warp of its own (about 12 resident warps per
+    // SM at 160 registers per thread), else the next power of two; PB_MCTS_TREES_PER_WARP overrides
+    const long long warp_slots = (long long)root->num_sms * 12;
+    int tpw = 1;
+    while (tpw < 32 && (v.n + tpw - 1) / tpw > warp_slots) tpw *= 2;
+    if (const char *t = getenv("PB_MCTS_TREES_PER_WARP")) {
+        const int req = atoi(t);
+        if (req >= 1 && req <= 32) tpw = req;
+    }
+    v.tpw = tpw;
     const size_t n = (size_t)v.n, L = (size_t)max_nodes, M = (size_t)v.M;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](auto **p, size_t bytes, int fill) {
@@ -91,7 +101,7 @@ int pb_mcts_reset_root(pb_mcts *m, const uint8_t *mask_dev, const float *value_d
     if (!m || !value_dev || !policy_dev)
         return fail(PB_ERR_INVALID_ARG, "pb_mcts_reset_root: null argument");
     DeviceGuard g(m->device);
-    k_mcts_reset_root<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+    k_mcts_reset_root<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, mask_dev, value_dev, policy_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -101,7 +111,7 @@ int pb_mcts_root_noise(pb_mcts *m, const uint8_t *mask_dev, const float *noise_d
                        void *stream) {
     if (!m || !noise_dev) return fail(PB_ERR_INVALID_ARG, "pb_mcts_root_noise: null argument");
     DeviceGuard g(m->device);
-    k_mcts_root_noise<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+    k_mcts_root_noise<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, m->root->st, mask_dev, noise_dev, 1.0f - mix, mix);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -111,7 +121,7 @@ int pb_mcts_select(pb_mcts *m, const uint8_t *active_dev, uint8_t *leaf_kind_dev
                    uint8_t *leaf_mask_dev, void *stream) {
     if (!m) return fail(PB_ERR_INVALID_ARG, "pb_mcts_select: null handle");
     DeviceGuard g(m->device);
-    k_mcts_select<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+    k_mcts_select<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, m->root->st, m->sim->st, m->root->seed, m->root->gid_base, active_dev, leaf_kind_dev,
         leaf_mask_dev);
     PB_CUDA(cudaGetLastError());
@@ -122,7 +132,7 @@ int pb_mcts_backprop(pb_mcts *m, const float *value_dev, const float *policy_dev
     if (!m || !value_dev || !policy_dev)
         return fail(PB_ERR_INVALID_ARG, "pb_mcts_backprop: null argument");
     DeviceGuard g(m->device);
-    k_mcts_backprop<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, value_dev,
+    k_mcts_backprop<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, value_dev,
                                                                                   policy_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -133,7 +143,7 @@ int pb_mcts_take_action(pb_mcts *m, const uint8_t *mask_dev, const uint8_t *acti
     if (!m || !actions_dev || !reward_dev || !done_dev || !status_dev)
         return fail(PB_ERR_INVALID_ARG, "pb_mcts_take_action: null argument");
     DeviceGuard g(m->device);
-    k_mcts_take_action<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+    k_mcts_take_action<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, m->root->st, rng_params(m->root), mask_dev, actions_dev, reward_dev, done_dev,
         status_dev);
     PB_CUDA(cudaGetLastError());
@@ -150,7 +160,7 @@ int pb_mcts_collect_act(pb_mcts *m, pb_engine *snap, int max_episode_length, int
         return fail(PB_ERR_INVALID_ARG,
                     "pb_mcts_collect_act: bad arguments (snap needs n * max_episode_length envs)");
     DeviceGuard g(m->device);
-    k_mcts_collect_act<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+    k_mcts_collect_act<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, m->root->st, rng_params(m->root), snap->st, max_episode_length, tree_size,
         remaining_dev, ep_len_dev, ep_mask_dev, ep_dist_dev, ep_value_dev, status_dev, flags_dev);
     PB_CUDA(cudaGetLastError());
@@ -161,7 +171,7 @@ int pb_mcts_query(pb_mcts *m, int what, void *out_dev, void *stream) {
     if (!m || !out_dev || what < 0 || what > MCTS_Q_ROOT_VISITS)
         return fail(PB_ERR_INVALID_ARG, "pb_mcts_query: bad arguments");
     DeviceGuard g(m->device);
-    k_mcts_query<<<mcts_grid(m->v.n), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, m->root->st,
+    k_mcts_query<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(m->v, m->root->st,
                                                                                what, out_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -201,7 +201,13 @@ def gpu_to_oracle_state(oracle, st):
     return out
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2])
+import os
+
+# PB_EXTRA_FUZZ_SEEDS="3,4,5" widens the fuzz campaign for a one-off run
+FUZZ_SEEDS = [0, 1, 2] + [int(s) for s in os.environ.get("PB_EXTRA_FUZZ_SEEDS", "").split(",") if s]
+
+
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
 def test_fuzzed_states_parity(pb, oracle, seed):
     """Random well-formed states near every rare branch (anger thresholds, fruit spawn/expiry, last
     pellet, mode flip, level-time penalty, fright expiry, ghost eating combos, every ticks_per_step

@@ -29,6 +29,10 @@ def wall(col, steps=300):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / steps * 1e3
 
+if "--graph-only" in sys.argv:   # A/B runs (PB_MCTS_TREES_PER_WARP, PB_MCTS_POOL_FACTOR)
+    colg = make(); colg.enable_cuda_graph()
+    print(f"{P} trees, tpw={os.environ.get('PB_MCTS_TREES_PER_WARP', 'auto')}: graph step {wall(colg):.3f} ms")
+    sys.exit(0)
 col = make()
 print(f"{P} trees, eager step: {wall(col):.3f} ms")
 fin = []
