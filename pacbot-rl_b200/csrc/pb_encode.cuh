@@ -41,12 +41,24 @@
 // is again slower (0.5351 ms).  Also measured, equal within noise or slower: 3 x 59 024 B images
 // with channel 0 inside, 2 warps x 2 double-buffered images, channel-1 values prepared in
 // registers before the wait or not, prefetch.global.L2 of the state of the env 256 / 1 024
-// tickets ahead (0.5413 / 0.5427 vs 0.5413 ms: the state fetch is not what the chain waits for),
+// tickets ahead (0.5413 / 0.5427 vs 0.5413 ms: the DRAM reads are only issued earlier, they stay
+// scattered through the write stream; see "the last 2 %" below),
 // and the shared-template encoder with 16 envs in flight per SM (pb_encode2.cuh, 0.602 ms: five
 // copies and <= 18 scattered 4-byte stores per env disturb the write stream more than they
-// help).  What is left to the bare-TMA ceiling (0.517 ms) is the per-env dependent chain "image
-// free -> ticket -> state -> rebuild -> fence -> issue", during which that warp's 55 KB are not
-// in flight; the microbenchmark with the same chain, hint and late ticket reaches 0.526 ms.
+// help).
+//
+// The last 2 %: state reads.  Two diagnostic builds (profiles/r01_ab_encoder.txt) separated the
+// suspects: without the per-env state fetch (every warp re-encodes one fixed state) the kernel
+// runs at 0.5211 ms = the bare-TMA rate, with the ticket atomic still on the critical path; with a
+// static env->warp map and no atomics it is far slower (0.62-0.64 ms).  So the residual was the
+// 176 B of state per env, and six images per SM instead of four (duplicate channels copied twice
+// by the TMA engine, 34 KB images) did NOT help (0.5233 vs 0.5205 ms): it is not latency hidden by
+// more copies in flight, it is the 11.5 MB of state arriving as ~360 k DRAM READ sectors scattered
+// through a 3.9 GB WRITE stream (read/write turnarounds on every HBM channel).  The state was
+// written by the step kernel just before and is still in L2 when this kernel starts, so the
+// prologue marks those lines evict_last (prefetch.global.L2::evict_last, 5 instructions per thread)
+// and the per-env fetches then hit L2: 0.5320 -> 0.5204 ms (7.46 TB/s, 99.5 % of the bare-TMA
+// ceiling of 0.517-0.518 ms).
 //
 // Per-lane roles are written BRANCH FREE (selects + one predicated store per lane).  A first
 // version used an if/else chain per lane group with nested conditionals; for particular states
@@ -93,6 +105,11 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
 // (tools/ab_encoder.sh)
 #ifndef PB_ENC_STORE_HINT
 #define PB_ENC_STORE_HINT 1
+#endif
+// PB_ENC_PIN_STATE (default 1): prefetch.global.L2::evict_last over the launch's packed state
+// before the first copy is issued; 0 for A/B runs
+#ifndef PB_ENC_PIN_STATE
+#define PB_ENC_PIN_STATE 1
 #endif
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
@@ -174,6 +191,26 @@ k_encode_obs(StateView st, float *__restrict__ out,
     // everything above overlapped the previous kernel (programmatic dependent launch); from here
     // on the env state and the ticket are read, so wait for the preceding grid to finish
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+#if PB_ENC_PIN_STATE
+    // The packed state of this launch (176 B per env, 11.5 MB for 65 536 envs) was written by the
+    // step kernel a moment ago and is (mostly) still in L2.  Mark its lines evict_last before the
+    // 3.9 GB write stream starts, so that the per-env state fetches below hit L2 instead of
+    // becoming DRAM reads scattered through the write stream (see the header).
+    {
+        const long long tid = (long long)blockIdx.x * ENC_THREADS + threadIdx.x;
+        const long long nthr = (long long)gridDim.x * ENC_THREADS;
+        auto pin = [](const void *p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); };
+        for (long long e = tid * 8; e < env_count; e += nthr * 8) {  // 16 B records: 8 per 128 B line
+            pin(st.core0 + env_first + e);
+            pin(st.core1 + env_first + e);
+            pin(st.ghosts + env_first + e);
+            pin(st.ghosts + st.npad + env_first + e);
+        }
+        for (long long e = tid * 32; e < env_count; e += nthr * 32)  // 4 B words: 32 per line
+            for (int w = 0; w < PEL_WORDS; w++) pin(st.pel + (long long)w * st.npad + env_first + e);
+    }
+#endif
 
     // image offset this lane patched for the previous env (sparse channels only)
     int patched = -1;
