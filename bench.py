@@ -55,6 +55,11 @@ def parse_args():
     ap.add_argument("--no-dqn", action="store_true")
     ap.add_argument("--dqn-iters", type=int, default=200)
     ap.add_argument("--no-mcts", action="store_true")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "flip", "chunks", "none"],
+                    help="auto: flip while both state buffers fit L2 comfortably (<= 64 MB), else none; "
+                         "flip: double-buffered state, k_step of step t+1 overlaps k_encode_obs of step t "
+                         "(two streams); chunks: in place, chunk-skewed two-stream pipeline; none: k_step "
+                         "then k_encode_obs on one stream")
     ap.add_argument("--mcts-steps", type=int, default=400, help="search iterations timed in the mcts leg")
     return ap.parse_args()
 
@@ -346,7 +351,68 @@ def main():
     slot_ctr = [0]
     enc_events = []
 
-    def hot_step(call_idx: int, time_encode: bool):
+    # Default (--pipeline flip): two streams and double-buffered env state (pacbot-rl_b200/rollout.py):
+    # the step kernel of step t+1 runs while the encoder is still streaming step t, so the 10 us of
+    # k_step are no longer exposed every step.  --pipeline chunks: the in-place variant (a single
+    # encode chunk is split in two halves that share a ring slot).  --pipeline none: k_step then
+    # k_encode_obs back to back on one stream.
+    pipe = None
+    mode = args.pipeline
+    if mode == "auto":  # double buffering pays while both state buffers stay L2 resident
+        # (measured at 2 097 152 envs per GPU, 352 MB of state: flip 123.5, chunks 124.0-124.4,
+        # none 124.1-124.2 M env-steps/s -- nothing to win once the state streams from HBM)
+        mode = "flip" if n * 176 * 2 <= 64 * 2**20 else "none"
+    if mode != "none" and n >= 2:
+        from pacbot_rl_b200.rollout import DoubleBufferedRandomRollout, PipelinedRandomRollout
+
+        if mode == "flip":   # double-buffered state: step t+1 overlaps encode t
+            pchunks = chunks
+            pipe = DoubleBufferedRandomRollout(env, chunks=pchunks)
+            launches_per_step = 1 + len(pchunks)
+        else:                         # "chunks": in place, step of one chunk overlaps encode of another
+            half = (n + 1) // 2
+            pchunks = chunks if len(chunks) >= 2 else [(0, half), (half, n - half)]
+            pipe = PipelinedRandomRollout(env, chunks=pchunks)
+            launches_per_step = 2 * len(pchunks)
+        done = pipe.done
+        timing = [None]
+        window = [False]
+
+        def obs_out(c: int, first: int, cnt: int):
+            if len(chunks) >= 2:
+                slot = ring[slot_ctr[0] % n_slots]
+                slot_ctr[0] += 1
+                return slot[:cnt]
+            if c == 0:
+                slot_ctr[0] += 1
+            return ring[(slot_ctr[0] - 1) % n_slots][first:first + cnt]
+
+        def on_encode(c: int, stream, before: bool):
+            # encoder launches run back to back on the encode stream (each one's prologue overlaps
+            # the previous one's tail); timing events go around WINDOWS of 8 consecutive steps so
+            # that no event sits between two launches inside a window
+            if timing[0] in ("open", "open+close") and before and c == 0:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                enc_events.append([ev, None, 0, 0])
+                window[0] = True
+            if not before and window[0]:
+                enc_events[-1][2] += pchunks[c][1]
+                enc_events[-1][3] += 1
+                if timing[0] in ("close", "open+close") and c == len(pchunks) - 1:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(stream)
+                    enc_events[-1][1] = ev
+                    window[0] = False
+
+    def hot_step(call_idx: int, time_encode: bool, it: int = -1):
+        if pipe is not None:
+            last = it % 16 == 7 or it == args.steps - 1
+            timing[0] = "open" if it % 16 == 0 else ("close" if last else None)
+            if it % 16 == 0 and last:  # a one-step window (tiny --steps)
+                timing[0] = "open+close"
+            pipe.step(call_idx, obs_out, on_encode)
+            return
         # random valid action per env + PacmanGym.step, one launch (pb_step_random)
         env.step_random(call_idx=call_idx, actions_out=actions, mask_out=mask, reward_out=reward,
                         done_out=done)
@@ -360,7 +426,7 @@ def main():
             env.obs_range(first, cnt, slot[:cnt])
         if time_encode:
             e1.record()
-            enc_events.append((e0, e1))
+            enc_events.append([e0, e1, n, len(chunks)])
 
     def barrier():
         if world > 1:
@@ -372,6 +438,8 @@ def main():
     for _ in range(max(3, args.warmup)):
         hot_step(call, False)
         call += 1
+    if pipe is not None:
+        pipe.join()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
@@ -381,14 +449,23 @@ def main():
         # the encoder launches are bracketed by CUDA events on every 8th step only: an event
         # record between k_step and k_encode_obs breaks their programmatic-dependent-launch
         # adjacency, which the other 7 steps keep (as real callers of step_obs do)
-        hot_step(call, it % 8 == 0)
+        hot_step(call, it % 8 == 0, it)
         call += 1
+    if pipe is not None:
+        pipe.join()  # the timing stream waits for both pipeline streams
     ev1.record()
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_total = ev0.elapsed_time(ev1)
-    enc_ms = sum(a.elapsed_time(b) for a, b in enc_events) / (len(enc_events) * len(chunks))
+    enc_events = [e for e in enc_events if e[1] is not None]  # drop a window left open at the end
+    enc_total_ms = sum(e[0].elapsed_time(e[1]) for e in enc_events)
+    enc_total_envs = sum(e[2] for e in enc_events)
+    enc_launches = sum(e[3] for e in enc_events)
+    if enc_launches == 0:  # cannot happen with the windows above; keep the line printable anyway
+        enc_total_ms, enc_total_envs, enc_launches = ms_total, n * args.steps, len(chunks) * args.steps
+    enc_ms = enc_total_ms / enc_launches
+    enc_envs_per_launch = enc_total_envs / enc_launches
     episodes = int(done.sum().item())
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -465,7 +542,7 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    enc_gbs = chunk * ENCODE_BYTES_PER_ENV / (enc_ms * 1e-3) / 1e9
+    enc_gbs = enc_envs_per_launch * ENCODE_BYTES_PER_ENV / (enc_ms * 1e-3) / 1e9
     line = {
         "metric": "env_steps_per_sec_incl_obs",
         "value": value,
@@ -497,13 +574,20 @@ def main():
             "peak": peak,
             "unit": "GB/s",
             "frac": enc_gbs / peak,
-            "traffic": encode_traffic(chunk),
+            "traffic": encode_traffic(int(enc_envs_per_launch)),
             "traffic_source": "profiles/encode_traffic.json (dram__bytes_read.sum + "
                               "dram__bytes_write.sum of one ncu --set full capture, per launch)",
             "peak_source": peak_src,
-            "bytes_per_launch": chunk * ENCODE_BYTES_PER_ENV,
+            "bytes_per_launch": int(enc_envs_per_launch * ENCODE_BYTES_PER_ENV),
             "avg_launch_ms": enc_ms,
+            "envs_per_launch": int(enc_envs_per_launch),
         },
+        "pipeline": {
+            "flip": "two streams, double-buffered state (pb_step_random_flip): k_step of step t+1 "
+                    "overlaps k_encode_obs of step t (pacbot-rl_b200/rollout.py)",
+            "chunks": "two streams, in place: k_step of one chunk overlaps k_encode_obs of another",
+            "none": "none: k_step then k_encode_obs on one stream",
+        }[mode if pipe is not None else "none"],
         "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "episodes_finished_last_step": episodes,

@@ -186,6 +186,22 @@ int pb_sample_actions(pb_engine *e, uint8_t *actions_dev, uint64_t call_idx, voi
  * (uint8 [n], may be NULL).  Bit-identical to calling the two entry points in sequence. */
 int pb_step_random(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev, int32_t *reward_dev,
                    uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, void *stream);
+/* Same for envs [first, first + count) only; every array is still indexed by the absolute env
+ * index (pass the same full-size arrays).  Together with pb_encode_obs_range this lets a caller
+ * software-pipeline a rollout over two streams: step chunk B of step t+1 while chunk A of step t
+ * is still being encoded (disjoint envs, so no hazard) -- see rollout.py. */
+int pb_step_random_range(pb_engine *e, int64_t first, int64_t count, uint64_t call_idx,
+                         uint8_t *actions_out_dev, int32_t *reward_dev, uint8_t *done_dev,
+                         uint8_t *mask_out_dev, int auto_reset, void *stream);
+/* pb_step_random with DOUBLE-BUFFERED state: reads the current state buffer, writes the stepped
+ * state into the engine's second buffer (allocated on first use, +176 B per env) and makes that
+ * the current one.  The buffer just read stays intact, so an observation encode of the previous
+ * state that is still running on ANOTHER stream is not disturbed: step t+1 can overlap encode t
+ * (rollout.py).  The caller orders the streams: this launch must come after the encode of state
+ * t-1 has finished (it overwrites that buffer). */
+int pb_step_random_flip(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev,
+                        int32_t *reward_dev, uint8_t *done_dev, uint8_t *mask_out_dev,
+                        int auto_reset, void *stream);
 
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */

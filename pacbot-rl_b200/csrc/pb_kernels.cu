@@ -86,19 +86,29 @@ __device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
 // action stream of the counter RNG, keyed by call_idx), i.e. k_sample_actions fused in; the
 // chosen action is reported through actions_out (may be nullptr).
 __global__ void __launch_bounds__(STEP_THREADS)
-k_step(StateView st, RngParams rp, const uint8_t *__restrict__ actions,
+k_step(StateView st, StateView dst, RngParams rp, const uint8_t *__restrict__ actions,
        int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
        uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action,
-       uint8_t *__restrict__ actions_out, unsigned long long call_idx) {
+       uint8_t *__restrict__ actions_out, unsigned long long call_idx, long long env_first,
+       long long env_count) {
     // let a programmatically-dependent kernel (the observation encoder) start its prologue now;
     // it still waits for this whole grid (griddepcontrol.wait) before reading the state
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (i >= st.n) return;
+    // envs [env_first, env_first + env_count); every array is indexed by the absolute env index
+    const long long k = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    const long long i = env_first + k;
+    if (k >= env_count) return;
     EnvR s;
     load_env(st, i, s);
+    // double-buffered stepping (pb_step_random_flip): the new state goes to `dst`, `st` stays
+    // intact for an encoder launch that is still reading it; in place when dst == st
+    if (dst.pel != st.pel) {
+#pragma unroll 4
+        for (int w = 0; w < PEL_WORDS; w++)
+            dst.pel[(long long)w * dst.npad + i] = st.pel[(long long)w * st.npad + i];
+    }
     int action;
     if (actions) {
         action = actions[i];
@@ -113,15 +123,16 @@ k_step(StateView st, RngParams rp, const uint8_t *__restrict__ actions,
         reward[i] = 0;
         done_out[i] = 0;
         if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
+        if (dst.pel != st.pel) store_env(dst, i, s);
         return;
     }
-    const PelRef pel{st.pel + i, st.npad};
+    const PelRef pel{dst.pel + i, dst.npad};
     const RngCtx rng = make_rng(rp, i);
     int rew;
     bool done;
     gym_step(s, pel, c_tab, s_walls, rng, action, rew, done);
     if (done && auto_reset) gym_reset(s, pel, c_tab, s_walls, rng, true);
-    store_env(st, i, s);
+    store_env(dst, i, s);
     reward[i] = rew;
     done_out[i] = done ? 1 : 0;
     if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
@@ -305,6 +316,7 @@ struct pb_engine {
     uint64_t seed = 0;
     long long gid_base = 0;
     StateView st{};
+    StateView st_alt{};  // second state buffer, allocated by the first pb_step_random_flip
     const uint32_t *tape = nullptr;
     long long tape_len = 0;
     unsigned long long *bad_action = nullptr;  // device
@@ -437,6 +449,10 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->st.core1);
     cudaFree(e->st.ghosts);
     cudaFree(e->st.pel);
+    cudaFree(e->st_alt.core0);
+    cudaFree(e->st_alt.core1);
+    cudaFree(e->st_alt.ghosts);
+    cudaFree(e->st_alt.pel);
     cudaFree(e->bad_action);
     cudaFree(e->stg_actions);
     cudaFree(e->stg_reward);
@@ -554,8 +570,8 @@ int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8
         return fail(PB_ERR_INVALID_ARG, "pb_step: null argument");
     DeviceGuard g(e->device);
     k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action, nullptr, 0ull);
+        e->st, e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->bad_action, nullptr, 0ull, 0ll, e->n);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -564,11 +580,54 @@ int pb_step_random(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev, in
                    uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, void *stream) {
     if (!e || !reward_dev || !done_dev)
         return fail(PB_ERR_INVALID_ARG, "pb_step_random: null argument");
+    return pb_step_random_range(e, 0, e->n, call_idx, actions_out_dev, reward_dev, done_dev,
+                                mask_out_dev, auto_reset, stream);
+}
+
+int pb_step_random_range(pb_engine *e, int64_t first, int64_t count, uint64_t call_idx,
+                         uint8_t *actions_out_dev, int32_t *reward_dev, uint8_t *done_dev,
+                         uint8_t *mask_out_dev, int auto_reset, void *stream) {
+    if (!e || !reward_dev || !done_dev || first < 0 || count < 0 || first + count > e->n)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_random_range: bad arguments");
+    if (count == 0) return PB_OK;
     DeviceGuard g(e->device);
-    k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        e->st, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action, actions_out_dev, call_idx);
+    k_step<<<grid_for(count), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, e->st, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->bad_action, actions_out_dev, call_idx, first, count);
     PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_step_random_flip(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev,
+                        int32_t *reward_dev, uint8_t *done_dev, uint8_t *mask_out_dev,
+                        int auto_reset, void *stream) {
+    if (!e || !reward_dev || !done_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_random_flip: null argument");
+    DeviceGuard g(e->device);
+    if (!e->st_alt.pel) {  // first use: the second state buffer (same layout)
+        StateView a{};
+        a.npad = e->st.npad;
+        a.n = e->st.n;
+        cudaError_t err = cudaMalloc(&a.core0, sizeof(uint4) * e->npad);
+        if (err == cudaSuccess) err = cudaMalloc(&a.core1, sizeof(uint4) * e->npad);
+        if (err == cudaSuccess) err = cudaMalloc(&a.ghosts, sizeof(uint4) * 2 * e->npad);
+        if (err == cudaSuccess) err = cudaMalloc(&a.pel, sizeof(uint32_t) * PEL_WORDS * e->npad);
+        if (err != cudaSuccess) {
+            cudaFree(a.core0);
+            cudaFree(a.core1);
+            cudaFree(a.ghosts);
+            cudaFree(a.pel);
+            return fail(PB_ERR_CUDA, std::string("pb_step_random_flip: ") + cudaGetErrorString(err));
+        }
+        e->st_alt = a;
+    }
+    k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, e->st_alt, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->bad_action, actions_out_dev, call_idx, 0ll, e->n);
+    PB_CUDA(cudaGetLastError());
+    // from here on "the state" is the buffer just written; launches already enqueued keep the
+    // StateView they captured
+    std::swap(e->st, e->st_alt);
     return PB_OK;
 }
 

@@ -221,10 +221,15 @@ class BatchedPacmanGym:
 
     def step_random(self, *, call_idx: Optional[int] = None, actions_out: Optional[torch.Tensor] = None,
                     mask_out: Optional[torch.Tensor] = None, reward_out: Optional[torch.Tensor] = None,
-                    done_out: Optional[torch.Tensor] = None):
+                    done_out: Optional[torch.Tensor] = None, first: int = 0,
+                    count: Optional[int] = None, flip: bool = False):
         """sample_actions() + step() fused into one launch (random-policy rollouts).  Returns
-        (reward, done); the actions taken land in `actions_out` (uint8 [N]) if given."""
+        (reward, done); the actions taken land in `actions_out` (uint8 [N]) if given.
+        `first` / `count` restrict the launch to envs [first, first+count); the arrays stay
+        full size and are indexed by the absolute env index."""
         n = self.num_envs
+        if count is None:
+            count = n - first
         reward = self._new((n,), torch.int32) if reward_out is None else self._check_tensor(
             reward_out, (n,), torch.int32, "reward_out")
         done = self._new((n,), torch.uint8) if done_out is None else self._check_tensor(
@@ -236,9 +241,16 @@ class BatchedPacmanGym:
         if call_idx is None:
             call_idx = self._sample_calls
             self._sample_calls += 1
-        check(self._L.pb_step_random(self._h, int(call_idx), aptr, C.c_void_p(reward.data_ptr()),
-                                     C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
-                                     self._stream()))
+        if flip:
+            if first != 0 or count != n:
+                raise ValueError("flip=True steps every env")
+            check(self._L.pb_step_random_flip(self._h, int(call_idx), aptr, C.c_void_p(reward.data_ptr()),
+                                              C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
+                                              self._stream()))
+        else:
+            check(self._L.pb_step_random_range(self._h, int(first), int(count), int(call_idx), aptr,
+                                               C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()),
+                                               mptr, int(self.auto_reset), self._stream()))
         return reward, done.view(torch.bool)
 
     def check_actions(self) -> None:
