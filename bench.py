@@ -492,7 +492,22 @@ def main():
         outs = (h_reward, h_done, h_mask)
         checksum = 0
 
+        host_roll = None
+        if pipe is not None and mode == "flip" and n <= chunk:
+            # the same host-in / host-out step with the double-buffered state: the step kernel of
+            # call t+1 does not queue behind the encode of call t (rollout.HostActionRollout)
+            from pacbot_rl_b200.rollout import HostActionRollout
+
+            host_roll = HostActionRollout(env)
+            h_reward, h_done, h_mask = (host_roll.reward.numpy(), host_roll.done.numpy(),
+                                        host_roll.mask.numpy())
+
         def e2e_step(i: int):
+            if host_roll is not None:
+                slot = ring[slot_ctr[0] % n_slots]
+                slot_ctr[0] += 1
+                host_roll.step(host_actions[i % pool], slot[:n])
+                return
             a = host_actions[i % pool].numpy()
             if n <= chunk:  # one C-ABI call: H2D actions, step, encode, D2H reward/done/mask
                 slot = ring[slot_ctr[0] % n_slots]
@@ -512,6 +527,8 @@ def main():
         for i in range(k_e2e):
             e2e_step(i)
             checksum += int(h_reward[0]) + int(h_done[-1])   # the host reads the step's result
+        if host_roll is not None:
+            host_roll.join()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -520,10 +537,12 @@ def main():
             dt = float(t.item())
         e2e = {"value": n * world * k_e2e / dt, "unit": "env-steps/s",
                "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * (4 + 1 + 5), "steps": k_e2e,
-               "what": "BatchedPacmanGym.step_host -> pb_step_host: host actions in, "
-                       "reward/done/mask back to the host (read by the host every step; the D2H "
-                       "copies ride a side stream while the encoder runs), observation encoded "
-                       "into the device-resident ring (it is consumed on the GPU)"}
+               "what": ("rollout.HostActionRollout (pb_step_flip + pb_encode_obs on two streams)"
+                        if host_roll is not None else "BatchedPacmanGym.step_host -> pb_step_host")
+                       + ": pinned host actions in, reward/done/mask back to pinned host memory and "
+                         "read by the host every step (the D2H copies ride a side stream while the "
+                         "encoder runs), observation encoded into the device-resident ring (it is "
+                         "consumed on the GPU)"}
         # variant that also drags the full observation back to the host (PCIe-bound by design)
         if rank == 0 and world == 1:
             n_small = min(n, 4096)

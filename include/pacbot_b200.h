@@ -202,6 +202,11 @@ int pb_step_random_range(pb_engine *e, int64_t first, int64_t count, uint64_t ca
 int pb_step_random_flip(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev,
                         int32_t *reward_dev, uint8_t *done_dev, uint8_t *mask_out_dev,
                         int auto_reset, void *stream);
+/* The same double-buffered step with caller-supplied actions (pb_step semantics; actions_dev ==
+ * NULL draws random valid actions like pb_step_random, then call_idx / actions_out_dev apply). */
+int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
+                 uint8_t *actions_out_dev, int32_t *reward_dev, uint8_t *done_dev,
+                 uint8_t *mask_out_dev, int auto_reset, void *stream);
 
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */

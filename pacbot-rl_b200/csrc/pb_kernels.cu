@@ -601,8 +601,15 @@ int pb_step_random_range(pb_engine *e, int64_t first, int64_t count, uint64_t ca
 int pb_step_random_flip(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev,
                         int32_t *reward_dev, uint8_t *done_dev, uint8_t *mask_out_dev,
                         int auto_reset, void *stream) {
+    return pb_step_flip(e, nullptr, call_idx, actions_out_dev, reward_dev, done_dev, mask_out_dev,
+                        auto_reset, stream);
+}
+
+int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
+                 uint8_t *actions_out_dev, int32_t *reward_dev, uint8_t *done_dev,
+                 uint8_t *mask_out_dev, int auto_reset, void *stream) {
     if (!e || !reward_dev || !done_dev)
-        return fail(PB_ERR_INVALID_ARG, "pb_step_random_flip: null argument");
+        return fail(PB_ERR_INVALID_ARG, "pb_step_flip: null argument");
     DeviceGuard g(e->device);
     if (!e->st_alt.pel) {  // first use: the second state buffer (same layout)
         StateView a{};
@@ -622,7 +629,7 @@ int pb_step_random_flip(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_de
         e->st_alt = a;
     }
     k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        e->st, e->st_alt, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
+        e->st, e->st_alt, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
         e->bad_action, actions_out_dev, call_idx, 0ll, e->n);
     PB_CUDA(cudaGetLastError());
     // from here on "the state" is the buffer just written; launches already enqueued keep the

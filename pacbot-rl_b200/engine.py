@@ -197,7 +197,8 @@ class BatchedPacmanGym:
         check(self._L.pb_reset(self._h, None if m is None else C.c_void_p(m.data_ptr()), self._stream()))
 
     def step(self, actions, *, check_actions: bool = True, mask_out: Optional[torch.Tensor] = None,
-             reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None):
+             reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None,
+             flip: bool = False):
         """PacmanGym.step for all envs -> (reward int32[N], done bool[N]).
 
         check_actions=True synchronises and raises ValueError("Invalid action") like the
@@ -212,9 +213,14 @@ class BatchedPacmanGym:
         if mask_out is not None:
             mptr = C.c_void_p(self._check_tensor(
                 mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
-        check(self._L.pb_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(reward.data_ptr()),
-                              C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
-                              self._stream()))
+        if flip:  # double-buffered: the state just read stays intact (rollout.py)
+            check(self._L.pb_step_flip(self._h, C.c_void_p(a.data_ptr()), 0, None,
+                                       C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()), mptr,
+                                       int(self.auto_reset), self._stream()))
+        else:
+            check(self._L.pb_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(reward.data_ptr()),
+                                  C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
+                                  self._stream()))
         if check_actions:
             self.check_actions()
         return reward, done.view(torch.bool)

@@ -142,3 +142,65 @@ class DoubleBufferedRandomRollout:
         cur.wait_stream(self.enc_stream)
         cur.wait_stream(self.step_stream)
         self._started = False
+
+
+class HostActionRollout:
+    """End-to-end stepping with HOST action / result buffers, pipelined like
+    DoubleBufferedRandomRollout: what `BatchedPacmanGym.step_host` does (pinned actions host->device,
+    step, observation encode into a device buffer, reward / done / mask device->host, read by the
+    host every step), except that the step of call t+1 no longer queues behind the encode of call
+    t.  step() returns when reward / done / mask of THIS step are in the pinned host arrays; the
+    observation is complete after join() (or once a later step() has returned)."""
+
+    def __init__(self, env: BatchedPacmanGym) -> None:
+        self.env = env
+        n, dev = env.num_envs, env.device
+        self.step_stream = torch.cuda.Stream(dev)
+        self.enc_stream = torch.cuda.Stream(dev)
+        self.copy_stream = torch.cuda.Stream(dev)
+        self._enc_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._step_done = torch.cuda.Event()
+        self._t = 0
+        self._started = False
+        self._actions = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._reward = torch.empty(n, dtype=torch.int32, device=dev)
+        self._done = torch.empty(n, dtype=torch.bool, device=dev)
+        self._mask = torch.empty((n, 5), dtype=torch.bool, device=dev)
+        self.reward = torch.empty(n, dtype=torch.int32).pin_memory()
+        self.done = torch.empty(n, dtype=torch.bool).pin_memory()
+        self.mask = torch.empty((n, 5), dtype=torch.bool).pin_memory()
+
+    def step(self, actions_pinned: torch.Tensor, obs_out: torch.Tensor):
+        """actions_pinned: uint8 [n] host tensor (pinned for an asynchronous copy); obs_out:
+        float32 [n,17,28,31] device tensor.  Returns (reward, done, mask) pinned host tensors,
+        overwritten by the next call."""
+        env = self.env
+        if not self._started:
+            cur = torch.cuda.current_stream(env.device)
+            for s in (self.step_stream, self.enc_stream, self.copy_stream):
+                s.wait_stream(cur)
+            self._started = True
+        with torch.cuda.stream(self.step_stream):
+            self._actions.copy_(actions_pinned, non_blocking=True)
+            self.step_stream.wait_event(self._enc_done[self._t & 1])
+            env.step(self._actions, check_actions=False, mask_out=self._mask, reward_out=self._reward,
+                     done_out=self._done, flip=True)
+            self._step_done.record(self.step_stream)
+        with torch.cuda.stream(self.enc_stream):
+            self.enc_stream.wait_event(self._step_done)
+            env.obs(out=obs_out)
+            self._enc_done[self._t & 1].record(self.enc_stream)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._step_done)
+            self.reward.copy_(self._reward, non_blocking=True)
+            self.done.copy_(self._done, non_blocking=True)
+            self.mask.copy_(self._mask, non_blocking=True)
+        self.copy_stream.synchronize()   # the host reads the results of every step
+        self._t += 1
+        return self.reward, self.done, self.mask
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream(self.env.device)
+        for s in (self.step_stream, self.enc_stream, self.copy_stream):
+            cur.wait_stream(s)
+        self._started = False

@@ -87,3 +87,29 @@ def test_double_buffered_rollout_matches_sequential(pb, n, chunks):
     a.reset(m)
     b.reset(m)
     assert a.get_state().tobytes() == b.get_state().tobytes()
+
+
+def test_host_action_rollout_matches_step_host(pb):
+    """HostActionRollout (pinned actions in, pinned results out, double-buffered state) == the
+    one-call path BatchedPacmanGym.step_host, step for step."""
+    from pacbot_rl_b200.rollout import HostActionRollout
+
+    n, steps = 3000, 25
+    a, b = make(pb, n, seed=41), make(pb, n, seed=41)
+    rng = np.random.default_rng(1)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = [torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0") for _ in range(2)]
+    roll = HostActionRollout(b)
+    pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(steps):
+        acts = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(acts, obs_out=obs_a)
+        pinned.numpy()[:] = acts
+        r_b, d_b, m_b = roll.step(pinned, obs_b[t & 1])
+        assert np.array_equal(r_a, r_b.numpy()) and np.array_equal(d_a, d_b.numpy()), f"step {t}"
+        assert np.array_equal(m_a, m_b.numpy()), f"mask at step {t}"
+        if t % 6 == 5 or t == steps - 1:
+            roll.join()
+            torch.cuda.synchronize()
+            assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at step {t}"
+            assert a.get_state().tobytes() == b.get_state().tobytes()
