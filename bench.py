@@ -467,8 +467,12 @@ def main():
     enc_ms = enc_total_ms / enc_launches
     enc_envs_per_launch = enc_total_envs / enc_launches
     episodes = int(done.sum().item())
+    ms_by_rank = [ms_total / args.steps]
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        ms_by_rank = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     value = n * world * args.steps / (ms_total * 1e-3)
@@ -570,6 +574,7 @@ def main():
         "steps": args.steps,
         "warmup": max(3, args.warmup),
         "ms_per_step": ms_total / args.steps,
+        "ms_per_step_by_rank": [round(x, 5) for x in ms_by_rank],
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
