@@ -1,9 +1,17 @@
-"""Software-pipelined random-policy rollouts: the step kernel of one half of the envs runs while
-the observation encoder is still streaming the other half to HBM.
+"""Software-pipelined rollouts: the step kernel runs while the observation encoder is still
+streaming the previous observations to HBM.
 
 A rollout step is `k_step` (10 us, latency bound: one thread per env) followed by `k_encode_obs`
-(0.52 ms per 65 536 envs, HBM-write bound).  On one stream the 10 us are exposed every step.  The
-envs are independent, so the batch is split into chunks and two streams are used:
+(0.52 ms per 65 536 envs, HBM-write bound).  On one stream the 10 us are exposed every step.
+Three drivers, all bit-identical to the one-stream order (tests/test_rollout_gpu.py):
+
+  DoubleBufferedRandomRollout  random valid actions; the engine's second state buffer lets step t+1
+                               overlap encode t (what bench.py measures by default)
+  HostActionRollout            the same with host action / result buffers (bench.py `e2e`)
+  PipelinedRandomRollout       in place: the batch is split into chunks that are skewed over the
+                               two streams (no second buffer; pays one more encoder prologue/tail)
+
+PipelinedRandomRollout in detail -- the envs are independent, so with two chunks A and B:
 
     encode stream : enc(t, A)   enc(t, B)     enc(t+1, A)   enc(t+1, B)   ...
     step stream   :      step(t+1, A)   step(t+1, B)   step(t+2, A)  ...
