@@ -362,7 +362,15 @@ def main():
         # (measured at 2 097 152 envs per GPU, 352 MB of state: flip 123.5, chunks 124.0-124.4,
         # none 124.1-124.2 M env-steps/s -- nothing to win once the state streams from HBM)
         mode = "flip" if n * 176 * 2 <= 64 * 2**20 else "none"
-    if mode != "none" and n >= 2:
+    # flip with a single encode launch per step: ONE C call per step (pb_rollout_random_step does
+    # the stream / event choreography inside the library; a busy host cannot put bubbles between
+    # the 0.52 ms encoder launches)
+    flipc = mode == "flip" and len(chunks) == 1 and n >= 2
+    flip_window = [None, 0, 0]  # [open event, envs, launches] of the current timing window
+    if flipc:
+        flip_enc_stream = env.rollout_streams()[1]
+        launches_per_step = 2
+    if mode != "none" and n >= 2 and not flipc:
         from pacbot_rl_b200.rollout import DoubleBufferedRandomRollout, PipelinedRandomRollout
 
         if mode == "flip":   # double-buffered state: step t+1 overlaps encode t
@@ -406,6 +414,26 @@ def main():
                     window[0] = False
 
     def hot_step(call_idx: int, time_encode: bool, it: int = -1):
+        if flipc:
+            # timing events go around windows of 8 consecutive steps on the engine's encode stream
+            # (no event between two encoder launches inside a window)
+            if it >= 0 and it % 16 == 0:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(flip_enc_stream)
+                flip_window[:] = [ev, 0, 0]
+            slot = ring[slot_ctr[0] % n_slots]
+            slot_ctr[0] += 1
+            env.rollout_random_step(slot[:n], call_idx=call_idx, actions_out=actions, mask_out=mask,
+                                    reward_out=reward, done_out=done)
+            if flip_window[0] is not None:
+                flip_window[1] += n
+                flip_window[2] += 1
+                if it % 16 == 7 or it == args.steps - 1:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(flip_enc_stream)
+                    enc_events.append([flip_window[0], ev, flip_window[1], flip_window[2]])
+                    flip_window[0] = None
+            return
         if pipe is not None:
             last = it % 16 == 7 or it == args.steps - 1
             timing[0] = "open" if it % 16 == 0 else ("close" if last else None)
@@ -440,6 +468,8 @@ def main():
         call += 1
     if pipe is not None:
         pipe.join()
+    if flipc:
+        env.rollout_join()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
@@ -453,6 +483,8 @@ def main():
         call += 1
     if pipe is not None:
         pipe.join()  # the timing stream waits for both pipeline streams
+    if flipc:
+        env.rollout_join()
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -496,21 +528,16 @@ def main():
         outs = (h_reward, h_done, h_mask)
         checksum = 0
 
-        host_roll = None
-        if pipe is not None and mode == "flip" and n <= chunk:
-            # the same host-in / host-out step with the double-buffered state: the step kernel of
-            # call t+1 does not queue behind the encode of call t (rollout.HostActionRollout)
-            from pacbot_rl_b200.rollout import HostActionRollout
-
-            host_roll = HostActionRollout(env)
-            h_reward, h_done, h_mask = (host_roll.reward.numpy(), host_roll.done.numpy(),
-                                        host_roll.mask.numpy())
+        # flip mode: the same host-in / host-out step as ONE pipelined C call
+        # (pb_rollout_host_step): the step kernel of call t+1 does not queue behind the encode of
+        # call t
+        host_roll = flipc
 
         def e2e_step(i: int):
-            if host_roll is not None:
+            if host_roll:
                 slot = ring[slot_ctr[0] % n_slots]
                 slot_ctr[0] += 1
-                host_roll.step(host_actions[i % pool], slot[:n])
+                env.rollout_host_step(host_actions[i % pool].numpy(), slot[:n], outs)
                 return
             a = host_actions[i % pool].numpy()
             if n <= chunk:  # one C-ABI call: H2D actions, step, encode, D2H reward/done/mask
@@ -531,8 +558,8 @@ def main():
         for i in range(k_e2e):
             e2e_step(i)
             checksum += int(h_reward[0]) + int(h_done[-1])   # the host reads the step's result
-        if host_roll is not None:
-            host_roll.join()
+        if host_roll:
+            env.rollout_join()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -541,8 +568,9 @@ def main():
             dt = float(t.item())
         e2e = {"value": n * world * k_e2e / dt, "unit": "env-steps/s",
                "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * (4 + 1 + 5), "steps": k_e2e,
-               "what": ("rollout.HostActionRollout (pb_step_flip + pb_encode_obs on two streams)"
-                        if host_roll is not None else "BatchedPacmanGym.step_host -> pb_step_host")
+               "what": ("BatchedPacmanGym.rollout_host_step -> pb_rollout_host_step (pb_step_flip + "
+                        "pb_encode_obs on two engine-owned streams)"
+                        if host_roll else "BatchedPacmanGym.step_host -> pb_step_host")
                        + ": pinned host actions in, reward/done/mask back to pinned host memory and "
                          "read by the host every step (the D2H copies ride a side stream while the "
                          "encoder runs), observation encoded into the device-resident ring (it is "
@@ -607,11 +635,11 @@ def main():
             "envs_per_launch": int(enc_envs_per_launch),
         },
         "pipeline": {
-            "flip": "two streams, double-buffered state (pb_step_random_flip): k_step of step t+1 "
-                    "overlaps k_encode_obs of step t (pacbot-rl_b200/rollout.py)",
+            "flip": "two streams, double-buffered state: k_step of step t+1 overlaps k_encode_obs of "
+                    "step t (one pb_rollout_random_step call per step)",
             "chunks": "two streams, in place: k_step of one chunk overlaps k_encode_obs of another",
             "none": "none: k_step then k_encode_obs on one stream",
-        }[mode if pipe is not None else "none"],
+        }[mode if (pipe is not None or flipc) else "none"],
         "gpu_launches": launches_per_step * args.steps * world,
         "clocks": clocks,
         "episodes_finished_last_step": episodes,

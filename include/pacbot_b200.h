@@ -208,6 +208,28 @@ int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
                  uint8_t *actions_out_dev, int32_t *reward_dev, uint8_t *done_dev,
                  uint8_t *mask_out_dev, int auto_reset, void *stream);
 
+/* ---- pipelined rollout steps (one C call per step) ------------------------------------------- */
+/* A rollout step = pb_step_flip + pb_encode_obs on two ENGINE-OWNED streams, so that the step
+ * kernel of step t+1 runs while the encoder is still streaming step t to HBM (the step only
+ * waits for the encode of step t-1, whose state buffer it overwrites).  `stream` is consulted at
+ * the first step after pb_create / pb_rollout_join only: the engine's streams start after the
+ * work already queued on it.  The observations and the device-side outputs are complete for a
+ * consumer on `stream` after pb_rollout_join(e, stream); until then do not touch the engine
+ * through other entry points.  Results are bit-identical to pb_step(_random) + pb_encode_obs. */
+/* random valid actions, everything stays on the device (pb_step_random semantics) */
+int pb_rollout_random_step(pb_engine *e, uint64_t call_idx, uint8_t *actions_out_dev,
+                           int32_t *reward_dev, uint8_t *done_dev, uint8_t *mask_out_dev,
+                           int auto_reset, float *obs_out_dev, int64_t env_stride_floats,
+                           void *stream);
+/* host actions in, reward/done/mask back on the host when the call returns (pb_step_host
+ * semantics; the observation is complete after pb_rollout_join or after a later step returned) */
+int pb_rollout_host_step(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                         uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
+                         int64_t env_stride_floats, void *stream);
+int pb_rollout_join(pb_engine *e, void *stream);
+/* the two engine-owned streams (cudaStream_t), e.g. to record timing events on them */
+int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream);
+
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */
 int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream);

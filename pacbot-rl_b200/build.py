@@ -19,6 +19,7 @@ HEADERS = [
     os.path.join(CSRC, "pb_encode2.cuh"),
     os.path.join(CSRC, "pb_mcts.cuh"),
     os.path.join(CSRC, "pb_mcts_abi.inl"),
+    os.path.join(CSRC, "pb_rollout_abi.inl"),
     os.path.join(os.path.dirname(HERE), "include", "pacbot_b200.h"),
 ]
 NVCC_FLAGS = [

@@ -333,6 +333,12 @@ struct pb_engine {
     // pb_step_host: results travel device->host on a side stream while the encoder runs
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_step = nullptr;
+    // pb_rollout_*: two internal streams, double-buffered state (created on first use)
+    cudaStream_t roll_step = nullptr, roll_enc = nullptr;
+    cudaEvent_t ev_roll_step = nullptr, ev_roll_fork = nullptr, ev_roll_join = nullptr;
+    cudaEvent_t ev_enc_done[2] = {nullptr, nullptr};
+    unsigned long long roll_t = 0;
+    bool roll_started = false;
 };
 constexpr unsigned int TICKET_RING = 64;
 
@@ -462,6 +468,11 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->tickets);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
+    if (e->roll_step) cudaStreamDestroy(e->roll_step);
+    if (e->roll_enc) cudaStreamDestroy(e->roll_enc);
+    for (cudaEvent_t ev : {e->ev_roll_step, e->ev_roll_fork, e->ev_roll_join, e->ev_enc_done[0],
+                           e->ev_enc_done[1]})
+        if (ev) cudaEventDestroy(ev);
     delete e;
     return PB_OK;
 }
@@ -938,3 +949,4 @@ int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64
 }  // extern "C"
 
 #include "pb_mcts_abi.inl"
+#include "pb_rollout_abi.inl"

@@ -259,6 +259,65 @@ class BatchedPacmanGym:
                                                mptr, int(self.auto_reset), self._stream()))
         return reward, done.view(torch.bool)
 
+    # ------------------------------------------------------------------ pipelined rollout steps
+    def rollout_random_step(self, obs_out: Optional[torch.Tensor], *, call_idx: Optional[int] = None,
+                            actions_out: Optional[torch.Tensor] = None,
+                            mask_out: Optional[torch.Tensor] = None,
+                            reward_out: Optional[torch.Tensor] = None,
+                            done_out: Optional[torch.Tensor] = None):
+        """step_random() + obs() as ONE pipelined C call (pb_rollout_random_step): the step kernel
+        of this call overlaps the encoder of the previous call on engine-owned streams
+        (double-buffered state).  Outputs are complete after rollout_join()."""
+        n = self.num_envs
+        reward = self._new((n,), torch.int32) if reward_out is None else self._check_tensor(
+            reward_out, (n,), torch.int32, "reward_out")
+        done = self._new((n,), torch.uint8) if done_out is None else self._check_tensor(
+            done_out.view(torch.uint8), (n,), torch.uint8, "done_out")
+        aptr = None if actions_out is None else C.c_void_p(self._check_tensor(
+            actions_out, (n,), torch.uint8, "actions_out").data_ptr())
+        mptr = None if mask_out is None else C.c_void_p(self._check_tensor(
+            mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        optr = None if obs_out is None else C.c_void_p(self._check_tensor(
+            obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
+        if call_idx is None:
+            call_idx = self._sample_calls
+            self._sample_calls += 1
+        check(self._L.pb_rollout_random_step(self._h, int(call_idx), aptr, C.c_void_p(reward.data_ptr()),
+                                             C.c_void_p(done.data_ptr()), mptr, int(self.auto_reset),
+                                             optr, OBS_FLOATS, self._stream()))
+        return reward, done.view(torch.bool)
+
+    def rollout_host_step(self, actions: np.ndarray, obs_out: Optional[torch.Tensor], out: tuple):
+        """step_host() as one pipelined C call (pb_rollout_host_step): `actions` uint8 [N] host
+        array (pinned for full speed), `out` = (reward int32[N], done 1-byte[N], mask 1-byte[N,5]
+        or None) host arrays filled when the call returns; the observation lands in the device
+        tensor `obs_out` and is complete after rollout_join() (or once a later call returned)."""
+        n = self.num_envs
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        reward, done, mask = out
+        if (a.shape != (n,) or reward.shape != (n,) or reward.dtype != np.int32 or done.shape != (n,)
+                or done.dtype.itemsize != 1 or (mask is not None and (mask.shape != (n, NUM_ACTIONS)
+                                                                      or mask.dtype.itemsize != 1))):
+            raise ValueError("rollout_host_step: expected uint8[N] actions and (int32[N], 1-byte[N], "
+                             "1-byte[N,5] or None) outputs")
+        optr = None if obs_out is None else C.c_void_p(self._check_tensor(
+            obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
+        check(self._L.pb_rollout_host_step(
+            self._h, a.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
+            done.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p),
+            int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
+
+    def rollout_join(self) -> None:
+        """Make the current stream wait for every pipelined rollout step enqueued so far."""
+        check(self._L.pb_rollout_join(self._h, self._stream()))
+
+    def rollout_streams(self):
+        """(step_stream, encode_stream) of the pipelined rollout as torch ExternalStreams."""
+        s, e = C.c_void_p(), C.c_void_p()
+        check(self._L.pb_rollout_streams(self._h, C.byref(s), C.byref(e)))
+        return (torch.cuda.ExternalStream(s.value, device=self.device),
+                torch.cuda.ExternalStream(e.value, device=self.device))
+
     def check_actions(self) -> None:
         bad = C.c_int64(-1)
         check(self._L.pb_check_actions(self._h, C.byref(bad), self._stream()))

@@ -113,3 +113,55 @@ def test_host_action_rollout_matches_step_host(pb):
             torch.cuda.synchronize()
             assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at step {t}"
             assert a.get_state().tobytes() == b.get_state().tobytes()
+
+
+def test_c_rollout_random_step_matches_sequential(pb):
+    """pb_rollout_random_step: the same pipeline as DoubleBufferedRandomRollout, one C call per
+    step on engine-owned streams."""
+    n, steps = 5000, 33
+    a, b = make(pb, n, seed=77), make(pb, n, seed=77)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = [torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0") for _ in range(2)]
+    rew = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    done = torch.empty(n, dtype=torch.bool, device="cuda:0")
+    mask = torch.empty((n, 5), dtype=torch.bool, device="cuda:0")
+    acts = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    for t in range(steps):
+        exp_actions = a.sample_actions(call_idx=t)
+        r_a, d_a = a.step(exp_actions)
+        a.obs(obs_a)
+        b.rollout_random_step(obs_b[t & 1], call_idx=t, actions_out=acts, mask_out=mask, reward_out=rew,
+                              done_out=done)
+        if t % 8 == 7 or t == steps - 1:
+            b.rollout_join()
+            torch.cuda.synchronize()
+            assert torch.equal(exp_actions, acts) and torch.equal(r_a, rew) and torch.equal(d_a, done), f"step {t}"
+            assert torch.equal(a.action_mask(), mask)
+            assert a.get_state().tobytes() == b.get_state().tobytes(), f"state differs at step {t}"
+            assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at step {t}"
+    s, e = b.rollout_streams()
+    assert s.cuda_stream != e.cuda_stream
+
+
+def test_c_rollout_host_step_matches_step_host(pb):
+    n, steps = 3000, 21
+    a, b = make(pb, n, seed=5), make(pb, n, seed=5)
+    rng = np.random.default_rng(2)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = [torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0") for _ in range(2)]
+    outs = (np.empty(n, np.int32), np.empty(n, np.bool_), np.empty((n, 5), np.bool_))
+    for t in range(steps):
+        acts = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(acts, obs_out=obs_a)
+        b.rollout_host_step(acts, obs_b[t & 1], outs)
+        assert np.array_equal(r_a, outs[0]) and np.array_equal(d_a, outs[1]) and np.array_equal(m_a, outs[2])
+        if t % 5 == 4 or t == steps - 1:
+            b.rollout_join()
+            torch.cuda.synchronize()
+            assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at step {t}"
+            assert a.get_state().tobytes() == b.get_state().tobytes()
+    bad = rng.integers(0, 5, n, dtype=np.uint8)
+    bad[17] = 9
+    with pytest.raises(ValueError, match="Invalid action"):
+        b.rollout_host_step(bad, obs_b[0], outs)
+    b.rollout_join()
