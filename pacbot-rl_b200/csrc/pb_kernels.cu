@@ -85,7 +85,14 @@ __device__ __forceinline__ int kth_set_bit(uint32_t m, int k) {
 // actions == nullptr: every env draws a uniformly random VALID action from its own mask (the
 // action stream of the counter RNG, keyed by call_idx), i.e. k_sample_actions fused in; the
 // chosen action is reported through actions_out (may be nullptr).
-__global__ void __launch_bounds__(STEP_THREADS)
+// Launched with STEP_THREADS threads per CTA, or with STEP_THREADS_WIDE when it has to share the
+// SMs with the observation encoder (pb_step_flip): the encoder's CTA leaves 6 000 B of an SM's
+// shared memory, every resident CTA of this kernel takes 1 152 B of it (128 B of walls + the 1 KB
+// system reservation), so six 128-thread CTAs on one SM keep that SM's encoder CTA from
+// launching.  With 512-thread CTAs at most four fit an SM (2 048 threads) and the encoder always
+// finds room, whichever of the two kernels the hardware happens to start first.
+constexpr int STEP_THREADS_WIDE = 512;
+__global__ void __launch_bounds__(STEP_THREADS_WIDE)
 k_step(StateView st, StateView dst, RngParams rp, const uint8_t *__restrict__ actions,
        int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
        uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action,
@@ -97,7 +104,7 @@ k_step(StateView st, StateView dst, RngParams rp, const uint8_t *__restrict__ ac
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
     // envs [env_first, env_first + env_count); every array is indexed by the absolute env index
-    const long long k = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i = env_first + k;
     if (k >= env_count) return;
     EnvR s;
@@ -414,7 +421,12 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    // PB_NO_PDL=1 launches the encoder with plain stream ordering (A/B runs, tools/e2e_probe.py)
+    static const bool no_pdl = [] {
+        const char *v = getenv("PB_NO_PDL");
+        return v && v[0] == '1';
+    }();
+    cfg.numAttrs = no_pdl ? 0 : 1;
     PB_CUDA(cudaLaunchKernelEx(&cfg, kern, e->st, out_dev, stride, first, count, ticket,
                                slot_index, slot_stride));
     return PB_OK;
@@ -639,7 +651,8 @@ int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
         }
         e->st_alt = a;
     }
-    k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+    const unsigned wide_grid = (unsigned)((e->n + STEP_THREADS_WIDE - 1) / STEP_THREADS_WIDE);
+    k_step<<<wide_grid, STEP_THREADS_WIDE, 0, (cudaStream_t)stream>>>(
         e->st, e->st_alt, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
         e->bad_action, actions_out_dev, call_idx, 0ll, e->n);
     PB_CUDA(cudaGetLastError());

@@ -21,6 +21,8 @@ def run(variant, steps=1000):
             r._step_done.record(r.step_stream)
         with torch.cuda.stream(r.enc_stream):
             r.enc_stream.wait_event(r._step_done)
+            if "tev" in variant: torch.cuda.Event(enable_timing=True).record(r.enc_stream)
+            if "pev" in variant: torch.cuda.Event().record(r.enc_stream)
             env.obs(out=ring[i % 3])
             r._enc_done[r._t & 1].record(r.enc_stream)
         if "nod2h" not in variant:
@@ -28,7 +30,17 @@ def run(variant, steps=1000):
                 r.copy_stream.wait_event(r._step_done)
                 r.reward.copy_(r._reward, non_blocking=True); r.done.copy_(r._done, non_blocking=True); r.mask.copy_(r._mask, non_blocking=True)
         if "nosync" not in variant:
-            (r.copy_stream if "nod2h" not in variant else r.step_stream).synchronize()
+            st = (r.copy_stream if "nod2h" not in variant else r.step_stream)
+            if "blockev" in variant:
+                ev = torch.cuda.Event(blocking=True); ev.record(st); ev.synchronize()
+            elif "sleep" in variant:
+                ev = torch.cuda.Event(); ev.record(st)
+                while not ev.query(): time.sleep(20e-6)
+            else:
+                st.synchronize()
+            if "delay" in variant:
+                t_end = time.perf_counter() + 150e-6
+                while time.perf_counter() < t_end: pass
         r._t += 1
     for i in range(5): step(i)
     r.join(); torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -36,5 +48,5 @@ def run(variant, steps=1000):
     r.join(); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"{variant:24s} {dt/steps*1e3:.4f} ms/step  {n*steps/dt/1e6:.2f} M/s", flush=True)
-for v in ["nosync", "full", "nosync", "noh2d+nosync", "nod2h+nosync", "nod2h+noh2d+nosync", "nosync", "full"]:
+for v in ["nosync", "full", "full+delay", "nod2h+noh2d", "nod2h+noh2d+delay", "full"]:
     run(v)
