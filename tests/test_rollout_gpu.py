@@ -143,25 +143,41 @@ def test_c_rollout_random_step_matches_sequential(pb):
     assert s.cuda_stream != e.cuda_stream
 
 
-def test_c_rollout_host_step_matches_step_host(pb):
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable-staged", "pinned-zero-copy"])
+def test_c_rollout_host_step_matches_step_host(pb, pinned):
+    """Pageable host buffers go through staging copies; pinned ones are read / written by the step
+    kernel itself and completion is a polled word in mapped memory (no stream sync per step)."""
     n, steps = 3000, 21
     a, b = make(pb, n, seed=5), make(pb, n, seed=5)
     rng = np.random.default_rng(2)
     obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
     obs_b = [torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0") for _ in range(2)]
-    outs = (np.empty(n, np.int32), np.empty(n, np.bool_), np.empty((n, 5), np.bool_))
+    if pinned:
+        keep = [torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory(),
+                torch.empty((n, 5), dtype=torch.bool).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()]
+        outs = tuple(t.numpy() for t in keep[:3])
+        act_buf = keep[3].numpy()
+    else:
+        outs = (np.empty(n, np.int32), np.empty(n, np.bool_), np.empty((n, 5), np.bool_))
+        act_buf = np.empty(n, np.uint8)
     for t in range(steps):
-        acts = rng.integers(0, 5, n, dtype=np.uint8)
-        r_a, d_a, m_a = a.step_host(acts, obs_out=obs_a)
-        b.rollout_host_step(acts, obs_b[t & 1], outs)
-        assert np.array_equal(r_a, outs[0]) and np.array_equal(d_a, outs[1]) and np.array_equal(m_a, outs[2])
+        act_buf[:] = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(act_buf.copy(), obs_out=obs_a)
+        b.rollout_host_step(act_buf, obs_b[t & 1], outs)
+        assert np.array_equal(r_a, outs[0]) and np.array_equal(d_a, outs[1]) and np.array_equal(m_a, outs[2]), f"step {t}"
         if t % 5 == 4 or t == steps - 1:
             b.rollout_join()
             torch.cuda.synchronize()
             assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at step {t}"
             assert a.get_state().tobytes() == b.get_state().tobytes()
-    bad = rng.integers(0, 5, n, dtype=np.uint8)
-    bad[17] = 9
+    before = b.get_state()
+    act_buf[:] = rng.integers(0, 5, n, dtype=np.uint8)
+    act_buf[17] = 9
     with pytest.raises(ValueError, match="Invalid action"):
-        b.rollout_host_step(bad, obs_b[0], outs)
+        b.rollout_host_step(act_buf, obs_b[0], outs)
+    b.rollout_join()
+    torch.cuda.synchronize()
+    assert b.get_state()[17:18].tobytes() == before[17:18].tobytes()   # env.rs:83-88: env untouched
+    act_buf[17] = 0
+    b.rollout_host_step(act_buf, obs_b[0], outs)                        # and the engine keeps working
     b.rollout_join()
