@@ -10,7 +10,9 @@ What changed relative to the reference loop (and nothing else):
     reference keeps a deque of 59 KB NumPy observations and stacks + uploads them per batch
     (:189-197);
   * greedy evaluation runs `--eval_envs` episodes in parallel on the device;
-  * wandb is optional and off by default; metrics go to a JSONL file; no interactive visualiser.
+  * wandb is optional and off by default; metrics go to a JSONL file; no interactive visualiser;
+  * under torchrun every rank runs its own trees / envs / experience buffer and the gradients are
+    averaged with one NCCL all-reduce per batch (the reference is single process).
 
 Run:  python -m pacbot_rl_b200.train_alphazero --num_iters 20 [--device cuda:0]
 """
@@ -29,6 +31,7 @@ import torch.nn.functional as F
 from . import models
 from ._lib import NUM_ACTIONS, OBS_SHAPE
 from .alphazero import AlphaZeroConfig, BatchedExperienceCollector
+from .dist_utils import allreduce_mean_grads, rank_world
 from .engine import BatchedPacmanGym
 
 # names and defaults exactly as the reference (train_alphazero.py:22-38)
@@ -111,16 +114,26 @@ class ExperienceBuffer:
 class AlphaZeroTrainer:
     def __init__(self, args) -> None:
         self.args = args
-        self.device = torch.device(args.device or "cuda")
-        torch.manual_seed(args.seed)
+        # under torchrun: one process per GPU, every rank collects with its own trees (global env
+        # ids rank * num_parallel_envs ...), gradients are averaged with one all-reduce per batch
+        self.rank, local_rank, self.world = rank_world()
+        self.device = torch.device(args.device or f"cuda:{local_rank}")
+        torch.cuda.set_device(self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=self.device)
+        torch.manual_seed(args.seed)  # identical initial weights on every rank
         model_class = getattr(models, args.model)
         self.model = model_class(OBS_SHAPE, NUM_ACTIONS + 1).to(self.device)
+        torch.manual_seed(args.seed + 7919 * (self.rank + 1))  # per-rank batch sampling / root noise
         self.has_model_updated = False
         self.collector = BatchedExperienceCollector(
             self.model_evaluator,
             AlphaZeroConfig(args.tree_size, args.max_episode_length, args.discount_factor,
                             args.num_parallel_envs),
-            device=self.device, seed=args.seed)
+            device=self.device, seed=args.seed, env_id_base=self.rank * args.num_parallel_envs)
         self.buffer = ExperienceBuffer(args.experience_buffer_size, args.batch_size, self.device, args.seed)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.learning_rate)
         self.num_exp_steps_needed = self.buffer.capacity  # start by filling the buffer (:149)
@@ -199,6 +212,7 @@ class AlphaZeroTrainer:
             loss = value_loss + a.policy_loss_weight * policy_loss
             self.optimizer.zero_grad()
             loss.backward()
+            allreduce_mean_grads(self.model.parameters(), self.world)
             grad_norm = torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=a.grad_clip_norm,
                                                        error_if_nonfinite=True)
             self.optimizer.step()
@@ -211,7 +225,7 @@ class AlphaZeroTrainer:
             self.has_model_updated = True
         out = {f"avg_{k}": float(torch.stack(v).mean()) for k, v in stats.items() if k != "grad_norm"}
         out["max_grad_norm"] = float(torch.stack(stats["grad_norm"]).max())
-        out["avg_predicted_value"] = float(predicted_values.mean()) / a.reward_scale
+        out["avg_predicted_value"] = float(predicted_values.detach().mean()) / a.reward_scale
         out["avg_target_value"] = float(value_target.mean()) / a.reward_scale
         return out
 
@@ -223,7 +237,7 @@ class AlphaZeroTrainer:
 
     def train(self) -> None:
         a = self.args
-        log = open(a.metrics_file, "a") if a.metrics_file else None
+        log = open(a.metrics_file, "a") if (a.metrics_file and self.rank == 0) else None
         for iter_num in range(a.num_iters):
             t0 = time.perf_counter()
             with torch.no_grad():
@@ -234,6 +248,9 @@ class AlphaZeroTrainer:
             t2 = time.perf_counter()
             metrics.update(iter=iter_num, collected_steps=collected, collect_s=t1 - t0, train_s=t2 - t1,
                            search_iterations=self.collector.search_iterations, buffer=len(self.buffer))
+            if self.rank != 0:
+                continue
+            metrics["world_size"] = self.world
             if iter_num % a.evaluate_iters == 0:
                 score, steps = self.evaluate_episode()
                 metrics.update(eval_episode_score=score, eval_episode_steps=steps)
@@ -257,6 +274,10 @@ def main(argv=None) -> None:
         print(json.dumps(dict(zip(("eval_episode_score", "eval_episode_steps"), trainer.evaluate_episode()))))
         return
     trainer.train()
+    if trainer.world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
