@@ -416,8 +416,10 @@ def main():
     def hot_step(call_idx: int, time_encode: bool, it: int = -1):
         if flipc:
             # timing events go around windows of 8 consecutive steps on the engine's encode stream
-            # (no event between two encoder launches inside a window)
-            if it >= 0 and it % 16 == 0:
+            # (no event between two encoder launches inside a window), one window every 64 steps:
+            # a timing event is a host-visible completion and costs the running encoder ~14 us
+            # (DESIGN.md section 9), so they are kept rare
+            if it >= 0 and it % 64 == 0:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(flip_enc_stream)
                 flip_window[:] = [ev, 0, 0]
@@ -428,16 +430,16 @@ def main():
             if flip_window[0] is not None:
                 flip_window[1] += n
                 flip_window[2] += 1
-                if it % 16 == 7 or it == args.steps - 1:
+                if it % 64 == 7 or it == args.steps - 1:
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record(flip_enc_stream)
                     enc_events.append([flip_window[0], ev, flip_window[1], flip_window[2]])
                     flip_window[0] = None
             return
         if pipe is not None:
-            last = it % 16 == 7 or it == args.steps - 1
-            timing[0] = "open" if it % 16 == 0 else ("close" if last else None)
-            if it % 16 == 0 and last:  # a one-step window (tiny --steps)
+            last = it % 64 == 7 or it == args.steps - 1
+            timing[0] = "open" if it % 64 == 0 else ("close" if last else None)
+            if it % 64 == 0 and last:  # a one-step window (tiny --steps)
                 timing[0] = "open+close"
             pipe.step(call_idx, obs_out, on_encode)
             return
