@@ -130,10 +130,55 @@ def test_collector_value_recursion_and_shapes(pymcts):
 
 def test_collector_truncation_bootstraps_from_the_root_value(pymcts):
     # max_episode_length 1: every action ends an episode; its value is reward + 0.99 * value of
-    # the NEW root (alphazero.rs:180-184) unless the game ended
-    noise = NoiseSource(2)
-    c = pymcts.OracleCollector(8, 1, 0.99, 2, 5, 0, uniform_evaluator, noise.oracle)
+    # the NEW root (alphazero.rs:180-184) unless the game ended.  Rebuild the expected items from
+    # the MCTS primitives (same seed, ids, evaluator and noise => same trees).
+    tree_size, P, seed, base = 8, 3, 5, 40
+    noise_c, noise_m = NoiseSource(P), NoiseSource(P)
+    c = pymcts.OracleCollector(tree_size, 1, 0.99, P, seed, base, np_evaluator, noise_c.oracle)
+    m = pymcts.OracleMCTS(P, 1, 0, seed, base, np_evaluator, noise_m.oracle)   # new(true, false)
+    m.reset()
+    for _ in range(tree_size - 1):          # num_search_iters_remaining = tree_size - 1
+        m.search_iteration()
+    obs = [m.root_obs(i) for i in range(P)]
+    masks = [m.root_mask(i) for i in range(P)]
+    dists = [m.action_distribution(i) for i in range(P)]
+    best = [m.best_action(i) for i in range(P)]
+    reward, done = m.take_action(best)
+    expected = [np.float32(reward[i]) if done[i]
+                else np.float32(reward[i]) + np.float32(0.99) * m.value(i) for i in range(P)]
     items = c.generate_experience()
-    assert 1 <= len(items) <= 2
-    # tree of 8 nodes with a zero evaluator: the value is a small multiple of pellet rewards
-    assert np.isfinite(items["value"]).all()
+    assert len(items) == P                  # all trees act in the same step, env order
+    for i in range(P):
+        assert np.array_equal(items["obs"][i].view(np.uint32), obs[i].view(np.uint32))
+        assert np.array_equal(items["action_mask"][i].astype(bool), masks[i])
+        assert np.array_equal(items["action_distribution"][i].view(np.uint32), dists[i].view(np.uint32))
+        assert items["value"][i].view(np.uint32) == np.float32(expected[i]).view(np.uint32)
+
+
+def test_collector_discounted_returns_within_an_episode(pymcts):
+    # end_episode (alphazero.rs:163-170): value[k] = reward[k] + 0.99 * value[k+1], last one
+    # bootstrapped if truncated.  With max_episode_length 3 rebuild one episode by hand.
+    tree_size, L, seed, base = 6, 3, 9, 7
+    noise_c, noise_m = NoiseSource(1), NoiseSource(1)
+    c = pymcts.OracleCollector(tree_size, L, 0.99, 1, seed, base, uniform_evaluator, noise_c.oracle)
+    m = pymcts.OracleMCTS(1, 1, 0, seed, base, uniform_evaluator, noise_m.oracle)
+    m.reset()
+    rewards, ended = [], False
+    remaining = tree_size - 1
+    while len(rewards) < L and not ended:
+        for _ in range(remaining):
+            m.search_iteration()
+        r, d = m.take_action([m.best_action(0)])
+        rewards.append(np.float32(r[0]))
+        ended = bool(d[0])
+        remaining = max(tree_size - m.node_count(0), 0)
+    values = list(rewards)
+    if not ended:
+        values[-1] = values[-1] + np.float32(0.99) * m.value(0)
+    nxt = np.float32(0.0)
+    for k in range(len(values) - 1, -1, -1):
+        values[k] = np.float32(values[k] + np.float32(0.99) * nxt)
+        nxt = values[k]
+    items = c.generate_experience()
+    assert len(items) == len(values)
+    assert np.array_equal(items["value"].view(np.uint32), np.array(values, np.float32).view(np.uint32))
