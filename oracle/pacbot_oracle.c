@@ -407,11 +407,14 @@ static void ghost_plan(po_game_state *g, int i, po_gym *rng_owner) {
         tr = GHOST_SCATTER[i][0];
         tc = GHOST_SCATTER[i][1];
     }
-    int exit_here = gh->loc.row == HOUSE_EXIT_ROW && gh->loc.col == HOUSE_EXIT_COL;
-    int exit_next = gh->next_loc.row == HOUSE_EXIT_ROW && gh->next_loc.col == HOUSE_EXIT_COL;
-    if (gh->spawning && !exit_here && !exit_next) {
-        tr = HOUSE_EXIT_ROW;
-        tc = HOUSE_EXIT_COL;
+    /* [E15] a spawning ghost is lured out of the house: until it stands on red's spawn cell
+     * (11,13, the cell above the house exit) or is about to step onto it, that cell is its
+     * target; from there on it targets by mode even though `spawning` is only cleared by the
+     * next update() */
+    if (gh->spawning && !loc_collides(&gh->loc, &GHOST_SPAWN[PO_RED]) &&
+        !loc_collides(&gh->next_loc, &GHOST_SPAWN[PO_RED])) {
+        tr = GHOST_SPAWN[PO_RED].row;
+        tc = GHOST_SPAWN[PO_RED].col;
     }
     int n_valid = 0, valid[4], d2[4];
     uint8_t rev = reversed_dir(gh->next_loc.dir);

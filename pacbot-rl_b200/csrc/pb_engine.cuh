@@ -262,12 +262,14 @@ __device__ __forceinline__ void plan_ghost(EnvR &s, const int i, const uint32_t 
         tr = scatter_row(i);
         tc = scatter_col(i);
     }
+    // a spawning ghost heads for red's spawn cell (11,13), just outside the ghost house, until it
+    // stands on it or is about to (ledger item E15)
     const bool spawning = (s.gflags >> i) & 1;
-    const bool exit_here = g.row == EXIT_ROW && g.col == EXIT_COL;
-    const bool exit_next = g.nrow == EXIT_ROW && g.ncol == EXIT_COL;
-    if (spawning && !exit_here && !exit_next) {
-        tr = EXIT_ROW;
-        tc = EXIT_COL;
+    const bool out_here = g.row == RED_SPAWN_ROW && g.col == RED_SPAWN_COL;
+    const bool out_next = g.nrow == RED_SPAWN_ROW && g.ncol == RED_SPAWN_COL;
+    if (spawning && !out_here && !out_next) {
+        tr = RED_SPAWN_ROW;
+        tc = RED_SPAWN_COL;
     }
     const int rev = reversed(g.ndir);
     int valid = 0, best = UP, best_d = 0x7fffffff;
@@ -307,7 +309,7 @@ __device__ __forceinline__ void update_tick(EnvR &s, const uint32_t *walls, cons
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         GhostR &g = s.g[i];
-        if (g.row == 11 && g.col == 13) s.gflags &= ~(1 << i);  // reached red's spawn: spawned
+        if (g.row == RED_SPAWN_ROW && g.col == RED_SPAWN_COL) s.gflags &= ~(1 << i);  // spawned
         if ((s.gflags >> (4 + i)) & 1) {
             s.gflags &= ~(1 << (4 + i));
             g.fright = 0;

@@ -41,7 +41,8 @@ constexpr int GHOST_FRIGHT_STEPS = 40;
 constexpr int EMPTY = 32;
 constexpr int FRUIT_ROW = 17, FRUIT_COL = 13;
 constexpr int PAC_SPAWN_ROW = 23, PAC_SPAWN_COL = 13;
-constexpr int EXIT_ROW = 12, EXIT_COL = 13;
+constexpr int EXIT_ROW = 12, EXIT_COL = 13;          // ghost-house exit
+constexpr int RED_SPAWN_ROW = 11, RED_SPAWN_COL = 13; // red's spawn cell, just outside the house
 constexpr int INIT_PELLET_COUNT = 244;
 
 // ---- wrapper constants (/root/reference/pacbot_rs/src/env.rs:23-38) ---------------------------

@@ -282,3 +282,26 @@ def test_oracle_long_random_rollout_invariants(oracle):
             assert (o[:, 0].reshape(n, -1).sum(1) == 580).all()
             assert np.array_equal(o[:, 2], o[:, 3]) and np.array_equal(o[:, 4:8], o[:, 8:12])
     assert episodes > 20
+
+
+def test_oracle_engine_assumption_house_exit_paths(oracle):
+    """[UPSTREAM-RECALL] dependent (ledger E5/E15): on a fresh game with Pac-Man parked on his
+    spawn cell (12 ticks per step = one ghost update per step) the ghosts leave the house after
+    0 / 5 / 16 / 32 trapped bounces, are lured to red's spawn cell (11,13) while `spawning`, and
+    from that cell on head for their scatter corners: orange turns LEFT along row 11 (a target of
+    the house exit (12,13) would send it up at (11,12))."""
+    b = fresh(oracle, 1)
+    place(b, 23, 13, ticks_per_step=12)
+    cells = [[] for _ in range(4)]
+    for t in range(44):
+        r, d = b.step(np.array([STAY], np.uint8))
+        assert not d[0]
+        s = b.export_state()[0]
+        for i in range(4):
+            cells[i].append((int(s["g_row"][i]), int(s["g_col"][i]), int(s["g_spawning"][i])))
+    assert cells[0][:4] == [(11, 13, 1), (11, 12, 0), (10, 12, 0), (9, 12, 0)]
+    assert cells[1][5:11] == [(14, 13, 1), (13, 13, 1), (12, 13, 1), (11, 13, 1), (11, 12, 0), (10, 12, 0)]
+    assert cells[2][17:24] == [(13, 11, 1), (13, 12, 1), (13, 13, 1), (12, 13, 1), (11, 13, 1),
+                               (11, 14, 0), (11, 15, 0)]
+    assert cells[3][33:43] == [(13, 15, 1), (13, 14, 1), (13, 13, 1), (12, 13, 1), (11, 13, 1),
+                               (11, 12, 0), (11, 11, 0), (11, 10, 0), (11, 9, 0), (12, 9, 0)]
