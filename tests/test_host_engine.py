@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, assert_states_equal, oracle_to_gpu_state
+from conftest import ROOT, assert_states_equal
 
 HE_DIR = os.path.join(ROOT, "tests", "host_engine")
 HE_SO = os.path.join(HE_DIR, "_build", "libhost_engine.so")
@@ -134,38 +134,45 @@ def test_device_engine_source_matches_oracle_on_cpu(he, pb, oracle, auto_reset):
     assert episodes > 100, episodes
 
 
-def test_device_engine_source_fuzzed_states(he, pb, oracle):
-    """Random well-formed states next to the rare branches (few pellets left, fruit, anger
-    thresholds, level timer, frightened ghosts on Pac-Man, empty locations), imported on both
-    sides and stepped."""
-    n, steps = 4096, 40
-    rng = np.random.default_rng(5)
-    tape = rng.integers(0, 2**32, size=(n, 127), dtype=np.uint32)
-    cfg = np.zeros(n, np.uint8)
-    ob = oracle.OracleBatch(n, cfg, tape)
-    hb = HostEngineBatch(he, pb, n, cfg, tape)
-    # start from oracle rollouts, then perturb the counters the rare branches key on
-    ob.reset()
-    for t in range(30):
-        ob.step(random_actions(rng, ob.action_mask()), auto_reset=True)
-    st = ob.export_state()
-    st["mode_steps"] = rng.integers(0, 4, n)
-    st["level_steps"] = rng.integers(0, 6, n)
-    st["update_period"] = rng.choice([1, 2, 4, 8, 10, 12], n)
-    st["fruit_steps"] = rng.integers(0, 3, n)
-    fr = rng.random((n, 4)) < 0.3
-    st["g_fright"] = np.where(fr, rng.integers(1, 4, (n, 4)), 0)
-    st["ghost_combo"] = rng.integers(0, 4, n)
-    ob.import_state(st)
-    st = ob.export_state()
-    hb.st[:] = oracle_to_gpu_state(pb, st)
+# PB_EXTRA_FUZZ_SEEDS="3,4,5" widens both campaigns for a one-off run (same switch as the GPU suite)
+EXTRA = [int(x) for x in os.environ.get("PB_EXTRA_FUZZ_SEEDS", "").split(",") if x]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2] + EXTRA)
+def test_device_engine_source_fuzzed_states(he, pb, oracle, seed):
+    """The fuzz generator of the GPU suite (test_parity_gpu.fuzz_states: random well-formed states
+    next to every rare branch -- anger thresholds, fruit spawn / expiry, last pellet, mode flip,
+    level-time penalty, fright expiry, ghost-eating combos, every ticks_per_step and update
+    period), imported on both sides and stepped; everything compared after every step."""
+    from test_parity_gpu import fuzz_states, gpu_to_oracle_state
+
+    n, steps = 2048, 12
+    rng = np.random.default_rng(100 + seed)
+    tape = rng.integers(0, 2**32, size=(n, 211), dtype=np.uint32)
+    st = fuzz_states(rng, pb, n)
+    ob = oracle.OracleBatch(n, st["cfg_flags"], tape)
+    hb = HostEngineBatch(he, pb, n, st["cfg_flags"], tape)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    hb.st[:] = st
+    assert_states_equal(ob.export_state(), hb.st, "import")
+    seen_done = 0
     for t in range(steps):
-        a = random_actions(rng, ob.action_mask())
-        r_o, d_o = ob.step(a, auto_reset=True)
-        r_h, d_h, m_h, _ = hb.step(a, auto_reset=True)
+        a = random_actions(rng, ob.action_mask(), p_wild=0.2)
+        r_o, d_o = ob.step(a, auto_reset=False)
+        r_h, d_h, m_h, _ = hb.step(a, auto_reset=False)
         assert np.array_equal(r_o, r_h), f"reward differs at step {t}"
         assert np.array_equal(d_o.astype(bool), d_h), f"done differs at step {t}"
+        assert np.array_equal(ob.action_mask(), m_h), f"mask differs at step {t}"
         assert_states_equal(ob.export_state(), hb.st, f"fuzz step {t}")
+        seen_done += int(d_h.sum())
+    final = hb.st
+    assert seen_done > 0 and (final["curr_level"] > 1).any() and (final["curr_lives"] < 3).any()
+    assert (final["update_period"] < 12).any()
+
+
+@pytest.mark.parametrize("seed", EXTRA)
+def test_device_engine_source_extra_campaign(he, pb, oracle, seed):
+    run_campaign(he, pb, oracle, n=2048, steps=400, seed=1000 + seed, auto_reset=bool(seed & 1))
 
 
 def test_invalid_action_leaves_env_untouched(he, pb, oracle):
