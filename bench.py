@@ -246,6 +246,12 @@ def cpu_baseline(n_envs: int, n_steps: int, threads: int, seed: int):
     }
 
 
+def workload_name(envs_per_gpu: int) -> str:
+    """config.workload, identical in both arms (the reference arm times a bounded sample of it)"""
+    return (f"{envs_per_gpu} envs/GPU batched step+observation encode, random valid actions, "
+            "auto reset, random_start for half the envs, random_ticks (BASELINE.json configs[1])")
+
+
 def run_reference(args, rank: int, world: int):
     """Reference arm: the CPU implementation of the path on all host threads (rank 0 only)."""
     if rank != 0:
@@ -277,11 +283,11 @@ def run_reference(args, rank: int, world: int):
         "vs_baseline": None,
         "dtype": "int32+f32",
         "data": "synthetic",
-        "config": {"workload": "65,536 envs batched step+observation encode, random valid actions "
-                               "(BASELINE.json configs[1])",
+        "config": {"workload": workload_name(args.envs_per_gpu),
+                   "envs_per_gpu": args.envs_per_gpu,
                    "sample_envs_per_step": n_envs, "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_envs} of 65536 envs per step x {args.steps} steps, C "
+                         "sample": f"{n_envs} of {args.envs_per_gpu} envs per step x {args.steps} steps, C "
                                    f"restatement of pacbot_rs under oracle/ (Rust crate not buildable "
                                    f"here), {threads} pthreads"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
@@ -611,9 +617,7 @@ def main():
         "dtype": "int32+f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{n} envs/GPU batched step+observation encode, random valid actions, "
-                        "auto reset, random_start for half the envs, random_ticks "
-                        "(BASELINE.json configs[1])",
+            "workload": workload_name(n),
             "envs_per_gpu": n,
             "obs_ring": f"{n_slots} slots x {slot_bytes / 1e9:.2f} GB per GPU (outputs >> 126 MB L2; "
                         "the 11.5 MB packed state is re-read every step by construction)",
