@@ -454,7 +454,8 @@ uint32_t pb_maze_pellet_row(int row) {
     return rows[row];
 }
 int pb_maze_node(int k, int *row, int *col) {
-    if (k < 0 || k >= NUM_NODES || !row || !col) return PB_ERR_INVALID_ARG;
+    if (k < 0 || k >= NUM_NODES || !row || !col)
+        return fail(PB_ERR_INVALID_ARG, "pb_maze_node: node index out of range or null output");
     *row = H_TABLES.node_rc[k] & 0xff;
     *col = H_TABLES.node_rc[k] >> 8;
     return PB_OK;
