@@ -169,9 +169,6 @@ k_encode_obs(StateView st, float *__restrict__ out,
              long long env_stride, long long env_first, long long env_count,
              unsigned int *__restrict__ ticket, const long long *__restrict__ slot_index,
              long long slot_stride) {
-    // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
-    // replayed while the replay ring advances
-    if (slot_index) out += *slot_index * slot_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * IMG_BYTES);
@@ -191,6 +188,10 @@ k_encode_obs(StateView st, float *__restrict__ out,
     // everything above overlapped the previous kernel (programmatic dependent launch); from here
     // on the env state and the ticket are read, so wait for the preceding grid to finish
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
+    // replayed while the replay ring advances.  Read AFTER the wait: under programmatic dependent
+    // launch nothing written by the preceding grid is visible before it.
+    if (slot_index) out += *reinterpret_cast<const volatile long long *>(slot_index) * slot_stride;
 
 #if PB_ENC_PIN_STATE
     // The packed state of this launch (176 B per env, 11.5 MB for 65 536 envs) was written by the

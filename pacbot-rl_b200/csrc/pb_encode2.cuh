@@ -29,7 +29,6 @@ __global__ void __launch_bounds__(E2_THREADS, 1)
 k_encode_obs_tpl(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
                  long long env_count, unsigned int *__restrict__ ticket,
                  const long long *__restrict__ slot_index, long long slot_stride) {
-    if (slot_index) out += *slot_index * slot_stride;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *zeros = reinterpret_cast<float *>(smem_raw);
@@ -48,6 +47,10 @@ k_encode_obs_tpl(StateView st, float *__restrict__ out, long long env_stride, lo
     fence_proxy_async_smem();
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
+    // replayed while the replay ring advances.  Read AFTER the wait: under programmatic dependent
+    // launch nothing written by the preceding grid is visible before it.
+    if (slot_index) out += *reinterpret_cast<const volatile long long *>(slot_index) * slot_stride;
 
     // tickets: `cur` in hand, `pend` (lane 0) requested one env ago
     unsigned int cur = 0, pend = 0;
