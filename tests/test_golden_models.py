@@ -1,0 +1,96 @@
+"""CPU tests against tests/golden/models_v1.json -- OUTPUTS OF THE REFERENCE ITSELF: the fixture
+was produced by importing /root/reference/src/{models,policies,utils}.py in the build container
+and parsing the hyper-parameter tables of its training scripts (tools/make_golden_models.py).
+Pins SURVEY.md 8(a) rows a15 (MaxQPolicy), a16 (QNetV2, and NetV2 of row f4) and the
+hyper-parameter defaults of a17 / f4.  Floating point: same torch build on CPU, still compared with
+an explicit tolerance of 1e-5 relative (written here) rather than bitwise."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from make_golden_models import OBS_SHAPE, det_masks, det_obs, det_params  # noqa: E402  (no reference import at module level)
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def fx():
+    with open(os.path.join(ROOT, "tests", "golden", "models_v1.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def models(pb):
+    from pacbot_rl_b200 import models as m
+
+    return m
+
+
+@pytest.mark.parametrize("cls,out_dim", [("QNetV2", 5), ("NetV2", 6)])
+def test_network_matches_reference_module(models, fx, cls, out_dim):
+    g = fx[cls]
+    torch.set_num_threads(1)
+    torch.manual_seed(g["init_seed"])
+    net = getattr(models, cls)(OBS_SHAPE, out_dim)
+    # same parameter names, order and shapes => state dicts and checkpoints interchange
+    assert [[k, list(v.shape)] for k, v in net.state_dict().items()] == g["keys"]
+    assert sum(p.numel() for p in net.parameters()) == g["num_params"] == 156934
+    # same initialisation under the same seed (orthogonal, heads / last layer zero)
+    sums = [float(p.detach().double().sum()) for p in net.parameters()]
+    abs_sums = [float(p.detach().double().abs().sum()) for p in net.parameters()]
+    np.testing.assert_allclose(sums, g["init_sums"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(abs_sums, g["init_abs_sums"], rtol=RTOL, atol=1e-6)
+    # same function: deterministic weights and inputs, outputs from the reference's module
+    det_params(net, seed=7)
+    net.eval()
+    with torch.no_grad():
+        out = net(det_obs(6, seed=11))
+    np.testing.assert_allclose(out.double().numpy(), np.array(g["det_forward"]), rtol=RTOL, atol=1e-6)
+    # the NHWC mode the trainers use computes the same function
+    with torch.no_grad():
+        out_cl = net.use_channels_last()(det_obs(6, seed=11))
+    np.testing.assert_allclose(out_cl.double().numpy(), np.array(g["det_forward"]), rtol=1e-4, atol=1e-5)
+
+
+def test_maxq_policy_matches_reference(models, fx, pb):
+    from pacbot_rl_b200.policies import EpsilonGreedy, MaxQPolicy
+
+    net = models.QNetV2(OBS_SHAPE, 5)
+    det_params(net, seed=7)
+    net.eval()
+    obs, masks = det_obs(24, seed=17), det_masks(24, seed=13)
+    pol = MaxQPolicy(net)
+    assert pol(obs, masks).tolist() == fx["QNetV2"]["maxq_actions"]
+    assert len(set(fx["QNetV2"]["maxq_actions"])) >= 4   # the fixture exercises the masking
+    # EpsilonGreedy (policies.py:16-41): greedy iff rand > epsilon.  epsilon = 0 is always greedy;
+    # epsilon = 1 never is, and then only valid actions are drawn
+    assert EpsilonGreedy(pol, 5, 0.0)(obs, masks).tolist() == fx["QNetV2"]["maxq_actions"]
+    torch.manual_seed(0)
+    eg = EpsilonGreedy(pol, 5, 1.0)
+    seen = set()
+    for _ in range(50):
+        a = eg(obs, masks)
+        assert bool(masks[torch.arange(24), a].all())
+        seen.update(a.tolist())
+    assert seen == {0, 1, 2, 3, 4}
+
+
+def test_lerp_and_hyperparameter_defaults(fx, pb):
+    from pacbot_rl_b200 import train_alphazero, train_dqn
+
+    for a, b, t, want in fx["lerp"]:
+        assert train_dqn.lerp(a, b, t) == want
+    for mod, key in ((train_dqn, "hyperparams_dqn"), (train_alphazero, "hyperparams_alphazero")):
+        ours = [[k, v] for k, v in mod.hyperparam_defaults.items()]
+        assert ours == fx[key], key
+        # and they are what the command line parser hands out
+        ns = mod.build_parser().parse_args([])
+        for k, v in fx[key]:
+            assert getattr(ns, k) == v and type(getattr(ns, k)) is type(v), k
