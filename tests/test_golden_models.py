@@ -94,3 +94,30 @@ def test_lerp_and_hyperparameter_defaults(fx, pb):
         ns = mod.build_parser().parse_args([])
         for k, v in fx[key]:
             assert getattr(ns, k) == v and type(getattr(ns, k)) is type(v), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_live_reference_checkpoint_round_trip(models, tmp_path):
+    """Where the reference tree exists (the build container): a checkpoint written the way
+    train_dqn.save_checkpoint writes `q_net-latest.safetensors` loads STRICTLY into the reference's
+    own `models.QNetV2` and computes the same Q-values, and the other way round (row f3)."""
+    import importlib.util
+
+    import safetensors.torch
+
+    spec = importlib.util.spec_from_file_location("_ref_models", "/root/reference/src/models.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ours = models.QNetV2(OBS_SHAPE, 5).use_channels_last()
+    det_params(ours, seed=3)
+    path = str(tmp_path / "q_net-latest.safetensors")
+    safetensors.torch.save_file({k: v.contiguous() for k, v in ours.state_dict().items()}, path)
+    theirs = ref.QNetV2(OBS_SHAPE, 5)
+    theirs.load_state_dict(safetensors.torch.load_file(path), strict=True)
+    obs = det_obs(5, seed=23)
+    with torch.no_grad():
+        np.testing.assert_allclose(ours.eval()(obs).numpy(), theirs.eval()(obs).numpy(), rtol=1e-4, atol=1e-5)
+    back = models.QNetV2(OBS_SHAPE, 5)
+    back.load_state_dict(theirs.state_dict(), strict=True)
+    with torch.no_grad():
+        np.testing.assert_allclose(back.eval()(obs).numpy(), theirs(obs).numpy(), rtol=RTOL, atol=1e-6)
