@@ -158,7 +158,7 @@ class OracleBatch:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # module globals are already torn down at interpreter exit
             lib().po_batch_destroy(h)
 
     def reset(self, mask: np.ndarray | None = None) -> None:

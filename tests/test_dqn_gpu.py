@@ -203,44 +203,34 @@ def test_two_stage_reset_matches_reference_loop(pb, oracle):
     buf._in_phase1 = ~buf.envs.first_ai_done()
     assert buf._in_phase1.cpu().numpy().tolist() == with_super.tolist()
 
-    # ---- reference semantics, env by env, on the oracle ----
-    def t(x):
-        return torch.from_numpy(x)
+    # ---- reference semantics, env by env, on the oracle: replay_reference.restated_env_loop, which
+    # tests/test_reference_replay_live.py checks against the reference's own replay_buffer.py ----
+    from replay_reference import restated_env_loop
 
-    expected = []   # per env: list of (obs_bits, action, reward, done)
+    def as_numpy(policy):
+        return lambda obs, mask: policy(torch.from_numpy(obs), torch.from_numpy(mask)).numpy()
+
+    expected = []   # per env: list of (obs_bits, action, reward, done, next_mask)
     for i in range(n):
         ob = oracle.OracleBatch(1, ((np.arange(n) < n * 0.5).astype(np.uint8) | 2)[i:i + 1], tape[i:i + 1])
         ob.import_state(st[i:i + 1])
-        rec, steps_left = [], total_steps
-        in_phase1 = not ob.first_ai_done()[0]
-        while steps_left > 0:
-            obs, mask = ob.obs(), ob.action_mask()
-            if in_phase1:    # reset_env's inner loop: old policy, not recorded, re-reset on death
-                a = old(t(obs), t(mask)).numpy().astype(np.uint8)
-                _, d = ob.step(a, auto_reset=True)
-                in_phase1 = not ob.first_ai_done()[0]
-            else:
-                a = main(t(obs), t(mask)).numpy().astype(np.uint8)
-                r, d = ob.step(a, auto_reset=True)
-                rec.append((obs.view(np.uint32).copy(), int(a[0]), int(r[0]), bool(d[0])))
-                if d[0]:     # reset_env(env) after a recorded terminal transition
-                    in_phase1 = not ob.first_ai_done()[0]
-            steps_left -= 1
-        expected.append(rec)
+        expected.append(restated_env_loop(ob, as_numpy(main), as_numpy(old), max_env_steps=total_steps))
 
     for _ in range(total_steps):
         buf.generate_experience_step()
     w = buf._weight.cpu().numpy()
     obs_ring = buf._obs.cpu().numpy().view(np.uint32)
     acts, rews, dones = buf._actions.cpu().numpy(), buf._rewards.cpu().numpy(), buf._done.cpu().numpy()
+    next_masks = buf._next_mask.cpu().numpy()
     passed_through_phase1 = 0
     for i in range(n):
-        got = [(obs_ring[s, i], int(acts[s, i]), int(rews[s, i]), bool(dones[s, i]))
+        got = [(obs_ring[s, i], int(acts[s, i]), int(rews[s, i]), bool(dones[s, i]), next_masks[s, i])
                for s in range(total_steps) if w[s, i] > 0]
         assert len(got) == len(expected[i]), (i, len(got), len(expected[i]))
         for k, (g, e) in enumerate(zip(got, expected[i])):
-            assert g[1:] == e[1:], (i, k, g[1:], e[1:])
+            assert g[1:4] == e[1:4], (i, k, g[1:4], e[1:4])
             assert np.array_equal(g[0], e[0][0]), (i, k)
+            assert np.array_equal(g[4], e[4]), (i, k, "next_action_mask")
         if with_super[i] and len(got) > 0:
             passed_through_phase1 += 1
     assert passed_through_phase1 >= 1
