@@ -39,6 +39,41 @@ class ReplayBatch(NamedTuple):
     next_action_masks: torch.Tensor  # bool    [B, 5], all False where done
 
 
+@torch.no_grad()
+def reset_env(envs: BatchedPacmanGym, policy_old: Optional[Policy], max_steps: int = 100_000) -> None:
+    """`reset_env` (replay_buffer.py:44-54) for every env of `envs`, synchronous form: reset, then
+    `policy_old` plays until `first_ai_done()`, an env that dies on the way being reset again.
+    Envs that are through wait -- parked in a second engine and restored after every step -- until
+    the last one is.  `ReplayBuffer` does the same thing interleaved with recording (per-env phase
+    flag); this form is for callers that need every env through phase 1 before they go on
+    (`evaluate_episode`, train_dqn.py:95-96).  `policy_old=None` is a plain `reset()` (the
+    reference cannot start without `q_net-old.safetensors`).  The reference would loop
+    forever on an old policy that never finishes; here the loop stops after `max_steps`."""
+    envs.reset()
+    if policy_old is None:
+        return
+    n, dev = envs.num_envs, envs.device
+    waiting = ~envs.first_ai_done()
+    if not bool(waiting.any()):
+        return
+    parked = BatchedPacmanGym(n, False, False, device=dev)
+    ids = torch.arange(n, dtype=torch.int64, device=dev)
+    obs = envs.obs()
+    auto = envs.auto_reset
+    envs.auto_reset = True                      # "the first ai died :( try again" (:52-54)
+    try:
+        for _ in range(max_steps):
+            through = torch.where(waiting, -1, ids).contiguous()   # negative index = skip
+            parked.copy_envs_from(envs, through, through)
+            envs.step_obs(policy_old(obs, envs.action_mask()), obs)
+            envs.copy_envs_from(parked, through, through)
+            waiting = waiting & ~envs.first_ai_done()
+            if not bool(waiting.any()):
+                break
+    finally:
+        envs.auto_reset = auto
+
+
 class ReplayBuffer:
     def __init__(
         self,

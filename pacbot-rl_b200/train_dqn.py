@@ -32,7 +32,7 @@ import torch.nn.functional as F
 from . import models
 from .engine import BatchedPacmanGym
 from .policies import EpsilonGreedy, MaxQPolicy
-from .replay_buffer import ReplayBuffer
+from .replay_buffer import ReplayBuffer, reset_env
 
 # names and defaults exactly as the reference (train_dqn.py:26-42)
 hyperparam_defaults = {
@@ -221,10 +221,11 @@ class DQNTrainer:
     # ------------------------------------------------------------------ evaluation (:88-113)
     @torch.no_grad()
     def evaluate_episode(self, max_steps: int = 1000, num_envs: int = 1) -> dict:
-        """Greedy episode(s) from the fixed start (random_start=False, random_ticks=False)."""
+        """Greedy episode(s) from the fixed start (random_start=False, random_ticks=False), after
+        the old policy's phase when there is one (`reset_env(gym)`, train_dqn.py:95-96)."""
         env = BatchedPacmanGym(num_envs, False, False, device=self.device, seed=self.cfg.seed + 17,
                                env_id_base=10_000_000 + self.iter_num * num_envs)
-        env.reset()
+        reset_env(env, self.replay.phase1_policy)
         pellets_start = env.remaining_pellets()
         self.q_net.eval()
         policy = MaxQPolicy(self.q_net)

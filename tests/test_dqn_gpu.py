@@ -234,3 +234,52 @@ def test_two_stage_reset_matches_reference_loop(pb, oracle):
         if with_super[i] and len(got) > 0:
             passed_through_phase1 += 1
     assert passed_through_phase1 >= 1
+
+
+def test_synchronous_reset_env_matches_reference_loop(pb, oracle):
+    """`replay_buffer.reset_env` (the form evaluate_episode uses, train_dqn.py:95-96): every env is
+    reset and played by the old policy until first_ai_done(); envs that are through (here: the ones
+    built without super pellets) are parked and must come out untouched.  Expectation: the
+    reference's loop (replay_buffer.py:44-54) env by env on the oracle, same draw tape."""
+    import torch
+    from conftest import assert_obs_equal, assert_states_equal
+    from pacbot_rl_b200.replay_buffer import reset_env
+    from replay_reference import OLD_POLICY_CHANNELS, bfs_policy
+
+    n = 8
+    rng = np.random.default_rng(9)
+    tape = rng.integers(0, 2**32, size=(n, 1021), dtype=np.uint32)
+    no_super = np.arange(n) % 4 == 3
+    env = pb.BatchedPacmanGym(n, False, False, device="cuda:0", seed=0, remove_super_pellets=no_super)
+    env.set_draw_tape(torch.from_numpy(tape.view(np.int32)).cuda())
+    old_np = bfs_policy(OLD_POLICY_CHANNELS)
+    calls = []
+
+    def old(obs, masks):   # exact-cell BFS on the host: the same function on both sides
+        calls.append(1)
+        return torch.from_numpy(old_np(obs.cpu().numpy(), masks.cpu().numpy())).to(obs.device)
+
+    reset_env(env, old)
+    assert not env.auto_reset and bool(env.first_ai_done().all())
+    ob = oracle.OracleBatch(n, no_super.astype(np.uint8) << 3, tape)
+    ob.reset()
+    longest = 0
+    for i in range(n):
+        one = oracle.OracleBatch(1, (no_super.astype(np.uint8) << 3)[i:i + 1], tape[i:i + 1])
+        one.reset()
+        k = 0
+        while not one.first_ai_done()[0]:
+            one.step(old_np(one.obs(), one.action_mask()), auto_reset=True)
+            k += 1
+        longest = max(longest, k)
+        st = ob.export_state()
+        st[i] = one.export_state()[0]
+        ob.import_state(st)
+        assert (k == 0) == bool(no_super[i])
+    assert len(calls) == longest > 100          # stops as soon as the last env is through
+    assert_states_equal(ob.export_state(), env.get_state(), "after reset_env")
+    assert_obs_equal(ob.obs(), env.obs().cpu().numpy(), "after reset_env")
+    # no old policy: a plain reset (SURVEY Q1)
+    reset_env(env, None)
+    ob.reset()
+    assert_states_equal(ob.export_state(), env.get_state(), "plain reset")
