@@ -121,3 +121,46 @@ def test_live_reference_checkpoint_round_trip(models, tmp_path):
     back.load_state_dict(theirs.state_dict(), strict=True)
     with torch.no_grad():
         np.testing.assert_allclose(back.eval()(obs).numpy(), theirs(obs).numpy(), rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_live_reference_epsilon_greedy_distribution(pb):
+    """EpsilonGreedy is random on both sides (the reference draws with Python's `random` and
+    `torch.rand`, policies.py:29-39), so the comparison is statistical: per mask pattern the
+    empirical action distribution of the reference's class, run live, and of ours agree within
+    5 sigma of the binomial noise, and both match the closed form
+    P(a) = (1 - eps) * [a == greedy] + eps * valid(a) / n_valid."""
+    import importlib.util
+    import random
+
+    from pacbot_rl_b200.policies import EpsilonGreedy
+
+    sys.path.insert(0, "/root/reference/src")   # policies.py imports `models` by bare name
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_policies", "/root/reference/src/policies.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        sys.path.remove("/root/reference/src")
+    masks = torch.tensor([[1, 1, 0, 0, 1], [1, 0, 0, 0, 0], [1, 1, 1, 1, 1], [1, 0, 1, 1, 0]], dtype=torch.bool)
+    greedy = torch.tensor([4, 0, 2, 3])
+    eps, reps = 0.3, 4000
+    big_masks, big_greedy = masks.repeat(reps, 1), greedy.repeat(reps)
+
+    class Fixed:   # stands in for MaxQPolicy: the greedy action travels in the "observation", so it
+        def __call__(self, o, m):   # works for the greedy subset (reference) and the full batch (ours)
+            return o[:, 0].long()
+
+    obs = big_greedy.float().unsqueeze(1)
+    random.seed(1)
+    torch.manual_seed(1)
+    a_ref = ref.EpsilonGreedy(Fixed(), 5, eps)(obs, big_masks)
+    a_our = EpsilonGreedy(Fixed(), 5, eps)(obs, big_masks)
+    for k in range(len(masks)):
+        valid = masks[k].float()
+        want = eps * valid / valid.sum()
+        want[greedy[k]] += 1 - eps
+        for a in (a_ref, a_our):
+            freq = torch.bincount(a[k::len(masks)], minlength=5).float() / reps
+            sigma = torch.sqrt(want * (1 - want) / reps) + 1e-9
+            assert bool(((freq - want).abs() <= 5 * sigma + 1e-12).all()), (k, freq, want)
