@@ -93,12 +93,23 @@ def test_no_cpu_fallback(pb):
 
 
 def test_product_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "pacbot-rl_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, fn)).read()
-                assert "pyoracle" not in src and "pacbot_oracle" not in src, fn
+    """Neither the oracle nor any other test infrastructure (the MCTS oracle, the host build of
+    the device engine under tests/host_engine/) is reachable from the product package, the C-ABI
+    header or the root alias module."""
+    import re
+
+    # imports, includes and library loads -- a comment naming an oracle file is not a dependency
+    banned = re.compile(r"pyoracle|pymcts|libpacbot_oracle|host_engine|from oracle|import oracle|"
+                        r"#\s*include[^\n]*oracle")
+    files = [os.path.join(ROOT, "pacbot_rl_b200.py"), os.path.join(ROOT, "include", "pacbot_b200.h")]
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "pacbot-rl_b200")):
+        files += [os.path.join(dirpath, fn) for fn in names
+                  if fn.endswith((".py", ".cu", ".cuh", ".h", ".inl"))]
+    assert len(files) > 20
+    for path in files:
+        src = open(path).read()
+        hit = banned.search(src)
+        assert hit is None, (path, hit.group(0))
 
 
 def test_create_rejects_empty_batch(pb):
