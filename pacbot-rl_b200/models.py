@@ -6,6 +6,8 @@
 either side load in the other (`q_net-latest.pt` / `.safetensors`, train_dqn.py:239-253)."""
 from __future__ import annotations
 
+import copy
+
 import torch
 from torch import nn
 
@@ -16,6 +18,17 @@ def init_orthogonal(module: nn.Module) -> None:
         for p in module.parameters():
             if p.dim() >= 2:
                 nn.init.orthogonal_(p)
+
+
+def portable_copy(net: nn.Module) -> nn.Module:
+    """A detached copy of `net` with plain row-major parameters, for checkpoints.  The trainers
+    keep conv weights in NHWC (`use_channels_last`); a pickled module written that way breaks the
+    reference's export path (`to_safetensors.py`: `save_file(q_net.state_dict())` refuses
+    non-contiguous tensors) and any other consumer that expects the layout the reference writes."""
+    out = copy.deepcopy(net).to(memory_format=torch.contiguous_format)
+    if getattr(out, "_channels_last", False):
+        out._channels_last = False
+    return out
 
 
 class QNetV2(nn.Module):

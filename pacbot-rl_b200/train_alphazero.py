@@ -232,7 +232,7 @@ class AlphaZeroTrainer:
     def save_checkpoint(self, iter_num: int) -> None:  # train_alphazero.py:252-262
         d = Path(self.args.checkpoint_dir)
         d.mkdir(exist_ok=True)
-        torch.save(self.model, d / "model-latest.pt")
+        torch.save(models.portable_copy(self.model), d / "model-latest.pt")   # row-major weights
         shutil.copyfile(d / "model-latest.pt", d / f"model-iter{iter_num:07}.pt")
 
     def train(self) -> None:

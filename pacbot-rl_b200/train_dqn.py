@@ -262,16 +262,17 @@ class DQNTrainer:
         d = Path(checkpoint_dir)
         d.mkdir(exist_ok=True, parents=True)
         pt = d / "q_net-latest.pt"
-        torch.save(self.q_net, pt)
+        # plain row-major tensors (what the reference writes and its to_safetensors.py / candle
+        # loader expect), whatever memory format the live network uses
+        net = models.portable_copy(self.q_net)
+        torch.save(net, pt)
         shutil.copyfile(pt, d / f"q_net-iter{iter_num:07}.pt")
         if iter_num % 1_000 == 0:
             try:
                 import safetensors.torch
 
-                # plain row-major tensors under the reference's key names (candle_qnet.rs:18-44),
-                # whatever memory format the live network uses
-                sd = {k: v.detach().contiguous() for k, v in self.q_net.state_dict().items()}
-                safetensors.torch.save_file(sd, d / "q_net-latest.safetensors")
+                # the reference's key names (candle_qnet.rs:18-44)
+                safetensors.torch.save_file(net.state_dict(), d / "q_net-latest.safetensors")
             except ImportError:
                 pass
 

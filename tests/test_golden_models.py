@@ -110,8 +110,15 @@ def test_live_reference_checkpoint_round_trip(models, tmp_path):
     spec.loader.exec_module(ref)
     ours = models.QNetV2(OBS_SHAPE, 5).use_channels_last()
     det_params(ours, seed=3)
+    assert not ours.backbone[0].weight.is_contiguous()          # NHWC weights, as the trainers keep them
+    # what save_checkpoint pickles: a row-major copy.  The reference's export script
+    # (to_safetensors.py: torch.load + save_file(q_net.state_dict())) refuses non-contiguous tensors
+    pt = str(tmp_path / "q_net-latest.pt")
+    torch.save(models.portable_copy(ours), pt)
+    loaded = torch.load(pt, map_location="cpu", weights_only=False)
+    assert all(v.is_contiguous() for v in loaded.state_dict().values())
     path = str(tmp_path / "q_net-latest.safetensors")
-    safetensors.torch.save_file({k: v.contiguous() for k, v in ours.state_dict().items()}, path)
+    safetensors.torch.save_file(loaded.state_dict(), path)      # the line of to_safetensors.py
     theirs = ref.QNetV2(OBS_SHAPE, 5)
     theirs.load_state_dict(safetensors.torch.load_file(path), strict=True)
     obs = det_obs(5, seed=23)
