@@ -305,3 +305,21 @@ def test_oracle_engine_assumption_house_exit_paths(oracle):
                                (11, 14, 0), (11, 15, 0)]
     assert cells[3][33:43] == [(13, 15, 1), (13, 14, 1), (13, 13, 1), (12, 13, 1), (11, 13, 1),
                                (11, 12, 0), (11, 11, 0), (11, 10, 0), (11, 9, 0), (12, 9, 0)]
+
+
+def test_action_mask_literal_examples(oracle, golden):
+    """SURVEY.md Appendix G, spelled out: masks are [Stay, Down, Up, Left, Right] (env.rs:293-302);
+    the only four-way junctions are (5,6), (5,21), (20,6), (20,21); degree histogram 254/30/4."""
+    T, F = True, False
+    want = {(23, 13): [T, F, F, T, T], (1, 1): [T, T, F, F, T], (5, 6): [T, T, T, T, T],
+            (29, 26): [T, F, T, T, F], (14, 9): [T, T, T, T, F], (11, 13): [T, F, F, T, T]}
+    b = fresh(oracle, len(want))
+    st = b.export_state()
+    for i, (r, c) in enumerate(want):
+        st["pac_row"][i], st["pac_col"][i] = r, c
+    b.import_state(st)
+    assert b.action_mask().tolist() == list(want.values())
+    nodes = [tuple(n) for n in golden["node_coords"]]
+    four = [n for n, va in zip(nodes, golden["valid_actions"]) if sum(va[1:]) == 4]
+    assert four == [(5, 6), (5, 21), (20, 6), (20, 21)]
+    assert golden["degree_histogram"] == {"2": 254, "3": 30, "4": 4}
