@@ -187,3 +187,54 @@ def test_invalid_action_leaves_env_untouched(he, pb, oracle):
     assert bad == 17
     for i in (17, 40):
         assert hb.st[i] == before[i] and r[i] == 0 and not d[i]
+
+
+# ---- the GPU suite's own scenario tests, re-run with the host build in place of the GPU ----------
+class _HostEnv:
+    """The few methods test_parity_gpu's helpers call on a BatchedPacmanGym."""
+
+    def __init__(self, hb, auto_reset):
+        self.hb, self.auto_reset = hb, auto_reset
+
+    def reset(self):
+        self.hb.reset()
+
+    def set_state(self, st):
+        self.hb.st[:] = st
+
+
+def _patch_parity_helpers(monkeypatch, he, pb):
+    import test_parity_gpu as tp
+
+    def make_pair(pb_, oracle_, n, cfg, tape, auto_reset=False, seed=0):
+        cfg = np.asarray(cfg, np.uint8)
+        return (oracle_.OracleBatch(n, cfg, tape),
+                _HostEnv(HostEngineBatch(he, pb, n, cfg, tape, seed=seed), auto_reset))
+
+    def compare_step(ob, env, actions, t, auto_reset, check_obs):
+        r_o, d_o = ob.step(actions, auto_reset=auto_reset)
+        r_h, d_h, m_h, _ = env.hb.step(actions, auto_reset=auto_reset)
+        assert np.array_equal(r_o, r_h), f"reward differs at step {t}"
+        assert np.array_equal(d_o.astype(bool), d_h), f"done differs at step {t}"
+        assert np.array_equal(ob.action_mask(), m_h), f"mask differs at step {t}"
+        assert_states_equal(ob.export_state(), env.hb.st, f"step {t}")
+        return d_o
+
+    monkeypatch.setattr(tp, "make_pair", make_pair)
+    monkeypatch.setattr(tp, "compare_step", compare_step)
+    return tp
+
+
+def test_scripted_scenarios_on_the_host_build(he, pb, oracle, monkeypatch):
+    """test_parity_gpu.test_scripted_scenarios (deaths both ways, 1-4 ghost
+    combos, fright expiry, mode flips, level-time penalty, super pellet, fruit, anger, last pellet,
+    every ticks_per_step) with its own scenario list and guards, the host build standing in for
+    the GPU engine (observations are not compared here: the encoder is GPU-only)."""
+    tp = _patch_parity_helpers(monkeypatch, he, pb)
+    tp.test_scripted_scenarios(pb, oracle)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33])
+def test_odd_batch_sizes_on_the_host_build(he, pb, oracle, monkeypatch, n):
+    tp = _patch_parity_helpers(monkeypatch, he, pb)
+    tp.test_odd_batch_sizes(pb, oracle, n)
