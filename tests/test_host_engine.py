@@ -238,3 +238,23 @@ def test_scripted_scenarios_on_the_host_build(he, pb, oracle, monkeypatch):
 def test_odd_batch_sizes_on_the_host_build(he, pb, oracle, monkeypatch, n):
     tp = _patch_parity_helpers(monkeypatch, he, pb)
     tp.test_odd_batch_sizes(pb, oracle, n)
+
+
+def test_host_build_reproduces_golden_trajectory(he, pb):
+    """The committed trajectory fixture (tests/golden/trajectory_v1.npz), replayed by the host build
+    of the device engine: reward, done, mask and the digest of the full state at every step (the
+    observation digest needs the encoder, i.e. the GPU test of the same fixture)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_trajectory import state_digest
+
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "trajectory_v1.npz")))
+    hb = HostEngineBatch(he, pb, len(g["cfg"]), g["cfg"], g["tape"])
+    hb.reset()
+    for t in range(g["actions"].shape[0]):
+        assert np.array_equal(hb.action_mask(), g["masks"][t]), f"mask differs at step {t}"
+        r, d, _, _ = hb.step(g["actions"][t], auto_reset=True)
+        assert np.array_equal(r, g["reward"][t]), f"reward differs at step {t}"
+        assert np.array_equal(d, g["done"][t]), f"done differs at step {t}"
+        assert state_digest(hb.st) == g["state_digest"][t], f"state differs at step {t}"
