@@ -252,6 +252,36 @@ void hm_mcts_query(void *h, int what, void *out) {
     HMcts *m = static_cast<HMcts *>(h);
     launch(m->v, [&] { k_mcts_query(m->v, m->root->st, what, out); });
 }
+// pb_mcts_collect_act: the env-step half of generate_experience_step for all trees
+int hm_mcts_collect_act(void *h, void *snap_h, int max_len, int tree_size, int32_t *remaining,
+                        int32_t *ep_len, uint8_t *ep_mask, float *ep_dist, float *ep_value,
+                        uint8_t *status, uint32_t *flags) {
+    HMcts *m = static_cast<HMcts *>(h);
+    HEngine *snap = static_cast<HEngine *>(snap_h);
+    if (snap->st.n < m->v.n * (long long)max_len) return PB_ERR_INVALID_ARG;
+    launch(m->v, [&] {
+        k_mcts_collect_act(m->v, m->root->st, rng_params(m->root), snap->st, max_len, tree_size,
+                           remaining, ep_len, ep_mask, ep_dist, ep_value, status, flags);
+    });
+    return PB_OK;
+}
+
+// pb_copy_envs (k_copy_envs: one warp per copy, 128-thread blocks)
+int hm_engine_copy_envs(void *dst_h, const int64_t *dst_idx, void *src_h, const int64_t *src_idx,
+                        int64_t count) {
+    HEngine *dst = static_cast<HEngine *>(dst_h), *src = static_cast<HEngine *>(src_h);
+    if ((!dst_idx && count > dst->st.n) || (!src_idx && count > src->st.n)) return PB_ERR_INVALID_ARG;
+    const unsigned blocks = (unsigned)((count * 32 + 127) / 128);
+    for (unsigned b = 0; b < blocks; b++)
+        for (unsigned t = 0; t < 128; t++) {
+            blockIdx.x = b;
+            threadIdx.x = t;
+            k_copy_envs(dst->st, reinterpret_cast<const long long *>(dst_idx), src->st,
+                        reinterpret_cast<const long long *>(src_idx), count);
+        }
+    return PB_OK;
+}
+
 // returns the sticky error bits (and clears them), *epoch_out = completed search iterations
 unsigned hm_mcts_check(void *h, uint64_t *epoch_out) {
     HMcts *m = static_cast<HMcts *>(h);

@@ -53,6 +53,10 @@ def hm(pb):
     L.hm_mcts_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     L.hm_mcts_check.restype = C.c_uint
     L.hm_mcts_check.argtypes = [vp, vp]
+    L.hm_mcts_collect_act.restype = C.c_int
+    L.hm_mcts_collect_act.argtypes = [vp, vp, C.c_int, C.c_int] + [vp] * 7
+    L.hm_engine_copy_envs.restype = C.c_int
+    L.hm_engine_copy_envs.argtypes = [vp, vp, vp, vp, i64]
     for name, args in dict(
             hm_engine_destroy=[vp], hm_engine_reset=[vp, vp], hm_engine_get_state=[vp, vp],
             hm_engine_set_state=[vp, vp], hm_engine_action_mask=[vp, vp], hm_mcts_destroy=[vp],
@@ -78,6 +82,9 @@ def _mask_np(mask, n):
 
 class HostEnv:
     """The part of BatchedPacmanGym the MCTS tests use, on the host build of the engine."""
+
+    device = torch.device("cpu")
+    oracle = None   # set by the fixtures: observations come from the env oracle
 
     def __init__(self, L, pb, n, random_start, random_ticks, *, device=None, seed=0, env_id_base=0):
         self.L, self.pb, self.num_envs, self.seed, self.env_id_base = L, pb, n, seed, env_id_base
@@ -109,6 +116,46 @@ class HostEnv:
         self.L.hm_engine_action_mask(self.h, m.ctypes.data)
         return torch.from_numpy(m.astype(bool))
 
+    @property
+    def _h(self):          # the name the product's host code uses for the engine handle
+        return self.h
+
+    def obs_range(self, first, count, out):
+        """What k_encode_obs writes for envs [first, first + count): the oracle's observation of
+        the same states (the encoder itself is GPU-only and has its own parity tests)."""
+        st = gpu_to_oracle_state(self.oracle, self.get_state()[first:first + count])
+        ob = self.oracle.OracleBatch(count, np.zeros(count, np.uint8), None)
+        ob.import_state(st)
+        out.copy_(torch.from_numpy(ob.obs()))
+        return out
+
+    def obs(self, out=None):
+        if out is None:
+            out = torch.empty((self.num_envs, 17, 28, 31), dtype=torch.float32)
+        return self.obs_range(0, self.num_envs, out)
+
+    def copy_envs_from(self, src, src_index=None, dst_index=None, count=None):
+        def ptr(t):
+            return None if t is None else np.ascontiguousarray(t.cpu().numpy(), np.int64)
+
+        si, di = ptr(src_index), ptr(dst_index)
+        if count is None:
+            count = len(di) if di is not None else len(si) if si is not None else min(self.num_envs, src.num_envs)
+        assert self.L.hm_engine_copy_envs(self.h, _ptr(di), src.h, _ptr(si), int(count)) == 0
+
+
+class _CollectActABI:
+    """`mcts._L` as pacbot-rl_b200/alphazero.py uses it: pb_mcts_collect_act with the C ABI's
+    argument list, on host pointers."""
+
+    def __init__(self, L):
+        self._lib = L
+
+    def pb_mcts_collect_act(self, mcts_h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask, ep_dist,
+                            ep_value, status, flags, stream):
+        return self._lib.hm_mcts_collect_act(mcts_h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask,
+                                             ep_dist, ep_value, status, flags)
+
 
 class HostMCTS:
     """pacbot-rl_b200/mcts.py::BatchedMCTS re-stated over the host build of the kernels."""
@@ -121,16 +168,24 @@ class HostMCTS:
         factor = int(os.environ.get("PB_MCTS_POOL_FACTOR", "8"))
         tpw = int(os.environ.get("PB_MCTS_TREES_PER_WARP", "1"))
         self.h = L.hm_mcts_create(env.h, self.sim.h, self.max_nodes, factor, tpw)
-        self._obs_oracle = oracle.OracleBatch(n, np.zeros(n, np.uint8), None)
+        self.device = env.device
+        self._h = self.h
+        self._L = _CollectActABI(L)
 
     def __del__(self):
         if getattr(self, "h", None):
             self.L.hm_mcts_destroy(self.h)
             self.h = None
 
-    def _obs_of(self, engine):   # what k_encode_obs would write for `engine` (the oracle's obs)
-        self._obs_oracle.import_state(gpu_to_oracle_state(self.oracle, engine.get_state()))
-        return torch.from_numpy(self._obs_oracle.obs())
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return None
+
+    def _obs_of(self, engine):
+        return engine.obs()
 
     def _evaluate(self, obs, mask):
         value, policy = self.evaluator(obs, mask)
@@ -224,6 +279,19 @@ def host_pb(hm, pb, oracle, monkeypatch):
     monkeypatch.setattr(pb.mcts, "BatchedMCTS",
                         lambda env, ev, max_nodes, **kw: HostMCTS(hm, pb, oracle, env, ev, max_nodes, **kw))
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(HostEnv, "oracle", oracle)
+
+    # pacbot-rl_b200/alphazero.py resolves these two names in its own namespace; with the stand-ins
+    # in place the product's BatchedExperienceCollector (its host-side episode bookkeeping
+    # included) runs UNMODIFIED over the host build of the kernels
+    class MCTSFactory:
+        _p = staticmethod(HostMCTS._p)
+
+        def __new__(cls, env, ev, max_nodes, **kw):
+            return HostMCTS(hm, pb, oracle, env, ev, max_nodes, **kw)
+
+    monkeypatch.setattr(pb.alphazero, "BatchedPacmanGym", pb.BatchedPacmanGym)
+    monkeypatch.setattr(pb.alphazero, "BatchedMCTS", MCTSFactory)
     return pb
 
 
@@ -264,3 +332,13 @@ def test_trees_per_warp_mapping_does_not_change_results(host_pb, pymcts, tpw, mo
 
     monkeypatch.setenv("PB_MCTS_TREES_PER_WARP", tpw)
     tg.test_ponder_grows_each_tree_to_the_requested_size(host_pb, pymcts)
+
+
+def test_product_collector_runs_over_the_host_kernels_and_matches_oracle(host_pb, pymcts):
+    """test_mcts_gpu.test_collector_matches_oracle: the product's BatchedExperienceCollector
+    (pacbot-rl_b200/alphazero.py, unmodified -- search budget, episode records, truncation
+    bootstrap, discounted returns, hand-out order) over the host build of k_mcts_collect_act and
+    friends, against the oracle's ExperienceCollector: items bit for bit."""
+    import test_mcts_gpu as tg
+
+    tg.test_collector_matches_oracle(host_pb, pymcts)
