@@ -2,12 +2,15 @@
 the host (tests/host_engine/host_mcts.cpp) against the scalar MCTS oracle (oracle/mcts_oracle.c, a
 restatement of pacbot_rs/src/mcts.rs): the GPU suite's own test bodies
 (test_mcts_gpu.test_search_take_action_and_reset_match_oracle, ..ponder..) are re-run with a host
-stand-in for `BatchedPacmanGym` / `BatchedMCTS`, so tree statistics, rewards and env states are
+stand-in for the engine (`HostEnv`), so tree statistics, rewards and env states are
 compared bit for bit over search / re-root / fresh-root / compaction / reset cycles without a GPU.
 
-Test infrastructure only (like tests/test_host_engine.py): `HostMCTS` below re-implements the
-host-side orchestration of pacbot-rl_b200/mcts.py with NumPy, the leaf observations come from the
-env oracle (the encoder is GPU-only), and the GPU tests remain the parity tests proper."""
+The product's host code -- pacbot-rl_b200/mcts.py (`BatchedMCTS`) and alphazero.py
+(`BatchedExperienceCollector`) -- runs UNMODIFIED in these tests: only the engine object is the
+host stand-in `HostEnv` (the product's `BatchedPacmanGym` refuses to exist without a CUDA device,
+by design) and the C calls go through `HostABI` into the host build.  Leaf observations come from
+the env oracle (the encoder is GPU-only).  Test infrastructure only, like tests/test_host_engine.py;
+the GPU tests remain the parity tests proper."""
 import ctypes as C
 import os
 import subprocess
@@ -22,9 +25,6 @@ from test_parity_gpu import gpu_to_oracle_state
 HE_DIR = os.path.join(ROOT, "tests", "host_engine")
 HM_SO = os.path.join(HE_DIR, "_build", "libhost_mcts.so")
 CSRC = os.path.join(ROOT, "pacbot-rl_b200", "csrc")
-Q = dict(best_action=0, action_distribution=1, policy_prior=2, action_values=3, value=4, max_depth=5,
-         node_count=6, root_visits=7)                       # MCTS_Q_* of pb_mcts.cuh
-ST_REROOTED, ST_NEEDS_ROOT, ST_WAS_DONE, ST_BAD_ACTION = 2, 3, 4, 5
 ERR = {1: "node pool full", 2: "tried to expand the same child twice", 4: "search from a finished env"}
 
 
@@ -86,6 +86,10 @@ class HostEnv:
     device = torch.device("cpu")
     oracle = None   # set by the fixtures: observations come from the env oracle
 
+    @property
+    def _L(self):          # `env._L`: the library object the product's host code calls into
+        return HostABI(self.L)
+
     def __init__(self, L, pb, n, random_start, random_ticks, *, device=None, seed=0, env_id_base=0):
         self.L, self.pb, self.num_envs, self.seed, self.env_id_base = L, pb, n, seed, env_id_base
         rs = np.broadcast_to(np.asarray(random_start, bool), (n,))
@@ -144,154 +148,86 @@ class HostEnv:
         assert self.L.hm_engine_copy_envs(self.h, _ptr(di), src.h, _ptr(si), int(count)) == 0
 
 
-class _CollectActABI:
-    """`mcts._L` as pacbot-rl_b200/alphazero.py uses it: pb_mcts_collect_act with the C ABI's
-    argument list, on host pointers."""
+class HostABI:
+    """The pb_mcts_* entry points of include/pacbot_b200.h (argument lists as in the C ABI, stream
+    ignored) on top of the host build: what pacbot-rl_b200/mcts.py and alphazero.py call through
+    `env._L`.  Handles are the harness's pointers; tensors are CPU tensors, so `data_ptr()` is a
+    host pointer."""
+
+    last_error = ""
 
     def __init__(self, L):
         self._lib = L
 
-    def pb_mcts_collect_act(self, mcts_h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask, ep_dist,
+    def pb_mcts_create(self, out_ref, root_h, sim_h, max_nodes):
+        factor = int(os.environ.get("PB_MCTS_POOL_FACTOR", "8"))     # as pb_mcts_create reads them
+        tpw = int(os.environ.get("PB_MCTS_TREES_PER_WARP", "1"))
+        out_ref._obj.value = self._lib.hm_mcts_create(root_h, sim_h, max_nodes, factor, tpw)
+        return 0
+
+    def pb_mcts_destroy(self, h):
+        self._lib.hm_mcts_destroy(h)
+        return 0
+
+    def pb_mcts_reset_root(self, h, mask, value, policy, stream):
+        self._lib.hm_mcts_reset_root(h, mask, value, policy)
+        return 0
+
+    def pb_mcts_root_noise(self, h, mask, noise, mix, stream):
+        self._lib.hm_mcts_root_noise(h, mask, noise, mix)
+        return 0
+
+    def pb_mcts_select(self, h, active, leaf_kind, leaf_mask, stream):
+        self._lib.hm_mcts_select(h, active, leaf_kind, leaf_mask)
+        return 0
+
+    def pb_mcts_backprop(self, h, value, policy, stream):
+        self._lib.hm_mcts_backprop(h, value, policy)
+        return 0
+
+    def pb_mcts_take_action(self, h, mask, actions, reward, done, status, stream):
+        self._lib.hm_mcts_take_action(h, mask, actions, reward, done, status)
+        return 0
+
+    def pb_mcts_query(self, h, what, out, stream):
+        self._lib.hm_mcts_query(h, what, out)
+        return 0
+
+    def pb_mcts_check(self, h, epoch_ref, stream):
+        err = self._lib.hm_mcts_check(h, C.addressof(epoch_ref._obj))
+        if err:   # the message pb_mcts_check composes (pb_mcts_abi.inl)
+            HostABI.last_error = "pb_mcts: " + "; ".join(v for k, v in ERR.items() if err & k)
+            return -1
+        return 0
+
+    def pb_mcts_collect_act(self, h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask, ep_dist,
                             ep_value, status, flags, stream):
-        return self._lib.hm_mcts_collect_act(mcts_h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask,
+        return self._lib.hm_mcts_collect_act(h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask,
                                              ep_dist, ep_value, status, flags)
 
 
-class HostMCTS:
-    """pacbot-rl_b200/mcts.py::BatchedMCTS re-stated over the host build of the kernels."""
-
-    def __init__(self, L, pb, oracle, env, evaluator, max_nodes, *, noise_fn=None, noise_mix=0.25):
-        self.L, self.pb, self.oracle, self.env, self.evaluator = L, pb, oracle, env, evaluator
-        self.max_nodes, self.noise_fn, self.noise_mix = int(max_nodes), noise_fn, float(noise_mix)
-        n = self.num_envs = env.num_envs
-        self.sim = HostEnv(L, pb, n, False, False, seed=env.seed, env_id_base=env.env_id_base)
-        factor = int(os.environ.get("PB_MCTS_POOL_FACTOR", "8"))
-        tpw = int(os.environ.get("PB_MCTS_TREES_PER_WARP", "1"))
-        self.h = L.hm_mcts_create(env.h, self.sim.h, self.max_nodes, factor, tpw)
-        self.device = env.device
-        self._h = self.h
-        self._L = _CollectActABI(L)
-
-    def __del__(self):
-        if getattr(self, "h", None):
-            self.L.hm_mcts_destroy(self.h)
-            self.h = None
-
-    @staticmethod
-    def _p(t):
-        return None if t is None else C.c_void_p(t.data_ptr())
-
-    def _stream(self):
-        return None
-
-    def _obs_of(self, engine):
-        return engine.obs()
-
-    def _evaluate(self, obs, mask):
-        value, policy = self.evaluator(obs, mask)
-        return (np.ascontiguousarray(value.cpu().numpy(), np.float32).reshape(-1),
-                np.ascontiguousarray(policy.cpu().numpy(), np.float32).reshape(-1, 5))
-
-    def check(self):
-        epoch = C.c_uint64(0)
-        err = self.L.hm_mcts_check(self.h, C.addressof(epoch))
-        if err:
-            raise ValueError("pb_mcts: " + "; ".join(v for k, v in ERR.items() if err & k))
-        return int(epoch.value)
-
-    def add_root_noise(self, mask=None):
-        m = _mask_np(mask, self.num_envs)
-        num_valid = self.env.action_mask().sum(dim=1)
-        if self.noise_fn is not None:
-            noise = self.noise_fn(num_valid, None if m is None else torch.from_numpy(m))
-        else:   # the product's sampler (a torch function; runs on CPU tensors as well)
-            noise = self.pb.mcts.dirichlet_root_noise(num_valid)
-        noise = np.ascontiguousarray(noise.cpu().numpy(), np.float32)
-        self.L.hm_mcts_root_noise(self.h, _ptr(m), noise.ctypes.data, self.noise_mix)
-
-    def reset_root(self, mask=None, index=None):
-        m = _mask_np(mask, self.num_envs)
-        value, policy = self._evaluate(self._obs_of(self.env), self.env.action_mask())
-        self.L.hm_mcts_reset_root(self.h, _ptr(m), value.ctypes.data, policy.ctypes.data)
-        self.add_root_noise(m)
-
-    def reset(self, mask=None, index=None):
-        self.env.reset(mask)
-        self.reset_root(mask)
-
-    def search_iteration(self, active=None):
-        n = self.num_envs
-        a = _mask_np(active, n)
-        kind = np.zeros(n, np.uint8)
-        lmask = np.zeros((n, 5), np.uint8)
-        self.L.hm_mcts_select(self.h, _ptr(a), kind.ctypes.data, lmask.ctypes.data)
-        value, policy = self._evaluate(self._obs_of(self.sim), torch.from_numpy(lmask.astype(bool)))
-        self.L.hm_mcts_backprop(self.h, value.ctypes.data, policy.ctypes.data)
-
-    def ponder(self, max_tree_size):
-        if max_tree_size > self.max_nodes:
-            raise ValueError(f"max_tree_size {max_tree_size} exceeds max_nodes {self.max_nodes}")
-        remaining = (max_tree_size - self.node_count()).clamp(min=0)
-        for it in range(int(remaining.max().item())):
-            self.search_iteration(remaining > it)
-        return self.best_action()
-
-    def take_action(self, actions, mask=None):
-        n = self.num_envs
-        m = _mask_np(mask, n)
-        a = np.ascontiguousarray(actions.cpu().numpy(), np.uint8)
-        reward, done, status = np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
-        self.L.hm_mcts_take_action(self.h, _ptr(m), a.ctypes.data, reward.ctypes.data, done.ctypes.data,
-                                   status.ctypes.data)
-        if (status == ST_WAS_DONE).any():
-            raise RuntimeError("take_action on a finished env")
-        if (status == ST_BAD_ACTION).any():
-            raise ValueError("Invalid action")
-        if (status == ST_NEEDS_ROOT).any():
-            self.reset_root(status == ST_NEEDS_ROOT)
-        if (status == ST_REROOTED).any():
-            self.add_root_noise(status == ST_REROOTED)
-        return torch.from_numpy(reward), torch.from_numpy(done.astype(bool)), torch.from_numpy(status)
-
-    def _query(self, what, shape, dtype):
-        out = np.zeros(shape, dtype)
-        self.L.hm_mcts_query(self.h, Q[what], out.ctypes.data)
-        return torch.from_numpy(out)
-
-
-for _name, _shape, _dtype in [("best_action", 1, np.int32), ("action_distribution", 5, np.float32),
-                              ("policy_prior", 5, np.float32), ("action_values", 5, np.float32),
-                              ("value", 1, np.float32), ("max_depth", 1, np.int32),
-                              ("node_count", 1, np.int32), ("root_visits", 1, np.int32)]:
-    def _make(name=_name, width=_shape, dtype=_dtype):
-        def query(self):
-            return self._query(name, (self.num_envs,) if width == 1 else (self.num_envs, width), dtype)
-        return query
-    setattr(HostMCTS, _name, _make())
+def _check(rc):   # pacbot-rl_b200/_lib.py::check with the adapter's error text
+    if rc != 0:
+        raise ValueError(HostABI.last_error)
 
 
 @pytest.fixture
 def host_pb(hm, pb, oracle, monkeypatch):
-    """`pb` with BatchedPacmanGym / mcts.BatchedMCTS replaced by the host stand-ins, and
-    Tensor.cuda() as the identity (the re-used GPU test bodies call it on their masks)."""
-    monkeypatch.setattr(pb, "BatchedPacmanGym",
-                        lambda n, rs=False, rt=False, **kw: HostEnv(hm, pb, n, rs, rt, **kw))
-    monkeypatch.setattr(pb.mcts, "BatchedMCTS",
-                        lambda env, ev, max_nodes, **kw: HostMCTS(hm, pb, oracle, env, ev, max_nodes, **kw))
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    """`pb` with `BatchedPacmanGym` replaced by the host stand-in wherever the product's host code
+    resolves that name.  pacbot-rl_b200/mcts.py (`BatchedMCTS`) and alphazero.py
+    (`BatchedExperienceCollector`) then run UNMODIFIED -- tensors on the CPU, C calls through
+    HostABI into the host build of the kernels.  `Tensor.cuda()` becomes the identity (the re-used
+    GPU test bodies call it on their masks) and the CUDA stream argument is dropped."""
+    def make_env(n, rs=False, rt=False, **kw):
+        return HostEnv(hm, pb, n, rs, rt, **kw)
+
     monkeypatch.setattr(HostEnv, "oracle", oracle)
-
-    # pacbot-rl_b200/alphazero.py resolves these two names in its own namespace; with the stand-ins
-    # in place the product's BatchedExperienceCollector (its host-side episode bookkeeping
-    # included) runs UNMODIFIED over the host build of the kernels
-    class MCTSFactory:
-        _p = staticmethod(HostMCTS._p)
-
-        def __new__(cls, env, ev, max_nodes, **kw):
-            return HostMCTS(hm, pb, oracle, env, ev, max_nodes, **kw)
-
-    monkeypatch.setattr(pb.alphazero, "BatchedPacmanGym", pb.BatchedPacmanGym)
-    monkeypatch.setattr(pb.alphazero, "BatchedMCTS", MCTSFactory)
+    for mod in (pb, pb.mcts, pb.alphazero):
+        monkeypatch.setattr(mod, "BatchedPacmanGym", make_env)
+    monkeypatch.setattr(pb.mcts.BatchedMCTS, "_stream", lambda self: None)
+    monkeypatch.setattr(pb.mcts, "check", _check)
+    monkeypatch.setattr(pb.alphazero, "check", _check)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     return pb
 
 
