@@ -1,8 +1,10 @@
 // host_mcts.cpp -- TEST INFRASTRUCTURE: the device MCTS kernels of the product
 // (pacbot-rl_b200/csrc/pb_mcts.cuh: k_mcts_reset_root / root_noise / select / backprop /
-// take_action / query) compiled for the HOST with g++ and run thread by thread, so that
-// tests/test_host_mcts.py can diff the *same source the GPU executes* against the scalar MCTS
-// oracle (oracle/mcts_oracle.c) in a container without a GPU.  A "launch" here is a loop over
+// take_action / collect_act / query, k_copy_envs) and a host engine object around the device game
+// logic (create / reset / step / state access), compiled for the HOST with g++ and run thread by
+// thread, so that tests/test_host_mcts.py and tests/test_host_replay.py can run the product's
+// Python host code over the *same source the GPU executes* and diff it against the scalar
+// oracles (oracle/) in a container without a GPU.  A "launch" here is a loop over
 // (block, thread) with threadIdx / blockIdx set before every call; the kernels have no
 // intra-launch communication (one thread owns one tree), so the order does not matter.
 // The glue around the kernels mirrors pacbot-rl_b200/csrc/pb_kernels.cu (load_env, store_env,
@@ -83,6 +85,8 @@ struct HEngine {
     StateView st{};
     uint64_t seed = 0;
     long long gid_base = 0;
+    const uint32_t *tape = nullptr;   // pb_set_draw_tape: borrowed, [n][tape_len]
+    long long tape_len = 0;
     std::vector<uint4> core0, core1, ghosts;
     std::vector<uint32_t> pel;
 };
@@ -97,7 +101,7 @@ struct HMcts {
     unsigned int error = 0;
 };
 
-RngParams rng_params(const HEngine *e) { return RngParams{e->seed, e->gid_base, nullptr, 0}; }
+RngParams rng_params(const HEngine *e) { return RngParams{e->seed, e->gid_base, e->tape, e->tape_len}; }
 
 template <class F>
 void launch(const MctsView &v, F kernel) {
@@ -151,6 +155,45 @@ void hm_engine_reset(void *h, const uint8_t *mask) {
         gym_reset(s, pel, c_tab, walls, make_rng(rng_params(e), i), true);
         store_env(e->st, i, s);
     }
+}
+
+void hm_engine_set_tape(void *h, const uint32_t *tape, int64_t tape_len) {
+    HEngine *e = static_cast<HEngine *>(h);
+    e->tape = tape;
+    e->tape_len = tape ? tape_len : 0;
+}
+
+// pb_step: what one k_step thread does (pb_kernels.cu), actions given by the caller; returns the
+// index of the first invalid action or -1
+int64_t hm_engine_step(void *h, const uint8_t *actions, int32_t *reward, uint8_t *done_out,
+                       uint8_t *mask_out, int auto_reset) {
+    HEngine *e = static_cast<HEngine *>(h);
+    uint32_t walls[32];
+    load_walls(walls);
+    int64_t bad = -1;
+    for (long long i = 0; i < e->st.n; i++) {
+        EnvR s;
+        load_env(e->st, i, s);
+        const int action = actions[i];
+        if (action > 4) {   // env.rs:83-88: "Invalid action" -- env untouched
+            if (bad < 0) bad = i;
+            reward[i] = 0;
+            done_out[i] = 0;
+            if (mask_out) write_mask(mask_out, i, action_mask_bits(s, walls));
+            continue;
+        }
+        const PelRef pel{e->st.pel + i, e->st.npad};
+        const RngCtx rng = make_rng(rng_params(e), i);
+        int rew;
+        bool done;
+        gym_step(s, pel, c_tab, walls, rng, action, rew, done);
+        if (done && auto_reset) gym_reset(s, pel, c_tab, walls, rng, true);
+        store_env(e->st, i, s);
+        reward[i] = rew;
+        done_out[i] = done ? 1 : 0;
+        if (mask_out) write_mask(mask_out, i, action_mask_bits(s, walls));
+    }
+    return bad;
 }
 
 void hm_engine_get_state(void *h, pb_env_state *out) {
