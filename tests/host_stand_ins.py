@@ -107,14 +107,60 @@ class HostEnv:
         m = _mask_np(mask, self.num_envs)
         self.L.hm_engine_reset(self.h, _ptr(m))
 
-    def get_state(self):
+    def get_state(self, first=0, count=None):
         st = np.zeros(self.num_envs, self.pb.ENV_STATE_DTYPE)
         self.L.hm_engine_get_state(self.h, st.ctypes.data)
-        return st
+        return st[first:(self.num_envs if count is None else first + count)].copy()
 
-    def set_state(self, st):
-        st = np.ascontiguousarray(st, self.pb.ENV_STATE_DTYPE)
-        self.L.hm_engine_set_state(self.h, st.ctypes.data)
+    def set_state(self, st, first=0):
+        full = self.get_state()
+        full[first:first + len(st)] = np.ascontiguousarray(st, self.pb.ENV_STATE_DTYPE)
+        self.L.hm_engine_set_state(self.h, full.ctypes.data)
+        self.cfg = (full["cfg_flags"] & 0x0F).astype(np.uint8)
+
+    # ---- what pacbot-rl_b200/gym.py (the per-env PacmanGym drop-in) asks of its engine -------------
+    @property
+    def _cfg(self):
+        return self.cfg
+
+    @property
+    def random_start(self):
+        return (self.cfg & 1).astype(bool)
+
+    @random_start.setter
+    def random_start(self, value):   # pb_set_cfg_flags
+        st = self.get_state()
+        v = np.broadcast_to(np.asarray(value, bool), (self.num_envs,)).astype(np.uint8)
+        st["cfg_flags"] = (st["cfg_flags"] & ~np.uint8(1)) | v
+        self.set_state(st)
+
+    def step_host(self, actions, obs_out=None, want_mask=True, out=None):   # pb_step_host
+        n = self.num_envs
+        a = np.ascontiguousarray(actions, np.uint8)
+        reward, done, mask = np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros((n, 5), np.uint8)
+        bad = self.L.hm_engine_step(self.h, a.ctypes.data, reward.ctypes.data, done.ctypes.data,
+                                    mask.ctypes.data, int(self.auto_reset))
+        if bad >= 0:
+            raise ValueError("Invalid action")   # PB_ERR_INVALID_ACTION through _lib.check
+        return reward, done.astype(bool), (mask.astype(bool) if want_mask else None)
+
+    def obs_numpy(self, first=0, count=None):   # pb_obs_host
+        count = self.num_envs - first if count is None else count
+        out = torch.empty((count, 17, 28, 31), dtype=torch.float32)
+        return self.obs_range(first, count, out).numpy().copy()
+
+    def clone_env_from(self, dst_index, src, src_index):   # pb_clone_env
+        self.copy_envs_from(src, torch.tensor([src_index]), torch.tensor([dst_index]))
+        self.cfg[dst_index] = src.cfg[src_index]
+
+    def view(self, index):
+        return self.pb.gym.PacmanGymView(self, index)
+
+    def score(self):
+        return self._scalar(lambda s: int(s["curr_score"])).to(torch.int32)
+
+    def lives(self):
+        return self._scalar(lambda s: int(s["curr_lives"])).to(torch.int32)
 
     def action_mask(self, out=None):
         m = np.zeros((self.num_envs, 5), np.uint8)
@@ -265,7 +311,7 @@ def host_pb(hm, pb, oracle, monkeypatch):
         return HostEnv(hm, pb, n, rs, rt, **kw)
 
     monkeypatch.setattr(HostEnv, "oracle", oracle)
-    for mod in (pb, pb.mcts, pb.alphazero, pb.replay_buffer):
+    for mod in (pb, pb.mcts, pb.alphazero, pb.replay_buffer, pb.gym):
         monkeypatch.setattr(mod, "BatchedPacmanGym", make_env)
     monkeypatch.setattr(pb.mcts.BatchedMCTS, "_stream", lambda self: None)
     monkeypatch.setattr(pb.mcts, "check", _check)
