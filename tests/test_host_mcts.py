@@ -63,3 +63,18 @@ def test_product_collector_runs_over_the_host_kernels_and_matches_oracle(host_pb
     import test_mcts_gpu as tg
 
     tg.test_collector_matches_oracle(host_pb, pymcts)
+
+
+def test_mcts_context_drop_in_surface_on_cpu(host_pb):
+    """pacbot_rs.MCTSContext drop-in (mcts.py over gym.py, both unmodified) with the reference's
+    NumPy evaluator, as train_alphazero.py:119-131 drives it."""
+    import test_mcts_gpu as tg
+
+    tg.test_mcts_context_drop_in_surface(host_pb)
+
+
+def test_experience_collector_drop_in_surface_on_cpu(host_pb):
+    """pacbot_rs.ExperienceCollector drop-in: NumPy evaluator in, list of ExperienceItem out."""
+    import test_mcts_gpu as tg
+
+    tg.test_experience_collector_drop_in_surface(host_pb)
