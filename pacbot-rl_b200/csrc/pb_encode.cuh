@@ -92,6 +92,33 @@ constexpr int CH_VEC = CH_FLOATS / 4;                   // 217 float4 per channe
 static_assert(ENC_SMEM <= 227 * 1024, "encoder images must fit the 227 KB shared memory");
 static_assert(IMG_BYTES % 16 == 0 && CH_BYTES % 16 == 0, "bulk copies move 16 B granules");
 
+#ifdef PB_HOST_EMULATION
+// The test suite compiles this kernel for the HOST (one OS thread per lane, tests/README.md) to
+// diff it against the oracle without a GPU.  Only the data movement primitives differ there:
+// plain copies instead of cp.async / TMA bulk copies, nothing to fence or wait for.  The GPU
+// build never defines PB_HOST_EMULATION; its token stream is the #else branch, unchanged.
+#ifndef PB_ENC_STORE_HINT
+#define PB_ENC_STORE_HINT 1
+#endif
+#ifndef PB_ENC_PIN_STATE
+#define PB_ENC_PIN_STATE 0
+#endif
+inline void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) { memcpy(gdst, ssrc, bytes); }
+inline uint64_t l2_policy_evict_first() { return 0; }
+inline void bulk_store_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t) {
+    memcpy(gdst, ssrc, bytes);
+}
+inline void bulk_commit() {}
+template <int N>
+inline void bulk_wait_read() {}
+inline void bulk_wait_all() {}
+inline void fence_proxy_async_smem() {}
+inline void cp_async_4(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 4); }
+inline void cp_async_16(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+inline void grid_dependency_wait() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -145,6 +172,10 @@ __device__ __forceinline__ void cp_async_16(void *sdst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// wait for the preceding grid of the stream (programmatic dependent launch)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif  // PB_HOST_EMULATION
+
 __device__ __forceinline__ bool on_board(int row, int col) {
     return (unsigned)row < (unsigned)ROWS && (unsigned)col < (unsigned)COLS;
 }
@@ -187,7 +218,7 @@ k_encode_obs(StateView st, float *__restrict__ out,
     __syncthreads();  // the template is read by every warp's bulk copies
     // everything above overlapped the previous kernel (programmatic dependent launch); from here
     // on the env state and the ticket are read, so wait for the preceding grid to finish
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    grid_dependency_wait();
     // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
     // replayed while the replay ring advances.  Read AFTER the wait: under programmatic dependent
     // launch nothing written by the preceding grid is visible before it.
