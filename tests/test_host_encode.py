@@ -95,3 +95,34 @@ def test_encoder_source_on_a_rollout_and_ranges(henc, pb, oracle):
     for cnt in (1, 31, 33):
         assert_obs_equal(ob.obs()[:cnt], henc(st[:cnt]), f"{cnt} envs")
     assert_obs_equal(ob.obs()[100:177], henc(st, first=100, count=77), "sub-range")
+
+
+def test_host_builds_reproduce_golden_trajectory_including_observations(henc, pb):
+    """tests/golden/trajectory_v1.npz end to end on the CPU with product sources only: the host
+    build of the engine steps the envs, the host-emulated encoder writes their observations; the
+    fixture's per-step digests of the full state AND of the float32 observations must come out
+    (the GPU test of the same fixture does this through the C ABI)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_trajectory import obs_digest, state_digest
+    from test_host_engine import HE_SO, HostEngineBatch, _build
+
+    _build()
+    lib = C.CDLL(HE_SO)
+    lib.he_step.restype = C.c_int64
+    lib.he_step.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_int64]
+    lib.he_reset.restype = None
+    lib.he_reset.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_uint64, C.c_int64,
+                             C.c_void_p, C.c_int64]
+    lib.he_action_mask.restype = None
+    lib.he_action_mask.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "trajectory_v1.npz")))
+    hb = HostEngineBatch(lib, pb, len(g["cfg"]), g["cfg"], g["tape"])
+    hb.reset()
+    for t in range(g["actions"].shape[0]):
+        r, d, _, _ = hb.step(g["actions"][t], auto_reset=True)
+        assert np.array_equal(r, g["reward"][t]) and np.array_equal(d, g["done"][t]), t
+        assert state_digest(hb.st) == g["state_digest"][t], f"state differs at step {t}"
+        assert obs_digest(henc(hb.st)) == g["obs_digest"][t], f"observation differs at step {t}"
