@@ -237,6 +237,13 @@ int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream);
 /* ---- state access (parity tests, MCTS-style cloning, checkpointing); synchronous ------------- */
 int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out_host);
 int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in_host);
+/* The same, ordered on `stream`: only that stream and the engine's own streams are synchronised
+ * (pb_get_state / pb_set_state wait for the whole device).  This is what the per-env drop-in
+ * getters (score(), lives(), ... env.rs:269-289) go through: a training graph replaying on
+ * another stream is not stalled by them. */
+int pb_get_state_on(pb_engine *e, int64_t first, int64_t count, pb_env_state *out_host, void *stream);
+int pb_set_state_on(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in_host,
+                    void *stream);
 /* #[derive(Clone)] on PacmanGym (env.rs:96): copy env src_i of `src` over env dst_i of `dst` */
 int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t src_i, void *stream);
 
@@ -251,7 +258,11 @@ int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t sr
 int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
                  uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
                  int64_t env_stride_floats, void *stream);
-/* obs of envs [first, first+count) straight to a host buffer (obs_numpy for a per-env view). */
+/* obs_numpy() (env.rs:305-307) of envs [first, first+count) straight to a host buffer.  The
+ * range is encoded in chunks of 1 024 envs into two device staging buffers; each chunk crosses
+ * PCIe on an internal stream while the next one is being encoded.  A pinned / registered
+ * destination receives the copies directly (PCIe-bound); a pageable one goes through two pinned
+ * bounce buffers with the host memcpy overlapped.  Returns when obs_host is complete. */
 int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, void *stream);
 
 /* ---- on-device DQN helpers (reference: src/policies.py, src/replay_buffer.py) ---------------- */
@@ -260,12 +271,63 @@ int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, voi
  * q_dev float32 [n][5]; mask_dev uint8 [n][5] or NULL (= current action_mask()). */
 int pb_select_actions(pb_engine *e, const float *q_dev, const uint8_t *mask_dev, float epsilon,
                       uint8_t *actions_dev, uint64_t call_idx, void *stream);
+/* pb_select_actions with epsilon (float32) and the call index (int64) read from DEVICE memory at
+ * kernel time: a captured CUDA graph follows the epsilon schedule and the step counter while it
+ * is replayed. */
+int pb_select_actions_dev(pb_engine *e, const float *q_dev, const uint8_t *mask_dev,
+                          const float *epsilon_dev, const int64_t *call_idx_dev,
+                          uint8_t *actions_dev, void *stream);
 /* Gather `count` observations (float32 [PB_OBS_FLOATS] each) from ring slots idx_dev[k]
  * (int64 slot numbers) of ring_dev (slot stride in floats) into the dense out_dev, writing zeros
  * where zero_mask_dev[k] != 0 (the `next_obs is None` case, train_dqn.py:154-159). */
 int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64_t *idx_dev,
                   const uint8_t *zero_mask_dev, int64_t count, float *out_dev, int device,
                   void *stream);
+
+/* ---- replay ring (reference: src/replay_buffer.py:57-143, collate of train_dqn.py:152-165) ---
+ * A TIME ring of R slots x n envs.  Slot s = t % R holds the observation before action t (written
+ * by pb_encode_obs_ring) and, per env, action uint8 / reward int32 / done uint8 / next action mask
+ * uint8[5] / valid uint8 of transition t, each a dense [R][n] array owned by the caller; flat index
+ * = s * n + env; next_obs of a transition is slot (s + 1) % R.  The step counter t is an int64 in
+ * DEVICE memory read at kernel time (CUDA-graph replay). */
+/* deque.append for one step of all envs (replay_buffer.py:107-137): slot t % R receives the
+ * transition (next mask = mask_dev & ~done; valid = 1, or !in_phase1_dev[i] for the steps of
+ * reset_env's old policy, replay_buffer.py:44-54, which are not recorded); slot (t+1) % R becomes
+ * "current observation only" (valid = 0).  mask_dev is the mask AFTER the step (pb_step's). */
+int pb_replay_record(int64_t n_envs, int64_t ring_slots, const int64_t *t_dev,
+                     const uint8_t *actions_dev, const int32_t *reward_dev, const uint8_t *done_dev,
+                     const uint8_t *mask_dev, const uint8_t *in_phase1_dev, uint8_t *ring_actions,
+                     int32_t *ring_rewards, uint8_t *ring_done, uint8_t *ring_next_mask,
+                     uint8_t *ring_valid, int device, void *stream);
+/* random.sample(buffer, batch) (replay_buffer.py:141-143): `batch` DISTINCT flat indices of valid
+ * transitions, uniform over all such subsets and orders: the valid flags are compacted in
+ * ascending order into a list of m entries, then position j = 0..batch-1 swaps with position
+ * j + ((raw_j * (m - j)) >> 32), raw_j = pb_replay_raw(seed, *call_idx_dev, j) (partial
+ * Fisher-Yates).  *num_valid_out_dev (may be NULL) receives m; if m < batch the draws are WITH
+ * replacement over the m entries (index 0 if m == 0) -- check m before training.
+ * Limits: batch <= 4 096, total = R * n <= pb_replay_sample_capacity() (the list lives in
+ * shared memory). */
+uint32_t pb_replay_raw(uint64_t seed, uint64_t call_idx, uint32_t j);
+int64_t pb_replay_sample_capacity(void);
+int pb_replay_sample(const uint8_t *ring_valid_dev, int64_t total, int64_t batch, uint64_t seed,
+                     const int64_t *call_idx_dev, int64_t *idx_out_dev, int32_t *num_valid_out_dev,
+                     int device, void *stream);
+/* The collate of train_dqn.py:153-165 for the transitions idx_dev[0..batch): obs and next_obs
+ * (zeros where done: `next_obs is None`) as float32 [batch][17][28][31], dense NCHW or, with
+ * channels_last != 0, in channels-last memory order ([batch][28][31][17]: what the NHWC
+ * convolutions of the Q-network read without a layout conversion); actions int64, rewards
+ * float32 (raw, unscaled), done uint8, next masks uint8 [batch][5]. */
+int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
+                      const int64_t *idx_dev, int64_t batch, const uint8_t *ring_actions,
+                      const int32_t *ring_rewards, const uint8_t *ring_done,
+                      const uint8_t *ring_next_mask, float *obs_out_dev, float *next_obs_out_dev,
+                      int channels_last, int64_t *actions_out_dev, float *rewards_out_dev,
+                      uint8_t *done_out_dev, uint8_t *next_mask_out_dev, int device, void *stream);
+/* last_obs of the policy forward (replay_buffer.py:109): the n observations of slot t % R, dense
+ * NCHW or channels-last. */
+int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
+                       const int64_t *t_dev, float *out_dev, int channels_last, int device,
+                       void *stream);
 
 /* Batched #[derive(Clone)] (env.rs:96) between engines on one device: for k in [0, count) copy
  * env src_idx_dev[k] of `src` over env dst_idx_dev[k] of `dst` (int64 device arrays; NULL =

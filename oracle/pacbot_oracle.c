@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 /* ======================================================================================== */
 /* Maze tables                                                                              */
@@ -859,6 +860,7 @@ struct po_batch {
     struct tape_ctx {
         const uint32_t *base;
         int64_t len;
+        uint64_t key; /* counter mode: env_key(seed, gid) */
     } *ctx;
 };
 
@@ -866,6 +868,78 @@ static uint32_t tape_draw(void *vctx, uint32_t ctr) {
     struct tape_ctx *c = (struct tape_ctx *)vctx;
     if (!c->base || c->len <= 0) return 0u;
     return c->base[(int64_t)(ctr % (uint32_t)c->len)];
+}
+
+/* ---- the product's counter RNG (include/pacbot_b200.h "Counter RNG"), restated so that a run
+ * WITHOUT a draw tape (what bench.py times) can be replayed on the oracle --------------------- */
+static uint64_t po_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static uint64_t po_env_key(uint64_t seed, uint64_t gid) {
+    return po_mix64(seed + 0x9e3779b97f4a7c15ull * (gid + 1ull));
+}
+uint32_t po_counter_draw_raw(uint64_t seed, uint64_t gid, uint32_t ctr) {
+    return (uint32_t)(po_mix64(po_env_key(seed, gid) + (uint64_t)ctr * 0x9e3779b97f4a7c15ull +
+                               0x632be59bd9b4e019ull) >> 32);
+}
+uint32_t po_counter_action_raw(uint64_t seed, uint64_t gid, uint64_t call) {
+    return (uint32_t)(po_mix64(po_env_key(seed, gid) + call * 0xd1342543de82ef95ull +
+                               0xa0761d6478bd642full) >> 32);
+}
+static uint32_t counter_key_draw(void *vctx, uint32_t ctr) {
+    struct tape_ctx *c = (struct tape_ctx *)vctx;
+    return (uint32_t)(po_mix64(c->key + (uint64_t)ctr * 0x9e3779b97f4a7c15ull +
+                               0x632be59bd9b4e019ull) >> 32);
+}
+
+/* ---- the batch loops run on all host threads once the batch is large enough to pay: a plain
+ * pthread fork/join per call (no OpenMP runtime in this image's gcc) -------------------------- */
+#define PO_PAR_MIN 2048
+typedef void (*po_range_fn)(void *arg, int64_t lo, int64_t hi);
+typedef struct {
+    po_range_fn fn;
+    void *arg;
+    int64_t lo, hi;
+} po_par_task;
+static void *po_par_thread(void *v) {
+    po_par_task *t = (po_par_task *)v;
+    t->fn(t->arg, t->lo, t->hi);
+    return NULL;
+}
+static int po_host_threads(void) {
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("PO_THREADS");
+        long v = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+        n = v < 1 ? 1 : (v > 256 ? 256 : (int)v);
+    }
+    return n;
+}
+static void po_parallel_for(int64_t n, int64_t min_par, po_range_fn fn, void *arg) {
+    int nt = po_host_threads();
+    if (n < min_par || nt <= 1) {
+        fn(arg, 0, n);
+        return;
+    }
+    if ((int64_t)nt > n) nt = (int)n;
+    pthread_t th[256];
+    po_par_task task[256];
+    int started = 0;
+    for (int t = 0; t < nt; t++) {
+        task[t].fn = fn;
+        task[t].arg = arg;
+        task[t].lo = n * t / nt;
+        task[t].hi = n * (t + 1) / nt;
+        if (t == nt - 1 || pthread_create(&th[t], NULL, po_par_thread, &task[t]) != 0) {
+            /* last share (or a thread that could not be created) runs on the caller */
+            fn(arg, task[t].lo, t == nt - 1 ? task[t].hi : n);
+            break;
+        }
+        started++;
+    }
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
 }
 
 po_batch *po_batch_create(int64_t n, const uint8_t *cfg, const uint32_t *tape, int64_t tape_len) {
@@ -884,6 +958,14 @@ po_batch *po_batch_create(int64_t n, const uint8_t *cfg, const uint32_t *tape, i
     }
     return b;
 }
+/* switch every env to counter draws keyed (seed, gid_base + i): draw number c of env i becomes
+ * pb_draw_raw(seed, gid_base + i, c), exactly what the CUDA engine uses without a tape */
+void po_batch_set_counter_rng(po_batch *b, uint64_t seed, int64_t gid_base) {
+    for (int64_t i = 0; i < b->n; i++) {
+        b->ctx[i].key = po_env_key(seed, (uint64_t)(gid_base + i));
+        po_gym_set_draws(&b->envs[i], counter_key_draw, &b->ctx[i]);
+    }
+}
 void po_batch_destroy(po_batch *b) {
     if (!b) return;
     free(b->envs);
@@ -891,39 +973,119 @@ void po_batch_destroy(po_batch *b) {
     free(b);
 }
 po_gym *po_batch_env(po_batch *b, int64_t i) { return &b->envs[i]; }
+
+typedef struct {
+    po_batch *b;
+    const uint8_t *in8;   /* reset mask / actions */
+    uint8_t *out8;        /* done / mask / sampled actions */
+    int32_t *reward;
+    float *obs;
+    po_flat_state *flat_out;
+    const po_flat_state *flat_in;
+    int64_t first;        /* obs_range */
+    int auto_reset;
+    uint64_t seed, call_idx;
+    int64_t gid_base;
+    int64_t first_bad;    /* per call: min over shares, merged under `lock` */
+    pthread_mutex_t lock;
+} po_call;
+
+static void r_reset(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++)
+        if (!c->in8 || c->in8[i]) po_gym_reset(&c->b->envs[i]);
+}
 void po_batch_reset(po_batch *b, const uint8_t *mask) {
-    for (int64_t i = 0; i < b->n; i++)
-        if (!mask || mask[i]) po_gym_reset(&b->envs[i]);
+    po_call c = {.b = b, .in8 = mask};
+    po_parallel_for(b->n, PO_PAR_MIN, r_reset, &c);
+}
+static void r_step(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    int64_t bad = -1;
+    for (int64_t i = lo; i < hi; i++) {
+        int32_t r = 0;
+        uint8_t d = 0;
+        if (po_gym_step(&c->b->envs[i], c->in8[i], &r, &d) != 0) {
+            if (bad < 0) bad = i;
+            c->reward[i] = 0;
+            c->out8[i] = 0;
+            continue;
+        }
+        c->reward[i] = r;
+        c->out8[i] = d;
+        if (d && c->auto_reset) po_gym_reset(&c->b->envs[i]);
+    }
+    if (bad >= 0) {
+        pthread_mutex_lock(&c->lock);
+        if (c->first_bad < 0 || bad < c->first_bad) c->first_bad = bad;
+        pthread_mutex_unlock(&c->lock);
+    }
 }
 int64_t po_batch_step(po_batch *b, const uint8_t *actions, int32_t *reward, uint8_t *done,
                       int auto_reset) {
-    int64_t first_bad = -1;
-    for (int64_t i = 0; i < b->n; i++) {
-        int32_t r = 0;
-        uint8_t d = 0;
-        if (po_gym_step(&b->envs[i], actions[i], &r, &d) != 0) {
-            if (first_bad < 0) first_bad = i;
-            reward[i] = 0;
-            done[i] = 0;
-            continue;
-        }
-        reward[i] = r;
-        done[i] = d;
-        if (d && auto_reset) po_gym_reset(&b->envs[i]);
-    }
-    return first_bad;
+    po_call c = {.b = b, .in8 = actions, .out8 = done, .reward = reward, .auto_reset = auto_reset,
+                 .first_bad = -1};
+    pthread_mutex_init(&c.lock, NULL);
+    po_parallel_for(b->n, PO_PAR_MIN, r_step, &c);
+    pthread_mutex_destroy(&c.lock);
+    return c.first_bad;
+}
+static void r_mask(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++) po_gym_action_mask(&c->b->envs[i], c->out8 + 5 * i);
 }
 void po_batch_action_mask(po_batch *b, uint8_t *out) {
-    for (int64_t i = 0; i < b->n; i++) po_gym_action_mask(&b->envs[i], out + 5 * i);
+    po_call c = {.b = b, .out8 = out};
+    po_parallel_for(b->n, PO_PAR_MIN, r_mask, &c);
+}
+static void r_obs(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++)
+        po_gym_obs(&c->b->envs[c->first + i], c->obs + (size_t)PO_OBS_FLOATS * (size_t)i);
 }
 void po_batch_obs(po_batch *b, float *out) {
-    for (int64_t i = 0; i < b->n; i++) po_gym_obs(&b->envs[i], out + (size_t)PO_OBS_FLOATS * i);
+    po_call c = {.b = b, .obs = out, .first = 0};
+    po_parallel_for(b->n, 256, r_obs, &c);
+}
+/* observations of envs [first, first + count) only (large batches are compared chunk by chunk) */
+void po_batch_obs_range(po_batch *b, int64_t first, int64_t count, float *out) {
+    po_call c = {.b = b, .obs = out, .first = first};
+    po_parallel_for(count, 256, r_obs, &c);
+}
+static void r_export(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++) po_gym_export(&c->b->envs[i], &c->flat_out[i]);
 }
 void po_batch_export(po_batch *b, po_flat_state *out) {
-    for (int64_t i = 0; i < b->n; i++) po_gym_export(&b->envs[i], &out[i]);
+    po_call c = {.b = b, .flat_out = out};
+    po_parallel_for(b->n, PO_PAR_MIN, r_export, &c);
+}
+static void r_import(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++) po_gym_import(&c->b->envs[i], &c->flat_in[i]);
 }
 void po_batch_import(po_batch *b, const po_flat_state *in) {
-    for (int64_t i = 0; i < b->n; i++) po_gym_import(&b->envs[i], &in[i]);
+    po_call c = {.b = b, .flat_in = in};
+    po_parallel_for(b->n, PO_PAR_MIN, r_import, &c);
+}
+/* uniformly random VALID action per env from the policy stream of the counter RNG (the product's
+ * pb_sample_actions / pb_step_random): k-th set bit of the mask, k = (raw * popcount) >> 32 */
+static void r_sample(void *v, int64_t lo, int64_t hi) {
+    po_call *c = (po_call *)v;
+    for (int64_t i = lo; i < hi; i++) {
+        uint8_t m[5], valid[5];
+        int nv = 0;
+        po_gym_action_mask(&c->b->envs[i], m);
+        for (int k = 0; k < 5; k++)
+            if (m[k]) valid[nv++] = (uint8_t)k;
+        const uint32_t raw = po_counter_action_raw(c->seed, (uint64_t)(c->gid_base + i), c->call_idx);
+        c->out8[i] = valid[((uint64_t)raw * (uint64_t)nv) >> 32];
+    }
+}
+void po_batch_sample_actions(po_batch *b, uint64_t seed, int64_t gid_base, uint64_t call_idx,
+                             uint8_t *out) {
+    po_call c = {.b = b, .out8 = out, .seed = seed, .gid_base = gid_base, .call_idx = call_idx};
+    po_parallel_for(b->n, PO_PAR_MIN, r_sample, &c);
 }
 
 /* ======================================================================================== */

@@ -183,6 +183,15 @@ void po_batch_action_mask(po_batch *b, uint8_t *out /* n*5 */);
 void po_batch_obs(po_batch *b, float *out /* n*PO_OBS_FLOATS */);
 void po_batch_export(po_batch *b, po_flat_state *out /* n */);
 void po_batch_import(po_batch *b, const po_flat_state *in /* n */);
+void po_batch_obs_range(po_batch *b, int64_t first, int64_t count, float *out);
+/* The product's counter RNG (include/pacbot_b200.h), restated: game-draw stream and policy stream.
+ * po_batch_set_counter_rng replaces the tape by draws keyed (seed, gid_base + i);
+ * po_batch_sample_actions is pb_sample_actions / pb_step_random's action choice. */
+uint32_t po_counter_draw_raw(uint64_t seed, uint64_t gid, uint32_t ctr);
+uint32_t po_counter_action_raw(uint64_t seed, uint64_t gid, uint64_t call);
+void po_batch_set_counter_rng(po_batch *b, uint64_t seed, int64_t gid_base);
+void po_batch_sample_actions(po_batch *b, uint64_t seed, int64_t gid_base, uint64_t call_idx,
+                             uint8_t *out /* n */);
 
 /* ---- CPU baseline rollout (bench.py cpu_baseline / --impl reference) ----------------------- */
 /* Random-valid-action rollout of n_envs for n_steps env-steps each, step + full obs encode per

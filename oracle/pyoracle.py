@@ -103,6 +103,13 @@ def lib() -> C.CDLL:
         L.po_batch_obs.argtypes = [vp, vp]
         L.po_batch_export.argtypes = [vp, vp]
         L.po_batch_import.argtypes = [vp, vp]
+        L.po_batch_obs_range.argtypes = [vp, i64, i64, vp]
+        L.po_batch_set_counter_rng.argtypes = [vp, C.c_uint64, i64]
+        L.po_batch_sample_actions.argtypes = [vp, C.c_uint64, i64, C.c_uint64, vp]
+        L.po_counter_draw_raw.restype = C.c_uint32
+        L.po_counter_draw_raw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        L.po_counter_action_raw.restype = C.c_uint32
+        L.po_counter_action_raw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.po_batch_env.restype = vp
         L.po_batch_env.argtypes = [vp, i64]
         L.po_gym_first_ai_done.argtypes = [vp]
@@ -188,6 +195,24 @@ class OracleBatch:
         lib().po_batch_obs(self._h, _ptr(out))
         return out
 
+    def obs_range(self, first: int, count: int) -> np.ndarray:
+        """obs() of envs [first, first + count) (large batches are compared chunk by chunk)."""
+        assert 0 <= first and first + count <= self.n
+        out = np.empty((count,) + OBS_SHAPE, np.float32)
+        lib().po_batch_obs_range(self._h, first, count, _ptr(out))
+        return out
+
+    def set_counter_rng(self, seed: int, gid_base: int = 0) -> None:
+        """Replace the tape by the product's counter RNG keyed (seed, gid_base + i): what the
+        CUDA engine draws when no tape is installed (include/pacbot_b200.h "Counter RNG")."""
+        lib().po_batch_set_counter_rng(self._h, seed & 0xFFFFFFFFFFFFFFFF, gid_base)
+
+    def sample_actions(self, seed: int, gid_base: int, call_idx: int) -> np.ndarray:
+        """pb_sample_actions / pb_step_random's choice: uniformly random valid action per env."""
+        out = np.zeros(self.n, np.uint8)
+        lib().po_batch_sample_actions(self._h, seed & 0xFFFFFFFFFFFFFFFF, gid_base, call_idx, _ptr(out))
+        return out
+
     def export_state(self) -> np.ndarray:
         out = np.zeros(self.n, FLAT_DTYPE)
         lib().po_batch_export(self._h, _ptr(out))
@@ -207,6 +232,51 @@ class OracleBatch:
     def is_done(self) -> np.ndarray:
         L = lib()
         return np.array([bool(L.po_gym_is_done(L.po_batch_env(self._h, i))) for i in range(self.n)])
+
+
+def flat_from_product(st: np.ndarray) -> np.ndarray:
+    """Product `pb_env_state` records (pacbot_rl_b200.ENV_STATE_DTYPE, what `get_state` returns)
+    -> oracle flat states for `OracleBatch.import_state`."""
+    out = np.zeros(len(st), FLAT_DTYPE)
+    for f in out.dtype.names:
+        if f in st.dtype.names:
+            out[f] = st[f]
+    out["random_start"] = st["cfg_flags"] & 1
+    out["random_ticks"] = (st["cfg_flags"] >> 1) & 1
+    out["randomize_ghosts"] = (st["cfg_flags"] >> 2) & 1
+    out["remove_super_pellets"] = (st["cfg_flags"] >> 3) & 1
+    return out
+
+
+def cfg_flags_of(flat: np.ndarray) -> np.ndarray:
+    """cfg_flags byte of the product's state record from an oracle flat state."""
+    return (flat["random_start"].astype(np.uint8) | (flat["random_ticks"].astype(np.uint8) << 1)
+            | (flat["randomize_ghosts"].astype(np.uint8) << 2)
+            | (flat["remove_super_pellets"].astype(np.uint8) << 3))
+
+
+# fields shared by the oracle's flat state and the product's pb_env_state
+COMMON_FIELDS = [
+    "curr_ticks", "rng_ctr", "pellets", "level_steps", "curr_score", "num_pellets", "last_score",
+    "update_period", "mode", "paused", "pause_on_update", "mode_steps", "curr_level",
+    "curr_lives", "ghost_combo", "fruit_steps", "last_action", "ticks_per_step",
+    "pac_row", "pac_col", "pac_dir", "g_row", "g_col", "g_dir", "g_next_row", "g_next_col",
+    "g_next_dir", "g_fright", "g_trapped", "g_spawning", "g_eaten",
+]
+
+
+def states_differ(flat: np.ndarray, product: np.ndarray):
+    """None if an oracle flat-state array and a product state array describe the same envs,
+    else a one-line description of the first difference."""
+    for f in COMMON_FIELDS:
+        a, b = flat[f], product[f]
+        if not np.array_equal(a, b):
+            bad = np.flatnonzero(np.asarray(a != b).reshape(len(a), -1).any(axis=1))
+            i = int(bad[0])
+            return f"field {f!r} differs for {len(bad)} envs; first env {i}: oracle={a[i]!r} gpu={b[i]!r}"
+    if not np.array_equal(cfg_flags_of(flat), product["cfg_flags"]):
+        return "cfg_flags differ"
+    return None
 
 
 def rollout(n_envs: int, n_steps: int, warmup: int = 0, seed: int = 0, n_threads: int = 1):

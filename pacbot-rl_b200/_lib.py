@@ -108,10 +108,20 @@ SIGNATURES = {
     "pb_check_actions": (_int, [_vp, C.POINTER(_i64), _vp]),
     "pb_get_state": (_int, [_vp, _i64, _i64, _vp]),
     "pb_set_state": (_int, [_vp, _i64, _i64, _vp]),
+    "pb_get_state_on": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "pb_set_state_on": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "pb_clone_env": (_int, [_vp, _i64, _vp, _i64, _vp]),
     "pb_step_host": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
     "pb_obs_host": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "pb_select_actions": (_int, [_vp, _vp, _vp, C.c_float, _vp, _u64, _vp]),
+    "pb_select_actions_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pb_replay_raw": (C.c_uint32, [_u64, _u64, C.c_uint32]),
+    "pb_replay_sample_capacity": (_i64, []),
+    "pb_replay_record": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "pb_replay_sample": (_int, [_vp, _i64, _i64, _u64, _vp, _vp, _vp, _int, _vp]),
+    "pb_replay_collate": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp,
+                                 _vp, _vp, _int, _vp]),
+    "pb_replay_slot_obs": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _vp]),
     "pb_gather_obs": (_int, [_vp, _i64, _vp, _vp, _i64, _vp, _int, _vp]),
     "pb_copy_envs": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "pb_mcts_create": (_int, [C.POINTER(_vp), _vp, _vp, _int]),

@@ -189,7 +189,12 @@ __device__ __forceinline__ int obs_cell(int row, int col) {  // env.rs:124: [col
 // their cells (state-dependent, deterministic mismatches in tests/test_parity_gpu.py fuzz seed 2;
 // gone with printf in the kernel).  A vote.sync whose result is consumed has to wait for all 32
 // lanes.  `v` must be a value the compiler cannot fold (the prefetched ticket).
+// The vote is a rendezvous, not a memory fence: CUDA only documents __syncwarp() (bar.warp.sync)
+// as ordering memory accesses among the participating lanes, so the barrier comes first (it is
+// the memory ordering between one lane's shared-memory stores / cp.async data and another lane's
+// reads or lane 0's bulk copy) and the consumed vote keeps ptxas from dropping the rendezvous.
 __device__ __forceinline__ bool warp_arrived(unsigned int v) {
+    __syncwarp();
     return __all_sync(0xffffffffu, v != 0xfffffffeu);
 }
 // offset of (channel, cell) inside the private image (channel 0 is not part of it)

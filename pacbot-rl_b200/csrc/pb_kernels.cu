@@ -25,7 +25,6 @@ __constant__ MazeTables c_tab;
 }  // namespace pb
 
 #include "pb_encode.cuh"
-#include "pb_encode2.cuh"
 
 namespace pb {
 
@@ -230,11 +229,16 @@ k_sample_actions(StateView st, RngParams rp, uint8_t *__restrict__ actions,
 __global__ void __launch_bounds__(STEP_THREADS)
 k_select_actions(StateView st, RngParams rp, const float *__restrict__ q,
                  const uint8_t *__restrict__ mask_in, float epsilon,
-                 uint8_t *__restrict__ actions, unsigned long long call_idx) {
+                 uint8_t *__restrict__ actions, unsigned long long call_idx,
+                 const float *__restrict__ epsilon_ptr, const long long *__restrict__ call_ptr) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
     const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
     if (i >= st.n) return;
+    // pb_select_actions_dev: both live in device memory and are read at kernel time, so that a
+    // captured CUDA graph follows the epsilon schedule and the step counter while it is replayed
+    if (epsilon_ptr) epsilon = *epsilon_ptr;
+    if (call_ptr) call_idx = (unsigned long long)*call_ptr;
     uint32_t m;
     if (mask_in) {
         m = 0;
@@ -332,8 +336,13 @@ struct pb_engine {
     int32_t *stg_reward = nullptr;
     uint8_t *stg_done = nullptr;
     uint8_t *stg_mask = nullptr;
-    float *stg_obs = nullptr;
-    long long stg_obs_envs = 0;
+    // pb_obs_host: two device staging buffers (encode chunk k+1 while chunk k crosses PCIe) and,
+    // for pageable destinations, two pinned bounce buffers
+    float *stg_obs[2] = {nullptr, nullptr};
+    float *pin_obs[2] = {nullptr, nullptr};
+    long long stg_obs_envs = 0, pin_obs_envs = 0;
+    cudaEvent_t ev_obs_enc[2] = {nullptr, nullptr}, ev_obs_copy[2] = {nullptr, nullptr};
+
     int num_sms = 148;
     unsigned int *tickets = nullptr;  // ring of work counters for k_encode_obs launches
     unsigned int ticket_next = 0;
@@ -390,21 +399,12 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
                   long long count, cudaStream_t s, const long long *slot_index = nullptr,
                   long long slot_stride = 0) {
     if (count <= 0) return PB_OK;
-    // two encoders with identical output: image-per-warp (k_encode_obs) and shared-template
-    // (k_encode_obs_tpl); PB_ENCODER=img|tpl selects, default below
-    static const bool use_tpl = [] {
-        const char *v = getenv("PB_ENCODER");
-        return v ? (strcmp(v, "tpl") == 0) : false;
-    }();
     static thread_local int attr_set_for = -1;
     if (attr_set_for != e->device) {
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
-        PB_CUDA(cudaFuncSetAttribute(k_encode_obs_tpl, cudaFuncAttributeMaxDynamicSharedMemorySize, E2_SMEM));
         attr_set_for = e->device;
     }
-    auto kern = use_tpl ? k_encode_obs_tpl : k_encode_obs;
-    const int warps = use_tpl ? E2_WARPS : ENC_WARPS;
-    long long blocks = (count + warps - 1) / warps;
+    long long blocks = (count + ENC_WARPS - 1) / ENC_WARPS;
     if (blocks > e->num_sms) blocks = e->num_sms;
     // {ticket, finished-warp count} pair; the last warp of a launch zeroes both again, so no
     // memset node is needed per launch (the ring only matters for launches on different streams)
@@ -414,20 +414,20 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     // kernel executes griddepcontrol.wait before it touches the env state or the ticket.
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(use_tpl ? E2_THREADS : ENC_THREADS);
-    cfg.dynamicSmemBytes = use_tpl ? E2_SMEM : ENC_SMEM;
+    cfg.blockDim = dim3(ENC_THREADS);
+    cfg.dynamicSmemBytes = ENC_SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    // PB_NO_PDL=1 launches the encoder with plain stream ordering (A/B runs, tools/e2e_probe.py)
+    // PB_NO_PDL=1 launches the encoder with plain stream ordering (A/B runs)
     static const bool no_pdl = [] {
         const char *v = getenv("PB_NO_PDL");
         return v && v[0] == '1';
     }();
     cfg.numAttrs = no_pdl ? 0 : 1;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, kern, e->st, out_dev, stride, first, count, ticket,
+    PB_CUDA(cudaLaunchKernelEx(&cfg, k_encode_obs, e->st, out_dev, stride, first, count, ticket,
                                slot_index, slot_stride));
     return PB_OK;
 }
@@ -477,7 +477,12 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->stg_reward);
     cudaFree(e->stg_done);
     cudaFree(e->stg_mask);
-    cudaFree(e->stg_obs);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(e->stg_obs[b]);
+        if (e->pin_obs[b]) cudaFreeHost(e->pin_obs[b]);
+        if (e->ev_obs_enc[b]) cudaEventDestroy(e->ev_obs_enc[b]);
+        if (e->ev_obs_copy[b]) cudaEventDestroy(e->ev_obs_copy[b]);
+    }
     cudaFree(e->tickets);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
@@ -732,7 +737,20 @@ int pb_select_actions(pb_engine *e, const float *q_dev, const uint8_t *mask_dev,
         return fail(PB_ERR_INVALID_ARG, "pb_select_actions: null argument");
     DeviceGuard g(e->device);
     k_select_actions<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
-        e->st, rng_params(e), q_dev, mask_dev, epsilon, actions_dev, call_idx);
+        e->st, rng_params(e), q_dev, mask_dev, epsilon, actions_dev, call_idx, nullptr, nullptr);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_select_actions_dev(pb_engine *e, const float *q_dev, const uint8_t *mask_dev,
+                          const float *epsilon_dev, const int64_t *call_idx_dev,
+                          uint8_t *actions_dev, void *stream) {
+    if (!e || !q_dev || !actions_dev || !epsilon_dev || !call_idx_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_select_actions_dev: null argument");
+    DeviceGuard g(e->device);
+    k_select_actions<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), q_dev, mask_dev, 0.0f, actions_dev, 0ull, epsilon_dev,
+        reinterpret_cast<const long long *>(call_idx_dev));
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -750,23 +768,42 @@ int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream) {
     return fail(PB_ERR_INVALID_ACTION, "Invalid action");
 }
 
-int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out) {
+// Work of the engine's own streams (pipelined rollout steps, result copies) that a state access
+// ordered on the caller's stream has to wait for.
+static int sync_engine_streams(pb_engine *e) {
+    for (cudaStream_t s : {e->roll_step, e->roll_enc, e->copy_stream})
+        if (s) PB_CUDA(cudaStreamSynchronize(s));
+    return PB_OK;
+}
+
+// whole_device: pb_get_state (no stream argument: waits for the whole device).  Otherwise only the
+// caller's stream and the engine's own streams are synchronised, and the copies are ordered on the
+// caller's stream: other streams of the process (a training graph, another engine) keep running.
+static int get_state_impl(pb_engine *e, int64_t first, int64_t count, pb_env_state *out,
+                          bool whole_device, cudaStream_t s) {
     if (!e || !out || first < 0 || count < 0 || first + count > e->n)
         return fail(PB_ERR_INVALID_ARG, "pb_get_state: bad arguments");
     if (count == 0) return PB_OK;
     DeviceGuard g(e->device);
-    PB_CUDA(cudaDeviceSynchronize());
+    if (whole_device) {
+        PB_CUDA(cudaDeviceSynchronize());
+        s = nullptr;
+    } else {
+        int rc = sync_engine_streams(e);
+        if (rc != PB_OK) return rc;
+    }
     const size_t c = (size_t)count;
     std::vector<uint4> c0(c), c1(c), ga(c), gb(c);
     std::vector<uint32_t> pel(c * PEL_WORDS);
-    PB_CUDA(cudaMemcpy(c0.data(), e->st.core0 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(c1.data(), e->st.core1 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(ga.data(), e->st.ghosts + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy(gb.data(), e->st.ghosts + e->npad + first, sizeof(uint4) * c,
-                       cudaMemcpyDeviceToHost));
-    PB_CUDA(cudaMemcpy2D(pel.data(), sizeof(uint32_t) * c, e->st.pel + first,
-                         sizeof(uint32_t) * e->npad, sizeof(uint32_t) * c, PEL_WORDS,
-                         cudaMemcpyDeviceToHost));
+    PB_CUDA(cudaMemcpyAsync(c0.data(), e->st.core0 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(c1.data(), e->st.core1 + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(ga.data(), e->st.ghosts + first, sizeof(uint4) * c, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(gb.data(), e->st.ghosts + e->npad + first, sizeof(uint4) * c,
+                            cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpy2DAsync(pel.data(), sizeof(uint32_t) * c, e->st.pel + first,
+                              sizeof(uint32_t) * e->npad, sizeof(uint32_t) * c, PEL_WORDS,
+                              cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
     for (size_t i = 0; i < c; i++) {
         EnvR s;
         unpack_env(c0[i], c1[i], ga[i], gb[i], s);
@@ -812,7 +849,15 @@ int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out) 
     return PB_OK;
 }
 
-int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in) {
+int pb_get_state(pb_engine *e, int64_t first, int64_t count, pb_env_state *out) {
+    return get_state_impl(e, first, count, out, true, nullptr);
+}
+int pb_get_state_on(pb_engine *e, int64_t first, int64_t count, pb_env_state *out, void *stream) {
+    return get_state_impl(e, first, count, out, false, (cudaStream_t)stream);
+}
+
+static int set_state_impl(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in,
+                          bool whole_device, cudaStream_t stream) {
     if (!e || !in || first < 0 || count < 0 || first + count > e->n)
         return fail(PB_ERR_INVALID_ARG, "pb_set_state: bad arguments");
     if (count == 0) return PB_OK;
@@ -863,16 +908,31 @@ int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state 
         for (int w = 0; w < PEL_WORDS; w++) pel[(size_t)w * c + i] = f[w];
     }
     DeviceGuard g(e->device);
-    PB_CUDA(cudaDeviceSynchronize());
-    PB_CUDA(cudaMemcpy(e->st.core0 + first, c0.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(e->st.core1 + first, c1.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(e->st.ghosts + first, ga.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy(e->st.ghosts + e->npad + first, gb.data(), sizeof(uint4) * c,
-                       cudaMemcpyHostToDevice));
-    PB_CUDA(cudaMemcpy2D(e->st.pel + first, sizeof(uint32_t) * e->npad, pel.data(),
-                         sizeof(uint32_t) * c, sizeof(uint32_t) * c, PEL_WORDS,
-                         cudaMemcpyHostToDevice));
+    if (whole_device) {
+        PB_CUDA(cudaDeviceSynchronize());
+        stream = nullptr;
+    } else {
+        int rc = sync_engine_streams(e);
+        if (rc != PB_OK) return rc;
+    }
+    PB_CUDA(cudaMemcpyAsync(e->st.core0 + first, c0.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(e->st.core1 + first, c1.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(e->st.ghosts + first, ga.data(), sizeof(uint4) * c, cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(e->st.ghosts + e->npad + first, gb.data(), sizeof(uint4) * c,
+                            cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpy2DAsync(e->st.pel + first, sizeof(uint32_t) * e->npad, pel.data(),
+                              sizeof(uint32_t) * c, sizeof(uint32_t) * c, PEL_WORDS,
+                              cudaMemcpyHostToDevice, stream));
+    // the host vectors above die with this call: the copies must have left them
+    PB_CUDA(cudaStreamSynchronize(stream));
     return PB_OK;
+}
+
+int pb_set_state(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in) {
+    return set_state_impl(e, first, count, in, true, nullptr);
+}
+int pb_set_state_on(pb_engine *e, int64_t first, int64_t count, const pb_env_state *in, void *stream) {
+    return set_state_impl(e, first, count, in, false, (cudaStream_t)stream);
 }
 
 int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t src_i,
@@ -921,25 +981,83 @@ int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host
     return PB_OK;
 }
 
+// Observations straight to host memory, PCIe-bound instead of pageable-bound: the range is cut
+// into chunks of OBS_HOST_CHUNK envs; chunk k is encoded into device staging buffer k & 1 on the
+// caller's stream and crosses PCIe on the engine's copy stream while chunk k + 1 is being
+// encoded.  A pinned (or registered) destination receives the copies directly; a pageable one
+// goes through two pinned bounce buffers, the host memcpy of chunk k overlapping the transfer of
+// chunk k + 1 (a cudaMemcpy into pageable memory is staged by the driver, synchronously, at a
+// fraction of the link rate).
+constexpr long long OBS_HOST_CHUNK = 1024;  // 60 MB per staging buffer
+
 int pb_obs_host(pb_engine *e, int64_t first, int64_t count, float *obs_host, void *stream) {
     if (!e || !obs_host || first < 0 || count < 0 || first + count > e->n)
         return fail(PB_ERR_INVALID_ARG, "pb_obs_host: bad arguments");
     if (count == 0) return PB_OK;
     DeviceGuard g(e->device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->stg_obs_envs < count) {
+    cudaStream_t c = e->copy_stream;
+    const long long chunk = count < OBS_HOST_CHUNK ? count : OBS_HOST_CHUNK;
+    const size_t env_bytes = sizeof(float) * OBS_FLOATS;
+    if (!e->ev_obs_enc[0])
+        for (int b = 0; b < 2; b++) {
+            PB_CUDA(cudaEventCreateWithFlags(&e->ev_obs_enc[b], cudaEventDisableTiming));
+            PB_CUDA(cudaEventCreateWithFlags(&e->ev_obs_copy[b], cudaEventDisableTiming));
+        }
+    const long long nchunks = (count + chunk - 1) / chunk;
+    if (e->stg_obs_envs < chunk) {  // grow-only; the second buffer only when there are >= 2 chunks
         PB_CUDA(cudaStreamSynchronize(s));
-        cudaFree(e->stg_obs);
-        e->stg_obs = nullptr;
+        PB_CUDA(cudaStreamSynchronize(c));
+        for (int b = 0; b < 2; b++) {
+            cudaFree(e->stg_obs[b]);
+            e->stg_obs[b] = nullptr;
+        }
         e->stg_obs_envs = 0;
-        PB_CUDA(cudaMalloc(&e->stg_obs, sizeof(float) * OBS_FLOATS * (size_t)count));
-        e->stg_obs_envs = count;
+        for (int b = 0; b < (chunk == OBS_HOST_CHUNK ? 2 : 1); b++)
+            PB_CUDA(cudaMalloc(&e->stg_obs[b], env_bytes * (size_t)chunk));
+        e->stg_obs_envs = chunk;
     }
-    int rc = launch_encode(e, e->stg_obs, OBS_FLOATS, first, count, s);
-    if (rc != PB_OK) return rc;
-    PB_CUDA(cudaMemcpyAsync(obs_host, e->stg_obs, sizeof(float) * OBS_FLOATS * (size_t)count,
-                            cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaStreamSynchronize(s));
+    if (nchunks > 1 && !e->stg_obs[1]) PB_CUDA(cudaMalloc(&e->stg_obs[1], env_bytes * (size_t)e->stg_obs_envs));
+    cudaPointerAttributes pa{};
+    const bool pinned_dst = cudaPointerGetAttributes(&pa, obs_host) == cudaSuccess &&
+                            (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (!pinned_dst && e->pin_obs_envs < chunk) {
+        for (int b = 0; b < 2; b++) {
+            if (e->pin_obs[b]) cudaFreeHost(e->pin_obs[b]);
+            e->pin_obs[b] = nullptr;
+        }
+        e->pin_obs_envs = 0;
+        for (int b = 0; b < 2; b++) PB_CUDA(cudaMallocHost(&e->pin_obs[b], env_bytes * (size_t)chunk));
+        e->pin_obs_envs = chunk;
+    }
+    // the copy stream starts after whatever it was doing for an earlier call
+    for (long long k = 0; k < nchunks + 2; k++) {
+        const int b = (int)(k & 1);
+        if (k >= 2) {
+            const long long kk = k - 2;  // chunk whose staging buffer is reused / drained now
+            const long long cnt = (kk + 1) * chunk <= count ? chunk : count - kk * chunk;
+            if (pinned_dst) {
+                if (k < nchunks) PB_CUDA(cudaStreamWaitEvent(s, e->ev_obs_copy[b], 0));
+            } else {
+                PB_CUDA(cudaEventSynchronize(e->ev_obs_copy[b]));
+                memcpy(obs_host + (size_t)kk * chunk * OBS_FLOATS, e->pin_obs[b], env_bytes * (size_t)cnt);
+            }
+        }
+        if (k >= nchunks) continue;
+        const long long cnt = (k + 1) * chunk <= count ? chunk : count - k * chunk;
+        int rc = launch_encode(e, e->stg_obs[b], OBS_FLOATS, first + k * chunk, cnt, s);
+        if (rc != PB_OK) return rc;
+        PB_CUDA(cudaEventRecord(e->ev_obs_enc[b], s));
+        PB_CUDA(cudaStreamWaitEvent(c, e->ev_obs_enc[b], 0));
+        float *dst = pinned_dst ? obs_host + (size_t)k * chunk * OBS_FLOATS : e->pin_obs[b];
+        PB_CUDA(cudaMemcpyAsync(dst, e->stg_obs[b], env_bytes * (size_t)cnt, cudaMemcpyDeviceToHost, c));
+        PB_CUDA(cudaEventRecord(e->ev_obs_copy[b], c));
+    }
+    if (pinned_dst) PB_CUDA(cudaStreamSynchronize(c));
+    // a later call on `s` may reuse the staging buffers: order it after the last copies
+    PB_CUDA(cudaStreamWaitEvent(s, e->ev_obs_copy[0], 0));
+    if (nchunks > 1) PB_CUDA(cudaStreamWaitEvent(s, e->ev_obs_copy[1], 0));
     return PB_OK;
 }
 
@@ -964,3 +1082,4 @@ int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64
 
 #include "pb_mcts_abi.inl"
 #include "pb_rollout_abi.inl"
+#include "pb_replay_abi.inl"

@@ -1,0 +1,280 @@
+// pb_replay_abi.inl -- pb_replay_*: the replay ring of the DQN loop on the device
+// (reference: /root/reference/src/replay_buffer.py:57-143 and the collate of
+// src/algorithms/train_dqn.py:152-165); included at the end of pb_kernels.cu.
+//
+// The ring is a TIME ring: slot s = t % R holds, for all n envs, the observation before action t
+// (written by k_encode_obs straight into the ring) and (action, reward, done, next mask, valid)
+// of transition t; next_obs of a transition is slot (s + 1) % R.  Every kernel below reads the
+// step counter t from DEVICE memory at kernel time, so one captured CUDA graph keeps working
+// while the ring advances.
+//
+//   k_replay_record   deque.append of one step for all envs (replay_buffer.py:130)
+//   k_replay_sample   random.sample(buffer, B): B distinct valid transitions, uniform
+//                     (replay_buffer.py:141-143): ordered compaction of the valid flags + a
+//                     partial Fisher-Yates shuffle in shared memory, counter RNG
+//   k_replay_collate  torch.stack of obs / next_obs (zeros where done) and the scalar columns
+//                     (train_dqn.py:153-165), obs optionally emitted CHANNELS-LAST so that the
+//                     Q-network's NHWC convolutions read it without a layout-conversion kernel
+//   k_replay_slot     last_obs of the policy forward: ring slot t % R, NCHW or NHWC
+
+namespace pb {
+
+__global__ void __launch_bounds__(128)
+k_replay_record(long long n, long long ring_slots, const long long *__restrict__ t_dev,
+                const uint8_t *__restrict__ actions, const int32_t *__restrict__ reward,
+                const uint8_t *__restrict__ done, const uint8_t *__restrict__ mask,
+                const uint8_t *__restrict__ in_phase1, uint8_t *__restrict__ ring_actions,
+                int32_t *__restrict__ ring_rewards, uint8_t *__restrict__ ring_done,
+                uint8_t *__restrict__ ring_next_mask, uint8_t *__restrict__ ring_valid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long t = *t_dev;
+    const long long s = (t % ring_slots) * n + i, nx = ((t + 1) % ring_slots) * n + i;
+    const uint8_t d = done[i];
+    ring_actions[s] = actions[i];
+    ring_rewards[s] = reward[i];
+    ring_done[s] = d;
+    // next_action_mask is [False] * 5 when the episode ended (replay_buffer.py:115-117)
+#pragma unroll
+    for (int k = 0; k < 5; k++) ring_next_mask[s * 5 + k] = d ? 0 : mask[i * 5 + k];
+    // steps played by the old policy of reset_env (replay_buffer.py:44-54) are not recorded
+    ring_valid[s] = in_phase1 ? (in_phase1[i] ? 0 : 1) : 1;
+    ring_valid[nx] = 0;  // slot t + 1 holds the current observation only
+}
+
+constexpr int SAMPLE_THREADS = 1024;
+constexpr int SAMPLE_SMEM_MAX = 227 * 1024 - SAMPLE_THREADS * 4;  // dynamic part
+// dynamic shared memory: int32 list[total] + uint32 raw[batch]
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_replay_sample(const uint8_t *__restrict__ ring_valid, long long total, int batch, uint64_t seed,
+                const long long *__restrict__ call_dev, long long *__restrict__ idx_out,
+                int *__restrict__ num_valid_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int *list = reinterpret_cast<int *>(smem_raw);
+    uint32_t *raw = reinterpret_cast<uint32_t *>(list + total);
+    __shared__ int s_scan[SAMPLE_THREADS];
+    const int tid = threadIdx.x;
+    const long long per = (total + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+    const long long lo = per * tid, hi = (lo + per < total) ? lo + per : total;
+    int cnt = 0;
+    for (long long j = lo; j < hi; j++) cnt += ring_valid[j] ? 1 : 0;
+    // block-wide inclusive scan of the per-thread counts (ordered compaction: the list is
+    // ascending in the flat ring index, whatever the thread schedule)
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < SAMPLE_THREADS; off <<= 1) {
+        const int v = (tid >= off) ? s_scan[tid - off] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int w = s_scan[tid] - cnt;
+    for (long long j = lo; j < hi; j++)
+        if (ring_valid[j]) list[w++] = (int)j;
+    const int m = s_scan[SAMPLE_THREADS - 1];
+    const unsigned long long call = (unsigned long long)*call_dev;
+    for (int j = tid; j < batch; j += SAMPLE_THREADS) raw[j] = replay_raw(seed, call, (uint32_t)j);
+    __syncthreads();
+    if (tid == 0) {
+        if (num_valid_out) *num_valid_out = m;
+        if (m >= batch) {
+            // partial Fisher-Yates: position j takes a uniformly chosen element of list[j..m)
+            for (int j = 0; j < batch; j++) {
+                const int r = j + (int)below(raw[j], (uint32_t)(m - j));
+                const int a = list[j], b = list[r];
+                list[r] = a;
+                list[j] = b;
+            }
+        }
+    }
+    __syncthreads();
+    // fewer valid transitions than the batch (the caller checks num_valid before it trains):
+    // sample with replacement over what there is instead of reading past the list
+    for (int j = tid; j < batch; j += SAMPLE_THREADS)
+        idx_out[j] = (m >= batch) ? list[j] : (m > 0 ? list[below(raw[j], (uint32_t)m)] : 0);
+}
+
+// One observation (17 x 868 floats, channel-major in the ring) to `dst`: a straight float4 copy,
+// or transposed to channels-last ([cell][17]) through a padded shared-memory tile.
+constexpr int TILE_STRIDE = CH_FLOATS + 1;   // 869: odd stride, conflict-free transposed reads
+constexpr int COLLATE_THREADS = 256;
+constexpr int COLLATE_SMEM = OBS_CH * TILE_STRIDE * 4;
+__device__ __forceinline__ void emit_obs(const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                         bool zero, bool nhwc, float *tile) {
+    if (zero) {
+        for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS)
+            dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    if (!nhwc) {
+        for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) dst[q] = __ldg(src + q);
+        return;
+    }
+    for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) {
+        const float4 v = __ldg(src + q);
+        const int ch = q / (CH_FLOATS / 4), cell = (q - ch * (CH_FLOATS / 4)) * 4;
+        float *t = tile + ch * TILE_STRIDE + cell;
+        t[0] = v.x;
+        t[1] = v.y;
+        t[2] = v.z;
+        t[3] = v.w;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) {
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = q * 4 + u, cell = j / OBS_CH, ch = j - cell * OBS_CH;
+            o[u] = tile[ch * TILE_STRIDE + cell];
+        }
+        dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void __launch_bounds__(COLLATE_THREADS)
+k_replay_collate(const float4 *__restrict__ ring_obs, long long n, long long ring_slots,
+                 const long long *__restrict__ idx, const uint8_t *__restrict__ ring_actions,
+                 const int32_t *__restrict__ ring_rewards, const uint8_t *__restrict__ ring_done,
+                 const uint8_t *__restrict__ ring_next_mask, float4 *__restrict__ obs_out,
+                 float4 *__restrict__ next_obs_out, int nhwc, long long *__restrict__ actions_out,
+                 float *__restrict__ rewards_out, uint8_t *__restrict__ done_out,
+                 uint8_t *__restrict__ next_mask_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    const long long k = blockIdx.x >> 1;
+    const bool is_next = blockIdx.x & 1;
+    const long long flat = idx[k];
+    const long long slot = flat / n, env = flat - slot * n;
+    const bool done = ring_done[flat] != 0;
+    if (!is_next) {
+        emit_obs(ring_obs + flat * (OBS_FLOATS / 4), obs_out + k * (OBS_FLOATS / 4), false, nhwc != 0, tile);
+        if (threadIdx.x == 0) {
+            actions_out[k] = ring_actions[flat];
+            rewards_out[k] = (float)ring_rewards[flat];
+            done_out[k] = done ? 1 : 0;
+        }
+        if (threadIdx.x < 5) next_mask_out[k * 5 + threadIdx.x] = ring_next_mask[flat * 5 + threadIdx.x];
+    } else {
+        // `next_obs is None` -> zeros (train_dqn.py:154-159); otherwise the next time slot
+        const long long nflat = ((slot + 1) % ring_slots) * n + env;
+        emit_obs(ring_obs + nflat * (OBS_FLOATS / 4), next_obs_out + k * (OBS_FLOATS / 4), done, nhwc != 0, tile);
+    }
+}
+
+__global__ void __launch_bounds__(COLLATE_THREADS)
+k_replay_slot(const float4 *__restrict__ ring_obs, long long n, long long ring_slots,
+              const long long *__restrict__ t_dev, float4 *__restrict__ out, int nhwc) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const long long flat = (*t_dev % ring_slots) * n + blockIdx.x;
+    emit_obs(ring_obs + flat * (OBS_FLOATS / 4), out + (long long)blockIdx.x * (OBS_FLOATS / 4), false,
+             nhwc != 0, reinterpret_cast<float *>(smem_raw));
+}
+
+}  // namespace pb
+
+namespace {
+int collate_smem_attr(int device) {
+    static thread_local int set_for = -1;
+    if (set_for != device) {
+        PB_CUDA(cudaFuncSetAttribute(k_replay_collate, cudaFuncAttributeMaxDynamicSharedMemorySize, COLLATE_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_replay_slot, cudaFuncAttributeMaxDynamicSharedMemorySize, COLLATE_SMEM));
+        set_for = device;
+    }
+    return PB_OK;
+}
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace
+
+extern "C" {
+
+uint32_t pb_replay_raw(uint64_t seed, uint64_t call_idx, uint32_t j) { return replay_raw(seed, call_idx, j); }
+
+int64_t pb_replay_sample_capacity(void) {
+    // list (4 B per ring entry) + 4 096 raw draws + the 4 KB scan array must fit 227 KB
+    return (int64_t)((SAMPLE_SMEM_MAX - 4 * 4096) / 4);
+}
+
+int pb_replay_record(int64_t n_envs, int64_t ring_slots, const int64_t *t_dev,
+                     const uint8_t *actions_dev, const int32_t *reward_dev, const uint8_t *done_dev,
+                     const uint8_t *mask_dev, const uint8_t *in_phase1_dev, uint8_t *ring_actions,
+                     int32_t *ring_rewards, uint8_t *ring_done, uint8_t *ring_next_mask,
+                     uint8_t *ring_valid, int device, void *stream) {
+    if (n_envs <= 0 || ring_slots < 2 || !t_dev || !actions_dev || !reward_dev || !done_dev ||
+        !mask_dev || !ring_actions || !ring_rewards || !ring_done || !ring_next_mask || !ring_valid)
+        return fail(PB_ERR_INVALID_ARG, "pb_replay_record: bad arguments");
+    DeviceGuard g(device);
+    k_replay_record<<<(unsigned)((n_envs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        n_envs, ring_slots, reinterpret_cast<const long long *>(t_dev), actions_dev, reward_dev,
+        done_dev, mask_dev, in_phase1_dev, ring_actions, ring_rewards, ring_done, ring_next_mask,
+        ring_valid);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_replay_sample(const uint8_t *ring_valid_dev, int64_t total, int64_t batch, uint64_t seed,
+                     const int64_t *call_idx_dev, int64_t *idx_out_dev, int32_t *num_valid_out_dev,
+                     int device, void *stream) {
+    if (!ring_valid_dev || !call_idx_dev || !idx_out_dev || total <= 0 || batch <= 0 ||
+        batch > 4096 || total > pb_replay_sample_capacity())
+        return fail(PB_ERR_INVALID_ARG,
+                    "pb_replay_sample: bad arguments (batch <= 4096, ring entries <= "
+                    "pb_replay_sample_capacity())");
+    DeviceGuard g(device);
+    const size_t smem = sizeof(int) * (size_t)total + sizeof(uint32_t) * (size_t)batch;
+    static thread_local int set_for = -1;
+    if (set_for != device) {
+        PB_CUDA(cudaFuncSetAttribute(k_replay_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE_SMEM_MAX));
+        set_for = device;
+    }
+    k_replay_sample<<<1, SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
+        ring_valid_dev, total, (int)batch, seed, reinterpret_cast<const long long *>(call_idx_dev),
+        reinterpret_cast<long long *>(idx_out_dev), num_valid_out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
+                      const int64_t *idx_dev, int64_t batch, const uint8_t *ring_actions,
+                      const int32_t *ring_rewards, const uint8_t *ring_done,
+                      const uint8_t *ring_next_mask, float *obs_out_dev, float *next_obs_out_dev,
+                      int channels_last, int64_t *actions_out_dev, float *rewards_out_dev,
+                      uint8_t *done_out_dev, uint8_t *next_mask_out_dev, int device, void *stream) {
+    if (!ring_obs_dev || !idx_dev || !ring_actions || !ring_rewards || !ring_done || !ring_next_mask ||
+        !obs_out_dev || !next_obs_out_dev || !actions_out_dev || !rewards_out_dev || !done_out_dev ||
+        !next_mask_out_dev || n_envs <= 0 || ring_slots < 2 || batch < 0 || !aligned16(ring_obs_dev) ||
+        !aligned16(obs_out_dev) || !aligned16(next_obs_out_dev))
+        return fail(PB_ERR_INVALID_ARG, "pb_replay_collate: bad arguments");
+    if (batch == 0) return PB_OK;
+    DeviceGuard g(device);
+    int rc = collate_smem_attr(device);
+    if (rc != PB_OK) return rc;
+    k_replay_collate<<<(unsigned)(2 * batch), COLLATE_THREADS, channels_last ? COLLATE_SMEM : 0,
+                       (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(ring_obs_dev), n_envs, ring_slots,
+        reinterpret_cast<const long long *>(idx_dev), ring_actions, ring_rewards, ring_done,
+        ring_next_mask, reinterpret_cast<float4 *>(obs_out_dev),
+        reinterpret_cast<float4 *>(next_obs_out_dev), channels_last,
+        reinterpret_cast<long long *>(actions_out_dev), rewards_out_dev, done_out_dev,
+        next_mask_out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
+                       const int64_t *t_dev, float *out_dev, int channels_last, int device,
+                       void *stream) {
+    if (!ring_obs_dev || !t_dev || !out_dev || n_envs <= 0 || ring_slots < 1 ||
+        !aligned16(ring_obs_dev) || !aligned16(out_dev))
+        return fail(PB_ERR_INVALID_ARG, "pb_replay_slot_obs: bad arguments");
+    DeviceGuard g(device);
+    int rc = collate_smem_attr(device);
+    if (rc != PB_OK) return rc;
+    k_replay_slot<<<(unsigned)n_envs, COLLATE_THREADS, channels_last ? COLLATE_SMEM : 0,
+                    (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(ring_obs_dev), n_envs, ring_slots,
+        reinterpret_cast<const long long *>(t_dev), reinterpret_cast<float4 *>(out_dev), channels_last);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -145,6 +145,11 @@ __host__ __device__ inline uint32_t action_raw(uint64_t seed, uint64_t gid, uint
     return (uint32_t)(mix64(env_key(seed, gid) + call * 0xd1342543de82ef95ull +
                             0xa0761d6478bd642full) >> 32);
 }
+// replay-sampling stream (pb_replay_sample): draw j of sampling call `call`
+__host__ __device__ inline uint32_t replay_raw(uint64_t seed, uint64_t call, uint32_t j) {
+    return (uint32_t)(mix64(mix64(seed + 0x9e3779b97f4a7c15ull * (call + 1ull)) +
+                            (uint64_t)j * 0xd1342543de82ef95ull + 0x8ebc6af09c88c6e3ull) >> 32);
+}
 // seed of the game-draw stream used by MCTS SIMULATIONS (pb_mcts.cuh): the cloned env of search
 // iteration `epoch` keeps its gid and rng_ctr but draws from a different seed, so a simulation
 // never sees the draws the real env is going to get

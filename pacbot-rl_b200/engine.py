@@ -432,6 +432,27 @@ class BatchedPacmanGym:
                                         C.c_void_p(a.data_ptr()), int(call_idx), self._stream()))
         return a
 
+    def select_actions_dev(self, q_values: torch.Tensor, epsilon: torch.Tensor,
+                           call_idx: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """select_actions() with `epsilon` (float32, 1 element) and `call_idx` (int64, 1 element)
+        read from DEVICE memory at kernel time (pb_select_actions_dev): CUDA-graph friendly."""
+        n = self.num_envs
+        q = self._check_tensor(q_values, (n, NUM_ACTIONS), torch.float32, "q_values")
+        if (epsilon.dtype != torch.float32 or epsilon.numel() != 1 or epsilon.device != self.device
+                or call_idx.dtype != torch.int64 or call_idx.numel() != 1 or call_idx.device != self.device):
+            raise ValueError("epsilon: 1-element float32, call_idx: 1-element int64, both on the engine device")
+        mptr = None
+        if mask is not None:
+            mptr = C.c_void_p(self._check_tensor(
+                mask.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask").data_ptr())
+        a = self._new((n,), torch.uint8) if out is None else self._check_tensor(
+            out, (n,), torch.uint8, "out")
+        check(self._L.pb_select_actions_dev(self._h, C.c_void_p(q.data_ptr()), mptr,
+                                            C.c_void_p(epsilon.data_ptr()), C.c_void_p(call_idx.data_ptr()),
+                                            C.c_void_p(a.data_ptr()), self._stream()))
+        return a
+
     # ------------------------------------------------------------------ host-buffer entry
     def step_host(self, actions: np.ndarray, obs_out: Optional[torch.Tensor] = None,
                   want_mask: bool = True, out: Optional[tuple] = None):
@@ -469,11 +490,20 @@ class BatchedPacmanGym:
             int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
         return reward, done, mask
 
-    def obs_numpy(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
-        """obs_numpy() of envs [first, first+count): float32 [count, 17, 28, 31] on the host."""
+    def obs_numpy(self, first: int = 0, count: Optional[int] = None,
+                  out: Optional[np.ndarray] = None) -> np.ndarray:
+        """obs_numpy() of envs [first, first+count): float32 [count, 17, 28, 31] on the host.
+        `out`: a C-contiguous float32 array to fill instead of a fresh one; give it PINNED memory
+        (e.g. `torch.empty(...).pin_memory().numpy()`) and the chunks cross PCIe at link speed
+        while the next chunk is being encoded (pb_obs_host); a pageable array goes through the
+        engine's pinned bounce buffers."""
         if count is None:
             count = self.num_envs - first
-        out = np.empty((count,) + OBS_SHAPE, np.float32)
+        if out is None:
+            out = np.empty((count,) + OBS_SHAPE, np.float32)
+        elif (out.dtype != np.float32 or out.shape != (count,) + OBS_SHAPE
+              or not out.flags.c_contiguous):
+            raise ValueError(f"out: expected a C-contiguous float32 array of shape {(count,) + OBS_SHAPE}")
         check(self._L.pb_obs_host(self._h, first, count, out.ctypes.data_as(C.c_void_p),
                                   self._stream()))
         return out
@@ -483,15 +513,17 @@ class BatchedPacmanGym:
         """Structured array (dtype `ENV_STATE_DTYPE` == C `pb_env_state`) of envs [first, +count)."""
         if count is None:
             count = self.num_envs - first
-        torch.cuda.synchronize(self.device)
         out = np.zeros(count, ENV_STATE_DTYPE)
-        check(self._L.pb_get_state(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
+        # ordered on the caller's current stream (+ the engine's own streams): no device-wide
+        # synchronisation, other streams of the process keep running
+        check(self._L.pb_get_state_on(self._h, first, count, out.ctypes.data_as(C.c_void_p),
+                                      self._stream()))
         return out
 
     def set_state(self, state: np.ndarray, first: int = 0) -> None:
         st = np.ascontiguousarray(state, dtype=ENV_STATE_DTYPE)
-        torch.cuda.synchronize(self.device)
-        check(self._L.pb_set_state(self._h, first, st.shape[0], st.ctypes.data_as(C.c_void_p)))
+        check(self._L.pb_set_state_on(self._h, first, st.shape[0], st.ctypes.data_as(C.c_void_p),
+                                      self._stream()))
         self._cfg[first:first + st.shape[0]] = st["cfg_flags"] & 0x0F
 
     def clone_env_from(self, dst_index: int, src: "BatchedPacmanGym", src_index: int) -> None:

@@ -5,12 +5,23 @@
 engine; `PacmanGymView` exposes the same read-only surface for env i of a `BatchedPacmanGym`."""
 from __future__ import annotations
 
+import itertools
+import os
+
 import numpy as np
 
 from ._lib import CFG_RANDOM_START, OBS_SHAPE
 from .engine import BatchedPacmanGym
 
 _WALL_ROWS = None
+
+# Defaults for objects built the reference's way, `PacmanGym(random_start, random_ticks)`: the
+# reference gives every env its own `rand::thread_rng()` stream (env.rs:146), so two fresh objects
+# must not replay the same random ticks / start node / frightened-ghost turns.  Unless the caller
+# passes `seed` / `env_id` (reproducible tests), every object gets the next env id of a
+# process-wide counter under a seed drawn once per process from the OS.
+_PROCESS_SEED = int.from_bytes(os.urandom(8), "little")
+_ENV_IDS = itertools.count()
 
 
 def _wall_at(row: int, col: int) -> bool:
@@ -92,11 +103,15 @@ class _SingleEnvSurface:
 class PacmanGym(_SingleEnvSurface):
     """pacbot_rs.PacmanGym(random_start, random_ticks) on the B200 engine."""
 
-    def __init__(self, random_start: bool, random_ticks: bool, *, device=None, seed: int = 0,
-                 env_id: int = 0) -> None:
+    def __init__(self, random_start: bool, random_ticks: bool, *, device=None, seed=None,
+                 env_id=None) -> None:
+        if seed is None:
+            seed = _PROCESS_SEED
+        if env_id is None:
+            env_id = next(_ENV_IDS)
         self._batch = BatchedPacmanGym(
-            1, bool(random_start), bool(random_ticks), device=device, seed=seed, env_id_base=env_id
-        )
+            1, bool(random_start), bool(random_ticks), device=device, seed=int(seed),
+            env_id_base=int(env_id))
         self._index = 0
 
     @property

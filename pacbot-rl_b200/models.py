@@ -76,6 +76,61 @@ class QNetV2(nn.Module):
         return value - adv.mean(dim=1, keepdim=True) + adv
 
 
+class QNet(nn.Module):
+    """The reference's first Q-network (models.py:17-63), selectable with `--model QNet`: two
+    conv+SiLU blocks (5x5 C->16, 3x3 16->32) and a 3x3 conv to 64 channels at full resolution,
+    global max over the board, SiLU, Linear 64->128, SiLU, dueling heads; same module nesting
+    (`backbone.{0.0,1.0,2}`, `fc.1`, `value_head.0`, `advantage_head.0`) for checkpoint exchange."""
+
+    def __init__(self, obs_shape, action_count: int) -> None:
+        super().__init__()
+        in_ch = int(obs_shape[0])
+        self.backbone = nn.Sequential(
+            nn.Sequential(nn.Conv2d(in_ch, 16, 5, padding="same"), nn.SiLU()),
+            nn.Sequential(nn.Conv2d(16, 32, 3, padding="same"), nn.SiLU()),
+            nn.Conv2d(32, 64, 3, padding="same"),
+        )
+        self.fc = nn.Sequential(nn.SiLU(), nn.Linear(64, 128), nn.SiLU())
+        self.value_head = nn.Sequential(nn.Linear(128, 1))
+        self.advantage_head = nn.Sequential(nn.Linear(128, action_count))
+        init_orthogonal(self)
+        with torch.no_grad():
+            for head in (self.value_head[-1], self.advantage_head[-1]):
+                head.weight.zero_()
+                head.bias.zero_()
+
+    def use_channels_last(self) -> "QNet":
+        self.to(memory_format=torch.channels_last)
+        self._channels_last = True
+        return self
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_channels_last", False):
+            obs = obs.contiguous(memory_format=torch.channels_last)
+        feat = self.fc(self.backbone(obs).amax(dim=(-2, -1)))
+        adv = self.advantage_head(feat)
+        return self.value_head(feat) - adv.mean(dim=1, keepdim=True) + adv
+
+
+class DebugMLPQNet(nn.Module):
+    """The reference's debugging MLP (models.py:150-167), `--model DebugMLPQNet`: flatten,
+    Linear -> 128, SiLU, Linear -> actions with a zeroed last layer (default init otherwise)."""
+
+    def __init__(self, obs_shape, action_count: int) -> None:
+        super().__init__()
+        n_in = 1
+        for d in obs_shape:
+            n_in *= int(d)
+        self.mlp = nn.Sequential(nn.Linear(n_in, 128), nn.SiLU(), nn.Linear(128, action_count))
+        with torch.no_grad():
+            self.mlp[-1].weight.zero_()
+            self.mlp[-1].bias.zero_()
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        # logical (C, H, W) order whatever the memory format of the batch
+        return self.mlp(obs.contiguous().view(obs.shape[0], -1))
+
+
 class NetV2(nn.Module):
     """The AlphaZero network (reference models.py:113-147): QNetV2's trunk with one linear head of
     `output_dim` outputs (5 policy logits + 1 value, train_alphazero.py:75), last layer zero

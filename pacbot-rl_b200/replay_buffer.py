@@ -2,18 +2,27 @@
 `ReplayBuffer` (/root/reference/src/replay_buffer.py:57-143) and `reset_env` (:44-54).
 
 Layout: a time ring of R = ceil(maxlen / N) + 1 slots; slot t % R holds, for all N envs, the
-observation BEFORE action t plus (action, reward, done, next_action_mask) of transition t.  The
-observation encoder writes straight into the ring (`pb_encode_obs_ring`), so `next_obs` of
+observation BEFORE action t plus (action, reward, done, next_action_mask, valid) of transition t.
+The observation encoder writes straight into the ring (`pb_encode_obs_ring`), so `next_obs` of
 transition t is simply slot (t+1) % R and is never copied; a finished episode's `next_obs` is
 "None" in the reference (zeros at collate time, train_dqn.py:154-159) and the slot then already
 holds the first observation of the next episode (the env was reset in the same kernel launch).
-One slot is always "current observation only", which is why R has the +1.  Sampling is uniform
-without replacement over the valid transitions (`random.sample`, replay_buffer.py:141-143) and
-the collate is two `pb_gather_obs` launches.
+One slot is always "current observation only", which is why R has the +1.
 
-Everything that depends on the ring position uses a DEVICE-side step counter (`_t_dev`), never
-a Python int, so `generate_experience_step` + `sample_batch` can be captured in a CUDA graph
-and replayed while the ring advances."""
+Every per-step and per-batch operation is one of the repo's own kernels behind the C ABI
+(include/pacbot_b200.h, csrc/pb_replay_abi.inl):
+
+    generate_experience_step   pb_replay_slot_obs (last_obs, NCHW or channels-last)
+                               -> Q-network forward (PyTorch/cuDNN)
+                               -> pb_select_actions_dev (epsilon-greedy over the Q-values)
+                               -> pb_step (+ auto reset) -> pb_encode_obs_ring -> pb_replay_record
+    sample_batch               pb_replay_sample (uniform, without replacement: random.sample,
+                               replay_buffer.py:141-143) -> pb_replay_collate (obs / next_obs /
+                               action / reward / done / next mask of the batch in one launch)
+
+Everything that depends on the ring position reads a DEVICE-side step counter (`_t_dev`), never a
+Python int, so `generate_experience_step` + `sample_batch` can be captured in a CUDA graph and
+replayed while the ring advances."""
 from __future__ import annotations
 
 import ctypes as C
@@ -23,15 +32,15 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NUM_ACTIONS, OBS_FLOATS, OBS_SHAPE, check
+from ._lib import NUM_ACTIONS, OBS_SHAPE, check
 from .engine import BatchedPacmanGym
-from .policies import Policy
+from .policies import EpsilonGreedy, MaxQPolicy, Policy
 
 
 class ReplayBatch(NamedTuple):
     """Collated transitions (what train_dqn.py:153-165 builds from a list of ReplayItems)."""
 
-    obs: torch.Tensor                # float32 [B, 17, 28, 31]
+    obs: torch.Tensor                # float32 [B, 17, 28, 31] (channels-last strides if asked)
     actions: torch.Tensor            # int64   [B]
     rewards: torch.Tensor            # float32 [B]   (raw env reward, unscaled)
     next_obs: torch.Tensor           # float32 [B, 17, 28, 31], zeros where done
@@ -74,6 +83,12 @@ def reset_env(envs: BatchedPacmanGym, policy_old: Optional[Policy], max_steps: i
         envs.auto_reset = auto
 
 
+def _channels_last_empty(shape, device) -> torch.Tensor:
+    """float32 [B, C, H, W] tensor whose memory order is [B, H, W, C] (torch.channels_last)."""
+    b, c, h, w = shape
+    return torch.empty((b, h, w, c), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
 class ReplayBuffer:
     def __init__(
         self,
@@ -86,12 +101,15 @@ class ReplayBuffer:
         seed: int = 0,
         env_id_base: int = 0,
         phase1_policy: Optional[Policy] = None,
+        channels_last: bool = False,
     ) -> None:
         self.policy = policy
         self.phase1_policy = phase1_policy
+        self.channels_last = bool(channels_last)
         n = int(num_parallel_envs)
         self.num_envs = n
         self.maxlen = int(maxlen)
+        self.seed = int(seed)
         self._slots = -(-self.maxlen // n)          # transitions kept: slots * n >= maxlen
         self._ring = self._slots + 1
         # replay_buffer.py:75-80: random_start for the first N * proportion envs, random_ticks all
@@ -100,17 +118,29 @@ class ReplayBuffer:
             seed=seed, env_id_base=env_id_base, auto_reset=True)
         dev = self.envs.device
         self.device = dev
+        self._L = _lib.load()
         r = self._ring
         self._obs = torch.zeros((r, n) + OBS_SHAPE, dtype=torch.float32, device=dev)
-        self._actions = torch.zeros((r, n), dtype=torch.int64, device=dev)
+        self._actions = torch.zeros((r, n), dtype=torch.uint8, device=dev)
         self._rewards = torch.zeros((r, n), dtype=torch.int32, device=dev)
         self._done = torch.zeros((r, n), dtype=torch.bool, device=dev)
         self._next_mask = torch.zeros((r, n, NUM_ACTIONS), dtype=torch.bool, device=dev)
-        self._weight = torch.zeros((r, n), dtype=torch.float32, device=dev)  # 1 = sampleable
+        self._valid = torch.zeros((r, n), dtype=torch.bool, device=dev)   # True = sampleable
         self._mask = torch.zeros((n, NUM_ACTIONS), dtype=torch.bool, device=dev)
         self._in_phase1 = torch.zeros(n, dtype=torch.bool, device=dev)
-        self._t = 0                                                  # host mirror (len, fill)
-        self._t_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # the counter kernels use
+        # per-step scratch (fixed addresses: CUDA-graph capture)
+        self._last_obs = (_channels_last_empty((n,) + OBS_SHAPE, dev) if self.channels_last
+                          else torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev))
+        self._act = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._done_step = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._eps_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._t = 0                                                  # host mirror of the step counter
+        self._t_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # the counter the kernels read
+        self._nxt_dev = torch.ones(1, dtype=torch.int64, device=dev)  # (t + 1) % R
+        self._sample_calls = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._num_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._batch_bufs: dict = {}
         self.envs.reset()
         self.envs.obs(out=self._obs[0])
         self.envs.action_mask(out=self._mask)
@@ -129,71 +159,142 @@ class ReplayBuffer:
         return NUM_ACTIONS
 
     def __len__(self) -> int:
-        return min(self._t, self._slots) * self.num_envs
+        """Number of RECORDED transitions that can be sampled (len(deque) in the reference).
+        Reads the device (one synchronisation)."""
+        return int(self._valid.sum().item())
 
     @property
     def capacity(self) -> int:
         return self._slots * self.num_envs
 
-    def fill(self) -> None:
-        """Generate experience until the buffer holds `capacity` transitions."""
+    def fill(self, min_valid: int = 1) -> None:
+        """Generate experience until the ring has wrapped once (the reference's `fill()` loops until
+        the deque holds `maxlen` items, replay_buffer.py:97-100) AND at least `min_valid` recorded
+        transitions can be sampled.  With the old policy of the two-stage reset, phase-1 steps
+        occupy ring slots without being recorded, so a freshly wrapped ring can hold fewer than
+        `capacity` transitions -- possibly fewer than a batch: callers pass their batch size."""
+        limit = 16 * self._ring + 64
         while self._t < self._slots:
             self.generate_experience_step()
+        while len(self) < max(1, min_valid):
+            if self._t >= limit:
+                raise RuntimeError(
+                    f"replay buffer: only {len(self)} recorded transitions after {self._t} steps of "
+                    f"{self.num_envs} envs (need {min_valid}); the old policy of the two-stage reset "
+                    "does not get through phase 1")
+            for _ in range(8):
+                self.generate_experience_step()
+
+    def _slot_ptrs(self):
+        return (C.c_void_p(self._actions.data_ptr()), C.c_void_p(self._rewards.data_ptr()),
+                C.c_void_p(self._done.data_ptr()), C.c_void_p(self._next_mask.data_ptr()))
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @torch.no_grad()
+    def _select(self, last_obs: torch.Tensor) -> torch.Tensor:
+        """actions uint8 [N] of `self.policy` for the current observations."""
+        pol = self.policy
+        if isinstance(pol, EpsilonGreedy) and isinstance(pol.original_policy, MaxQPolicy):
+            # EpsilonGreedy(MaxQPolicy(q_net)) (policies.py:16-59) as ONE launch after the forward:
+            # greedy iff rand > epsilon, else a uniformly random valid action; epsilon and the
+            # call index are read from device memory at kernel time
+            q = pol.original_policy.q_values(last_obs)
+            eps = pol.epsilon
+            if isinstance(eps, torch.Tensor):
+                eps_dev = eps.reshape(1) if eps.dtype == torch.float32 and eps.device == self.device \
+                    else self._eps_dev.copy_(eps.reshape(1))
+            else:
+                eps_dev = self._eps_dev.fill_(float(eps))
+            return self.envs.select_actions_dev(q.contiguous(), eps_dev, self._t_dev, mask=self._mask,
+                                                out=self._act)
+        return self._act.copy_(pol(last_obs, self._mask))
 
     @torch.no_grad()
     def generate_experience_step(self, count_on_host: bool = True) -> None:
         """One env-step for each parallel env, appended to the ring (replay_buffer.py:102-139).
         `count_on_host=False` is for CUDA-graph replay: the caller advances `_t` itself."""
         r, n = self._ring, self.num_envs
-        slot = self._t_dev % r
-        nxt = (self._t_dev + 1) % r
-        last_obs = self._obs.view(r, -1).index_select(0, slot).view((n,) + OBS_SHAPE)
-        actions = self.policy(last_obs, self._mask)
+        L, stream, dev = self._L, self._stream(), self.device.index
+        check(L.pb_replay_slot_obs(C.c_void_p(self._obs.data_ptr()), n, r, C.c_void_p(self._t_dev.data_ptr()),
+                                   C.c_void_p(self._last_obs.data_ptr()), int(self.channels_last), dev, stream))
+        actions = self._select(self._last_obs)
         if self.phase1_policy is not None:
-            actions = torch.where(self._in_phase1, self.phase1_policy(last_obs, self._mask), actions)
+            old = self.phase1_policy(self._last_obs, self._mask).to(torch.uint8)
+            actions = self._act.copy_(torch.where(self._in_phase1, old, actions))
         # step + auto reset, then the observation of the resulting state straight into slot t+1
-        reward, done = self.envs.step(actions, check_actions=False, mask_out=self._mask)
-        self.envs.obs_ring(self._obs, nxt)
-        self._actions.index_copy_(0, slot, actions.to(torch.int64).unsqueeze(0))
-        self._rewards.index_copy_(0, slot, reward.unsqueeze(0))
-        self._done.index_copy_(0, slot, done.unsqueeze(0))
-        # next_action_mask is [False]*5 when done (replay_buffer.py:115-117)
-        self._next_mask.index_copy_(0, slot, (self._mask & ~done.unsqueeze(1)).unsqueeze(0))
-        self._weight.index_copy_(0, slot, (~self._in_phase1).to(torch.float32).unsqueeze(0))
-        self._weight.index_fill_(0, nxt, 0.0)                     # slot t+1 is "current obs" only
+        self.envs.step(actions, check_actions=False, mask_out=self._mask, reward_out=self._reward,
+                       done_out=self._done_step)
+        self.envs.obs_ring(self._obs, self._nxt_dev)
+        a_p, r_p, d_p, m_p = self._slot_ptrs()
+        phase = C.c_void_p(self._in_phase1.data_ptr()) if self.phase1_policy is not None else None
+        check(L.pb_replay_record(n, r, C.c_void_p(self._t_dev.data_ptr()), C.c_void_p(actions.data_ptr()),
+                                 C.c_void_p(self._reward.data_ptr()), C.c_void_p(self._done_step.data_ptr()),
+                                 C.c_void_p(self._mask.data_ptr()), phase, a_p, r_p, d_p, m_p,
+                                 C.c_void_p(self._valid.data_ptr()), dev, stream))
         if self.phase1_policy is not None:
-            self._in_phase1 = (self._in_phase1 | done) & ~self.envs.first_ai_done()
+            self._in_phase1.copy_((self._in_phase1 | self._done_step) & ~self.envs.first_ai_done())
         self._t_dev += 1
+        torch.remainder(self._t_dev + 1, r, out=self._nxt_dev)
         if count_on_host:
             self._t += 1
 
+    def _batch_buffers(self, b: int):
+        bufs = self._batch_bufs.get(b)
+        if bufs is None:
+            dev = self.device
+            mk = (lambda: _channels_last_empty((b,) + OBS_SHAPE, dev)) if self.channels_last else (
+                lambda: torch.empty((b,) + OBS_SHAPE, dtype=torch.float32, device=dev))
+            bufs = dict(idx=torch.zeros(b, dtype=torch.int64, device=dev), obs=mk(), next_obs=mk(),
+                        actions=torch.zeros(b, dtype=torch.int64, device=dev),
+                        rewards=torch.zeros(b, dtype=torch.float32, device=dev),
+                        done=torch.zeros(b, dtype=torch.bool, device=dev),
+                        next_mask=torch.zeros((b, NUM_ACTIONS), dtype=torch.bool, device=dev))
+            self._batch_bufs[b] = bufs
+        return bufs
+
+    @torch.no_grad()
+    def sample_indices(self, batch_size: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`batch_size` distinct flat ring indices (slot * N + env) of recorded transitions,
+        uniform (random.sample).  `num_valid` afterwards holds the number of candidates."""
+        total = self._ring * self.num_envs
+        idx = self._batch_buffers(batch_size)["idx"] if out is None else out
+        if total <= self._L.pb_replay_sample_capacity() and batch_size <= 4096:
+            check(self._L.pb_replay_sample(C.c_void_p(self._valid.data_ptr()), total, batch_size,
+                                           self.seed & 0xFFFFFFFFFFFFFFFF,
+                                           C.c_void_p(self._sample_calls.data_ptr()),
+                                           C.c_void_p(idx.data_ptr()), C.c_void_p(self._num_valid.data_ptr()),
+                                           self.device.index, self._stream()))
+            self._sample_calls += 1
+        else:
+            # ring too large for the shared-memory list of pb_replay_sample: exponential-race
+            # top-k on the device (torch.multinomial without replacement)
+            idx.copy_(torch.multinomial(self._valid.view(-1).to(torch.float32), batch_size, replacement=False))
+            self._num_valid.copy_(self._valid.sum().to(torch.int32).reshape(1))
+        return idx
+
+    @property
+    def num_valid(self) -> int:
+        """Candidates the last `sample_indices` / `sample_batch` drew from (device read)."""
+        return int(self._num_valid.item())
+
     @torch.no_grad()
     def sample_batch(self, batch_size: int) -> ReplayBatch:
-        """Uniform sample without replacement + collate, all on device."""
-        r, n = self._ring, self.num_envs
-        flat = torch.multinomial(self._weight.view(-1), batch_size, replacement=False)
-        slot = flat // n
-        env = flat - slot * n
-        nxt_flat = ((slot + 1) % r) * n + env
-        done = self._done.view(-1)[flat]
-        obs = torch.empty((batch_size,) + OBS_SHAPE, dtype=torch.float32, device=self.device)
-        next_obs = torch.empty_like(obs)
-        L = _lib.load()
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        ring_ptr = C.c_void_p(self._obs.data_ptr())
-        check(L.pb_gather_obs(ring_ptr, OBS_FLOATS, C.c_void_p(flat.data_ptr()), None, batch_size,
-                              C.c_void_p(obs.data_ptr()), self.device.index, stream))
-        check(L.pb_gather_obs(ring_ptr, OBS_FLOATS, C.c_void_p(nxt_flat.data_ptr()),
-                              C.c_void_p(done.view(torch.uint8).data_ptr()), batch_size,
-                              C.c_void_p(next_obs.data_ptr()), self.device.index, stream))
-        return ReplayBatch(
-            obs=obs,
-            actions=self._actions.view(-1)[flat],
-            rewards=self._rewards.view(-1)[flat].to(torch.float32),
-            next_obs=next_obs,
-            done=done,
-            next_action_masks=self._next_mask.view(-1, NUM_ACTIONS)[flat],
-        )
+        """Uniform sample without replacement + collate, two launches, all on device.  The
+        returned tensors are per-batch-size buffers that the next call overwrites."""
+        b = self._batch_buffers(batch_size)
+        idx = self.sample_indices(batch_size)
+        a_p, r_p, d_p, m_p = self._slot_ptrs()
+        check(self._L.pb_replay_collate(
+            C.c_void_p(self._obs.data_ptr()), self.num_envs, self._ring, C.c_void_p(idx.data_ptr()),
+            batch_size, a_p, r_p, d_p, m_p, C.c_void_p(b["obs"].data_ptr()),
+            C.c_void_p(b["next_obs"].data_ptr()), int(self.channels_last),
+            C.c_void_p(b["actions"].data_ptr()), C.c_void_p(b["rewards"].data_ptr()),
+            C.c_void_p(b["done"].data_ptr()), C.c_void_p(b["next_mask"].data_ptr()),
+            self.device.index, self._stream()))
+        return ReplayBatch(obs=b["obs"], actions=b["actions"], rewards=b["rewards"],
+                           next_obs=b["next_obs"], done=b["done"], next_action_masks=b["next_mask"])
 
     @property
     def current_obs(self) -> torch.Tensor:

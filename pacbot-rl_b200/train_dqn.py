@@ -3,7 +3,14 @@
 :116-265, evaluation :88-113, checkpoint cadence :239-253).
 
 What changed relative to the reference loop (and nothing else):
-  * envs, replay ring, epsilon-greedy and the collate live on the GPU (no per-step host trip);
+  * envs, replay ring, epsilon-greedy, sampling and the collate are the repo's CUDA kernels (no
+    per-step host trip); the whole iteration is ONE CUDA graph.  The first three iterations run
+    eagerly (cuDNN autotune, optimizer state) and are ordinary, counted iterations; the graph is
+    captured before the fourth;
+  * the evaluation episode runs at the reference's cadence (every `evaluate_steps` = 10
+    iterations, train_dqn.py:220-229) but on a SIDE STREAM with a snapshot of the weights, in
+    chunks of 25 graph-captured env steps, while training goes on; the host only polls it.  Its
+    result is logged with the iteration it was started at;
   * metrics are reduced on the device and read back every `--log_every` iterations instead of a
     `loss.item()` sync per iteration;
   * the phase-1 "old policy" of `reset_env` is optional (its checkpoint is not in the reference
@@ -11,7 +18,8 @@ What changed relative to the reference loop (and nothing else):
   * wandb is optional and disabled by default (no network on the GPU box); metrics also go to a
     JSONL file;
   * under torchrun the envs shard per rank and gradients are averaged with ONE NCCL all-reduce
-    of the flat 156 934-float gradient per iteration.
+    of the flat 156 934-float gradient per iteration; a `max_seconds` stop is decided by rank 0
+    and broadcast, so every rank leaves the loop at the same iteration.
 
 Run:  python -m pacbot_rl_b200.train_dqn --num_iters 2000 [--device cuda:0]
 """
@@ -32,7 +40,7 @@ import torch.nn.functional as F
 from . import models
 from .engine import BatchedPacmanGym
 from .policies import EpsilonGreedy, MaxQPolicy
-from .replay_buffer import ReplayBuffer, reset_env
+from .replay_buffer import ReplayBatch, ReplayBuffer, reset_env
 
 # names and defaults exactly as the reference (train_dqn.py:26-42)
 hyperparam_defaults = {
@@ -72,6 +80,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--eval_envs", type=int, default=1,
                    help="greedy evaluation episodes run in parallel (the reference runs 1)")
+    p.add_argument("--no-eval-episodes", dest="eval_episodes", action="store_false", default=True,
+                   help="skip the evaluation episode every evaluate_steps iterations")
     p.add_argument("--no-checkpoints", action="store_true")
     p.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
                    help="keep the Q-network in NCHW (default: NHWC weights/activations for cuDNN)")
@@ -80,6 +90,153 @@ def build_parser() -> argparse.ArgumentParser:
     for name, default in hyperparam_defaults.items():
         p.add_argument(f"--{name}", type=type(default), default=default, help="Default: %(default)s")
     return p
+
+
+def dqn_targets(batch: ReplayBatch, q_net, target_q_net, discount_factor: float,
+                reward_scale: float) -> torch.Tensor:
+    """Double-DQN target (train_dqn.py:167-183): r * reward_scale + gamma * Q_target(s')[argmax_a
+    masked Q_online(s')], 0 where the episode ended.  A finished transition has an all-False next
+    mask: every Q is -inf there, exactly as in the reference, and the done mask zeroes it."""
+    with torch.no_grad():
+        masks = batch.next_action_masks
+        next_q = target_q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
+        online_next_q = q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
+        next_actions = online_next_q.argmax(dim=1)
+        returns = next_q.gather(1, next_actions.unsqueeze(1)).squeeze(1)
+        discounted = torch.where(batch.done, torch.zeros_like(returns), discount_factor * returns)
+        return batch.rewards * reward_scale + discounted
+
+
+def dqn_loss(batch: ReplayBatch, q_net, target_q: torch.Tensor):
+    """MSE between Q(s)[a] and the target (train_dqn.py:193-197) -> (loss, all Q-values)."""
+    all_q = q_net(batch.obs)
+    predicted = all_q.gather(1, batch.actions.unsqueeze(1)).squeeze(1)
+    return F.mse_loss(predicted, target_q), all_q
+
+
+EVAL_FIELDS = ("score", "steps", "cleared", "pellets_start", "pellets_end", "finished")
+
+
+class EpisodeEvaluator:
+    """`evaluate_episode` (train_dqn.py:88-113) for `num_envs` envs at once, resumable in chunks.
+
+    Per env, exactly the reference's loop: fixed start (random_start=False, random_ticks=False),
+    `reset_env`, then up to `max_steps` greedy steps until done; score / lives / pellets are read
+    after the step that ended the episode.  Finished envs keep being stepped (harmless, Q12) but
+    their statistics are frozen.  A chunk of `chunk` steps is captured in a CUDA graph after its
+    first eager run; `alive.any()` and the statistics travel to pinned host memory at the end of
+    every chunk, so the host decides between chunks without touching the device."""
+
+    def __init__(self, policy, device, num_envs: int = 1, max_steps: int = 1000, chunk: int = 25,
+                 seed: int = 17, env_id_base: int = 10_000_000, phase1_policy=None,
+                 use_graph: bool = True) -> None:
+        self.policy, self.device, self.n = policy, device, int(num_envs)
+        self.max_steps, self.chunk = int(max_steps), max(1, int(chunk))
+        self.phase1_policy, self.use_graph = phase1_policy, use_graph
+        self.env = BatchedPacmanGym(self.n, False, False, device=device, seed=seed, env_id_base=env_id_base)
+        n = self.n
+        z = lambda: torch.zeros(n, dtype=torch.int32, device=device)   # noqa: E731
+        self.obs = torch.empty((n, 17, 28, 31), dtype=torch.float32, device=device)
+        self.mask = torch.zeros((n, 5), dtype=torch.bool, device=device)
+        self.alive = torch.ones(n, dtype=torch.bool, device=device)
+        self.finished = torch.zeros(n, dtype=torch.bool, device=device)   # done within max_steps
+        self.steps, self.score, self.lives, self.pellets_end = z(), z(), z(), z()
+        self.pellets_start = z()
+        self.left = torch.zeros(1, dtype=torch.int32, device=device)    # steps left of max_steps
+        self.stats_dev = torch.zeros((6, n), dtype=torch.int32, device=device)
+        self.stats_host = torch.zeros((6, n), dtype=torch.int32).pin_memory()
+        self._graph = None
+        self._eager_chunks = 0
+        self.steps_run = 0
+
+    @torch.no_grad()
+    def begin(self) -> None:
+        """reset_env(gym) + pellets_start (train_dqn.py:95-97)."""
+        reset_env(self.env, self.phase1_policy)
+        self.pellets_start.copy_(self.env.remaining_pellets())
+        self.env.obs(out=self.obs)
+        self.alive.fill_(True)
+        self.finished.fill_(False)
+        for t in (self.steps, self.score, self.pellets_end):
+            t.zero_()
+        self.lives.fill_(3)
+        self.pellets_end.copy_(self.pellets_start)
+        self.left.fill_(self.max_steps)
+        self.steps_run = 0
+
+    @torch.no_grad()
+    def _step(self) -> None:
+        env = self.env
+        live = self.alive & (self.left > 0)
+        actions = self.policy(self.obs, env.action_mask(out=self.mask))
+        _, done = env.step_obs(actions, self.obs)
+        self.steps += live.int()
+        self.score.copy_(torch.where(live, env.score(), self.score))
+        self.lives.copy_(torch.where(live, env.lives(), self.lives))
+        self.pellets_end.copy_(torch.where(live, env.remaining_pellets(), self.pellets_end))
+        ended = live & done
+        self.finished |= ended
+        self.alive &= ~ended
+        self.left -= 1
+
+    @torch.no_grad()
+    def _chunk_body(self) -> None:
+        for _ in range(self.chunk):
+            self._step()
+        finished = self.finished   # `done` of the reference's loop; False if max_steps ran out
+        cleared = finished & (self.lives == 3)
+        self.stats_dev.copy_(torch.stack([
+            self.score, self.steps, cleared.int(), self.pellets_start,
+            torch.where(cleared, torch.zeros_like(self.pellets_end), self.pellets_end),
+            finished.int()]))
+        self.stats_host.copy_(self.stats_dev, non_blocking=True)
+
+    def run_chunk(self) -> None:
+        """Enqueue `chunk` more steps on the current stream (graph replay after the second chunk)."""
+        if self._graph is not None:
+            self._graph.replay()
+        elif self.use_graph and self._eager_chunks >= 2:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.device),
+                                  capture_error_mode="thread_local"):
+                self._chunk_body()
+            self._graph = g
+            g.replay()     # the capture pass executed nothing
+        else:
+            self._chunk_body()
+            self._eager_chunks += 1
+        self.steps_run += self.chunk
+
+    def all_finished(self) -> bool:
+        """Valid once the last enqueued chunk has completed (host reads pinned memory only)."""
+        return bool(self.stats_host[5].all()) or self.steps_run >= self.max_steps
+
+    def per_env(self) -> dict:
+        return {k: self.stats_host[i].clone() for i, k in enumerate(EVAL_FIELDS)}
+
+    def result(self) -> dict:
+        s = self.stats_host.float()
+        return {
+            "eval_episode_score": s[0].mean().item(),
+            "eval_episode_steps": s[1].mean().item(),
+            "cleared_board": s[2].mean().item(),
+            "eval_pellets_start": s[3].mean().item(),
+            "eval_pellets_end": s[4].mean().item(),
+        }
+
+
+def run_eval_episodes(env_policy, device, num_envs: int = 1, max_steps: int = 1000, seed: int = 17,
+                      env_id_base: int = 10_000_000, phase1_policy=None, chunk: int = 25) -> dict:
+    """Synchronous `evaluate_episode` for `num_envs` envs: per-env int32 tensors (host) for
+    score / steps / cleared / pellets_start / pellets_end / finished."""
+    ev = EpisodeEvaluator(env_policy, device, num_envs, max_steps, chunk, seed, env_id_base,
+                          phase1_policy, use_graph=False)
+    ev.begin()
+    while True:
+        ev.run_chunk()
+        torch.cuda.current_stream(device).synchronize()
+        if ev.all_finished():
+            return ev.per_env()
 
 
 class DQNTrainer:
@@ -94,7 +251,8 @@ class DQNTrainer:
         self.q_net = model_cls((17, 28, 31), 5).to(device)
         if cfg.finetune:
             self.q_net = torch.load(cfg.finetune, map_location=device, weights_only=False)
-        if cfg.channels_last and hasattr(self.q_net, "use_channels_last"):
+        nhwc = bool(cfg.channels_last and hasattr(self.q_net, "use_channels_last"))
+        if nhwc:
             self.q_net.use_channels_last()
         torch.manual_seed(cfg.seed * 1000003 + rank)
         self.target_q_net = copy.deepcopy(self.q_net).eval()
@@ -105,15 +263,18 @@ class DQNTrainer:
             old = model_cls((17, 28, 31), 5).to(device)
             old.load_state_dict(safetensors.torch.load_file(cfg.old_policy))
             phase1 = MaxQPolicy(old.eval())
-        # epsilon lives in a 0-dim device tensor so that changing it needs no re-capture
-        self._eps_t = torch.tensor(cfg.initial_epsilon if cfg.finetune else 1.0, device=device)
+        # epsilon lives in a device tensor so that changing it needs no re-capture
+        self._eps_t = torch.full((1,), cfg.initial_epsilon if cfg.finetune else 1.0, device=device)
         self._eps_host = float(self._eps_t)
         self._graph = None
+        self._want_graph = False
+        self._eager_iters = 0
+        self._side = torch.cuda.Stream(device)
         self.policy = EpsilonGreedy(MaxQPolicy(self.q_net), 5, self._eps_t)
         self.replay = ReplayBuffer(
             maxlen=cfg.replay_buffer_size, policy=self.policy, num_parallel_envs=cfg.num_parallel_envs,
             random_start_proportion=cfg.random_start_proportion, device=device, seed=cfg.seed,
-            env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1)
+            env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1, channels_last=nhwc)
         self.optimizer = torch.optim.Adam(self.q_net.parameters(), lr=cfg.learning_rate,
                                           capturable=True)
         self.params = [p for p in self.q_net.parameters()]
@@ -121,6 +282,14 @@ class DQNTrainer:
         # streaming metrics (device side)
         self._acc = torch.zeros(5, device=device)
         self._acc_n = 0
+        # evaluation on a side stream (created on first use)
+        self._eval: Optional[EpisodeEvaluator] = None
+        self._eval_net = None
+        self._eval_stream = None
+        self._eval_busy = False
+        self._eval_iter = -1
+        self._eval_event = None
+        self.eval_log: list = []
 
     # ------------------------------------------------------------------ one iteration
     @property
@@ -142,18 +311,9 @@ class DQNTrainer:
         host synchronisation and no host-dependent indexing, so it can be CUDA-graph captured."""
         cfg = self.cfg
         batch = self.replay.sample_batch(cfg.batch_size)
-        with torch.no_grad():  # double DQN target (train_dqn.py:167-183)
-            masks = batch.next_action_masks
-            next_q = self.target_q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
-            online_next_q = self.q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
-            next_actions = online_next_q.argmax(dim=1)
-            returns = next_q.gather(1, next_actions.unsqueeze(1)).squeeze(1)
-            discounted = torch.where(batch.done, torch.zeros_like(returns), cfg.discount_factor * returns)
-            target_q = batch.rewards * cfg.reward_scale + discounted
+        target_q = dqn_targets(batch, self.q_net, self.target_q_net, cfg.discount_factor, cfg.reward_scale)
         self.optimizer.zero_grad(set_to_none=False)
-        all_q = self.q_net(batch.obs)
-        predicted = all_q.gather(1, batch.actions.unsqueeze(1)).squeeze(1)
-        loss = F.mse_loss(predicted, target_q)
+        loss, all_q = dqn_loss(batch, self.q_net, target_q)
         loss.backward()
         if self.world > 1:
             self._allreduce_grads()
@@ -168,22 +328,34 @@ class DQNTrainer:
             self.replay.generate_experience_step(count_on_host=False)
 
     def capture_graph(self) -> None:
-        """Capture `_iteration_body` into ONE CUDA graph (the reference iteration is hundreds of
-        tiny launches + Python; here a replay is a single launch).  Needs >= 3 eager warm-up
-        iterations on a side stream first (optimizer state, cuDNN autotune, allocator)."""
-        side = torch.cuda.Stream(self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                self._iteration_body()
-                self.replay._t += self.cfg.experience_steps
-                self._acc_n += 1
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        """Switch to CUDA-graph mode: the next three iterations still run eagerly on a side stream
+        (cuDNN autotune, optimizer state, allocator) -- they are ordinary, counted iterations --
+        and `_iteration_body` is captured into ONE graph before the fourth (the reference
+        iteration is hundreds of tiny launches + Python; a replay is a single launch)."""
+        if self.replay.num_envs * self.replay._ring and len(self.replay) < self.cfg.batch_size:
+            raise RuntimeError(f"replay buffer holds {len(self.replay)} recorded transitions, fewer than "
+                               f"one batch ({self.cfg.batch_size}): call replay.fill(batch_size) first")
+        self._want_graph = True
+
+    def _run_body(self) -> None:
+        if self._graph is not None:
+            self._graph.replay()
+            return
+        if not self._want_graph:
             self._iteration_body()
-        # the capture pass does not execute anything; nothing to account for on the host
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if self._eager_iters >= 3:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._iteration_body()
+            self._graph.replay()    # the capture pass executed nothing
+            return
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self._iteration_body()
+        cur.wait_stream(self._side)
+        self._eager_iters += 1
 
     def train_iteration(self) -> None:
         cfg = self.cfg
@@ -194,10 +366,7 @@ class DQNTrainer:
         # assigning it before the (captured) body is equivalent.
         self.epsilon = lerp(cfg.initial_epsilon, cfg.final_epsilon,
                             self.iter_num / max(1, cfg.num_iters - 1))
-        if self._graph is not None:
-            self._graph.replay()
-        else:
-            self._iteration_body()
+        self._run_body()
         self.replay._t += cfg.experience_steps
         self._acc_n += 1
         self.iter_num += 1
@@ -219,43 +388,76 @@ class DQNTrainer:
                 "iters_averaged": n}
 
     # ------------------------------------------------------------------ evaluation (:88-113)
+    def _make_evaluator(self, num_envs: int, use_graph: bool) -> EpisodeEvaluator:
+        self._eval_net = copy.deepcopy(self.q_net).eval()
+        return EpisodeEvaluator(MaxQPolicy(self._eval_net), self.device, num_envs, 1000, 25,
+                                seed=self.cfg.seed + 17, env_id_base=10_000_000,
+                                phase1_policy=self.replay.phase1_policy, use_graph=use_graph)
+
     @torch.no_grad()
     def evaluate_episode(self, max_steps: int = 1000, num_envs: int = 1) -> dict:
-        """Greedy episode(s) from the fixed start (random_start=False, random_ticks=False), after
-        the old policy's phase when there is one (`reset_env(gym)`, train_dqn.py:95-96)."""
-        env = BatchedPacmanGym(num_envs, False, False, device=self.device, seed=self.cfg.seed + 17,
-                               env_id_base=10_000_000 + self.iter_num * num_envs)
-        reset_env(env, self.replay.phase1_policy)
-        pellets_start = env.remaining_pellets()
-        self.q_net.eval()
-        policy = MaxQPolicy(self.q_net)
-        obs = env.obs()
-        alive = torch.ones(num_envs, dtype=torch.bool, device=self.device)
-        steps = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
-        score = torch.zeros(num_envs, dtype=torch.int32, device=self.device)
-        lives = torch.full((num_envs,), 3, dtype=torch.int32, device=self.device)
-        pellets_end = pellets_start.clone()
-        for step_num in range(1, max_steps + 1):
-            actions = policy(obs, env.action_mask())
-            _, done = env.step_obs(actions, obs)
-            steps += alive.int()
-            # freeze the statistics of finished envs (they keep stepping: harmless, Q12)
-            now = alive & done
-            score = torch.where(alive, env.score(), score)
-            lives = torch.where(alive, env.lives(), lives)
-            pellets_end = torch.where(alive, env.remaining_pellets(), pellets_end)
-            alive = alive & ~now
-            if step_num % 32 == 0 and not bool(alive.any()):
-                break
-        cleared = (~alive) & (lives == 3)
-        pellets_end = torch.where(cleared, torch.zeros_like(pellets_end), pellets_end)
-        return {
-            "eval_episode_score": score.float().mean().item(),
-            "eval_episode_steps": steps.float().mean().item(),
-            "cleared_board": cleared.float().mean().item(),
-            "eval_pellets_start": pellets_start.float().mean().item(),
-            "eval_pellets_end": pellets_end.float().mean().item(),
-        }
+        """Synchronous greedy episode(s) from the fixed start, after the old policy's phase when
+        there is one (`reset_env(gym)`, train_dqn.py:95-96), with the CURRENT weights."""
+        net = copy.deepcopy(self.q_net).eval()
+        per = run_eval_episodes(MaxQPolicy(net), self.device, num_envs, max_steps,
+                                seed=self.cfg.seed + 17, env_id_base=10_000_000 + self.iter_num * num_envs,
+                                phase1_policy=self.replay.phase1_policy)
+        f = {k: v.float().mean().item() for k, v in per.items()}
+        return {"eval_episode_score": f["score"], "eval_episode_steps": f["steps"],
+                "cleared_board": f["cleared"], "eval_pellets_start": f["pellets_start"],
+                "eval_pellets_end": f["pellets_end"]}
+
+    def maybe_evaluate(self, force: bool = False) -> None:
+        """Call after `train_iteration()`.  Starts an evaluation episode when the iteration just
+        finished is a multiple of `evaluate_steps` (train_dqn.py:220), on the evaluation stream
+        with a snapshot of the weights, and otherwise just advances a running one by a chunk when
+        its last chunk has completed (`event.query()`, no blocking)."""
+        if not self.cfg.eval_episodes:
+            return
+        due = force or (self.iter_num - 1) % self.cfg.evaluate_steps == 0
+        if self._eval_busy:
+            self._poll_evaluation(block=due)   # one evaluation at a time, like the reference
+        if due and not self._eval_busy:
+            self._start_evaluation()
+
+    def _start_evaluation(self) -> None:
+        if self._eval is None:
+            self._eval_stream = torch.cuda.Stream(self.device)
+            self._eval = self._make_evaluator(self.cfg.eval_envs, self.cfg.cuda_graph)
+            self._eval_event = torch.cuda.Event()
+        cur = torch.cuda.current_stream(self.device)
+        es = self._eval_stream
+        es.wait_stream(cur)                       # weights of the iteration just enqueued
+        with torch.cuda.stream(es), torch.no_grad():
+            torch._foreach_copy_(list(self._eval_net.parameters()), list(self.q_net.parameters()))
+            snap = torch.cuda.Event()
+            snap.record(es)
+            self._eval.begin()
+            self._eval.run_chunk()
+            self._eval_event.record(es)
+        cur.wait_event(snap)                      # the next optimizer step waits for the snapshot only
+        self._eval_busy, self._eval_iter = True, self.iter_num - 1
+
+    def _poll_evaluation(self, block: bool = False) -> None:
+        while self._eval_busy:
+            if block:
+                self._eval_event.synchronize()
+            elif not self._eval_event.query():
+                return
+            if self._eval.all_finished():
+                res = self._eval.result()
+                res["eval_iter"] = self._eval_iter
+                self.eval_log.append(res)
+                self._eval_busy = False
+                return
+            with torch.cuda.stream(self._eval_stream):
+                self._eval.run_chunk()
+                self._eval_event.record(self._eval_stream)
+            if not block:
+                return
+
+    def finish_evaluation(self) -> None:
+        self._poll_evaluation(block=True)
 
     # ------------------------------------------------------------------ checkpoints (:239-253)
     def save_checkpoint(self, checkpoint_dir: str, iter_num: int) -> None:
@@ -285,6 +487,7 @@ def train(cfg: argparse.Namespace, max_seconds: Optional[float] = None) -> DQNTr
     if device.type != "cuda":
         raise SystemExit("the B200 trainer needs a CUDA device (the env engine has no CPU path)")
     torch.cuda.set_device(device)
+    dist = None
     if world > 1:
         import torch.distributed as dist
 
@@ -299,19 +502,26 @@ def train(cfg: argparse.Namespace, max_seconds: Optional[float] = None) -> DQNTr
                    config={k: getattr(cfg, k) for k in hyperparam_defaults})
     trainer = DQNTrainer(cfg, device, rank, world)
     print(f"q_net has {sum(p.numel() for p in trainer.q_net.parameters())} parameters", flush=True)
-    trainer.replay.fill()
+    trainer.replay.fill(cfg.batch_size)
     trainer.epsilon = cfg.initial_epsilon
     if cfg.cuda_graph:
         trainer.capture_graph()
     metrics_f = open(cfg.metrics_file, "a") if (cfg.metrics_file and rank == 0) else None
     t0 = time.time()
-    last_t, last_it = t0, 0
+    last_t, last_it, evals_logged = t0, 0, 0
     for it in range(cfg.num_iters):
         trainer.train_iteration()
-        if (it + 1) % cfg.log_every == 0 or it == cfg.num_iters - 1:
+        if rank == 0:
+            trainer.maybe_evaluate()    # the evaluation episode is rank 0's, as the log is
+        last = it == cfg.num_iters - 1
+        if (it + 1) % cfg.log_every == 0 or last:
+            if last and rank == 0:
+                trainer.finish_evaluation()
             m = trainer.pop_metrics()
-            if (it + 1) % (cfg.log_every * cfg.evaluate_steps) == 0:
-                m.update(trainer.evaluate_episode(num_envs=cfg.eval_envs))
+            if len(trainer.eval_log) > evals_logged:   # the most recent finished evaluation
+                m.update(trainer.eval_log[-1])
+                m["evals_since_last_log"] = len(trainer.eval_log) - evals_logged
+                evals_logged = len(trainer.eval_log)
             now = time.time()
             m["iter"] = it + 1
             m["iters_per_sec"] = (it + 1 - last_it) / max(1e-9, now - last_t)
@@ -324,10 +534,18 @@ def train(cfg: argparse.Namespace, max_seconds: Optional[float] = None) -> DQNTr
                     metrics_f.flush()
                 if wandb:
                     wandb.log(m)
+            if max_seconds is not None:
+                # rank 0 decides, every rank obeys: leaving the loop at different iterations
+                # would hang the others in the in-graph all-reduce
+                stop = torch.tensor([1 if time.time() - t0 > max_seconds else 0], device=device)
+                if dist is not None:
+                    dist.broadcast(stop, src=0)
+                if bool(stop.item()):
+                    break
         if not cfg.no_checkpoints and rank == 0 and it % 500 == 0:
             trainer.save_checkpoint(cfg.checkpoint_dir, it)
-        if max_seconds is not None and time.time() - t0 > max_seconds:
-            break
+    if rank == 0:
+        trainer.finish_evaluation()
     if metrics_f:
         metrics_f.close()
     return trainer

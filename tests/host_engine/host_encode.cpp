@@ -57,6 +57,7 @@ static inline bool __all_sync(unsigned, bool pred) {
     w.bar.arrive_and_wait();
     return all;
 }
+static inline void __syncwarp() { g_warp[threadIdx.x >> 5].bar.arrive_and_wait(); }
 static inline void __syncthreads() { g_cta_bar->arrive_and_wait(); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }

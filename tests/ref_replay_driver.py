@@ -1,9 +1,11 @@
-"""Subprocess driver for tests/test_reference_replay_live.py: runs the reference's OWN
-src/replay_buffer.py (unmodified, imported from /root/reference/src) over a `pacbot_rs` shim whose
-`PacmanGym` is the scalar C oracle with an injected draw tape, and dumps what ended up in the
-reference's replay buffer.  Only runs where /root/reference exists (the build container).
+"""Subprocess driver for tests/test_reference_replay_live.py and
+tests/test_dropin_reference_gpu.py: runs the reference's OWN src/replay_buffer.py (unmodified,
+imported from /root/reference/src, or from the staged copy baseline/_ref/src on the GPU box) over a
+`pacbot_rs` shim and dumps what ended up in the reference's replay buffer.  The shim's `PacmanGym`
+is either the scalar C oracle (`oracle`) or this repo's drop-in `pacbot_rl_b200.PacmanGym` on the
+GPU (`product`: one 1-env CUDA engine per object), env i drawing from row i of the same tape.
 
-    python tests/ref_replay_driver.py <tape.npy> <out.npz> <n_envs> <steps>
+    python tests/ref_replay_driver.py <tape.npy> <out.npz> <n_envs> <steps> [oracle|product]
 
 What has to be faked for the import to succeed, and nothing else:
   * `pacbot_rs`            the Rust extension (not buildable here) -> oracle-backed PacmanGym
@@ -21,11 +23,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-REF_SRC = "/root/reference/src"
+REF_SRC = next((d for d in ("/root/reference/src", os.path.join(ROOT, "baseline", "_ref", "src"))
+                if os.path.isdir(d)), None)
 
 
 def main():
     tape_path, out_path, n_envs, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    backend = sys.argv[5] if len(sys.argv) > 5 else "oracle"
+    if REF_SRC is None:
+        raise SystemExit("reference sources not found (neither /root/reference/src nor baseline/_ref/src)")
     tape = np.load(tape_path)
     from oracle import pyoracle
     from replay_reference import MAIN_POLICY_CHANNELS, OLD_POLICY_CHANNELS, bfs_policy
@@ -33,7 +39,7 @@ def main():
     pyoracle.build()
     created = []
 
-    class PacmanGym:  # pacbot_rs.pyi:6-19 on top of the oracle
+    class OraclePacmanGym:  # pacbot_rs.pyi:6-19 on top of the oracle
         def __init__(self, random_start: bool, random_ticks: bool):
             i = len(created)
             cfg = np.array([int(bool(random_start)) | (int(bool(random_ticks)) << 1)], np.uint8)
@@ -59,6 +65,25 @@ def main():
 
         def obs_numpy(self):
             return self._b.obs()[0].copy()
+
+    if backend == "product":
+        import pacbot_rl_b200 as pb
+
+        class PacmanGym(pb.PacmanGym):   # the drop-in itself; only the draw tape is injected
+            def __init__(self, random_start: bool, random_ticks: bool):
+                i = len(created)
+                super().__init__(random_start, random_ticks, device="cuda:0")
+                row = np.ascontiguousarray(tape[i % len(tape)][None, :])
+                self._batch.set_draw_tape(torch.from_numpy(row.view(np.int32)).to("cuda:0"))
+                created.append(self)
+
+        def draws_used(e):
+            return int(e._batch.get_state()["rng_ctr"][0])
+    else:
+        PacmanGym = OraclePacmanGym
+
+        def draws_used(e):
+            return int(e._b.export_state()["rng_ctr"][0])
 
     shim = types.ModuleType("pacbot_rs")
     shim.PacmanGym = PacmanGym
@@ -100,7 +125,8 @@ def main():
         reward=np.array([it.reward for it in items], np.int64).reshape(steps, n_envs),
         done=np.array([it.next_obs is None for it in items]).reshape(steps, n_envs),
         next_mask=np.array([it.next_action_mask for it in items]).reshape(steps, n_envs, 5),
-        draws_used=np.array([int(e._b.export_state()["rng_ctr"][0]) for e in created]))
+        draws_used=np.array([draws_used(e) for e in created]),
+        final_score=np.array([e.score() for e in created]) if backend == "product" else np.zeros(0))
 
 
 if __name__ == "__main__":

@@ -53,7 +53,7 @@ def test_replay_ring_matches_oracle_rollout(pb, oracle):
         exp_mask = ob.action_mask() & ~d[:, None]
         assert np.array_equal(buf._next_mask[slot].cpu().numpy(), exp_mask), t
         assert np.array_equal(buf._obs[nxt].cpu().numpy().view(np.uint32), ob.obs().view(np.uint32)), t
-    assert len(buf) == min(steps, buf._slots) * n == int(buf._weight.sum().item())
+    assert len(buf) == min(steps, buf._slots) * n == int(buf._valid.sum().item())
 
 
 def _to_gpu_state(pb, st):
@@ -76,7 +76,7 @@ def test_sample_batch_collate_semantics(pb):
     assert buf.capacity == 313 * 32 and len(buf) == buf.capacity
     for _ in range(40):                      # wrap the ring
         buf.generate_experience_step()
-    assert len(buf) == buf.capacity and int(buf._weight.sum().item()) == buf.capacity
+    assert len(buf) == buf.capacity and int(buf._valid.sum().item()) == buf.capacity
     batch = buf.sample_batch(512)
     assert batch.obs.shape == (512, 17, 28, 31) and batch.next_obs.shape == batch.obs.shape
     assert batch.actions.dtype == torch.int64 and batch.rewards.dtype == torch.float32
@@ -86,12 +86,14 @@ def test_sample_batch_collate_semantics(pb):
     assert bool(((nz == 0) == batch.done).all())
     assert not bool(batch.next_action_masks[batch.done].any())
     assert bool(batch.next_action_masks[~batch.done][:, 0].all())   # Stay is always valid
-    # without replacement
-    flat = torch.multinomial(buf._weight.view(-1), 512, replacement=False)
-    assert flat.unique().numel() == 512
+    # without replacement, and only recorded transitions
+    flat = buf.sample_indices(512).clone()
+    assert flat.unique().numel() == 512 and buf.num_valid == buf.capacity
+    assert bool(buf._valid.view(-1)[flat].all())
     # the slot holding only the current observation is never sampled
     cur = buf._t % buf._ring
-    assert float(buf._weight[cur].sum()) == 0.0
+    assert int(buf._valid[cur].sum()) == 0
+    assert not bool((flat // buf.num_envs == cur).any())
     # reward sanity: sampled rewards are the stored ones
     assert bool((batch.rewards.abs() <= 3000 + 3000).all())
 
@@ -218,7 +220,7 @@ def test_two_stage_reset_matches_reference_loop(pb, oracle):
 
     for _ in range(total_steps):
         buf.generate_experience_step()
-    w = buf._weight.cpu().numpy()
+    w = buf._valid.cpu().numpy()
     obs_ring = buf._obs.cpu().numpy().view(np.uint32)
     acts, rews, dones = buf._actions.cpu().numpy(), buf._rewards.cpu().numpy(), buf._done.cpu().numpy()
     next_masks = buf._next_mask.cpu().numpy()
@@ -283,3 +285,325 @@ def test_synchronous_reset_env_matches_reference_loop(pb, oracle):
     reset_env(env, None)
     ob.reset()
     assert_states_equal(ob.export_state(), env.get_state(), "plain reset")
+
+
+# ------------------------------------------------------------------------------------------------
+# the replay kernels behind the C ABI (csrc/pb_replay_abi.inl)
+# ------------------------------------------------------------------------------------------------
+def _sample(pb, valid, batch, seed, call):
+    """pb_replay_sample through the C ABI -> (idx int64 [batch] host, num_valid)."""
+    import ctypes as C
+
+    import torch
+
+    L = pb._lib.load()
+    dev = valid.device
+    call_dev = torch.tensor([call], dtype=torch.int64, device=dev)
+    idx = torch.full((batch,), -1, dtype=torch.int64, device=dev)
+    m = torch.zeros(1, dtype=torch.int32, device=dev)
+    pb._lib.check(L.pb_replay_sample(
+        C.c_void_p(valid.data_ptr()), valid.numel(), batch, seed, C.c_void_p(call_dev.data_ptr()),
+        C.c_void_p(idx.data_ptr()), C.c_void_p(m.data_ptr()), dev.index,
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return idx.cpu().numpy(), int(m.item())
+
+
+def test_replay_sample_is_a_partial_fisher_yates_over_the_valid_list(pb):
+    """random.sample(buffer, k) (replay_buffer.py:141-143): k DISTINCT recorded transitions.  The
+    kernel is specified exactly (include/pacbot_b200.h): ascending list of the valid flat indices,
+    then position j swaps with j + ((raw_j * (m - j)) >> 32), raw_j = pb_replay_raw(seed, call, j).
+    Replayed here on the host draw by draw; plus the m < k and m == 0 edge cases, the size limits,
+    and uniformity over many calls."""
+    import torch
+
+    L = pb._lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    total, batch, seed = 314 * 32, 512, 0xC0FFEE
+    valid = (torch.rand(total, generator=g) > 0.35)
+    valid_dev = valid.to(dev)
+    for call in (0, 1, 977):
+        idx, m = _sample(pb, valid_dev, batch, seed, call)
+        lst = np.flatnonzero(valid.numpy()).tolist()
+        assert m == len(lst)
+        for j in range(batch):
+            r = j + ((L.pb_replay_raw(seed, call, j) * (m - j)) >> 32)
+            lst[j], lst[r] = lst[r], lst[j]
+        assert idx.tolist() == lst[:batch], call
+        assert len(set(idx.tolist())) == batch and valid.numpy()[idx].all()
+    # fewer valid transitions than the batch: with replacement over what there is; none: index 0
+    few = torch.zeros(total, dtype=torch.bool)
+    few[[7, 4000, 9999]] = True
+    idx, m = _sample(pb, few.to(dev), 64, seed, 3)
+    assert m == 3 and set(idx.tolist()) <= {7, 4000, 9999}
+    idx, m = _sample(pb, torch.zeros(total, dtype=torch.bool, device=dev), 64, seed, 3)
+    assert m == 0 and not idx.any()
+    # exactly as many as the batch: a permutation of all of them
+    exact = torch.zeros(total, dtype=torch.bool)
+    exact[torch.randperm(total, generator=g)[:64]] = True
+    idx, m = _sample(pb, exact.to(dev), 64, seed, 4)
+    assert m == 64 and sorted(idx.tolist()) == np.flatnonzero(exact.numpy()).tolist()
+    # limits are refused, not silently wrong
+    cap = L.pb_replay_sample_capacity()
+    assert cap >= total
+    big = torch.ones(cap + 1, dtype=torch.bool, device=dev)
+    with pytest.raises(Exception):
+        _sample(pb, big, 64, seed, 0)
+    with pytest.raises(Exception):
+        _sample(pb, valid_dev, 4097, seed, 0)
+    # uniformity: every valid transition is drawn equally often (4 sigma per cell, chi-square overall)
+    small = torch.zeros(2048, dtype=torch.bool)
+    small[::2] = True
+    small_dev, calls, k = small.to(dev), 1500, 128
+    hits = np.zeros(2048, np.int64)
+    first_pos = np.zeros(2048, np.int64)
+    for call in range(calls):
+        idx, m = _sample(pb, small_dev, k, seed + 1, call)
+        np.add.at(hits, idx, 1)
+        first_pos[idx[0]] += 1
+    assert hits[1::2].sum() == 0 and m == 1024
+    expect = calls * k / 1024
+    chi2 = ((hits[::2] - expect) ** 2 / expect).sum()
+    # without replacement the per-cell variance is expect * (1 - k/m): chi2 ~ (1 - k/m) * 1023
+    assert 0.875 * 1023 - 5 * np.sqrt(2 * 1023) < chi2 < 0.875 * 1023 + 5 * np.sqrt(2 * 1023), chi2
+    assert first_pos.max() < 12      # the first element is uniform too (mean 1.46 per cell)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_last):
+    """k_replay_record / k_replay_collate / k_replay_slot against the plain torch expressions they
+    replace (the collate of train_dqn.py:153-165), NCHW and channels-last output, values compared
+    bit for bit; a channels-last batch must have channels-last strides (that is what removes the
+    layout conversion in front of the NHWC convolutions)."""
+    import torch
+    from pacbot_rl_b200.models import QNetV2
+    from pacbot_rl_b200.policies import EpsilonGreedy, MaxQPolicy
+    from pacbot_rl_b200.replay_buffer import ReplayBuffer
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    q = QNetV2(pb.OBS_SHAPE, 5).to(dev)
+    if channels_last:
+        q.use_channels_last()
+    n, maxlen = 32, 2048
+    buf = ReplayBuffer(maxlen, EpsilonGreedy(MaxQPolicy(q), 5, 1.0), n, 0.5, dev, seed=9,
+                       channels_last=channels_last)
+    r = buf._ring
+    for t in range(r + 30):                      # wrap the ring
+        before = buf._obs[t % r].clone()
+        buf.generate_experience_step()
+        # last_obs handed to the policy == the ring slot of step t
+        assert torch.equal(buf._last_obs, before), t
+        assert buf._last_obs.is_contiguous(
+            memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        # what k_replay_record appended == the step's own outputs
+        s = t % r
+        assert torch.equal(buf._actions[s], buf._act) and torch.equal(buf._rewards[s], buf._reward)
+        assert torch.equal(buf._done[s], buf._done_step)
+        assert torch.equal(buf._next_mask[s], buf._mask & ~buf._done_step[:, None])
+        assert bool(buf._valid[s].all()) and not bool(buf._valid[(t + 1) % r].any())
+    assert int(buf._done.sum()) > 0              # finished episodes are in the ring
+    for b in (1, 7, 512):
+        batch = buf.sample_batch(b)
+        flat = buf._batch_buffers(b)["idx"]
+        slot, env = flat // n, flat % n
+        done = buf._done.view(-1)[flat]
+        assert torch.equal(batch.obs, buf._obs.view(-1, *pb.OBS_SHAPE)[flat])
+        nxt = buf._obs[(slot + 1) % r, env]
+        nxt[done] = 0.0                          # `next_obs is None` -> zeros (train_dqn.py:154-159)
+        assert torch.equal(batch.next_obs, nxt)
+        assert batch.actions.dtype == torch.int64 and torch.equal(batch.actions, buf._actions.view(-1)[flat].long())
+        assert batch.rewards.dtype == torch.float32 and torch.equal(batch.rewards, buf._rewards.view(-1)[flat].float())
+        assert torch.equal(batch.done, done)
+        assert torch.equal(batch.next_action_masks, buf._next_mask.view(-1, 5)[flat])
+        fmt = torch.channels_last if channels_last else torch.contiguous_format
+        assert batch.obs.is_contiguous(memory_format=fmt) and batch.next_obs.is_contiguous(memory_format=fmt)
+    assert bool(batch.done.any()) and not bool(batch.done.all())
+
+
+def test_fill_with_old_policy_waits_for_recorded_transitions(pb):
+    """With the two-stage reset every env starts in the old policy's phase and nothing is recorded
+    until it has eaten the super pellets: a ring that has merely wrapped can hold fewer recorded
+    transitions than a batch.  `fill(min_valid)` goes on until there are enough, `len()` reports
+    recorded transitions (len(deque) in the reference), and sampling only returns those."""
+    import torch
+    from pacbot_rl_b200.replay_buffer import ReplayBuffer
+    from replay_reference import OLD_POLICY_CHANNELS, bfs_policy
+
+    dev = torch.device("cuda:0")
+    old_np = bfs_policy(OLD_POLICY_CHANNELS)
+
+    def old(obs, masks):
+        return torch.from_numpy(old_np(obs.cpu().numpy(), masks.cpu().numpy())).to(obs.device)
+
+    n = 4
+    buf = ReplayBuffer(64, FirstValidPolicy(), n, 0.5, dev, seed=2, phase1_policy=old)
+    assert len(buf) == 0 and bool(buf._in_phase1.all())
+    for _ in range(buf._slots):
+        buf.generate_experience_step()
+    assert len(buf) == 0                         # the ring wrapped, nothing recorded yet
+    buf.fill(min_valid=24)
+    assert 24 <= len(buf) <= buf.capacity
+    idx = buf.sample_indices(16)
+    assert bool(buf._valid.view(-1)[idx].all()) and idx.unique().numel() == 16
+    assert buf.num_valid == len(buf)
+
+    class Never:   # an old policy that never gets through phase 1: fill() must say so, not spin
+        def __call__(self, obs, masks):
+            return torch.zeros(obs.shape[0], dtype=torch.int64, device=obs.device)
+
+    stuck = ReplayBuffer(64, FirstValidPolicy(), n, 0.0, dev, seed=2, phase1_policy=Never())
+    with pytest.raises(RuntimeError, match="recorded transitions"):
+        stuck.fill(min_valid=8)
+
+
+# ------------------------------------------------------------------------------------------------
+# a17: the double-DQN target / loss arithmetic against the reference's own expressions
+# ------------------------------------------------------------------------------------------------
+def _reference_target_and_loss(q_net, target_q_net, obs_batch, next_obs_batch, done_mask,
+                               next_action_masks, action_batch, raw_rewards, reward_scale, discount_factor):
+    """train_dqn.py:153-197 with the same statements (index assignment, fancy indexing)."""
+    import torch
+    import torch.nn.functional as F
+
+    n = obs_batch.shape[0]
+    reward_batch = torch.tensor([r * reward_scale for r in raw_rewards.tolist()], device=obs_batch.device)
+    with torch.no_grad():
+        next_q_values = target_q_net(next_obs_batch)
+        next_q_values[~next_action_masks] = -torch.inf
+        online_next_q_values = q_net(next_obs_batch)
+        online_next_q_values[~next_action_masks] = -torch.inf
+        next_actions = online_next_q_values.argmax(dim=1)
+        returns = next_q_values[range(n), next_actions]
+        discounted_returns = discount_factor * returns
+        discounted_returns[done_mask] = 0.0
+        target_q_values = reward_batch + discounted_returns
+    all_predicted_q_values = q_net(obs_batch)
+    predicted_q_values = all_predicted_q_values[range(n), action_batch]
+    loss = F.mse_loss(predicted_q_values, target_q_values)
+    return target_q_values, loss, all_predicted_q_values
+
+
+def test_double_dqn_target_and_loss_match_reference_expressions(pb):
+    """One fixed ReplayBatch through `dqn_targets` / `dqn_loss` (what `_iteration_body` runs) vs
+    the reference's statements (train_dqn.py:167-197): on the same device with the same networks
+    (tolerance 1e-6: same cuDNN kernels underneath, only the target/loss arithmetic differs) and
+    on the CPU in float64 (rtol 1e-5 on target and loss, TF32 off).  The batch has finished
+    transitions (done, all-False next mask, zero next_obs), partial next masks, negative and large
+    rewards; reward_scale and gamma are not the defaults."""
+    import copy
+
+    import torch
+    from pacbot_rl_b200 import train_dqn
+    from pacbot_rl_b200.models import QNetV2
+    from pacbot_rl_b200.replay_buffer import ReplayBatch
+
+    dev = torch.device("cuda:0")
+    old_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(11)
+        q_net = QNetV2(pb.OBS_SHAPE, 5).to(dev)
+        with torch.no_grad():                    # the heads start at zero: make Q depend on the input
+            for head in (q_net.value_head, q_net.advantage_head):
+                for p in head.parameters():
+                    p.normal_(0.0, 0.5)
+        target_q_net = copy.deepcopy(q_net)
+        with torch.no_grad():
+            for p in target_q_net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        b = 96
+        g = torch.Generator(device="cpu").manual_seed(12)
+        obs = (torch.rand((b,) + pb.OBS_SHAPE, generator=g) < 0.1).float() * torch.rand((b,) + pb.OBS_SHAPE, generator=g)
+        next_obs = (torch.rand((b,) + pb.OBS_SHAPE, generator=g) < 0.1).float() * torch.rand((b,) + pb.OBS_SHAPE, generator=g)
+        done = torch.rand(b, generator=g) < 0.3
+        masks = torch.rand((b, 5), generator=g) < 0.6
+        masks[:, 0] = True
+        masks[done] = False                      # [False] * 5 when the episode ended
+        next_obs[done] = 0.0
+        actions = torch.randint(0, 5, (b,), generator=g)
+        rewards = torch.randint(-250, 3200, (b,), generator=g).float()
+        batch = ReplayBatch(obs.to(dev), actions.to(dev), rewards.to(dev), next_obs.to(dev), done.to(dev),
+                            masks.to(dev))
+        gamma, scale = 0.97, 1 / 40
+        target = train_dqn.dqn_targets(batch, q_net, target_q_net, gamma, scale)
+        loss, all_q = train_dqn.dqn_loss(batch, q_net, target)
+        q_net.zero_grad()
+        loss.backward()
+        grads = [p.grad.clone() for p in q_net.parameters()]
+        assert bool(torch.isfinite(target).all()) and bool((target[done.to(dev)] == (rewards.to(dev) * scale)[done.to(dev)]).all())
+        # (1) the reference statements on the same device
+        q_net.zero_grad()
+        t_ref, l_ref, q_ref = _reference_target_and_loss(
+            q_net, target_q_net, batch.obs, batch.next_obs, batch.done, batch.next_action_masks,
+            batch.actions, rewards, scale, gamma)
+        l_ref.backward()
+        torch.testing.assert_close(target, t_ref, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(loss, l_ref, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(all_q, q_ref, rtol=1e-6, atol=1e-6)
+        for got, p in zip(grads, q_net.parameters()):
+            torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-6)
+        # (2) the reference statements on the CPU in float64
+        q64, t64 = copy.deepcopy(q_net).cpu().double(), copy.deepcopy(target_q_net).cpu().double()
+        t_cpu, l_cpu, _ = _reference_target_and_loss(
+            q64, t64, obs.double(), next_obs.double(), done, masks, actions, rewards.double(), scale, gamma)
+        torch.testing.assert_close(target.cpu().double(), t_cpu.double(), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(loss.cpu().double(), l_cpu.double(), rtol=1e-5, atol=1e-6)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+
+
+# ------------------------------------------------------------------------------------------------
+# f2: batched evaluate_episode against the reference's per-env loop on the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("max_steps,with_old_policy", [(400, True), (75, False)])
+def test_evaluate_episode_matches_reference_loop(pb, oracle, max_steps, with_old_policy):
+    """`run_eval_episodes(num_envs=K)` vs `evaluate_episode` (train_dqn.py:88-113) run env by env on
+    the oracle with the same draws: score, steps, cleared, pellets_start and pellets_end per env.
+    The policies are host functions of exactly representable observation cells, so both sides
+    compute the same actions; 75 steps is shorter than any episode (the truncated case)."""
+    import torch
+    from pacbot_rl_b200 import train_dqn
+    from replay_reference import MAIN_POLICY_CHANNELS, OLD_POLICY_CHANNELS, bfs_policy
+
+    dev = torch.device("cuda:0")
+    k, seed, base = 6, 23, 10_000_000
+    main_np, old_np = bfs_policy(MAIN_POLICY_CHANNELS), bfs_policy(OLD_POLICY_CHANNELS)
+
+    def on_device(f):
+        return lambda obs, masks: torch.from_numpy(f(obs.cpu().numpy(), masks.cpu().numpy())).to(obs.device)
+
+    per = train_dqn.run_eval_episodes(on_device(main_np), dev, k, max_steps, seed=seed, env_id_base=base,
+                                      phase1_policy=on_device(old_np) if with_old_policy else None)
+    finished = 0
+    for i in range(k):
+        gym = oracle.OracleBatch(1, np.zeros(1, np.uint8), None)   # random_start=False, random_ticks=False
+        gym.set_counter_rng(seed, base + i)
+
+        def st():
+            return gym.export_state()[0]
+
+        # reset_env(gym) (replay_buffer.py:44-54)
+        gym.reset()
+        if with_old_policy:
+            while not gym.first_ai_done()[0]:
+                _, d = gym.step(old_np(gym.obs(), gym.action_mask()))
+                if d[0]:
+                    gym.reset()
+        pellets_start = int(st()["num_pellets"])
+        done = False
+        for step_num in range(1, max_steps + 1):
+            _, d = gym.step(main_np(gym.obs(), gym.action_mask()))
+            done = bool(d[0])
+            if done:
+                break
+        cleared = done and int(st()["curr_lives"]) == 3
+        pellets_end = 0 if cleared else int(st()["num_pellets"])
+        expect = (int(st()["curr_score"]), step_num, int(cleared), pellets_start, pellets_end, int(done))
+        got = tuple(int(per[f][i]) for f in train_dqn.EVAL_FIELDS)
+        assert got == expect, (i, got, expect)
+        finished += int(done)
+    if max_steps == 75:
+        assert finished == 0
+    else:
+        assert finished >= 1

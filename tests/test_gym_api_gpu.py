@@ -213,19 +213,3 @@ def test_step_random_equals_sample_then_step(pb):
         r_b, d_b = b_env.step(sampled)
         assert torch.equal(acts, sampled) and torch.equal(r_a, r_b) and torch.equal(d_a, d_b)
     assert np.array_equal(a_env.get_state(), b_env.get_state())
-
-
-def test_template_encoder_variant_is_bit_exact(pb):
-    """The alternative observation encoder (shared zero/wall templates + single-cell global
-    stores, PB_ENCODER=tpl, csrc/pb_encode2.cuh) must produce the same bits: run the oracle-checked
-    smoke rollout in a subprocess with the variant selected."""
-    import os
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PB_ENCODER="tpl")
-    res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"],
-                         cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert "bit-exact" in res.stdout

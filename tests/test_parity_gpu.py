@@ -464,3 +464,83 @@ def test_full_size_properties_2m_envs(pb):
     a = env.get_state(n - 4096, 4096)
     b = half.get_state(n // 2 - 4096, 4096)
     assert np.array_equal(a, b)
+
+
+def test_config1_65536_envs_every_step_vs_oracle(pb, oracle):
+    """BASELINE.json configs[1] at its full size, DIFFED (not property-tested): 65 536 envs, 32
+    hot steps (pb_step_random: device-drawn random valid action + PacmanGym.step + auto reset),
+    the counter RNG on both sides (the oracle restates it, po_batch_set_counter_rng /
+    po_batch_sample_actions).  Actions, reward, done, mask and the full state are compared every
+    step for all envs; the observation bits every 8th step and after the last one, in 8 192-env
+    chunks (a full batch of observations is 3.9 GB)."""
+    torch = torch_mod()
+    n, steps, seed, base, chunk = 65536, 32, 20261020, 5_000_000, 8192
+    start = np.arange(n) < n // 2
+    cfg = start.astype(np.uint8) | 2
+    ob = oracle.OracleBatch(n, cfg, None)
+    ob.set_counter_rng(seed, base)
+    env = pb.BatchedPacmanGym(n, start, True, device="cuda:0", seed=seed, env_id_base=base, auto_reset=True)
+    ob.reset()
+    env.reset()
+    assert_states_equal(ob.export_state(), env.get_state(), "reset")
+    stage = torch.empty((chunk,) + pb.OBS_SHAPE, dtype=torch.float32, device="cuda")
+    episodes = 0
+    for t in range(steps):
+        a_o = ob.sample_actions(seed, base, t)
+        r_o, d_o = ob.step(a_o, auto_reset=True)
+        acts = torch.empty(n, dtype=torch.uint8, device="cuda")
+        r_g, d_g = env.step_random(call_idx=t, actions_out=acts)
+        assert np.array_equal(a_o, acts.cpu().numpy()), f"actions differ at step {t}"
+        assert np.array_equal(r_o, r_g.cpu().numpy()), f"reward differs at step {t}"
+        assert np.array_equal(d_o, d_g.cpu().numpy()), f"done differs at step {t}"
+        assert np.array_equal(ob.action_mask(), env.action_mask().cpu().numpy()), f"mask differs at step {t}"
+        assert_states_equal(ob.export_state(), env.get_state(), f"step {t}")
+        episodes += int(d_o.sum())
+        if t % 8 == 7 or t == steps - 1:
+            for first in range(0, n, chunk):
+                got = env.obs_range(first, chunk, stage).cpu().numpy()
+                assert_obs_equal(ob.obs_range(first, chunk), got, f"step {t} envs {first}..{first + chunk}")
+    assert episodes > 50, episodes
+
+
+def test_config2_2m_envs_sampled_slices_vs_oracle(pb, oracle):
+    """BASELINE.json configs[2] shard size (2 097 152 envs on one GPU): after 6 hot steps of the
+    whole population, eight 4 096-env slices spread over the shard are handed to the oracle
+    (pb_get_state -> import_state), both sides play 6 more hot steps, and everything the steps
+    produced for the slices is diffed: actions, reward, done, mask, state, observation bits."""
+    torch = torch_mod()
+    n, per, seed, base = 2 * 1024 * 1024, 4096, 77, 3_000_000_000
+    env = pb.BatchedPacmanGym(n, np.arange(n) < n // 2, True, device="cuda:0", seed=seed,
+                              env_id_base=base, auto_reset=True)
+    env.reset()
+    for t in range(6):
+        env.step_random(call_idx=t)
+    firsts = [0, 4096 * 37, n // 2 - per, n // 2, n // 2 + 4096 * 101, n - 3 * per - 17, n - 2 * per, n - per]
+    obs = []
+    for f in firsts:
+        st = env.get_state(f, per)
+        ob = oracle.OracleBatch(per, st["cfg_flags"].copy(), None)
+        ob.import_state(oracle.flat_from_product(st))
+        ob.set_counter_rng(seed, base + f)
+        obs.append(ob)
+    acts = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stage = torch.empty((per,) + pb.OBS_SHAPE, dtype=torch.float32, device="cuda")
+    episodes = 0
+    for t in range(6, 12):
+        r_g, d_g = env.step_random(call_idx=t, actions_out=acts)
+        a_h, r_h, d_h = acts.cpu().numpy(), r_g.cpu().numpy(), d_g.cpu().numpy()
+        m_h = env.action_mask().cpu().numpy()
+        for f, ob in zip(firsts, obs):
+            sl = slice(f, f + per)
+            a_o = ob.sample_actions(seed, base + f, t)
+            r_o, d_o = ob.step(a_o, auto_reset=True)
+            ctx = f"step {t} slice {f}"
+            assert np.array_equal(a_o, a_h[sl]), ctx + ": actions"
+            assert np.array_equal(r_o, r_h[sl]), ctx + ": reward"
+            assert np.array_equal(d_o, d_h[sl]), ctx + ": done"
+            assert np.array_equal(ob.action_mask(), m_h[sl]), ctx + ": mask"
+            assert oracle.states_differ(ob.export_state(), env.get_state(f, per)) is None, ctx
+            episodes += int(d_o.sum())
+            if t in (8, 11):
+                assert_obs_equal(ob.obs(), env.obs_range(f, per, stage).cpu().numpy(), ctx)
+    assert episodes > 0

@@ -145,8 +145,9 @@ def test_c_rollout_random_step_matches_sequential(pb):
 
 @pytest.mark.parametrize("pinned", [False, True], ids=["pageable-staged", "pinned-zero-copy"])
 def test_c_rollout_host_step_matches_step_host(pb, pinned):
-    """Pageable host buffers go through staging copies; pinned ones are read / written by the step
-    kernel itself and completion is a polled word in mapped memory (no stream sync per step)."""
+    """pb_rollout_host_step with pageable and with pinned host buffers (both go through the engine's
+    device staging buffers: actions H2D on the step stream, reward / done / mask D2H on the copy
+    stream while the encoder runs, one copy-stream synchronisation per step) against pb_step_host."""
     n, steps = 3000, 21
     a, b = make(pb, n, seed=5), make(pb, n, seed=5)
     rng = np.random.default_rng(2)
