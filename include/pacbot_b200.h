@@ -329,6 +329,25 @@ int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_s
                        const int64_t *t_dev, float *out_dev, int channels_last, int device,
                        void *stream);
 
+/* ---- device timeline (diagnostics; no counterpart in the reference) --------------------------
+ * Between pb_trace_begin and pb_trace_end every k_step / k_encode_obs launch of the engine
+ * records, in nanoseconds of the GPU's %globaltimer: begin = first CTA started, ready = first CTA
+ * past its wait for the preceding grid (programmatic dependent launch; == begin for k_step),
+ * end = last warp finished.  pb_trace_mark puts a one-thread kernel on `stream` that records the
+ * time it ran (the boundaries of a timed region in the same clock).  Records come back in launch
+ * order; launches beyond `capacity` are not recorded.  pb_trace_begin / pb_trace_end synchronise
+ * the device.  bench.py does not trace its timed loops; tools/timeline.py does. */
+#define PB_TRACE_MARK 0u
+#define PB_TRACE_STEP 1u
+#define PB_TRACE_ENCODE 2u
+typedef struct pb_trace_record {
+    uint64_t begin_ns, ready_ns, end_ns;
+    uint32_t kind, reserved;
+} pb_trace_record;
+int pb_trace_begin(pb_engine *e, int64_t capacity);
+int pb_trace_mark(pb_engine *e, void *stream);
+int pb_trace_end(pb_engine *e, pb_trace_record *out_host, int64_t max_records, int64_t *count);
+
 /* Batched #[derive(Clone)] (env.rs:96) between engines on one device: for k in [0, count) copy
  * env src_idx_dev[k] of `src` over env dst_idx_dev[k] of `dst` (int64 device arrays; NULL =
  * identity; negative or out-of-range entries are skipped).  Used for MCTS clones and for state

@@ -118,6 +118,9 @@ inline void cp_async_16(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 16); 
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 inline void grid_dependency_wait() {}
+inline unsigned long long global_timer_ns() { return 0; }
+inline void stamp_min(unsigned long long *, unsigned long long) {}   // pb_trace_*: GPU only
+inline void stamp_max(unsigned long long *, unsigned long long) {}
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -174,7 +177,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // wait for the preceding grid of the stream (programmatic dependent launch)
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// nanoseconds of the GPU's global timer (pb_trace_*: device timeline of the launches)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void stamp_min(unsigned long long *p, unsigned long long t) { atomicMin(p, t); }
+__device__ __forceinline__ void stamp_max(unsigned long long *p, unsigned long long t) { atomicMax(p, t); }
 #endif  // PB_HOST_EMULATION
+
+// One record of the device timeline (pb_trace_*): written by the launches of an engine while
+// tracing is on.  begin = earliest CTA start, ready = earliest moment a CTA had its dependencies
+// (the preceding grid) resolved, end = latest warp exit; all in %globaltimer nanoseconds.
+struct TraceRec {
+    unsigned long long begin, ready, end, kind;
+};
 
 __device__ __forceinline__ bool on_board(int row, int col) {
     return (unsigned)row < (unsigned)ROWS && (unsigned)col < (unsigned)COLS;
@@ -204,9 +222,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_obs(StateView st, float *__restrict__ out,
              long long env_stride, long long env_first, long long env_count,
              unsigned int *__restrict__ ticket, const long long *__restrict__ slot_index,
-             long long slot_stride) {
+             long long slot_stride, TraceRec *__restrict__ trace) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (trace && threadIdx.x == 0) stamp_min(&trace->begin, global_timer_ns());
     float *img = reinterpret_cast<float *>(smem_raw + (size_t)warp * IMG_BYTES);
     float4 *img4 = reinterpret_cast<float4 *>(img);
     float *wall_ch = reinterpret_cast<float *>(smem_raw + (size_t)ENC_WARPS * IMG_BYTES);
@@ -224,6 +243,7 @@ k_encode_obs(StateView st, float *__restrict__ out,
     // everything above overlapped the previous kernel (programmatic dependent launch); from here
     // on the env state and the ticket are read, so wait for the preceding grid to finish
     grid_dependency_wait();
+    if (trace && threadIdx.x == 0) stamp_min(&trace->ready, global_timer_ns());
     // ring-slot indirection: the slot number lives in device memory so that a CUDA graph can be
     // replayed while the replay ring advances.  Read AFTER the wait: under programmatic dependent
     // launch nothing written by the preceding grid is visible before it.
@@ -422,6 +442,7 @@ k_encode_obs(StateView st, float *__restrict__ out,
     }
     if (lane == 0) {
         bulk_wait_all();
+        if (trace) stamp_max(&trace->end, global_timer_ns());
         // ticket[1] counts finished warps; the last one re-arms {ticket, count} for the next launch
         const unsigned int finished = atomicAdd(ticket + 1, 1u);
         if (finished == gridDim.x * ENC_WARPS - 1) {

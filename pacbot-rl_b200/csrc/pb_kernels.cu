@@ -96,7 +96,12 @@ k_step(StateView st, StateView dst, RngParams rp, const uint8_t *__restrict__ ac
        int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
        uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action,
        uint8_t *__restrict__ actions_out, unsigned long long call_idx, long long env_first,
-       long long env_count) {
+       long long env_count, TraceRec *__restrict__ trace) {
+    if (trace && threadIdx.x == 0) {
+        const unsigned long long t = global_timer_ns();
+        atomicMin(&trace->begin, t);
+        atomicMin(&trace->ready, t);
+    }
     // let a programmatically-dependent kernel (the observation encoder) start its prologue now;
     // it still waits for this whole grid (griddepcontrol.wait) before reading the state
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -142,6 +147,15 @@ k_step(StateView st, StateView dst, RngParams rp, const uint8_t *__restrict__ ac
     reward[i] = rew;
     done_out[i] = done ? 1 : 0;
     if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
+    if (trace && (threadIdx.x & 31) == 0) atomicMax(&trace->end, global_timer_ns());
+}
+
+// A mark on a stream's timeline (pb_trace_mark): one thread, one timestamp.
+__global__ void k_trace_mark(TraceRec *trace) {
+    const unsigned long long t = global_timer_ns();
+    trace->begin = t;
+    trace->ready = t;
+    trace->end = t;
 }
 
 // =============================================================================================
@@ -355,6 +369,10 @@ struct pb_engine {
     cudaEvent_t ev_enc_done[2] = {nullptr, nullptr};
     unsigned long long roll_t = 0;
     bool roll_started = false;
+    // pb_trace_*: device timeline of this engine's k_step / k_encode_obs launches
+    TraceRec *trace = nullptr;
+    long long trace_cap = 0, trace_n = 0;
+    std::vector<uint32_t> trace_kinds;
 };
 constexpr unsigned int TICKET_RING = 64;
 
@@ -376,6 +394,13 @@ RngParams rng_params(const pb_engine *e) {
     return RngParams{e->seed, e->gid_base, e->tape, e->tape_len};
 }
 unsigned grid_for(long long n) { return (unsigned)((n + STEP_THREADS - 1) / STEP_THREADS); }
+
+// the next record of the engine's device timeline, or nullptr when tracing is off / full
+TraceRec *trace_slot(pb_engine *e, uint32_t kind) {
+    if (!e->trace || e->trace_n >= e->trace_cap) return nullptr;
+    e->trace_kinds[(size_t)e->trace_n] = kind;
+    return e->trace + e->trace_n++;
+}
 
 void flat_to_rows(const uint32_t *f, uint32_t rows[PB_ROWS]) {
     for (int r = 0; r < PB_ROWS; r++) rows[r] = 0;
@@ -427,8 +452,9 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
         return v && v[0] == '1';
     }();
     cfg.numAttrs = no_pdl ? 0 : 1;
+    TraceRec *trace = trace_slot(e, PB_TRACE_ENCODE);
     PB_CUDA(cudaLaunchKernelEx(&cfg, k_encode_obs, e->st, out_dev, stride, first, count, ticket,
-                               slot_index, slot_stride));
+                               slot_index, slot_stride, trace));
     return PB_OK;
 }
 }  // namespace
@@ -484,6 +510,7 @@ int pb_destroy(pb_engine *e) {
         if (e->ev_obs_copy[b]) cudaEventDestroy(e->ev_obs_copy[b]);
     }
     cudaFree(e->tickets);
+    cudaFree(e->trace);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
     if (e->roll_step) cudaStreamDestroy(e->roll_step);
@@ -600,7 +627,7 @@ int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8
     DeviceGuard g(e->device);
     k_step<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(
         e->st, e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action, nullptr, 0ull, 0ll, e->n);
+        e->bad_action, nullptr, 0ull, 0ll, e->n, trace_slot(e, PB_TRACE_STEP));
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -622,7 +649,7 @@ int pb_step_random_range(pb_engine *e, int64_t first, int64_t count, uint64_t ca
     DeviceGuard g(e->device);
     k_step<<<grid_for(count), STEP_THREADS, 0, (cudaStream_t)stream>>>(
         e->st, e->st, rng_params(e), nullptr, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action, actions_out_dev, call_idx, first, count);
+        e->bad_action, actions_out_dev, call_idx, first, count, trace_slot(e, PB_TRACE_STEP));
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -660,7 +687,7 @@ int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
     const unsigned wide_grid = (unsigned)((e->n + STEP_THREADS_WIDE - 1) / STEP_THREADS_WIDE);
     k_step<<<wide_grid, STEP_THREADS_WIDE, 0, (cudaStream_t)stream>>>(
         e->st, e->st_alt, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset,
-        e->bad_action, actions_out_dev, call_idx, 0ll, e->n);
+        e->bad_action, actions_out_dev, call_idx, 0ll, e->n, trace_slot(e, PB_TRACE_STEP));
     PB_CUDA(cudaGetLastError());
     // from here on "the state" is the buffer just written; launches already enqueued keep the
     // StateView they captured
@@ -1075,6 +1102,60 @@ int pb_gather_obs(const float *ring_dev, int64_t slot_stride_floats, const int64
         reinterpret_cast<const long long *>(idx_dev), zero_mask_dev,
         reinterpret_cast<float4 *>(out_dev));
     PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // extern "C"
+
+// ---- device timeline -------------------------------------------------------------------------
+extern "C" {
+
+int pb_trace_begin(pb_engine *e, int64_t capacity) {
+    if (!e || capacity <= 0 || capacity > (1 << 22))
+        return fail(PB_ERR_INVALID_ARG, "pb_trace_begin: bad arguments");
+    DeviceGuard g(e->device);
+    PB_CUDA(cudaDeviceSynchronize());
+    cudaFree(e->trace);
+    e->trace = nullptr;
+    e->trace_cap = e->trace_n = 0;
+    PB_CUDA(cudaMalloc(&e->trace, sizeof(TraceRec) * (size_t)capacity));
+    std::vector<TraceRec> init((size_t)capacity, TraceRec{~0ull, ~0ull, 0ull, 0ull});
+    PB_CUDA(cudaMemcpy(e->trace, init.data(), sizeof(TraceRec) * (size_t)capacity, cudaMemcpyHostToDevice));
+    e->trace_kinds.assign((size_t)capacity, 0u);
+    e->trace_cap = capacity;
+    return PB_OK;
+}
+
+int pb_trace_mark(pb_engine *e, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_trace_mark: null engine");
+    DeviceGuard g(e->device);
+    TraceRec *t = trace_slot(e, PB_TRACE_MARK);
+    if (!t) return PB_OK;
+    k_trace_mark<<<1, 1, 0, (cudaStream_t)stream>>>(t);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_trace_end(pb_engine *e, pb_trace_record *out_host, int64_t max_records, int64_t *count) {
+    if (!e || !count || (max_records > 0 && !out_host))
+        return fail(PB_ERR_INVALID_ARG, "pb_trace_end: bad arguments");
+    DeviceGuard g(e->device);
+    PB_CUDA(cudaDeviceSynchronize());
+    const long long n = e->trace_n < max_records ? e->trace_n : max_records;
+    std::vector<TraceRec> recs((size_t)(n > 0 ? n : 0));
+    if (n > 0)
+        PB_CUDA(cudaMemcpy(recs.data(), e->trace, sizeof(TraceRec) * (size_t)n, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; i++) {
+        out_host[i].begin_ns = recs[(size_t)i].begin;
+        out_host[i].ready_ns = recs[(size_t)i].ready;
+        out_host[i].end_ns = recs[(size_t)i].end;
+        out_host[i].kind = e->trace_kinds[(size_t)i];
+        out_host[i].reserved = 0;
+    }
+    *count = e->trace_n;
+    cudaFree(e->trace);
+    e->trace = nullptr;
+    e->trace_cap = e->trace_n = 0;
     return PB_OK;
 }
 

@@ -526,6 +526,27 @@ class BatchedPacmanGym:
                                       self._stream()))
         self._cfg[first:first + st.shape[0]] = st["cfg_flags"] & 0x0F
 
+    # ------------------------------------------------------------------ device timeline
+    TRACE_DTYPE = np.dtype([("begin_ns", np.uint64), ("ready_ns", np.uint64), ("end_ns", np.uint64),
+                            ("kind", np.uint32), ("reserved", np.uint32)])
+
+    def trace_begin(self, capacity: int = 4096) -> None:
+        """Record %globaltimer begin / ready / end of every k_step / k_encode_obs launch of this
+        engine from now on (pb_trace_begin; diagnostics, synchronises the device)."""
+        check(self._L.pb_trace_begin(self._h, int(capacity)))
+
+    def trace_mark(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """A one-thread timestamp kernel on `stream` (default: the current stream)."""
+        s = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        check(self._L.pb_trace_mark(self._h, s))
+
+    def trace_end(self) -> np.ndarray:
+        """Stop tracing; records in launch order (kind 0 = mark, 1 = k_step, 2 = k_encode_obs)."""
+        out = np.zeros(1 << 16, self.TRACE_DTYPE)
+        n = C.c_int64(0)
+        check(self._L.pb_trace_end(self._h, out.ctypes.data_as(C.c_void_p), len(out), C.byref(n)))
+        return out[:min(n.value, len(out))].copy()
+
     def clone_env_from(self, dst_index: int, src: "BatchedPacmanGym", src_index: int) -> None:
         """`PacmanGym.clone()` (env.rs:96 derive(Clone)): copy one env between engines."""
         check(self._L.pb_clone_env(self._h, dst_index, src._h, src_index, self._stream()))

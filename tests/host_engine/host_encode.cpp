@@ -107,7 +107,7 @@ int he_encode_obs(const pb_env_state *states, int64_t n, int64_t first, int64_t 
         lanes.emplace_back([&, t] {
             threadIdx = HostDim3{t, 0, 0};
             blockIdx = HostDim3{0, 0, 0};
-            k_encode_obs(st, out, (long long)OBS_FLOATS, first, count, ticket, nullptr, 0);
+            k_encode_obs(st, out, (long long)OBS_FLOATS, first, count, ticket, nullptr, 0, nullptr);
         });
     for (auto &th : lanes) th.join();
     return (ticket[0] == 0u && ticket[1] == 0u) ? 0 : -1;   // the last warp re-arms the ticket pair

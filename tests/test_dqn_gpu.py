@@ -487,8 +487,9 @@ def _reference_target_and_loss(q_net, target_q_net, obs_batch, next_obs_batch, d
 def test_double_dqn_target_and_loss_match_reference_expressions(pb):
     """One fixed ReplayBatch through `dqn_targets` / `dqn_loss` (what `_iteration_body` runs) vs
     the reference's statements (train_dqn.py:167-197): on the same device with the same networks
-    (tolerance 1e-6: same cuDNN kernels underneath, only the target/loss arithmetic differs) and
-    on the CPU in float64 (rtol 1e-5 on target and loss, TF32 off).  The batch has finished
+    (tolerance 1e-6: same cuDNN kernels underneath, only the target/loss arithmetic differs), on
+    the CPU in float32 with exactly-representable stand-in networks (rtol 1e-6 target, 1e-5 loss)
+    and on the CPU in float64 with the real networks (5e-4: cuDNN fp32 convolutions, TF32 off).  The batch has finished
     transitions (done, all-False next mask, zero next_obs), partial next masks, negative and large
     rewards; reward_scale and gamma are not the defaults."""
     import copy
@@ -541,14 +542,38 @@ def test_double_dqn_target_and_loss_match_reference_expressions(pb):
         torch.testing.assert_close(target, t_ref, rtol=1e-6, atol=1e-6)
         torch.testing.assert_close(loss, l_ref, rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(all_q, q_ref, rtol=1e-6, atol=1e-6)
-        for got, p in zip(grads, q_net.parameters()):
-            torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-6)
-        # (2) the reference statements on the CPU in float64
+        for got, p in zip(grads, q_net.parameters()):   # cuDNN's backward accumulates with atomics
+            torch.testing.assert_close(got, p.grad, rtol=1e-4, atol=1e-5)
+        # (2) the reference statements on the CPU, float32, with networks whose arithmetic is exact
+        # in any evaluation order (two cells, a power-of-two scale, one add): what is compared is
+        # the target / loss arithmetic alone, GPU product path vs CPU reference statements
+        class CellNet(torch.nn.Module):
+            def __init__(self, shift):
+                super().__init__()
+                self.w = torch.nn.Parameter(torch.tensor(2.0))
+                self.shift = shift
+
+            def forward(self, x):
+                return x[:, :5, 3, 4] * self.w + x[:, 5:10, 7 + self.shift, 9] - 0.5
+
+        q_cell, t_cell = CellNet(0), CellNet(1)
+        dense = ReplayBatch(torch.rand((b,) + pb.OBS_SHAPE, generator=g).to(dev), batch.actions, batch.rewards,
+                            (torch.rand((b,) + pb.OBS_SHAPE, generator=g) * (~done)[:, None, None, None]).to(dev),
+                            batch.done, batch.next_action_masks)
+        tgt = train_dqn.dqn_targets(dense, q_cell.to(dev), t_cell.to(dev), gamma, scale)
+        lss, _ = train_dqn.dqn_loss(dense, q_cell, tgt)
+        t_cpu, l_cpu, _ = _reference_target_and_loss(
+            copy.deepcopy(q_cell).cpu(), copy.deepcopy(t_cell).cpu(), dense.obs.cpu(), dense.next_obs.cpu(),
+            done, masks, actions, rewards, scale, gamma)
+        torch.testing.assert_close(tgt.cpu(), t_cpu, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(lss.cpu(), l_cpu, rtol=1e-5, atol=0)
+        # (3) the real networks on the CPU in float64: cuDNN's fp32 convolutions against a float64
+        # evaluation bound the agreement here, not the target arithmetic
         q64, t64 = copy.deepcopy(q_net).cpu().double(), copy.deepcopy(target_q_net).cpu().double()
         t_cpu, l_cpu, _ = _reference_target_and_loss(
             q64, t64, obs.double(), next_obs.double(), done, masks, actions, rewards.double(), scale, gamma)
-        torch.testing.assert_close(target.cpu().double(), t_cpu.double(), rtol=1e-5, atol=1e-5)
-        torch.testing.assert_close(loss.cpu().double(), l_cpu.double(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(target.cpu().double(), t_cpu.double(), rtol=5e-4, atol=5e-4)
+        torch.testing.assert_close(loss.cpu().double(), l_cpu.double(), rtol=5e-4, atol=1e-5)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
 

@@ -182,3 +182,35 @@ def test_c_rollout_host_step_matches_step_host(pb, pinned):
     act_buf[17] = 0
     b.rollout_host_step(act_buf, obs_b[0], outs)                        # and the engine keeps working
     b.rollout_join()
+
+
+def test_device_timeline_records_every_launch(pb):
+    """pb_trace_*: k_step / k_encode_obs launches record %globaltimer begin <= ready <= end, marks
+    bracket them on the caller's stream, records come back in launch order, tracing is off again
+    afterwards (the timed loops of bench.py run untraced)."""
+    n = 4096
+    env = make(pb, n, seed=3)
+    obs = torch.empty((2, n) + pb.OBS_SHAPE, device="cuda:0")
+    env.rollout_random_step(obs[0], call_idx=0)
+    env.rollout_join()
+    torch.cuda.synchronize()
+    env.trace_begin(64)
+    env.trace_mark()
+    for t in range(5):
+        env.rollout_random_step(obs[t & 1], call_idx=1 + t)
+    env.rollout_join()
+    env.trace_mark()
+    rec = env.trace_end()
+    assert rec["kind"].tolist() == [0] + [1, 2] * 5 + [0]
+    assert (rec["begin_ns"] <= rec["ready_ns"]).all() and (rec["ready_ns"] <= rec["end_ns"]).all()
+    steps, encs, marks = rec[rec["kind"] == 1], rec[rec["kind"] == 2], rec[rec["kind"] == 0]
+    assert marks[0]["end_ns"] <= steps[0]["begin_ns"] and encs[-1]["end_ns"] <= marks[1]["begin_ns"]
+    # an encoder reads the state its step wrote; the next step overlaps it
+    assert (steps["end_ns"] <= encs["ready_ns"]).all()
+    assert (encs["end_ns"][:-1] <= encs["ready_ns"][1:]).all()
+    assert (encs["end_ns"] - encs["ready_ns"]).min() > 10_000      # 4 096 obs = 242 MB: > 10 us
+    env.rollout_random_step(obs[0], call_idx=9)                    # untraced again
+    env.rollout_join()
+    torch.cuda.synchronize()
+    env.trace_begin(4)
+    assert len(env.trace_end()) == 0
