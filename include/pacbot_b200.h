@@ -209,7 +209,7 @@ int pb_step_flip(pb_engine *e, const uint8_t *actions_dev, uint64_t call_idx,
                  uint8_t *mask_out_dev, int auto_reset, void *stream);
 
 /* ---- pipelined rollout steps (one C call per step) ------------------------------------------- */
-/* A rollout step = pb_step_flip + pb_encode_obs on two ENGINE-OWNED streams, so that the step
+/* A rollout step = pb_step_flip + pb_encode_obs on ENGINE-OWNED streams, so that the step
  * kernel of step t+1 runs while the encoder is still streaming step t to HBM (the step only
  * waits for the encode of step t-1, whose state buffer it overwrites).  `stream` is consulted at
  * the first step after pb_create / pb_rollout_join only: the engine's streams start after the
@@ -227,7 +227,8 @@ int pb_rollout_host_step(pb_engine *e, const uint8_t *actions_host, int32_t *rew
                          uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
                          int64_t env_stride_floats, void *stream);
 int pb_rollout_join(pb_engine *e, void *stream);
-/* the two engine-owned streams (cudaStream_t), e.g. to record timing events on them */
+/* the engine-owned streams (cudaStream_t), e.g. to record timing events on them: the step stream
+ * and the encode stream of the MOST RECENT step (encoders alternate between two streams) */
 int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream);
 
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index

@@ -364,7 +364,12 @@ struct pb_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_step = nullptr;
     // pb_rollout_*: two internal streams, double-buffered state (created on first use)
-    cudaStream_t roll_step = nullptr, roll_enc = nullptr;
+    // two encode streams used alternately: the first CTAs of encoder t+1 start on the SMs that
+    // encoder t has already left (its tail and the next launch's prologue overlap)
+    cudaStream_t roll_step = nullptr, roll_enc[2] = {nullptr, nullptr};
+    int roll_enc_streams = 2;
+    const float *roll_last_obs = nullptr;   // output range of the previous rollout step's encoder
+    size_t roll_last_obs_bytes = 0;
     cudaEvent_t ev_roll_step = nullptr, ev_roll_fork = nullptr, ev_roll_join = nullptr;
     cudaEvent_t ev_enc_done[2] = {nullptr, nullptr};
     unsigned long long roll_t = 0;
@@ -514,7 +519,8 @@ int pb_destroy(pb_engine *e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
     if (e->roll_step) cudaStreamDestroy(e->roll_step);
-    if (e->roll_enc) cudaStreamDestroy(e->roll_enc);
+    for (cudaStream_t s : e->roll_enc)
+        if (s) cudaStreamDestroy(s);
     for (cudaEvent_t ev : {e->ev_roll_step, e->ev_roll_fork, e->ev_roll_join, e->ev_enc_done[0],
                            e->ev_enc_done[1]})
         if (ev) cudaEventDestroy(ev);
@@ -551,6 +557,19 @@ int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_
     } while (0)
     PB_CUDA_OR_FREE(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
     PB_CUDA_OR_FREE(cudaMemcpyToSymbol(c_tab, &H_TABLES, sizeof(MazeTables)));
+    // k_step shares the SMs with the observation encoder (pb_rollout_*), whose CTA needs the
+    // LARGEST shared-memory carve-out (225 KB).  An SM running k_step CTAs under a small carve-out
+    // cannot take an encoder CTA until they have drained and the SM is reconfigured: whenever
+    // k_step reached the SMs first, the encoder started 15 us late on 128 of 148 SMs (device
+    // timeline, profiles/r02_timeline_*: encoder 524 us instead of 514 us).  With the same
+    // carve-out preference on both kernels the launch order no longer matters.
+    // PB_STEP_CARVEOUT=0 restores the default (A/B runs).
+    {
+        const char *v = getenv("PB_STEP_CARVEOUT");
+        if (!(v && v[0] == '0'))
+            PB_CUDA_OR_FREE(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
+    }
     PB_CUDA_OR_FREE(cudaMalloc(&e->st.core0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->st.core1, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMalloc(&e->st.ghosts, sizeof(uint4) * 2 * e->npad));
@@ -798,7 +817,7 @@ int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream) {
 // Work of the engine's own streams (pipelined rollout steps, result copies) that a state access
 // ordered on the caller's stream has to wait for.
 static int sync_engine_streams(pb_engine *e) {
-    for (cudaStream_t s : {e->roll_step, e->roll_enc, e->copy_stream})
+    for (cudaStream_t s : {e->roll_step, e->roll_enc[0], e->roll_enc[1], e->copy_stream})
         if (s) PB_CUDA(cudaStreamSynchronize(s));
     return PB_OK;
 }

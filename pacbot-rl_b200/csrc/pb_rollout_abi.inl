@@ -1,20 +1,32 @@
 // pb_rollout_abi.inl -- pb_rollout_*: pipelined rollout steps with double-buffered env state on two
 // engine-owned streams (include/pacbot_b200.h); included at the end of pb_kernels.cu.
 //
-//     encode stream : enc(t)                enc(t+1)               ...
-//     step stream   :     step(t+1)              step(t+2)         ...
+//     encode stream 0 : enc(t)                                enc(t+2)         ...
+//     encode stream 1 :                     enc(t+1)                           ...
+//     step stream     :     step(t+1)            step(t+2)         ...
 //
 // step(t+1) reads state buffer t and writes buffer t+1 (pb_step_flip) while enc(t) is still
 // streaming buffer t to HBM; it waits only for enc(t-1), whose buffer it overwrites.  The whole
 // orchestration of a step is one C call (a handful of CUDA API calls), so a busy host does not
 // put bubbles into the stream of 0.52 ms encoder launches.
+//
+// Consecutive encoders go to two streams alternately and depend only on their own step kernel:
+// the encoder is one persistent CTA per SM (all of an SM's shared memory), so the CTAs of
+// enc(t+1) start SM by SM as the CTAs of enc(t) run out of tickets and exit.  On one stream the
+// device timeline (tools/timeline.py) showed 6 us between the last warp of one encoder and the
+// first working CTA of the next (launch + prologue: 222 KB of shared memory to zero, the wall
+// template, the L2 pinning of the state), i.e. 1.1 % of every step.  Encoders that write
+// overlapping output ranges (the same obs buffer twice in a row) stay serialised.
 
 namespace {
 
 int rollout_ensure(pb_engine *e) {
     if (e->roll_step) return PB_OK;
     PB_CUDA(cudaStreamCreateWithFlags(&e->roll_step, cudaStreamNonBlocking));
-    PB_CUDA(cudaStreamCreateWithFlags(&e->roll_enc, cudaStreamNonBlocking));
+    for (cudaStream_t &s : e->roll_enc) PB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    // PB_ROLL_ENC_STREAMS=1: every encoder on one stream (A/B runs)
+    const char *v = getenv("PB_ROLL_ENC_STREAMS");
+    e->roll_enc_streams = (v && v[0] == '1') ? 1 : 2;
     for (cudaEvent_t *ev : {&e->ev_roll_step, &e->ev_roll_fork, &e->ev_roll_join, &e->ev_enc_done[0],
                             &e->ev_enc_done[1]})
         PB_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -26,7 +38,8 @@ int rollout_fork(pb_engine *e, cudaStream_t user) {
     if (e->roll_started) return PB_OK;
     PB_CUDA(cudaEventRecord(e->ev_roll_fork, user));
     PB_CUDA(cudaStreamWaitEvent(e->roll_step, e->ev_roll_fork, 0));
-    PB_CUDA(cudaStreamWaitEvent(e->roll_enc, e->ev_roll_fork, 0));
+    for (cudaStream_t s : e->roll_enc) PB_CUDA(cudaStreamWaitEvent(s, e->ev_roll_fork, 0));
+    e->roll_last_obs = nullptr;
     PB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_roll_fork, 0));
     e->roll_started = true;
     return PB_OK;
@@ -43,12 +56,21 @@ int rollout_step_device(pb_engine *e, const uint8_t *actions_dev, uint64_t call_
                           auto_reset, e->roll_step);
     if (rc != PB_OK) return rc;
     PB_CUDA(cudaEventRecord(e->ev_roll_step, e->roll_step));
-    PB_CUDA(cudaStreamWaitEvent(e->roll_enc, e->ev_roll_step, 0));
+    cudaStream_t enc = e->roll_enc[e->roll_enc_streams == 2 ? slot : 0];
+    PB_CUDA(cudaStreamWaitEvent(enc, e->ev_roll_step, 0));
     if (obs_out_dev) {
-        rc = launch_encode(e, obs_out_dev, stride, 0, e->n, e->roll_enc);
+        // an encoder that writes where the previous one wrote must not overtake it
+        const size_t bytes = sizeof(float) * (size_t)stride * (size_t)e->n;
+        const char *lo = reinterpret_cast<const char *>(obs_out_dev);
+        const char *plo = reinterpret_cast<const char *>(e->roll_last_obs);
+        if (e->roll_last_obs && e->roll_t > 0 && lo < plo + e->roll_last_obs_bytes && plo < lo + bytes)
+            PB_CUDA(cudaStreamWaitEvent(enc, e->ev_enc_done[slot ^ 1], 0));
+        rc = launch_encode(e, obs_out_dev, stride, 0, e->n, enc);
         if (rc != PB_OK) return rc;
+        e->roll_last_obs = obs_out_dev;
+        e->roll_last_obs_bytes = bytes;
     }
-    PB_CUDA(cudaEventRecord(e->ev_enc_done[slot], e->roll_enc));
+    PB_CUDA(cudaEventRecord(e->ev_enc_done[slot], enc));
     e->roll_t += 1;
     return PB_OK;
 }
@@ -124,7 +146,7 @@ int pb_rollout_join(pb_engine *e, void *stream) {
     if (!e->roll_step) return PB_OK;
     DeviceGuard g(e->device);
     cudaStream_t user = (cudaStream_t)stream;
-    for (cudaStream_t s : {e->roll_step, e->roll_enc, e->copy_stream}) {
+    for (cudaStream_t s : {e->roll_step, e->roll_enc[0], e->roll_enc[1], e->copy_stream}) {
         PB_CUDA(cudaEventRecord(e->ev_roll_join, s));
         PB_CUDA(cudaStreamWaitEvent(user, e->ev_roll_join, 0));
     }
@@ -138,7 +160,9 @@ int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream) {
     int rc = rollout_ensure(e);
     if (rc != PB_OK) return rc;
     if (step_stream) *step_stream = e->roll_step;
-    if (encode_stream) *encode_stream = e->roll_enc;
+    // the stream the most recent encoder launch went to
+    if (encode_stream)
+        *encode_stream = e->roll_enc[e->roll_enc_streams == 2 ? (int)((e->roll_t + 1) & 1ull) : 0];
     return PB_OK;
 }
 

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--gate-cycles", type=int, default=2_000_000)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--summary-only", action="store_true")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -107,6 +108,8 @@ def main():
             f.write(text)
     for r in runs:
         print(json.dumps({k: v for k, v in r.items() if k != "rows"}))
+    if args.summary_only:
+        return
     print("first run, per step:")
     for r in runs[0]["rows"]:
         print("  step {step:3d}  k_step {k_step_begin:9.1f}..{k_step_end:9.1f}  enc begin {enc_begin:9.1f} "
