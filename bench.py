@@ -467,18 +467,19 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
     # 16 back-to-back launches and nothing else (no host launch latency, no pipeline fill). ----
     enc_windows = []   # (ms, launches, envs)
     if flip:
-        enc_stream = env.rollout_streams()[1]
         per_window = 16
         for _ in range(3):
             hot_step(call)
             call += 1
+            # consecutive encoders alternate between two engine-owned streams:
+            # rollout_streams()[1] is the stream of the encoder launch just enqueued
             e_open = torch.cuda.Event(enable_timing=True)
-            e_open.record(enc_stream)
+            e_open.record(env.rollout_streams()[1])
             for _ in range(per_window):
                 hot_step(call)
                 call += 1
             e_close = torch.cuda.Event(enable_timing=True)
-            e_close.record(enc_stream)
+            e_close.record(env.rollout_streams()[1])
             enc_windows.append((e_open, e_close, per_window, per_window * n))
         join()
     else:
@@ -518,9 +519,10 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
         "avg_launch_ms": avg_launch_ms,
         "envs_per_launch": int(envs_per_launch),
         "launches_timed": enc_launches,
-        "how": ("CUDA events on the encode stream around windows of 16 back-to-back launches, in a "
-                "separate pass right after the timed loop (same calls, k_step of the next step "
-                "running beside the encoder as in the timed loop)" if flip else
+        "how": ("CUDA events on the encode streams (end of launch i to end of launch i + 16) around "
+                "windows of 16 back-to-back launches, in a separate pass right after the timed loop "
+                "(same calls, k_step of the next step running beside the encoder as in the timed "
+                "loop): the steady-state period of the launch" if flip else
                 "CUDA events around the encoder launches of a step (one stream), in a separate "
                 "pass right after the timed loop"),
     }
@@ -994,8 +996,9 @@ def main():
         "hbm_roofline_frac_whole_step": (main_leg["value"] / world) * BYTES_PER_ENV_STEP / 1e9 / main_leg["peak"],
         "roofline": main_leg["roofline"],
         "pipeline": {
-            "flip": "two streams, double-buffered state: k_step of step t+1 overlaps k_encode_obs of "
-                    "step t (one pb_rollout_random_step call per step)",
+            "flip": "engine-owned streams, double-buffered state: k_step of step t+1 overlaps "
+                    "k_encode_obs of step t, consecutive encoders alternate between two streams (one "
+                    "pb_rollout_random_step call per step)",
             "none": "none: k_step then k_encode_obs on one stream",
         }[main_leg["mode"]],
         "gpu_launches": main_leg["launches_per_step"] * args.steps * world,

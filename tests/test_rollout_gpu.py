@@ -207,10 +207,38 @@ def test_device_timeline_records_every_launch(pb):
     assert marks[0]["end_ns"] <= steps[0]["begin_ns"] and encs[-1]["end_ns"] <= marks[1]["begin_ns"]
     # an encoder reads the state its step wrote; the next step overlaps it
     assert (steps["end_ns"] <= encs["ready_ns"]).all()
-    assert (encs["end_ns"][:-1] <= encs["ready_ns"][1:]).all()
+    # consecutive encoders run on two streams: the next one starts on the SMs the previous one has
+    # left, so they may overlap by a tail, never by more (one CTA per SM holds all its shared memory)
+    assert (encs["end_ns"][:-1] <= encs["end_ns"][1:]).all()
+    assert (encs["ready_ns"][1:] + 50_000 >= encs["end_ns"][:-1]).all()
     assert (encs["end_ns"] - encs["ready_ns"]).min() > 10_000      # 4 096 obs = 242 MB: > 10 us
     env.rollout_random_step(obs[0], call_idx=9)                    # untraced again
     env.rollout_join()
     torch.cuda.synchronize()
     env.trace_begin(4)
     assert len(env.trace_end()) == 0
+
+
+@pytest.mark.parametrize("n", [96, 700, 5000])
+def test_consecutive_encoders_into_one_buffer_stay_ordered(pb, n):
+    """Consecutive rollout encoders run on two streams and may overlap -- unless they write
+    overlapping output ranges: the SAME observation buffer handed to every step must end up
+    holding the last step's observations (small n: the two encoders would otherwise run fully
+    concurrently on disjoint SMs), also when the second range only partly overlaps the first."""
+    a, b = make(pb, n, seed=21), make(pb, n, seed=21)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    big = torch.zeros((n + 8,) + pb.OBS_SHAPE, device="cuda:0")
+    for t in range(12):
+        a.step_random(call_idx=t)
+        a.obs(obs_a)
+        # every step writes the same rows, except the last one, shifted by 8 envs (partial overlap)
+        dst = big[8:8 + n] if t == 11 else big[:n]
+        b.rollout_random_step(dst, call_idx=t)
+        if t in (5, 10):
+            b.rollout_join()
+            torch.cuda.synchronize()
+            assert torch.equal(big[:n], obs_a), f"step {t}"
+    b.rollout_join()
+    torch.cuda.synchronize()
+    assert torch.equal(big[8:8 + n], obs_a)
+    assert a.get_state().tobytes() == b.get_state().tobytes()
