@@ -314,10 +314,13 @@ int pb_replay_sample(const uint8_t *ring_valid_dev, int64_t total, int64_t batch
                      const int64_t *call_idx_dev, int64_t *idx_out_dev, int32_t *num_valid_out_dev,
                      int device, void *stream);
 /* The collate of train_dqn.py:153-165 for the transitions idx_dev[0..batch): obs and next_obs
- * (zeros where done: `next_obs is None`) as float32 [batch][17][28][31], dense NCHW or, with
- * channels_last != 0, in channels-last memory order ([batch][28][31][17]: what the NHWC
- * convolutions of the Q-network read without a layout conversion); actions int64, rewards
- * float32 (raw, unscaled), done uint8, next masks uint8 [batch][5]. */
+ * (zeros where done: `next_obs is None`) as float32 [batch][17][28][31], dense NCHW
+ * (channels_last == 0) or in channels-last memory order [batch][28][31][C] (what the NHWC
+ * convolutions of the Q-network read without a layout conversion): channels_last == 1 or 17
+ * gives C = 17; a multiple of 4 in 20..64 gives that many channels, those >= 17 all zero
+ * (cuDNN's tensor-core kernels for the first convolution need C % 8 == 0; the network pads its
+ * first weight with zero input channels, which leaves the result unchanged).  actions int64,
+ * rewards float32 (raw, unscaled), done uint8, next masks uint8 [batch][5]. */
 int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
                       const int64_t *idx_dev, int64_t batch, const uint8_t *ring_actions,
                       const int32_t *ring_rewards, const uint8_t *ring_done,
@@ -325,7 +328,7 @@ int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_sl
                       int channels_last, int64_t *actions_out_dev, float *rewards_out_dev,
                       uint8_t *done_out_dev, uint8_t *next_mask_out_dev, int device, void *stream);
 /* last_obs of the policy forward (replay_buffer.py:109): the n observations of slot t % R, dense
- * NCHW or channels-last. */
+ * NCHW or channels-last (channels_last as for pb_replay_collate). */
 int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_slots,
                        const int64_t *t_dev, float *out_dev, int channels_last, int device,
                        void *stream);

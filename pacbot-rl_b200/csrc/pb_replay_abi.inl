@@ -99,14 +99,19 @@ k_replay_sample(const uint8_t *__restrict__ ring_valid, long long total, int bat
 constexpr int TILE_STRIDE = CH_FLOATS + 1;   // 869: odd stride, conflict-free transposed reads
 constexpr int COLLATE_THREADS = 256;
 constexpr int COLLATE_SMEM = OBS_CH * TILE_STRIDE * 4;
+// `cpad`: 0 = channel-major copy (NCHW); otherwise the channel count of the channels-last output,
+// 17 (dense) or a multiple of 4 up to 64 whose channels >= 17 are written as zeros: cuDNN only has
+// tensor-core kernels for the first convolution when its input channels are a multiple of 8
+// (17 -> 32: 230 -> 140 us forward at batch 512, tools/experiments/pad_channels_probe.py).
 __device__ __forceinline__ void emit_obs(const float4 *__restrict__ src, float4 *__restrict__ dst,
-                                         bool zero, bool nhwc, float *tile) {
+                                         bool zero, int cpad, float *tile) {
+    const int out_vec = (cpad ? CH_FLOATS * cpad : OBS_FLOATS) / 4;
     if (zero) {
-        for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS)
+        for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS)
             dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
-    if (!nhwc) {
+    if (!cpad) {
         for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) dst[q] = __ldg(src + q);
         return;
     }
@@ -120,12 +125,12 @@ __device__ __forceinline__ void emit_obs(const float4 *__restrict__ src, float4 
         t[3] = v.w;
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) {
+    for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) {
         float o[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int j = q * 4 + u, cell = j / OBS_CH, ch = j - cell * OBS_CH;
-            o[u] = tile[ch * TILE_STRIDE + cell];
+            const int j = q * 4 + u, cell = j / cpad, ch = j - cell * cpad;
+            o[u] = ch < OBS_CH ? tile[ch * TILE_STRIDE + cell] : 0.0f;
         }
         dst[q] = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -146,8 +151,9 @@ k_replay_collate(const float4 *__restrict__ ring_obs, long long n, long long rin
     const long long flat = idx[k];
     const long long slot = flat / n, env = flat - slot * n;
     const bool done = ring_done[flat] != 0;
+    const long long out_vec = (nhwc ? CH_FLOATS * nhwc : OBS_FLOATS) / 4;   // float4 per output obs
     if (!is_next) {
-        emit_obs(ring_obs + flat * (OBS_FLOATS / 4), obs_out + k * (OBS_FLOATS / 4), false, nhwc != 0, tile);
+        emit_obs(ring_obs + flat * (OBS_FLOATS / 4), obs_out + k * out_vec, false, nhwc, tile);
         if (threadIdx.x == 0) {
             actions_out[k] = ring_actions[flat];
             rewards_out[k] = (float)ring_rewards[flat];
@@ -157,7 +163,7 @@ k_replay_collate(const float4 *__restrict__ ring_obs, long long n, long long rin
     } else {
         // `next_obs is None` -> zeros (train_dqn.py:154-159); otherwise the next time slot
         const long long nflat = ((slot + 1) % ring_slots) * n + env;
-        emit_obs(ring_obs + nflat * (OBS_FLOATS / 4), next_obs_out + k * (OBS_FLOATS / 4), done, nhwc != 0, tile);
+        emit_obs(ring_obs + nflat * (OBS_FLOATS / 4), next_obs_out + k * out_vec, done, nhwc, tile);
     }
 }
 
@@ -166,8 +172,9 @@ k_replay_slot(const float4 *__restrict__ ring_obs, long long n, long long ring_s
               const long long *__restrict__ t_dev, float4 *__restrict__ out, int nhwc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const long long flat = (*t_dev % ring_slots) * n + blockIdx.x;
-    emit_obs(ring_obs + flat * (OBS_FLOATS / 4), out + (long long)blockIdx.x * (OBS_FLOATS / 4), false,
-             nhwc != 0, reinterpret_cast<float *>(smem_raw));
+    const long long out_vec = (nhwc ? CH_FLOATS * nhwc : OBS_FLOATS) / 4;
+    emit_obs(ring_obs + flat * (OBS_FLOATS / 4), out + (long long)blockIdx.x * out_vec, false, nhwc,
+             reinterpret_cast<float *>(smem_raw));
 }
 
 }  // namespace pb
@@ -183,6 +190,14 @@ int collate_smem_attr(int device) {
     return PB_OK;
 }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// channels_last argument of the ABI -> channel count of the channels-last output (0 = NCHW),
+// or -1 if it is not 0, 1 (= 17), 17, or a multiple of 4 in 20..64
+int channels_arg(int channels_last) {
+    if (channels_last == 0) return 0;
+    if (channels_last == 1 || channels_last == OBS_CH) return OBS_CH;
+    if (channels_last > OBS_CH && channels_last <= 64 && (channels_last & 3) == 0) return channels_last;
+    return -1;
+}
 }  // namespace
 
 extern "C" {
@@ -242,8 +257,9 @@ int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_sl
     if (!ring_obs_dev || !idx_dev || !ring_actions || !ring_rewards || !ring_done || !ring_next_mask ||
         !obs_out_dev || !next_obs_out_dev || !actions_out_dev || !rewards_out_dev || !done_out_dev ||
         !next_mask_out_dev || n_envs <= 0 || ring_slots < 2 || batch < 0 || !aligned16(ring_obs_dev) ||
-        !aligned16(obs_out_dev) || !aligned16(next_obs_out_dev))
+        !aligned16(obs_out_dev) || !aligned16(next_obs_out_dev) || channels_arg(channels_last) < 0)
         return fail(PB_ERR_INVALID_ARG, "pb_replay_collate: bad arguments");
+    channels_last = channels_arg(channels_last);
     if (batch == 0) return PB_OK;
     DeviceGuard g(device);
     int rc = collate_smem_attr(device);
@@ -264,8 +280,9 @@ int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_s
                        const int64_t *t_dev, float *out_dev, int channels_last, int device,
                        void *stream) {
     if (!ring_obs_dev || !t_dev || !out_dev || n_envs <= 0 || ring_slots < 1 ||
-        !aligned16(ring_obs_dev) || !aligned16(out_dev))
+        !aligned16(ring_obs_dev) || !aligned16(out_dev) || channels_arg(channels_last) < 0)
         return fail(PB_ERR_INVALID_ARG, "pb_replay_slot_obs: bad arguments");
+    channels_last = channels_arg(channels_last);
     DeviceGuard g(device);
     int rc = collate_smem_attr(device);
     if (rc != PB_OK) return rc;

@@ -70,7 +70,17 @@ class QNetV2(nn.Module):
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_channels_last", False):
             obs = obs.contiguous(memory_format=torch.channels_last)
-        feat = self.backbone(obs)
+        first = self.backbone[0]
+        if obs.shape[1] > first.in_channels:
+            # zero-padded observation channels (ReplayBuffer(pad_channels=True)): the first weight
+            # gets matching zero input channels, so the result is that of the 17-channel
+            # convolution while cuDNN sees a channel count its tensor-core kernels accept
+            w = nn.functional.pad(first.weight, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels))
+            if getattr(self, "_channels_last", False):
+                w = w.contiguous(memory_format=torch.channels_last)
+            feat = self.backbone[1:](nn.functional.conv2d(obs, w, first.bias, padding="same"))
+        else:
+            feat = self.backbone(obs)
         value = self.value_head(feat)
         adv = self.advantage_head(feat)
         return value - adv.mean(dim=1, keepdim=True) + adv

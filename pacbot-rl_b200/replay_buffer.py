@@ -40,7 +40,8 @@ from .policies import EpsilonGreedy, MaxQPolicy, Policy
 class ReplayBatch(NamedTuple):
     """Collated transitions (what train_dqn.py:153-165 builds from a list of ReplayItems)."""
 
-    obs: torch.Tensor                # float32 [B, 17, 28, 31] (channels-last strides if asked)
+    obs: torch.Tensor                # float32 [B, 17, 28, 31] (channels-last strides, and 32
+                                     # channels of which 17..31 are zero, if asked)
     actions: torch.Tensor            # int64   [B]
     rewards: torch.Tensor            # float32 [B]   (raw env reward, unscaled)
     next_obs: torch.Tensor           # float32 [B, 17, 28, 31], zeros where done
@@ -89,6 +90,12 @@ def _channels_last_empty(shape, device) -> torch.Tensor:
     return torch.empty((b, h, w, c), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
 
 
+# channels of a zero-padded channels-last observation batch: cuDNN's tensor-core kernels for the
+# first convolution want input channels that are a multiple of 8 (tools/experiments/
+# pad_channels_probe.py: 17 -> 32 channels, 230 -> 140 us forward at batch 512)
+PADDED_CHANNELS = 32
+
+
 class ReplayBuffer:
     def __init__(
         self,
@@ -102,10 +109,19 @@ class ReplayBuffer:
         env_id_base: int = 0,
         phase1_policy: Optional[Policy] = None,
         channels_last: bool = False,
+        pad_channels: bool = False,
     ) -> None:
+        """`channels_last`: observation batches (`sample_batch`, the policy's `last_obs`) come out
+        in channels-last memory order; `pad_channels` (with channels_last): with `PADDED_CHANNELS`
+        channels, the ones past the 17th all zero -- for networks that accept that
+        (`QNetV2.forward` pads its first weight to match)."""
         self.policy = policy
         self.phase1_policy = phase1_policy
         self.channels_last = bool(channels_last)
+        self.obs_channels = PADDED_CHANNELS if (channels_last and pad_channels) else OBS_SHAPE[0]
+        # `channels_last` argument of pb_replay_collate / pb_replay_slot_obs
+        self._cl_arg = self.obs_channels if self.channels_last else 0
+        self._batch_shape = (self.obs_channels,) + tuple(OBS_SHAPE[1:])
         n = int(num_parallel_envs)
         self.num_envs = n
         self.maxlen = int(maxlen)
@@ -129,7 +145,7 @@ class ReplayBuffer:
         self._mask = torch.zeros((n, NUM_ACTIONS), dtype=torch.bool, device=dev)
         self._in_phase1 = torch.zeros(n, dtype=torch.bool, device=dev)
         # per-step scratch (fixed addresses: CUDA-graph capture)
-        self._last_obs = (_channels_last_empty((n,) + OBS_SHAPE, dev) if self.channels_last
+        self._last_obs = (_channels_last_empty((n,) + self._batch_shape, dev) if self.channels_last
                           else torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev))
         self._act = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._reward = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -218,7 +234,7 @@ class ReplayBuffer:
         r, n = self._ring, self.num_envs
         L, stream, dev = self._L, self._stream(), self.device.index
         check(L.pb_replay_slot_obs(C.c_void_p(self._obs.data_ptr()), n, r, C.c_void_p(self._t_dev.data_ptr()),
-                                   C.c_void_p(self._last_obs.data_ptr()), int(self.channels_last), dev, stream))
+                                   C.c_void_p(self._last_obs.data_ptr()), self._cl_arg, dev, stream))
         actions = self._select(self._last_obs)
         if self.phase1_policy is not None:
             old = self.phase1_policy(self._last_obs, self._mask).to(torch.uint8)
@@ -244,7 +260,7 @@ class ReplayBuffer:
         bufs = self._batch_bufs.get(b)
         if bufs is None:
             dev = self.device
-            mk = (lambda: _channels_last_empty((b,) + OBS_SHAPE, dev)) if self.channels_last else (
+            mk = (lambda: _channels_last_empty((b,) + self._batch_shape, dev)) if self.channels_last else (
                 lambda: torch.empty((b,) + OBS_SHAPE, dtype=torch.float32, device=dev))
             bufs = dict(idx=torch.zeros(b, dtype=torch.int64, device=dev), obs=mk(), next_obs=mk(),
                         actions=torch.zeros(b, dtype=torch.int64, device=dev),
@@ -289,7 +305,7 @@ class ReplayBuffer:
         check(self._L.pb_replay_collate(
             C.c_void_p(self._obs.data_ptr()), self.num_envs, self._ring, C.c_void_p(idx.data_ptr()),
             batch_size, a_p, r_p, d_p, m_p, C.c_void_p(b["obs"].data_ptr()),
-            C.c_void_p(b["next_obs"].data_ptr()), int(self.channels_last),
+            C.c_void_p(b["next_obs"].data_ptr()), self._cl_arg,
             C.c_void_p(b["actions"].data_ptr()), C.c_void_p(b["rewards"].data_ptr()),
             C.c_void_p(b["done"].data_ptr()), C.c_void_p(b["next_mask"].data_ptr()),
             self.device.index, self._stream()))

@@ -274,7 +274,8 @@ class DQNTrainer:
         self.replay = ReplayBuffer(
             maxlen=cfg.replay_buffer_size, policy=self.policy, num_parallel_envs=cfg.num_parallel_envs,
             random_start_proportion=cfg.random_start_proportion, device=device, seed=cfg.seed,
-            env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1, channels_last=nhwc)
+            env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1, channels_last=nhwc,
+            pad_channels=nhwc and isinstance(self.q_net, models.QNetV2) and phase1 is None)
         self.optimizer = torch.optim.Adam(self.q_net.parameters(), lr=cfg.learning_rate,
                                           capturable=True)
         self.params = [p for p in self.q_net.parameters()]

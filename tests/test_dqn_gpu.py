@@ -369,8 +369,9 @@ def test_replay_sample_is_a_partial_fisher_yates_over_the_valid_list(pb):
     assert first_pos.max() < 12      # the first element is uniform too (mean 1.46 per cell)
 
 
-@pytest.mark.parametrize("channels_last", [False, True])
-def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_last):
+@pytest.mark.parametrize("channels_last,pad", [(False, False), (True, False), (True, True)],
+                         ids=["nchw", "nhwc", "nhwc-padded32"])
+def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_last, pad):
     """k_replay_record / k_replay_collate / k_replay_slot against the plain torch expressions they
     replace (the collate of train_dqn.py:153-165), NCHW and channels-last output, values compared
     bit for bit; a channels-last batch must have channels-last strides (that is what removes the
@@ -387,13 +388,19 @@ def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_la
         q.use_channels_last()
     n, maxlen = 32, 2048
     buf = ReplayBuffer(maxlen, EpsilonGreedy(MaxQPolicy(q), 5, 1.0), n, 0.5, dev, seed=9,
-                       channels_last=channels_last)
+                       channels_last=channels_last, pad_channels=pad)
     r = buf._ring
+    assert buf.obs_channels == (32 if pad else 17)
+
+    def real(x):   # the 17 observation channels; padded ones must be zero
+        assert x.shape[1] == buf.obs_channels and not bool(x[:, 17:].any())
+        return x[:, :17]
+
     for t in range(r + 30):                      # wrap the ring
         before = buf._obs[t % r].clone()
         buf.generate_experience_step()
         # last_obs handed to the policy == the ring slot of step t
-        assert torch.equal(buf._last_obs, before), t
+        assert torch.equal(real(buf._last_obs), before), t
         assert buf._last_obs.is_contiguous(
             memory_format=torch.channels_last if channels_last else torch.contiguous_format)
         # what k_replay_record appended == the step's own outputs
@@ -408,10 +415,10 @@ def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_la
         flat = buf._batch_buffers(b)["idx"]
         slot, env = flat // n, flat % n
         done = buf._done.view(-1)[flat]
-        assert torch.equal(batch.obs, buf._obs.view(-1, *pb.OBS_SHAPE)[flat])
+        assert torch.equal(real(batch.obs), buf._obs.view(-1, *pb.OBS_SHAPE)[flat])
         nxt = buf._obs[(slot + 1) % r, env]
         nxt[done] = 0.0                          # `next_obs is None` -> zeros (train_dqn.py:154-159)
-        assert torch.equal(batch.next_obs, nxt)
+        assert torch.equal(real(batch.next_obs), nxt)
         assert batch.actions.dtype == torch.int64 and torch.equal(batch.actions, buf._actions.view(-1)[flat].long())
         assert batch.rewards.dtype == torch.float32 and torch.equal(batch.rewards, buf._rewards.view(-1)[flat].float())
         assert torch.equal(batch.done, done)
@@ -419,6 +426,14 @@ def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_la
         fmt = torch.channels_last if channels_last else torch.contiguous_format
         assert batch.obs.is_contiguous(memory_format=fmt) and batch.next_obs.is_contiguous(memory_format=fmt)
     assert bool(batch.done.any()) and not bool(batch.done.all())
+    # the network gives the same Q-values for the padded batch as for the 17 channels alone
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            torch.testing.assert_close(q(batch.obs), q(real(batch.obs).contiguous()), rtol=1e-5, atol=1e-6)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
 
 
 def test_fill_with_old_policy_waits_for_recorded_transitions(pb):
