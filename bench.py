@@ -973,8 +973,7 @@ def main():
     if sampler is not None:
         sampler.stop()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(dist, world)
         return
 
     cfg = workload_config(args, world)
@@ -1027,8 +1026,22 @@ def main():
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample_envs, args.cpu_sample_steps,
                                             os.cpu_count() or 1, args.seed)
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(dist, world)
+
+
+def shutdown(dist, world: int) -> None:
+    """Tear the process group down, but never sit in it: destroy_process_group() has been seen to
+    wait forever while a CUDA graph with captured NCCL kernels is still alive.  The JSON line is
+    out by now; a rank that is still here after 20 s leaves with exit code 0."""
+    if world <= 1:
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(20.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    dist.destroy_process_group()
+    timer.cancel()
 
 
 if __name__ == "__main__":

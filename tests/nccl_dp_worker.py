@@ -19,6 +19,9 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(240, exit=True)   # a hung collective must not hold the box
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -45,22 +48,29 @@ def main():
         assert torch.equal(w, w0), "initial weights differ between ranks"
     # the env shards differ: every rank owns its own global env-id range
     assert tr.replay.envs.env_id_base == rank * cfg.num_parallel_envs
-    batch = tr.replay.sample_batch(cfg.batch_size)
-    target = train_dqn.dqn_targets(batch, tr.q_net, tr.target_q_net, cfg.discount_factor, cfg.reward_scale)
-    tr.optimizer.zero_grad(set_to_none=False)
-    loss, _ = train_dqn.dqn_loss(batch, tr.q_net, target)
-    loss.backward()
-    local_g = flat([p.grad for p in tr.params]).clone()
-    every = gathered(local_g)
-    if world > 1:
-        assert not torch.equal(every[0], every[1]), "ranks produced identical gradients: envs not sharded"
-    mean = torch.stack(every).sum(0) / world
-    tr._allreduce_grads()
-    got = flat([p.grad for p in tr.params])
-    if world == 2:
-        assert torch.equal(got, mean), float((got - mean).abs().max())
-    else:
-        torch.testing.assert_close(got, mean, rtol=1e-5, atol=1e-7)
+    # on the trainer's side stream, like its own eager warm-up iterations: a backward on the legacy
+    # default stream would tie the parameters' gradient accumulation to a stream that a later
+    # graph capture may not depend on
+    side = tr._side
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        batch = tr.replay.sample_batch(cfg.batch_size)
+        target = train_dqn.dqn_targets(batch, tr.q_net, tr.target_q_net, cfg.discount_factor, cfg.reward_scale)
+        tr.optimizer.zero_grad(set_to_none=False)
+        loss, _ = train_dqn.dqn_loss(batch, tr.q_net, target)
+        loss.backward()
+        local_g = flat([p.grad for p in tr.params]).clone()
+        every = gathered(local_g)
+        if world > 1:
+            assert not torch.equal(every[0], every[1]), "ranks produced identical gradients: envs not sharded"
+        mean = torch.stack(every).sum(0) / world
+        tr._allreduce_grads()
+        got = flat([p.grad for p in tr.params])
+        if world == 2:
+            assert torch.equal(got, mean), float((got - mean).abs().max())
+        else:
+            torch.testing.assert_close(got, mean, rtol=1e-5, atol=1e-7)
+    torch.cuda.current_stream(dev).wait_stream(side)
     # the collective inside the captured graph
     tr.capture_graph()
     for _ in range(30):
@@ -74,9 +84,14 @@ def main():
     m = tr.pop_metrics()
     assert m["loss"] == m["loss"]   # finite (pop_metrics raises on a non-finite loss)
     dist.barrier()
+    torch.cuda.synchronize(dev)
     if rank == 0:
         print(f"DP_NCCL_OK world={world} loss={m['loss']:.6f}", flush=True)
-    dist.destroy_process_group()
+    # leave without tearing the communicator down: destroy_process_group() waits forever while a
+    # live CUDA graph still holds the captured NCCL kernels (observed: the run sat in it until the
+    # caller's timeout)
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -33,6 +33,6 @@ def test_nccl_gradient_is_the_mean_of_rank_gradients_and_weights_stay_in_sync(pb
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
          "--master-addr", "127.0.0.1", "--master-port", str(port),
          os.path.join(ROOT, "tests", "nccl_dp_worker.py")],
-        capture_output=True, text=True, timeout=900)
+        capture_output=True, text=True, timeout=420)
     assert res.returncode == 0, (res.stdout + res.stderr)[-4000:]
     assert f"DP_NCCL_OK world={world}" in res.stdout
