@@ -320,10 +320,12 @@ def run_reference(args, rank: int, world: int):
     emit(line)
 
 
-def reference_dqn(args):
+def reference_dqn(args, env: str = "oracle"):
     """configs[3] on the reference side: its UNMODIFIED src/algorithms/train_dqn.py (staged by
-    build() into the git-ignored baseline/_ref/, never committed) over the oracle-backed
-    `pacbot_rs` shim, `--device cuda` when there is a GPU.  None when not staged."""
+    build() into the git-ignored baseline/_ref/, never committed) over a `pacbot_rs` shim,
+    `--device cuda` when there is a GPU.  env "oracle": the C restatement under the shim (the
+    reference arm); env "product": this repo's drop-in `PacmanGym` under the shim, i.e. the
+    reference's own loop on the B200 engine (reported in the product arm).  None when disabled."""
     if args.no_dqn:
         return None
     tool = os.path.join(ROOT, "tools", "run_reference_dqn.py")
@@ -339,7 +341,7 @@ def reference_dqn(args):
     iters = 30 if device == "cuda" else 12
     try:
         res = subprocess.run([sys.executable, tool, "--iters", str(iters), "--device", device,
-                              "--env", "oracle", "--ref-src", ref_src],
+                              "--env", env, "--ref-src", ref_src],
                              capture_output=True, text=True, timeout=600)
         lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
         return json.loads(lines[-1]) if lines else {"unavailable": (res.stderr or "no output")[-300:]}
@@ -1015,6 +1017,10 @@ def main():
     if config2 is not None:
         line["config2"] = config2
     if dqn is not None:
+        # the drop-in claim, timed: the reference's unmodified train_dqn.py + replay_buffer.py with
+        # this engine's per-env `PacmanGym` as its `pacbot_rs.PacmanGym` (32 one-env engines, the
+        # reference's own host loop: obs_numpy / action_mask / step per env per step)
+        dqn["reference_loop_on_b200_engine"] = reference_dqn(args, env="product")
         line["dqn"] = dqn
     if dqn_dp is not None:
         line["dqn_dp"] = dqn_dp

@@ -133,6 +133,20 @@ class BatchedExperienceCollector:
             self._device_step()
         self._graph = graph
 
+    def _ensure_outbox(self, need: int) -> None:
+        """The outbox holds the states of finished episodes until `generate_experience` hands them
+        out.  P * L slots are enough for one hand-out of ordinary episodes; callers that keep
+        stepping without handing out (the graph warm-up with very short episodes, a benchmark loop
+        over `generate_experience_step`) make it grow instead of losing states."""
+        have = self.outbox.num_envs
+        if need <= have:
+            return
+        bigger = BatchedPacmanGym(max(need, 2 * have), False, False, device=self.device,
+                                  seed=self.outbox.seed, env_id_base=self.outbox.env_id_base)
+        if self._out_count:
+            bigger.copy_envs_from(self.outbox, count=self._out_count)
+        self.outbox = bigger
+
     # ------------------------------------------------------------------ host part of a step
     def _finish(self, finished: list) -> None:
         """Episodes that ended in this step (alphazero.rs:163-184) and trees that need a fresh
@@ -167,6 +181,7 @@ class BatchedExperienceCollector:
                 values[k] = values[k] + disc * nxt
                 nxt = values[k]
             # the snapshot slots are reused by this env's next episode: move the states out
+            self._ensure_outbox(self._out_count + n)
             src = torch.arange(i * L, i * L + n, device=dev)
             dst = torch.arange(self._out_count, self._out_count + n, device=dev)
             self.outbox.copy_envs_from(self.snap, src_index=src, dst_index=dst)

@@ -93,13 +93,16 @@ class ExperienceBuffer:
 
     def extend(self, batch) -> None:
         k = len(batch)
-        if k > self.capacity:  # a deque keeps the newest maxlen items
-            raise ValueError("more new items than the buffer holds")
+        src_slots, mask, value, dist = batch.state_slots, batch.action_mask, batch.value, batch.action_distribution
+        if k > self.capacity:  # a deque(maxlen) keeps the newest maxlen items
+            keep = slice(k - self.capacity, k)
+            src_slots, mask, value, dist = src_slots[keep], mask[keep], value[keep], dist[keep]
+            k = self.capacity
         slots = (self.head + torch.arange(k, device=self.device)) % self.capacity
-        self.states.copy_envs_from(batch.state_engine, src_index=batch.state_slots, dst_index=slots)
-        self.action_mask[slots] = batch.action_mask
-        self.value[slots] = batch.value
-        self.action_distribution[slots] = batch.action_distribution
+        self.states.copy_envs_from(batch.state_engine, src_index=src_slots, dst_index=slots)
+        self.action_mask[slots] = mask
+        self.value[slots] = value
+        self.action_distribution[slots] = dist
         self.head = (self.head + k) % self.capacity
         self.size = min(self.size + k, self.capacity)
 
