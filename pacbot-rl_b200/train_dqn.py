@@ -276,8 +276,10 @@ class DQNTrainer:
             random_start_proportion=cfg.random_start_proportion, device=device, seed=cfg.seed,
             env_id_base=rank * cfg.num_parallel_envs, phase1_policy=phase1, channels_last=nhwc,
             pad_channels=nhwc and isinstance(self.q_net, models.QNetV2) and phase1 is None)
+        # Adam as in the reference (train_dqn.py:136), as ONE fused multi-tensor kernel: the default
+        # foreach implementation is a dozen launches per step (0.43 ms of a 3.7 ms iteration)
         self.optimizer = torch.optim.Adam(self.q_net.parameters(), lr=cfg.learning_rate,
-                                          capturable=True)
+                                          capturable=True, fused=True)
         self.params = [p for p in self.q_net.parameters()]
         self.iter_num = 0
         # streaming metrics (device side)

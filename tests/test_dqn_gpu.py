@@ -647,3 +647,23 @@ def test_evaluate_episode_matches_reference_loop(pb, oracle, max_steps, with_old
         assert finished == 0
     else:
         assert finished >= 1
+
+
+def test_global_max_pool_matches_adaptive_max_pool_on_gpu(pb):
+    """models.GlobalMaxPool2d vs nn.AdaptiveMaxPool2d((1, 1)) on the device kernels the trainer
+    runs (channels-last, batch 512): same values, same gradient routing, ties included."""
+    import torch
+    from pacbot_rl_b200.models import GlobalMaxPool2d
+
+    torch.manual_seed(5)
+    x = torch.randn(512, 128, 4, 4, device="cuda:0")
+    x[:, ::7] = x[:, ::7].round()                 # plenty of tied maxima
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        a = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        b = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        ya, yb = torch.nn.AdaptiveMaxPool2d((1, 1))(a), GlobalMaxPool2d()(b)
+        assert torch.equal(ya, yb)
+        w = torch.randn_like(ya)
+        (ya * w).sum().backward()
+        (yb * w).sum().backward()
+        assert torch.equal(a.grad, b.grad)

@@ -181,3 +181,23 @@ def test_live_reference_epsilon_greedy_distribution(pb):
             freq = torch.bincount(a[k::len(masks)], minlength=5).float() / reps
             sigma = torch.sqrt(want * (1 - want) / reps) + 1e-9
             assert bool(((freq - want).abs() <= 5 * sigma + 1e-12).all()), (k, freq, want)
+
+
+def test_global_max_pool_is_adaptive_max_pool(models):
+    """GlobalMaxPool2d (one max-pool window over the map) vs nn.AdaptiveMaxPool2d((1, 1)), the
+    module the reference uses (models.py:96): same values and the same gradient routing, including
+    maps with tied maxima (first maximum in row-major order) -- NCHW and channels-last."""
+    torch.manual_seed(3)
+    x = torch.randn(5, 7, 4, 4)
+    x[0, 0] = 1.5                      # every cell tied
+    x[1, 2, 1, 2] = x[1, 2, 3, 0] = 9.0   # two tied maxima
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        a = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        b = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        ya = torch.nn.AdaptiveMaxPool2d((1, 1))(a)
+        yb = models.GlobalMaxPool2d()(b)
+        assert torch.equal(ya, yb) and yb.shape == (5, 7, 1, 1)
+        w = torch.randn_like(ya)
+        (ya * w).sum().backward()
+        (yb * w).sum().backward()
+        assert torch.equal(a.grad, b.grad)
