@@ -563,12 +563,14 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
                 s = slot_ctr[0] % n_slots
                 slot_ctr[0] += 1
                 env.step_host(a, obs_out=ring[s][:n], out=outs)
-            else:  # env population larger than a ring slot: encode chunk by chunk
-                env.step_host(a, obs_out=None, out=outs)
+            else:  # env population larger than a ring slot: encode chunk by chunk; the result
+                # copies of the step travel while the chunks are being encoded
+                env.step_host(a, out=outs, begin_only=True)
                 for first, cnt in chunks:
                     s = slot_ctr[0] % n_slots
                     slot_ctr[0] += 1
                     env.obs_range(first, cnt, ring[s][:cnt])
+                env.step_host_end()
 
         for i in range(3):
             e2e_step(i)
@@ -598,7 +600,8 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
                "what": ("BatchedPacmanGym.rollout_host_step -> pb_rollout_host_step (pb_step_flip + "
                         "pb_encode_obs on two engine-owned streams)"
                         if flip else "BatchedPacmanGym.step_host -> pb_step_host"
-                        + ("" if len(chunks) == 1 else " + pb_encode_obs_range per ring slot"))
+                        if len(chunks) == 1 else "BatchedPacmanGym.step_host(begin_only) -> "
+                        "pb_step_host_begin, pb_encode_obs_range per ring slot, pb_step_host_end")
                        + ": pinned host actions in, reward/done/mask back to pinned host memory and "
                          "read by the host every step (the D2H copies ride a side stream while the "
                          "encoder runs), observation encoded into the device-resident ring (it is "

@@ -259,6 +259,15 @@ int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t sr
 int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
                  uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
                  int64_t env_stride_floats, void *stream);
+/* pb_step_host without the observation, split in two for callers that enqueue their own work
+ * between a step and the moment they need its results (e.g. the chunked observation encodes of a
+ * population larger than its ring, pb_encode_obs_range): _begin enqueues the H2D copy of the
+ * actions, the step on `stream` and the D2H copies of reward / done / mask on a side stream, and
+ * returns; _end returns when the results are in the host buffers (PB_ERR_INVALID_ACTION as for
+ * pb_step_host).  One step in flight per engine; the host buffers must stay valid until _end. */
+int pb_step_host_begin(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                       uint8_t *done_host, uint8_t *mask_host, int auto_reset, void *stream);
+int pb_step_host_end(pb_engine *e, void *stream);
 /* obs_numpy() (env.rs:305-307) of envs [first, first+count) straight to a host buffer.  The
  * range is encoded in chunks of 1 024 envs into two device staging buffers; each chunk crosses
  * PCIe on an internal stream while the next one is being encoded.  A pinned / registered

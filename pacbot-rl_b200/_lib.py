@@ -112,6 +112,8 @@ SIGNATURES = {
     "pb_set_state_on": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "pb_clone_env": (_int, [_vp, _i64, _vp, _i64, _vp]),
     "pb_step_host": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
+    "pb_step_host_begin": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "pb_step_host_end": (_int, [_vp, _vp]),
     "pb_obs_host": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "pb_select_actions": (_int, [_vp, _vp, _vp, C.c_float, _vp, _u64, _vp]),
     "pb_select_actions_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

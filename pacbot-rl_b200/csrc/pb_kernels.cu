@@ -362,7 +362,9 @@ struct pb_engine {
     unsigned int ticket_next = 0;
     // pb_step_host: results travel device->host on a side stream while the encoder runs
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_step = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_host_copied = nullptr;
+    unsigned long long *host_bad = nullptr;  // pinned: invalid-action record of the step in flight
+    bool host_step_pending = false;
     // pb_rollout_*: two internal streams, double-buffered state (created on first use)
     // two encode streams used alternately: the first CTAs of encoder t+1 start on the SMs that
     // encoder t has already left (its tail and the next launch's prologue overlap)
@@ -518,6 +520,8 @@ int pb_destroy(pb_engine *e) {
     cudaFree(e->trace);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
+    if (e->ev_host_copied) cudaEventDestroy(e->ev_host_copied);
+    if (e->host_bad) cudaFreeHost(e->host_bad);
     if (e->roll_step) cudaStreamDestroy(e->roll_step);
     for (cudaStream_t s : e->roll_enc)
         if (s) cudaStreamDestroy(s);
@@ -583,6 +587,7 @@ int pb_create(pb_engine **out, int64_t n_envs, int device, uint64_t seed, int64_
     PB_CUDA_OR_FREE(cudaMemset(e->tickets, 0, sizeof(unsigned int) * 2 * TICKET_RING));
     PB_CUDA_OR_FREE(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     PB_CUDA_OR_FREE(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+    PB_CUDA_OR_FREE(cudaEventCreateWithFlags(&e->ev_host_copied, cudaEventDisableTiming));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core0, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.core1, 0, sizeof(uint4) * e->npad));
     PB_CUDA_OR_FREE(cudaMemset(e->st.ghosts, 0, sizeof(uint4) * 2 * e->npad));
@@ -992,39 +997,64 @@ int pb_clone_env(pb_engine *dst, int64_t dst_i, const pb_engine *src, int64_t sr
     return PB_OK;
 }
 
-int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
-                 uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
-                 int64_t env_stride_floats, void *stream) {
+int pb_step_host_begin(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                       uint8_t *done_host, uint8_t *mask_host, int auto_reset, void *stream) {
     if (!e || !actions_host || !reward_host || !done_host)
         return fail(PB_ERR_INVALID_ARG, "pb_step_host: null argument");
+    if (e->host_step_pending)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_host_begin: the previous step has not been ended");
     DeviceGuard g(e->device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (!e->host_bad) PB_CUDA(cudaMallocHost(&e->host_bad, sizeof(unsigned long long)));
     PB_CUDA(cudaMemcpyAsync(e->stg_actions, actions_host, (size_t)e->n, cudaMemcpyHostToDevice, s));
     int rc = pb_step(e, e->stg_actions, e->stg_reward, e->stg_done, mask_host ? e->stg_mask : nullptr,
                      auto_reset, stream);
     if (rc != PB_OK) return rc;
     // reward / done / mask only depend on k_step: ship them to the host on the side stream while
-    // the (much longer) observation encode runs on the caller's stream
+    // whatever the caller enqueues next on its stream (the much longer observation encode) runs
     PB_CUDA(cudaEventRecord(e->ev_step, s));
-    if (obs_out_dev) {
-        rc = pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
-        if (rc != PB_OK) return rc;
-    }
     cudaStream_t c = e->copy_stream;
     PB_CUDA(cudaStreamWaitEvent(c, e->ev_step, 0));
-    unsigned long long bad = ~0ull;
+    *e->host_bad = ~0ull;
     PB_CUDA(cudaMemcpyAsync(reward_host, e->stg_reward, sizeof(int32_t) * (size_t)e->n,
                             cudaMemcpyDeviceToHost, c));
     PB_CUDA(cudaMemcpyAsync(done_host, e->stg_done, (size_t)e->n, cudaMemcpyDeviceToHost, c));
     if (mask_host)
         PB_CUDA(cudaMemcpyAsync(mask_host, e->stg_mask, 5 * (size_t)e->n, cudaMemcpyDeviceToHost, c));
-    PB_CUDA(cudaMemcpyAsync(&bad, e->bad_action, sizeof(bad), cudaMemcpyDeviceToHost, c));
-    PB_CUDA(cudaStreamSynchronize(c));
-    if (bad != ~0ull) {
-        PB_CUDA(cudaMemsetAsync(e->bad_action, 0xff, sizeof(bad), s));
+    PB_CUDA(cudaMemcpyAsync(e->host_bad, e->bad_action, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c));
+    // the next step's kernel overwrites the staging buffers: it has to wait for these copies
+    PB_CUDA(cudaEventRecord(e->ev_host_copied, c));
+    e->host_step_pending = true;
+    return PB_OK;
+}
+
+int pb_step_host_end(pb_engine *e, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_step_host_end: null engine");
+    if (!e->host_step_pending) return PB_OK;
+    DeviceGuard g(e->device);
+    e->host_step_pending = false;
+    PB_CUDA(cudaStreamSynchronize(e->copy_stream));
+    PB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_host_copied, 0));
+    if (*e->host_bad != ~0ull) {
+        PB_CUDA(cudaMemsetAsync(e->bad_action, 0xff, sizeof(unsigned long long), (cudaStream_t)stream));
         return fail(PB_ERR_INVALID_ACTION, "Invalid action");
     }
     return PB_OK;
+}
+
+int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
+                 uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
+                 int64_t env_stride_floats, void *stream) {
+    int rc = pb_step_host_begin(e, actions_host, reward_host, done_host, mask_host, auto_reset, stream);
+    if (rc != PB_OK) return rc;
+    if (obs_out_dev) {
+        rc = pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
+        if (rc != PB_OK) {
+            pb_step_host_end(e, stream);
+            return rc;
+        }
+    }
+    return pb_step_host_end(e, stream);
 }
 
 // Observations straight to host memory, PCIe-bound instead of pageable-bound: the range is cut

@@ -455,13 +455,19 @@ class BatchedPacmanGym:
 
     # ------------------------------------------------------------------ host-buffer entry
     def step_host(self, actions: np.ndarray, obs_out: Optional[torch.Tensor] = None,
-                  want_mask: bool = True, out: Optional[tuple] = None):
+                  want_mask: bool = True, out: Optional[tuple] = None, begin_only: bool = False):
         """The per-call FFI shape: numpy actions in, numpy (reward, done, mask) out, with the
         host<->device copies inside the call.  The observation, if requested, is written to the
         DEVICE tensor `obs_out` (it feeds the Q-network / replay ring there).
 
         `out=(reward int32[N], done bool|uint8[N], mask bool|uint8[N,5] or None)` reuses caller
-        buffers (pin them for full-speed D2H); otherwise fresh pageable arrays are returned."""
+        buffers (pin them for full-speed D2H); otherwise fresh pageable arrays are returned.
+
+        `begin_only=True` (pb_step_host_begin; no `obs_out`): enqueue the copies and the step and
+        return at once; the arrays are filled when `step_host_end()` returns.  Whatever the caller
+        enqueues in between (chunked `obs_range` encodes) overlaps the result copies."""
+        if begin_only and obs_out is not None:
+            raise ValueError("begin_only: encode the observation yourself between begin and end")
         a = np.ascontiguousarray(actions, dtype=np.uint8)
         n = self.num_envs
         if a.shape != (n,):
@@ -483,12 +489,22 @@ class BatchedPacmanGym:
         if obs_out is not None:
             optr = C.c_void_p(self._check_tensor(
                 obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
-        check(self._L.pb_step_host(
-            self._h, a.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
-            done.ctypes.data_as(C.c_void_p),
-            None if mask is None else mask.ctypes.data_as(C.c_void_p),
-            int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
+        args = (self._h, a.ctypes.data_as(C.c_void_p), reward.ctypes.data_as(C.c_void_p),
+                done.ctypes.data_as(C.c_void_p),
+                None if mask is None else mask.ctypes.data_as(C.c_void_p), int(self.auto_reset))
+        if begin_only:
+            # the arrays must outlive the copies: kept until step_host_end()
+            self._host_step = (a, reward, done, mask)
+            check(self._L.pb_step_host_begin(*args, self._stream()))
+        else:
+            check(self._L.pb_step_host(*args, optr, OBS_FLOATS, self._stream()))
         return reward, done, mask
+
+    def step_host_end(self):
+        """Wait for the results of `step_host(..., begin_only=True)` -> (reward, done, mask)."""
+        check(self._L.pb_step_host_end(self._h, self._stream()))
+        out, self._host_step = getattr(self, "_host_step", None), None
+        return None if out is None else out[1:]
 
     def obs_numpy(self, first: int = 0, count: Optional[int] = None,
                   out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -242,3 +242,40 @@ def test_consecutive_encoders_into_one_buffer_stay_ordered(pb, n):
     torch.cuda.synchronize()
     assert torch.equal(big[8:8 + n], obs_a)
     assert a.get_state().tobytes() == b.get_state().tobytes()
+
+
+def test_split_host_step_matches_step_host(pb):
+    """pb_step_host_begin / _end with the caller's own chunked encodes in between == pb_step_host;
+    an invalid action is reported by _end and leaves that env untouched; a second _begin before
+    _end is refused."""
+    n, chunk = 5000, 2048
+    a, b = make(pb, n, seed=8), make(pb, n, seed=8)
+    rng = np.random.default_rng(4)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    outs = tuple(t.pin_memory().numpy() for t in (torch.empty(n, dtype=torch.int32), torch.empty(n, dtype=torch.bool),
+                                                  torch.empty((n, 5), dtype=torch.bool)))
+    for t in range(15):
+        acts = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(acts, obs_out=obs_a)
+        b.step_host(acts, out=outs, begin_only=True)
+        for first in range(0, n, chunk):
+            cnt = min(chunk, n - first)
+            b.obs_range(first, cnt, obs_b[first:first + cnt])
+        r_b, d_b, m_b = b.step_host_end()
+        assert r_b is outs[0]
+        assert np.array_equal(r_a, r_b) and np.array_equal(d_a, d_b) and np.array_equal(m_a, m_b), t
+    torch.cuda.synchronize()
+    assert torch.equal(obs_a, obs_b) and a.get_state().tobytes() == b.get_state().tobytes()
+    acts = rng.integers(0, 5, n, dtype=np.uint8)
+    b.step_host(acts, out=outs, begin_only=True)
+    with pytest.raises(ValueError, match="has not been ended"):
+        b.step_host(acts, out=outs, begin_only=True)
+    b.step_host_end()
+    before = b.get_state()
+    acts[77] = 9
+    b.step_host(acts, out=outs, begin_only=True)
+    with pytest.raises(ValueError, match="Invalid action"):
+        b.step_host_end()
+    after = b.get_state()
+    assert after[77].tobytes() == before[77].tobytes()       # env.rs:83-88: env untouched
