@@ -342,6 +342,24 @@ int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_s
                        const int64_t *t_dev, float *out_dev, int channels_last, int device,
                        void *stream);
 
+/* ---- Q-network convolution-block tail (reference: src/models.py:70-90) -------------------------
+ * `Conv2d -> MaxPool2d(2, ceil_mode=True) -> SiLU` (pool != 0) and `Conv2d -> SiLU` (pool == 0) of
+ * QNetV2 minus the convolution (which stays cuDNN, run WITHOUT its bias): bias add, 2x2 max pool
+ * and SiLU in one kernel, and their backward in one kernel.  Channels-last float32: x is
+ * [n][h][w][c]; z / y are [n][ho][wo][c] with ho = ceil(h / 2), wo = ceil(w / 2) (h, w without
+ * pool); c a multiple of 4 with (c / 4) dividing 256.
+ * fwd: z = max over the window of (x + bias) (first maximum in row-major window order, NaN wins:
+ * torch's rule), y = z / (1 + exp(-z)); idx = arg-max 0..3 per element (pool only).  z_out_dev
+ * may be NULL when no backward will follow; without pool it may alias x_dev.
+ * bwd: dx = dy * silu'(z) routed to the arg-max cell of each window (zeros elsewhere; every cell
+ * of dx is written), dbias[c] = sum of dy * silu'(z) (zeroed inside the call). */
+int pb_bias_pool_silu_fwd(const float *x_dev, const float *bias_dev, int64_t n, int64_t h, int64_t w,
+                          int64_t c, int pool, float *z_out_dev, float *y_out_dev, uint8_t *idx_out_dev,
+                          int device, void *stream);
+int pb_bias_pool_silu_bwd(const float *dy_dev, const float *z_dev, const uint8_t *idx_dev, int64_t n,
+                          int64_t h, int64_t w, int64_t c, int pool, float *dx_out_dev,
+                          float *dbias_out_dev, int device, void *stream);
+
 /* ---- device timeline (diagnostics; no counterpart in the reference) --------------------------
  * Between pb_trace_begin and pb_trace_end every k_step / k_encode_obs launch of the engine
  * records, in nanoseconds of the GPU's %globaltimer: begin = first CTA started, ready = first CTA

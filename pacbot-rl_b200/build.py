@@ -20,6 +20,7 @@ HEADERS = [
     os.path.join(CSRC, "pb_mcts_abi.inl"),
     os.path.join(CSRC, "pb_rollout_abi.inl"),
     os.path.join(CSRC, "pb_replay_abi.inl"),
+    os.path.join(CSRC, "pb_qnet_abi.inl"),
     os.path.join(os.path.dirname(HERE), "include", "pacbot_b200.h"),
 ]
 NVCC_FLAGS = [

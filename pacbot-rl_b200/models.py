@@ -28,7 +28,65 @@ def portable_copy(net: nn.Module) -> nn.Module:
     out = copy.deepcopy(net).to(memory_format=torch.contiguous_format)
     if getattr(out, "_channels_last", False):
         out._channels_last = False
+    if getattr(out, "_fused_blocks", False):
+        out._fused_blocks = False
     return out
+
+
+class _BiasPoolSiLU(torch.autograd.Function):
+    """`y = SiLU(maxpool2x2_ceil(x + bias))` (pool=True) or `y = SiLU(x + bias)` (pool=False) for a
+    channels-last float32 CUDA activation, forward and backward each ONE launch of the repo's
+    kernels (`pb_bias_pool_silu_fwd / _bwd`, csrc/pb_qnet_abi.inl) instead of torch's add_ +
+    max_pool2d + silu and their three backward kernels.  Same arithmetic as that composition
+    (reference models.py:70-90), see the kernel header."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, bias: torch.Tensor, pool: bool) -> torch.Tensor:
+        import ctypes as C
+
+        from . import _lib
+
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            raise ValueError("bias_pool_silu: float32 CUDA [N, C, H, W] activation expected")
+        x = x.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        ho, wo = ((h + 1) // 2, (w + 1) // 2) if pool else (h, w)
+        dev = x.device
+        y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        need_bwd = any(ctx.needs_input_grad[:2])
+        z = torch.empty_like(y) if need_bwd else None
+        idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=dev) if (need_bwd and pool) else None
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        _lib.check(_lib.load().pb_bias_pool_silu_fwd(
+            p(x), p(bias.contiguous()), n, h, w, c, int(pool), p(z), p(y), p(idx), dev.index,
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if need_bwd:
+            ctx.save_for_backward(z, idx) if pool else ctx.save_for_backward(z)
+            ctx.pool, ctx.in_shape = pool, (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+
+        saved = ctx.saved_tensors
+        z, idx = saved[0], (saved[1] if ctx.pool else None)
+        n, c, h, w = ctx.in_shape
+        dev = dy.device
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        db = torch.empty(c, dtype=torch.float32, device=dev)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        _lib.check(_lib.load().pb_bias_pool_silu_bwd(
+            p(dy), p(z), p(idx), n, h, w, c, int(ctx.pool), p(dx), p(db), dev.index,
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return dx, db, None
+
+
+def bias_pool_silu(x: torch.Tensor, bias: torch.Tensor, pool: bool) -> torch.Tensor:
+    return _BiasPoolSiLU.apply(x, bias, pool)
 
 
 class GlobalMaxPool2d(nn.Module):
@@ -78,9 +136,36 @@ class QNetV2(nn.Module):
         self._channels_last = True
         return self
 
+    def use_fused_blocks(self, enabled: bool = True) -> "QNetV2":
+        """Run the tail of every convolution block (bias, 2x2 max pool, SiLU) as the repo's fused
+        kernels (`bias_pool_silu`), forward and backward; the convolutions stay cuDNN.  Needs the
+        channels-last mode and CUDA float32 inputs; parameters and checkpoints are unchanged."""
+        if enabled and not getattr(self, "_channels_last", False):
+            self.use_channels_last()
+        self._fused_blocks = bool(enabled)
+        return self
+
+    def _forward_fused(self, obs: torch.Tensor) -> torch.Tensor:
+        bb = self.backbone
+        first = bb[0]
+        w = first.weight
+        if obs.shape[1] > first.in_channels:   # zero-padded observation channels, see forward()
+            w = nn.functional.pad(w, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels))
+        w = w.contiguous(memory_format=torch.channels_last)
+        h = bias_pool_silu(nn.functional.conv2d(obs, w, None, padding="same"), first.bias, False)
+        for i in (2, 5, 8):                     # Conv2d, MaxPool2d(2, ceil_mode=True), SiLU
+            conv = bb[i]
+            h = bias_pool_silu(nn.functional.conv2d(h, conv.weight, None, padding="same"), conv.bias, True)
+        feat = bb[11:](h)                       # grouped conv, global max pool, SiLU, Linear, SiLU
+        value = self.value_head(feat)
+        adv = self.advantage_head(feat)
+        return value - adv.mean(dim=1, keepdim=True) + adv
+
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_channels_last", False):
             obs = obs.contiguous(memory_format=torch.channels_last)
+        if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:
+            return self._forward_fused(obs)
         first = self.backbone[0]
         if obs.shape[1] > first.in_channels:
             # zero-padded observation channels (ReplayBuffer(pad_channels=True)): the first weight

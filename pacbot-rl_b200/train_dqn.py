@@ -85,6 +85,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-checkpoints", action="store_true")
     p.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
                    help="keep the Q-network in NCHW (default: NHWC weights/activations for cuDNN)")
+    p.add_argument("--no-fused-blocks", dest="fused_blocks", action="store_false", default=True,
+                   help="run bias / max-pool / SiLU of QNetV2's convolution blocks as separate torch "
+                        "kernels instead of the fused pb_bias_pool_silu kernels")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", default=True,
                    help="run the iteration eagerly instead of replaying one captured CUDA graph")
     for name, default in hyperparam_defaults.items():
@@ -254,6 +257,8 @@ class DQNTrainer:
         nhwc = bool(cfg.channels_last and hasattr(self.q_net, "use_channels_last"))
         if nhwc:
             self.q_net.use_channels_last()
+            if cfg.fused_blocks and hasattr(self.q_net, "use_fused_blocks"):
+                self.q_net.use_fused_blocks()
         torch.manual_seed(cfg.seed * 1000003 + rank)
         self.target_q_net = copy.deepcopy(self.q_net).eval()
         phase1 = None

@@ -667,3 +667,104 @@ def test_global_max_pool_matches_adaptive_max_pool_on_gpu(pb):
         (ya * w).sum().backward()
         (yb * w).sum().backward()
         assert torch.equal(a.grad, b.grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused tail of QNetV2's convolution blocks (csrc/pb_qnet_abi.inl)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,pool", [((512, 16, 28, 31), False), ((64, 32, 28, 31), True),
+                                        ((9, 64, 14, 16), True), ((3, 128, 7, 8), True), ((1, 32, 1, 1), True)])
+def test_bias_pool_silu_matches_torch_composition(pb, shape, pool):
+    """pb_bias_pool_silu_fwd / _bwd against what torch runs for `Conv2d -> [MaxPool2d(2,
+    ceil_mode=True)] -> SiLU` after the convolution (reference models.py:70-90): bias add, max
+    pool, SiLU and their backward.  Odd sizes (partial border windows), tied maxima (arg-max must
+    be torch's: first in row-major order) and NaN.  Forward bit for bit; backward to float32
+    rounding (torch sums the bias gradient in another order; FMA contraction may differ by an ulp)."""
+    import torch
+    import torch.nn.functional as F
+    from pacbot_rl_b200.models import bias_pool_silu
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(hash(shape) % 1000)
+    x = torch.randn(shape, generator=g)
+    x[:, ::3] = (x[:, ::3] * 2).round() / 2            # many ties inside windows
+    bias = torch.randn(shape[1], generator=g)
+    x = x.to(dev).contiguous(memory_format=torch.channels_last)
+    bias = bias.to(dev)
+    xa, ba = x.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    xb, bb = x.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    za = xa + ba.view(1, -1, 1, 1)
+    if pool:
+        za = F.max_pool2d(za, 2, ceil_mode=True)
+    ya = F.silu(za)
+    yb = bias_pool_silu(xb, bb, pool)
+    assert yb.shape == ya.shape and yb.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ya, yb)
+    w = torch.randn(ya.shape, generator=g).to(dev)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    torch.testing.assert_close(xb.grad, xa.grad, rtol=1e-5, atol=1e-6)
+    assert torch.equal(xb.grad == 0, xa.grad == 0)     # the same cells carry the gradient
+    torch.testing.assert_close(bb.grad, ba.grad, rtol=1e-4, atol=1e-4)
+    # NaN propagates like torch's pooling does; no backward buffers under no_grad
+    xn = x.clone()
+    xn[0, 0, 0, 0] = float("nan")
+    with torch.no_grad():
+        zn = xn + bias.view(1, -1, 1, 1)
+        ref = F.silu(F.max_pool2d(zn, 2, ceil_mode=True) if pool else zn)
+        got = bias_pool_silu(xn, bias, pool)
+    assert torch.equal(torch.isnan(ref), torch.isnan(got)) and bool(torch.isnan(got[0, 0, 0, 0]))
+    assert torch.equal(torch.nan_to_num(ref), torch.nan_to_num(got))
+
+
+def test_qnetv2_fused_blocks_match_the_plain_network(pb):
+    """QNetV2.use_fused_blocks(): same Q-values (bit for bit with TF32 off: the same cuDNN
+    convolutions, the tail arithmetic is identical) and the same gradients as the plain torch
+    module, for the 17-channel and the zero-padded 32-channel input, train and no_grad."""
+    import copy
+
+    import torch
+    from pacbot_rl_b200.models import QNetV2
+
+    dev = torch.device("cuda:0")
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(2)
+        plain = QNetV2(pb.OBS_SHAPE, 5).to(dev).use_channels_last()
+        with torch.no_grad():
+            for p in plain.parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.3)            # non-zero biases
+            for head in (plain.value_head, plain.advantage_head):
+                head[0].weight.normal_(0, 0.3)
+        fused = copy.deepcopy(plain).use_fused_blocks()
+        twin = copy.deepcopy(plain)              # the run-to-run noise of the plain module itself
+        g = torch.Generator(device="cpu").manual_seed(3)
+        obs = ((torch.rand((48,) + pb.OBS_SHAPE, generator=g) < 0.15).float()
+               * torch.rand((48,) + pb.OBS_SHAPE, generator=g)).to(dev)
+        for x in (obs, torch.nn.functional.pad(obs, (0, 0, 0, 0, 0, 15))):
+            with torch.no_grad():
+                assert torch.equal(plain(x), fused(x))
+            for net in (plain, fused, twin):
+                net.zero_grad()
+            qa, qb = plain(x), fused(x)
+            assert torch.equal(qa, qb)
+            (qa ** 2).sum().backward()
+            (qb ** 2).sum().backward()
+            (twin(x) ** 2).sum().backward()
+            # gradients, relative to each tensor's largest entry: 1e-6 (the bias gradients are
+            # summed in another order), or the difference between two runs of the PLAIN module
+            # where that is larger (cuDNN's fp32 weight-gradient kernel for the first convolution
+            # is not run-to-run deterministic: 1.5e-3 between identical plain networks)
+            for (name, pa), pf, pt in zip(plain.named_parameters(), fused.parameters(), twin.parameters()):
+                scale = float(pa.grad.abs().max())
+                err = float((pf.grad - pa.grad).abs().max()) / scale
+                noise = float((pt.grad - pa.grad).abs().max()) / scale
+                assert err <= max(1e-6, 3 * noise), (name, err, noise)
+        # checkpoints are written from a plain copy
+        from pacbot_rl_b200.models import portable_copy
+
+        assert not getattr(portable_copy(fused), "_fused_blocks", False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
