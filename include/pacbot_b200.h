@@ -342,6 +342,14 @@ int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_s
                        const int64_t *t_dev, float *out_dev, int channels_last, int device,
                        void *stream);
 
+/* evaluate_episode's bookkeeping (src/algorithms/train_dqn.py:99-111) after one step of all envs,
+ * one launch: stats_dev is int32 [7][n] with rows 0 score, 1 steps, 2 lives, 3 remaining pellets,
+ * 4 finished (done within max_steps), 5 alive, 6 steps left.  An env that is alive with steps left
+ * counts the step and re-reads score / lives / pellets from its state AFTER the step; done_dev[i]
+ * (pb_step's output for this step) then ends its episode and freezes the row values.  The caller
+ * initialises rows 5 (1) and 6 (max_steps) and zeroes the rest. */
+int pb_eval_track(pb_engine *e, const uint8_t *done_dev, int32_t *stats_dev, void *stream);
+
 /* ---- Q-network convolution-block tail (reference: src/models.py:70-90) -------------------------
  * `Conv2d -> MaxPool2d(2, ceil_mode=True) -> SiLU` (pool != 0) and `Conv2d -> SiLU` (pool == 0) of
  * QNetV2 minus the convolution (which stays cuDNN, run WITHOUT its bias): bias add, 2x2 max pool

@@ -124,6 +124,7 @@ SIGNATURES = {
     "pb_replay_collate": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp,
                                  _vp, _vp, _int, _vp]),
     "pb_replay_slot_obs": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _int, _vp]),
+    "pb_eval_track": (_int, [_vp, _vp, _vp, _vp]),
     "pb_bias_pool_silu_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _int, _vp]),
     "pb_bias_pool_silu_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _int, _vp]),
     "pb_trace_begin": (_int, [_vp, _i64]),

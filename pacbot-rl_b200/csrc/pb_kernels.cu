@@ -224,6 +224,32 @@ k_query(StateView st, int what, int32_t *__restrict__ out) {
 // =============================================================================================
 // k_sample_actions / k_select_actions (policies.py:16-59)
 // =============================================================================================
+// evaluate_episode's per-step bookkeeping (train_dqn.py:99-111) for all envs in one launch.  An env
+// is "live" while its episode has not ended and it has steps of max_steps left; a live env counts
+// the step and re-reads score / lives / remaining pellets AFTER it; the step that ends the episode
+// (done) freezes them.  stats rows: 0 score, 1 steps, 2 lives, 3 pellets_end, 4 finished
+// (done within max_steps), 5 alive, 6 steps left -- int32 [7][n].
+__global__ void __launch_bounds__(STEP_THREADS)
+k_eval_track(StateView st, const uint8_t *__restrict__ done, int32_t *__restrict__ stats) {
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i >= st.n) return;
+    const long long n = st.n;
+    const int left = stats[6 * n + i];
+    const bool live = stats[5 * n + i] != 0 && left > 0;
+    stats[6 * n + i] = left - 1;
+    if (!live) return;
+    EnvR s;
+    load_env(st, i, s);
+    stats[0 * n + i] = s.score;
+    stats[1 * n + i] += 1;
+    stats[2 * n + i] = s.lives;
+    stats[3 * n + i] = s.num_pellets;
+    if (done[i]) {
+        stats[4 * n + i] = 1;
+        stats[5 * n + i] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS)
 k_sample_actions(StateView st, RngParams rp, uint8_t *__restrict__ actions,
                  unsigned long long call_idx) {
@@ -769,6 +795,14 @@ int pb_query(pb_engine *e, int what, int32_t *out_dev, void *stream) {
         return fail(PB_ERR_INVALID_ARG, "pb_query: bad arguments");
     DeviceGuard g(e->device);
     k_query<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(e->st, what, out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_eval_track(pb_engine *e, const uint8_t *done_dev, int32_t *stats_dev, void *stream) {
+    if (!e || !done_dev || !stats_dev) return fail(PB_ERR_INVALID_ARG, "pb_eval_track: null argument");
+    DeviceGuard g(e->device);
+    k_eval_track<<<grid_for(e->n), STEP_THREADS, 0, (cudaStream_t)stream>>>(e->st, done_dev, stats_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -34,10 +34,13 @@ import time
 from pathlib import Path
 from typing import Optional
 
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 
 from . import models
+from ._lib import check
 from .engine import BatchedPacmanGym
 from .policies import EpsilonGreedy, MaxQPolicy
 from .replay_buffer import ReplayBatch, ReplayBuffer, reset_env
@@ -138,14 +141,12 @@ class EpisodeEvaluator:
         self.phase1_policy, self.use_graph = phase1_policy, use_graph
         self.env = BatchedPacmanGym(self.n, False, False, device=device, seed=seed, env_id_base=env_id_base)
         n = self.n
-        z = lambda: torch.zeros(n, dtype=torch.int32, device=device)   # noqa: E731
         self.obs = torch.empty((n, 17, 28, 31), dtype=torch.float32, device=device)
         self.mask = torch.zeros((n, 5), dtype=torch.bool, device=device)
-        self.alive = torch.ones(n, dtype=torch.bool, device=device)
-        self.finished = torch.zeros(n, dtype=torch.bool, device=device)   # done within max_steps
-        self.steps, self.score, self.lives, self.pellets_end = z(), z(), z(), z()
-        self.pellets_start = z()
-        self.left = torch.zeros(1, dtype=torch.int32, device=device)    # steps left of max_steps
+        # per-env bookkeeping, updated by ONE kernel per step (pb_eval_track): rows 0 score,
+        # 1 steps, 2 lives, 3 pellets_end, 4 finished (done within max_steps), 5 alive, 6 steps left
+        self.track = torch.zeros((7, n), dtype=torch.int32, device=device)
+        self.pellets_start = torch.zeros(n, dtype=torch.int32, device=device)
         self.stats_dev = torch.zeros((6, n), dtype=torch.int32, device=device)
         self.stats_host = torch.zeros((6, n), dtype=torch.int32).pin_memory()
         self._graph = None
@@ -158,40 +159,36 @@ class EpisodeEvaluator:
         reset_env(self.env, self.phase1_policy)
         self.pellets_start.copy_(self.env.remaining_pellets())
         self.env.obs(out=self.obs)
-        self.alive.fill_(True)
-        self.finished.fill_(False)
-        for t in (self.steps, self.score, self.pellets_end):
-            t.zero_()
-        self.lives.fill_(3)
-        self.pellets_end.copy_(self.pellets_start)
-        self.left.fill_(self.max_steps)
+        self.env.action_mask(out=self.mask)
+        t = self.track
+        t.zero_()
+        t[2].fill_(3)
+        t[3].copy_(self.pellets_start)
+        t[5].fill_(1)
+        t[6].fill_(self.max_steps)
         self.steps_run = 0
 
     @torch.no_grad()
     def _step(self) -> None:
+        """One greedy step of every env (train_dqn.py:99-105) + its bookkeeping: forward, step,
+        observation encode (one C call) and pb_eval_track."""
         env = self.env
-        live = self.alive & (self.left > 0)
-        actions = self.policy(self.obs, env.action_mask(out=self.mask))
-        _, done = env.step_obs(actions, self.obs)
-        self.steps += live.int()
-        self.score.copy_(torch.where(live, env.score(), self.score))
-        self.lives.copy_(torch.where(live, env.lives(), self.lives))
-        self.pellets_end.copy_(torch.where(live, env.remaining_pellets(), self.pellets_end))
-        ended = live & done
-        self.finished |= ended
-        self.alive &= ~ended
-        self.left -= 1
+        actions = self.policy(self.obs, self.mask)
+        _, done = env.step_obs(actions, self.obs, mask_out=self.mask)
+        check(env._L.pb_eval_track(env._h, C.c_void_p(done.data_ptr()), C.c_void_p(self.track.data_ptr()),
+                                   env._stream()))
 
     @torch.no_grad()
     def _chunk_body(self) -> None:
         for _ in range(self.chunk):
             self._step()
-        finished = self.finished   # `done` of the reference's loop; False if max_steps ran out
-        cleared = finished & (self.lives == 3)
+        t = self.track
+        finished = t[4] != 0             # `done` of the reference's loop; False if max_steps ran out
+        cleared = finished & (t[2] == 3)                                    # train_dqn.py:107
         self.stats_dev.copy_(torch.stack([
-            self.score, self.steps, cleared.int(), self.pellets_start,
-            torch.where(cleared, torch.zeros_like(self.pellets_end), self.pellets_end),
-            finished.int()]))
+            t[0], t[1], cleared.int(), self.pellets_start,
+            torch.where(cleared, torch.zeros_like(t[3]), t[3]),             # train_dqn.py:108
+            t[4]]))
         self.stats_host.copy_(self.stats_dev, non_blocking=True)
 
     def run_chunk(self) -> None:
