@@ -72,8 +72,10 @@ def parse_args():
     ap.add_argument("--no-mcts", action="store_true")
     ap.add_argument("--no-affinity", action="store_true",
                     help="do not pin this rank's host threads to its own slice of the GPU-local CPUs")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "flip", "none"],
-                    help="auto: flip while both state buffers fit L2 comfortably (<= 64 MB), else none; "
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "flip", "chunks", "none"],
+                    help="auto: flip while both state buffers fit L2 comfortably (<= 64 MB), else chunks; "
+                         "chunks: in place, k_step of one 65 536-env chunk beside the encoders of the "
+                         "other chunks (engine-owned streams, one C call per chunk); "
                          "flip: double-buffered state, k_step of step t+1 overlaps k_encode_obs of step t "
                          "(two engine-owned streams, one C call per step); none: k_step then "
                          "k_encode_obs on one stream")
@@ -391,11 +393,14 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
     if mode == "auto":  # double buffering pays while both state buffers stay L2 resident
         # (measured at 2 097 152 envs per GPU, 352 MB of state: flip 123.5, none 124.1-124.2 M
         # env-steps/s -- nothing to win once the state streams from HBM)
-        mode = "flip" if n * STATE_BYTES * 2 <= 64 * 2**20 else "none"
+        mode = "flip" if n * STATE_BYTES * 2 <= 64 * 2**20 else "chunks"
     if mode == "flip" and (len(chunks) != 1 or n < 2):
+        mode = "chunks"
+    if mode == "chunks" and len(chunks) < 2:
         mode = "none"
     flip = mode == "flip"
-    launches_per_step = 1 + len(chunks)
+    chunked = mode == "chunks"
+    launches_per_step = 2 * len(chunks) if chunked else 1 + len(chunks)
     slot_ctr = [0]
     last_slots = []     # (ring slot index, first env, count) of the most recent step
 
@@ -410,6 +415,16 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
             env.rollout_random_step(ring[s][:n], call_idx=call_idx, actions_out=actions, mask_out=mask,
                                     reward_out=reward, done_out=done)
             return
+        if chunked:
+            # one C call per chunk (pb_rollout_chunk_step): the chunk's k_step runs in place on the
+            # engine's step stream beside the encoders of the other chunks
+            for first, cnt in chunks:
+                s = slot_ctr[0] % n_slots
+                slot_ctr[0] += 1
+                last_slots.append((s, first, cnt))
+                env.rollout_chunk_step(first, cnt, ring[s][:cnt], call_idx=call_idx, actions_out=actions,
+                                       mask_out=mask, reward_out=reward, done_out=done)
+            return
         # random valid action per env + PacmanGym.step, one launch (pb_step_random) ...
         env.step_random(call_idx=call_idx, actions_out=actions, mask_out=mask, reward_out=reward,
                         done_out=done)
@@ -421,7 +436,7 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
             env.obs_range(first, cnt, ring[s][:cnt])
 
     def join():
-        if flip:
+        if flip or chunked:
             env.rollout_join()
 
     def barrier():
@@ -484,6 +499,25 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
             e_close.record(env.rollout_streams()[1])
             enc_windows.append((e_open, e_close, per_window, per_window * n))
         join()
+    elif chunked:
+        # one window per sweep: from the end of the sweep's first encoder launch to the end of its
+        # last one (the encoders alternate between two streams; rollout_streams()[1] is the stream
+        # of the launch just enqueued)
+        for _ in range(3):
+            opened = None
+            for first, cnt in chunks:
+                s = slot_ctr[0] % n_slots
+                slot_ctr[0] += 1
+                env.rollout_chunk_step(first, cnt, ring[s][:cnt], call_idx=call, actions_out=actions,
+                                       mask_out=mask, reward_out=reward, done_out=done)
+                if opened is None:
+                    opened = torch.cuda.Event(enable_timing=True)
+                    opened.record(env.rollout_streams()[1])
+            e_close = torch.cuda.Event(enable_timing=True)
+            e_close.record(env.rollout_streams()[1])
+            call += 1
+            enc_windows.append((opened, e_close, len(chunks) - 1, n - chunks[0][1]))
+        join()
     else:
         for _ in range(max(2, min(8, 64 // len(chunks)))):
             env.step_random(call_idx=call, actions_out=actions, mask_out=mask, reward_out=reward,
@@ -525,6 +559,10 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
                 "windows of 16 back-to-back launches, in a separate pass right after the timed loop "
                 "(same calls, k_step of the next step running beside the encoder as in the timed "
                 "loop): the steady-state period of the launch" if flip else
+                "CUDA events on the encode streams from the end of a sweep's first encoder launch to "
+                "the end of its last one (31 back-to-back launches on two alternating streams, the "
+                "k_step launches of the other chunks running beside them), in a separate pass right "
+                "after the timed loop" if chunked else
                 "CUDA events around the encoder launches of a step (one stream), in a separate "
                 "pass right after the timed loop"),
     }
@@ -563,6 +601,13 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
                 s = slot_ctr[0] % n_slots
                 slot_ctr[0] += 1
                 env.step_host(a, obs_out=ring[s][:n], out=outs)
+            elif chunked:  # one C call per chunk: actions H2D, k_step in place, encode, results D2H,
+                # nothing blocks until the sweep's results are awaited
+                for first, cnt in chunks:
+                    s = slot_ctr[0] % n_slots
+                    slot_ctr[0] += 1
+                    env.rollout_chunk_host_step(first, cnt, a, ring[s][:cnt], outs)
+                env.rollout_host_sync()
             else:  # env population larger than a ring slot: encode chunk by chunk; the result
                 # copies of the step travel while the chunks are being encoded
                 env.step_host(a, out=outs, begin_only=True)
@@ -599,7 +644,11 @@ def rollout_leg(cx, n: int, steps: int, warmup: int, ring_gb: float, chunk_envs:
                "ms_per_step_by_rank": [round(1e3 * x / e2e_steps, 5) for x in dt_by_rank],
                "what": ("BatchedPacmanGym.rollout_host_step -> pb_rollout_host_step (pb_step_flip + "
                         "pb_encode_obs on two engine-owned streams)"
-                        if flip else "BatchedPacmanGym.step_host -> pb_step_host"
+                        if flip else "BatchedPacmanGym.rollout_chunk_host_step -> "
+                        "pb_rollout_chunk_host_step per 65 536-env chunk (actions H2D, k_step in place "
+                        "on the step stream, pb_encode_obs_range on two alternating encode streams, "
+                        "results D2H), pb_rollout_host_sync once per step"
+                        if chunked else "BatchedPacmanGym.step_host -> pb_step_host"
                         if len(chunks) == 1 else "BatchedPacmanGym.step_host(begin_only) -> "
                         "pb_step_host_begin, pb_encode_obs_range per ring slot, pb_step_host_end")
                        + ": pinned host actions in, reward/done/mask back to pinned host memory and "
@@ -950,12 +999,15 @@ def main():
     config2 = None
     if not args.no_config2 and n != CONFIG2_ENVS:
         k2 = max(8, args.config2_steps)
-        leg = rollout_leg(cx, CONFIG2_ENVS, k2, 3, args.ring_gb, 65536, "none", args.seed + 1,
+        leg = rollout_leg(cx, CONFIG2_ENVS, k2, 3, args.ring_gb, 65536,
+                          "none" if args.pipeline == "none" else "chunks", args.seed + 1,
                           want_e2e=not args.no_e2e, e2e_steps=k2, verify=not args.no_verify)
         config2 = {
             "workload": f"{CONFIG2_ENVS} envs/GPU x {world} GPU(s) = {CONFIG2_ENVS * world} envs "
                         "(BASELINE.json configs[2]), same step + full f32 observation encode, 32 encoder "
-                        "launches of 65 536 envs per step into the ring",
+                        "launches of 65 536 envs per step into the ring"
+                        + (", each chunk's k_step in place beside the other chunks' encoders"
+                           if leg["mode"] == "chunks" else ""),
             "value": leg["value"], "unit": "env-steps/s", "steps": k2, "warmup": 3,
             "ms_per_step": leg["ms_per_step"],
             "ms_per_step_by_rank": [round(x, 4) for x in leg["ms_by_rank"]],
@@ -1003,6 +1055,9 @@ def main():
             "flip": "engine-owned streams, double-buffered state: k_step of step t+1 overlaps "
                     "k_encode_obs of step t, consecutive encoders alternate between two streams (one "
                     "pb_rollout_random_step call per step)",
+            "chunks": "engine-owned streams, in place: k_step of a chunk runs beside the encoders of "
+                      "the other chunks, consecutive encoders alternate between two streams (one "
+                      "pb_rollout_chunk_step call per chunk)",
             "none": "none: k_step then k_encode_obs on one stream",
         }[main_leg["mode"]],
         "gpu_launches": main_leg["launches_per_step"] * args.steps * world,

@@ -226,6 +226,31 @@ int pb_rollout_random_step(pb_engine *e, uint64_t call_idx, uint8_t *actions_out
 int pb_rollout_host_step(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host,
                          uint8_t *done_host, uint8_t *mask_host, int auto_reset, float *obs_out_dev,
                          int64_t env_stride_floats, void *stream);
+/* The same overlap for env populations walked chunk by chunk (the 2 M-env shard of a GPU: one
+ * encoder launch per ring slot), IN PLACE -- no second state buffer: k_step of envs
+ * [first, first + count) runs on the engine's step stream as soon as the encoder that read these
+ * envs in the previous sweep has finished, i.e. while the encoders of the other chunks stream to
+ * HBM; the chunk's encoder follows on one of two encode streams (alternating).  All arrays are
+ * indexed by the ABSOLUTE env index (like pb_step_random_range); obs_out_dev points at the
+ * observation of env `first`.  actions_dev == NULL draws random valid actions (pb_step_random
+ * semantics, call_idx / actions_out_dev apply), otherwise pb_step semantics with actions produced
+ * on `stream` (the step waits for the work queued there so far).  Per-env results are
+ * bit-identical to pb_step(_random) + pb_encode_obs_range; complete after pb_rollout_join.
+ * Replaces the per-env loop of src/replay_buffer.py:107-137 / the call pair env.rs:216-267 +
+ * env.rs:305-307 at shard scale. */
+int pb_rollout_chunk_step(pb_engine *e, int64_t first, int64_t count, const uint8_t *actions_dev,
+                          uint64_t call_idx, uint8_t *actions_out_dev, int32_t *reward_dev,
+                          uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset,
+                          float *obs_out_dev, int64_t env_stride_floats, void *stream);
+/* Host buffers (full-size arrays, absolute env index): the chunk's actions go host -> device on
+ * the step stream, its reward / done / mask come back on the copy stream while the encoders run.
+ * Nothing blocks: pb_rollout_host_sync returns when the results of every chunk issued so far are
+ * in host memory (and reports an invalid action, PB_ERR_INVALID_ACTION, like pb_step_host). */
+int pb_rollout_chunk_host_step(pb_engine *e, int64_t first, int64_t count,
+                               const uint8_t *actions_host, int32_t *reward_host,
+                               uint8_t *done_host, uint8_t *mask_host, int auto_reset,
+                               float *obs_out_dev, int64_t env_stride_floats, void *stream);
+int pb_rollout_host_sync(pb_engine *e);
 int pb_rollout_join(pb_engine *e, void *stream);
 /* the engine-owned streams (cudaStream_t), e.g. to record timing events on them: the step stream
  * and the encode stream of the MOST RECENT step (encoders alternate between two streams) */

@@ -103,6 +103,9 @@ SIGNATURES = {
     "pb_step_flip": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _int, _vp]),
     "pb_rollout_random_step": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
     "pb_rollout_host_step": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
+    "pb_rollout_chunk_step": (_int, [_vp, _i64, _i64, _vp, _u64, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
+    "pb_rollout_chunk_host_step": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
+    "pb_rollout_host_sync": (_int, [_vp]),
     "pb_rollout_join": (_int, [_vp, _vp]),
     "pb_rollout_streams": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "pb_check_actions": (_int, [_vp, C.POINTER(_i64), _vp]),

@@ -402,6 +402,20 @@ struct pb_engine {
     cudaEvent_t ev_enc_done[2] = {nullptr, nullptr};
     unsigned long long roll_t = 0;
     bool roll_started = false;
+    // pb_rollout_chunk_*: in-place chunked rollout; one record per encoder launch whose env range
+    // a later in-place step of the same envs has to wait for
+    struct RollChunk {
+        long long first, count;     // env range the encoder reads
+        const char *out_lo;         // output range it writes
+        size_t out_bytes;
+        int stream;                 // index into roll_enc
+        cudaEvent_t enc_done;
+    };
+    std::vector<RollChunk> roll_chunks;
+    unsigned long long roll_chunk_ctr = 0;
+    int roll_last_enc = 0;                   // roll_enc index of the most recent encoder launch
+    cudaEvent_t ev_roll_copied = nullptr;    // last result copy of a host chunk
+    bool roll_host_pending = false;
     // pb_trace_*: device timeline of this engine's k_step / k_encode_obs launches
     TraceRec *trace = nullptr;
     long long trace_cap = 0, trace_n = 0;
@@ -551,8 +565,9 @@ int pb_destroy(pb_engine *e) {
     if (e->roll_step) cudaStreamDestroy(e->roll_step);
     for (cudaStream_t s : e->roll_enc)
         if (s) cudaStreamDestroy(s);
+    for (auto &r : e->roll_chunks) cudaEventDestroy(r.enc_done);
     for (cudaEvent_t ev : {e->ev_roll_step, e->ev_roll_fork, e->ev_roll_join, e->ev_enc_done[0],
-                           e->ev_enc_done[1]})
+                           e->ev_enc_done[1], e->ev_roll_copied})
         if (ev) cudaEventDestroy(ev);
     delete e;
     return PB_OK;

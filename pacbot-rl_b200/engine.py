@@ -307,6 +307,68 @@ class BatchedPacmanGym:
             done.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p),
             int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
 
+    def rollout_chunk_step(self, first: int, count: int, obs_out: Optional[torch.Tensor], *,
+                           actions: Optional[torch.Tensor] = None, call_idx: Optional[int] = None,
+                           actions_out: Optional[torch.Tensor] = None,
+                           mask_out: Optional[torch.Tensor] = None,
+                           reward_out: Optional[torch.Tensor] = None,
+                           done_out: Optional[torch.Tensor] = None):
+        """One chunk of the in-place chunked rollout (pb_rollout_chunk_step): step envs
+        [first, first+count) (random valid actions unless `actions`, uint8 [N], is given) and
+        encode their observations into `obs_out` (float32 [count,17,28,31]) on engine-owned
+        streams; the step of a chunk overlaps the encoders of the other chunks.  The arrays stay
+        full size and are indexed by the absolute env index.  Complete after rollout_join()."""
+        n = self.num_envs
+        if first < 0 or count < 0 or first + count > n:
+            raise ValueError("rollout_chunk_step: env range out of bounds")
+        reward = self._new((n,), torch.int32) if reward_out is None else self._check_tensor(
+            reward_out, (n,), torch.int32, "reward_out")
+        done = self._new((n,), torch.uint8) if done_out is None else self._check_tensor(
+            done_out.view(torch.uint8), (n,), torch.uint8, "done_out")
+        aptr = None if actions_out is None else C.c_void_p(self._check_tensor(
+            actions_out, (n,), torch.uint8, "actions_out").data_ptr())
+        iptr = None if actions is None else C.c_void_p(self._check_tensor(
+            actions, (n,), torch.uint8, "actions").data_ptr())
+        mptr = None if mask_out is None else C.c_void_p(self._check_tensor(
+            mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        optr = None if obs_out is None else C.c_void_p(self._check_tensor(
+            obs_out, (count,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
+        if call_idx is None:
+            call_idx = self._sample_calls
+        check(self._L.pb_rollout_chunk_step(self._h, int(first), int(count), iptr, int(call_idx), aptr,
+                                            C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()),
+                                            mptr, int(self.auto_reset), optr, OBS_FLOATS, self._stream()))
+        return reward, done.view(torch.bool)
+
+    def rollout_chunk_host_step(self, first: int, count: int, actions: np.ndarray,
+                                obs_out: Optional[torch.Tensor], out: tuple) -> None:
+        """rollout_chunk_step with HOST buffers (pb_rollout_chunk_host_step): `actions` uint8 [N]
+        and `out` = (reward int32[N], done 1-byte[N], mask 1-byte[N,5] or None) are full-size host
+        arrays (pinned for asynchronous copies); only [first, first+count) is read / written.
+        Returns at once; the results are on the host after rollout_host_sync()."""
+        n = self.num_envs
+        reward, done, mask = out
+        if (not isinstance(actions, np.ndarray) or actions.dtype != np.uint8 or actions.shape != (n,)
+                or not actions.flags.c_contiguous or reward.shape != (n,) or reward.dtype != np.int32
+                or done.shape != (n,) or done.dtype.itemsize != 1
+                or (mask is not None and (mask.shape != (n, NUM_ACTIONS) or mask.dtype.itemsize != 1))):
+            raise ValueError("rollout_chunk_host_step: expected contiguous uint8[N] actions and "
+                             "(int32[N], 1-byte[N], 1-byte[N,5] or None) outputs")
+        if first < 0 or count < 0 or first + count > n:
+            raise ValueError("rollout_chunk_host_step: env range out of bounds")
+        optr = None if obs_out is None else C.c_void_p(self._check_tensor(
+            obs_out, (count,) + OBS_SHAPE, torch.float32, "obs_out").data_ptr())
+        check(self._L.pb_rollout_chunk_host_step(
+            self._h, int(first), int(count), actions.ctypes.data_as(C.c_void_p),
+            reward.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p),
+            None if mask is None else mask.ctypes.data_as(C.c_void_p), int(self.auto_reset), optr,
+            OBS_FLOATS, self._stream()))
+
+    def rollout_host_sync(self) -> None:
+        """Block until the results of every rollout_chunk_host_step issued so far are on the host;
+        raises ValueError("Invalid action") if one of them carried an action > 4."""
+        check(self._L.pb_rollout_host_sync(self._h))
+
     def rollout_join(self) -> None:
         """Make the current stream wait for every pipelined rollout step enqueued so far."""
         check(self._L.pb_rollout_join(self._h, self._stream()))

@@ -279,3 +279,106 @@ def test_split_host_step_matches_step_host(pb):
         b.step_host_end()
     after = b.get_state()
     assert after[77].tobytes() == before[77].tobytes()       # env.rs:83-88: env untouched
+
+
+@pytest.mark.parametrize("n,chunk", [(5000, 2048), (4096, 1024), (777, 100)])
+def test_chunked_rollout_matches_sequential(pb, n, chunk):
+    """pb_rollout_chunk_step: the shard is walked chunk by chunk, every chunk's k_step in place on
+    the step stream beside the encoders of the other chunks (two encode streams).  Per env the
+    sequence of launches is unchanged, so state / reward / done / mask / actions / observations are
+    those of step_random + obs, sweep after sweep -- also when consecutive encoders share a buffer."""
+    sweeps = 24
+    a, b = make(pb, n, seed=61), make(pb, n, seed=61)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = [torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0") for _ in range(2)]
+    rew = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    done = torch.empty(n, dtype=torch.bool, device="cuda:0")
+    mask = torch.empty((n, 5), dtype=torch.bool, device="cuda:0")
+    acts = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+    chunks = [(f, min(chunk, n - f)) for f in range(0, n, chunk)]
+    for t in range(sweeps):
+        exp_actions = a.sample_actions(call_idx=t)
+        r_a, d_a = a.step(exp_actions)
+        a.obs(obs_a)
+        for first, cnt in chunks:
+            b.rollout_chunk_step(first, cnt, obs_b[t & 1][first:first + cnt], call_idx=t, actions_out=acts,
+                                 mask_out=mask, reward_out=rew, done_out=done)
+        if t % 7 == 6 or t == sweeps - 1:
+            b.rollout_join()
+            torch.cuda.synchronize()
+            assert torch.equal(exp_actions, acts) and torch.equal(r_a, rew) and torch.equal(d_a, done), f"sweep {t}"
+            assert torch.equal(a.action_mask(), mask)
+            assert a.get_state().tobytes() == b.get_state().tobytes(), f"state differs at sweep {t}"
+            assert torch.equal(obs_a, obs_b[t & 1]), f"observations differ at sweep {t}"
+    # every chunk into the SAME small buffer: the encoders must stay ordered, the last one wins
+    small = torch.empty((chunk,) + pb.OBS_SHAPE, device="cuda:0")
+    a.step_random(call_idx=sweeps)
+    a.obs(obs_a)
+    for first, cnt in chunks:
+        b.rollout_chunk_step(first, cnt, small[:cnt], call_idx=sweeps)
+    b.rollout_join()
+    torch.cuda.synchronize()
+    first, cnt = chunks[-1]
+    assert torch.equal(small[:cnt], obs_a[first:first + cnt])
+    if len(chunks) > 1 and cnt < chunk:
+        f2 = chunks[-2][0]
+        assert torch.equal(small[cnt:], obs_a[f2 + cnt:f2 + chunk])
+    # with explicit device actions, and mixed with the double-buffered form on the same engine
+    for t in range(sweeps + 1, sweeps + 7):
+        exp_actions = a.sample_actions(call_idx=t)
+        r_a, d_a = a.step(exp_actions)
+        a.obs(obs_a)
+        if t % 3 == 0:
+            b.rollout_random_step(obs_b[t & 1], call_idx=t, reward_out=rew, done_out=done, mask_out=mask)
+        else:
+            for first, cnt in chunks:
+                b.rollout_chunk_step(first, cnt, obs_b[t & 1][first:first + cnt], actions=exp_actions,
+                                     mask_out=mask, reward_out=rew, done_out=done)
+    b.rollout_join()
+    torch.cuda.synchronize()
+    assert torch.equal(r_a, rew) and torch.equal(d_a, done) and torch.equal(a.action_mask(), mask)
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+    assert torch.equal(obs_a, obs_b[t & 1])
+
+
+def test_chunked_host_rollout_matches_step_host(pb):
+    """pb_rollout_chunk_host_step / pb_rollout_host_sync: pinned host actions in, reward / done /
+    mask back per chunk on the copy stream, one host synchronisation per sweep == pb_step_host;
+    an invalid action is reported by the sync and leaves that env untouched."""
+    n, chunk, sweeps = 5000, 1536, 18
+    a, b = make(pb, n, seed=19), make(pb, n, seed=19)
+    rng = np.random.default_rng(6)
+    obs_a = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    obs_b = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    keep = [torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.bool).pin_memory(),
+            torch.empty((n, 5), dtype=torch.bool).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()]
+    outs = tuple(t.numpy() for t in keep[:3])
+    act_buf = keep[3].numpy()
+    chunks = [(f, min(chunk, n - f)) for f in range(0, n, chunk)]
+    for t in range(sweeps):
+        act_buf[:] = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(act_buf.copy(), obs_out=obs_a)
+        for first, cnt in chunks:
+            b.rollout_chunk_host_step(first, cnt, act_buf, obs_b[first:first + cnt], outs)
+        b.rollout_host_sync()
+        assert np.array_equal(r_a, outs[0]) and np.array_equal(d_a, outs[1]) and np.array_equal(m_a, outs[2]), f"sweep {t}"
+        if t % 5 == 4 or t == sweeps - 1:
+            b.rollout_join()
+            torch.cuda.synchronize()
+            assert torch.equal(obs_a, obs_b), f"observations differ at sweep {t}"
+            assert a.get_state().tobytes() == b.get_state().tobytes()
+    before = b.get_state()
+    act_buf[:] = rng.integers(0, 5, n, dtype=np.uint8)
+    act_buf[1700] = 7
+    for first, cnt in chunks:
+        b.rollout_chunk_host_step(first, cnt, act_buf, obs_b[first:first + cnt], outs)
+    with pytest.raises(ValueError, match="Invalid action"):
+        b.rollout_host_sync()
+    b.rollout_join()
+    torch.cuda.synchronize()
+    assert b.get_state()[1700:1701].tobytes() == before[1700:1701].tobytes()   # env.rs:83-88
+    act_buf[1700] = 0
+    for first, cnt in chunks:
+        b.rollout_chunk_host_step(first, cnt, act_buf, obs_b[first:first + cnt], outs)
+    b.rollout_host_sync()                                                      # and it keeps working
+    b.rollout_join()
