@@ -909,6 +909,44 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
     return out
 
 
+def dropin_leg(cx, seed: int, steps: int = 3000):
+    """configs[0]'s call pattern on the B200 engine: ONE env object driven the reference's way
+    (src/replay_buffer.py:107-137 -- action_mask(), step(), is_done(), obs_numpy(), action_mask()
+    per env-step, reset() on done), through the per-env drop-in `PacmanGym`.  Wall clock per
+    env-step; the old path (one device round trip per question) is timed beside it."""
+    np, pb = cx.np, cx.pb
+    rng = np.random.default_rng(seed)
+
+    def drive(gym, k, ask):
+        t0 = time.perf_counter()
+        for _ in range(k):
+            mask = ask["mask"](gym)
+            valid = [a for a in range(5) if mask[a]]
+            _reward, done = gym.step(valid[int(rng.integers(len(valid)))])
+            if ask["done"](gym) or done:
+                gym.reset()
+            ask["obs"](gym)
+            ask["mask"](gym)
+        return (time.perf_counter() - t0) / k
+
+    gym = pb.PacmanGym(True, True, device=cx.dev, seed=seed, env_id=777)
+    gym.reset()
+    new_way = {"mask": lambda g: g.action_mask(), "done": lambda g: g.is_done(), "obs": lambda g: g.obs_numpy()}
+    surface = pb.gym._SingleEnvSurface     # the general per-question entry points (what views use)
+    old_way = {"mask": lambda g: surface.action_mask(g), "done": lambda g: surface.is_done(g),
+               "obs": lambda g: surface.obs_numpy(g)}
+    drive(gym, 200, new_way)
+    us_new = 1e6 * drive(gym, steps, new_way)
+    drive(gym, 50, old_way)
+    us_old = 1e6 * drive(gym, max(200, steps // 10), old_way)
+    return {"us_per_env_step": us_new, "env_steps_per_sec": 1e6 / us_new,
+            "us_per_env_step_one_round_trip_per_question": us_old,
+            "what": "pacbot_rl_b200.PacmanGym, one env per object: action_mask + step + is_done + "
+                    "obs_numpy + action_mask per env-step as replay_buffer.py:107-137 calls them; step() "
+                    "is ONE device round trip (pb_step_snapshot_host) and the getters answer from its "
+                    "snapshot"}
+
+
 def obs_to_host_leg(cx, env, n: int):
     """The reference loop's own per-env call (`obs_numpy`, env.rs:305-307) at batch scale: encode +
     D2H of full observations into PINNED host memory, chunked and double buffered
@@ -1079,6 +1117,7 @@ def main():
         # this engine's per-env `PacmanGym` as its `pacbot_rs.PacmanGym` (32 one-env engines, the
         # reference's own host loop: obs_numpy / action_mask / step per env per step)
         dqn["reference_loop_on_b200_engine"] = reference_dqn(args, env="product")
+        dqn["dropin_per_env"] = dropin_leg(cx, args.seed)
         line["dqn"] = dqn
     if dqn_dp is not None:
         line["dqn_dp"] = dqn_dp

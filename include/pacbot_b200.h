@@ -256,6 +256,19 @@ int pb_rollout_join(pb_engine *e, void *stream);
  * and the encode stream of the MOST RECENT step (encoders alternate between two streams) */
 int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream);
 
+/* ---- the per-env drop-in's round trip (engines of up to PB_SNAPSHOT_MAX_ENVS envs) ------------ */
+/* What the reference's loop reads per env and step (src/replay_buffer.py:107-137,
+ * src/algorithms/train_dqn.py:95-113) in ONE stream synchronisation: optionally step every env
+ * with `actions_host` (uint8 [n]; NULL = no step; pb_step semantics, reward int32 [n] / done
+ * uint8 [n] returned), then info_host int32 [n][8] = score, lives, is_done, first_ai_done,
+ * remaining_pellets, ticks_per_step, level, curr_ticks (env.rs:269-289), mask_host uint8 [n][5]
+ * (env.rs:293-302) and obs_host float [n][17][28][31] (env.rs:305-307); any output may be NULL.
+ * Returns PB_ERR_INVALID_ACTION if an action was > 4 (that env untouched, env.rs:83-88). */
+#define PB_SNAPSHOT_MAX_ENVS 1024
+int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_reset,
+                          int32_t *reward_host, uint8_t *done_host, int32_t *info_host,
+                          uint8_t *mask_host, float *obs_host, void *stream);
+
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */
 int pb_check_actions(pb_engine *e, int64_t *first_bad_env, void *stream);

@@ -221,6 +221,35 @@ k_query(StateView st, int what, int32_t *__restrict__ out) {
     out[i] = v;
 }
 
+// Everything the reference's per-env loop reads besides the observation (env.rs:269-302), for a
+// small engine, in one launch: info[i][0..7] = score, lives, is_done, first_ai_done,
+// remaining_pellets, ticks_per_step, level, curr_ticks; the action mask; and the engine's
+// invalid-action record, which is handed over and cleared.
+__global__ void __launch_bounds__(STEP_THREADS)
+k_snapshot(StateView st, int32_t *__restrict__ info, uint8_t *__restrict__ mask_out,
+           unsigned long long *bad_action, unsigned long long *__restrict__ bad_out) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+    if (i == 0) {
+        *bad_out = *bad_action;
+        *bad_action = ~0ull;
+    }
+    if (i >= st.n) return;
+    EnvR s;
+    load_env(st, i, s);
+    int32_t *o = info + i * 8;
+    o[0] = s.score;
+    o[1] = s.lives;
+    o[2] = is_done(s);
+    o[3] = first_ai_done(st, i, s);
+    o[4] = s.num_pellets;
+    o[5] = s.tps;
+    o[6] = s.level;
+    o[7] = (int)s.ticks;
+    write_mask(mask_out, i, action_mask_bits(s, s_walls));
+}
+
 // =============================================================================================
 // k_sample_actions / k_select_actions (policies.py:16-59)
 // =============================================================================================
@@ -416,6 +445,10 @@ struct pb_engine {
     int roll_last_enc = 0;                   // roll_enc index of the most recent encoder launch
     cudaEvent_t ev_roll_copied = nullptr;    // last result copy of a host chunk
     bool roll_host_pending = false;
+    // pb_step_snapshot_host: one contiguous device block + its pinned mirror, and pinned actions
+    // that k_step reads in place (zero copy)
+    unsigned char *snap_dev = nullptr, *snap_pin = nullptr;
+    uint8_t *snap_actions_pin = nullptr;
     // pb_trace_*: device timeline of this engine's k_step / k_encode_obs launches
     TraceRec *trace = nullptr;
     long long trace_cap = 0, trace_n = 0;
@@ -558,6 +591,9 @@ int pb_destroy(pb_engine *e) {
     }
     cudaFree(e->tickets);
     cudaFree(e->trace);
+    cudaFree(e->snap_dev);
+    if (e->snap_pin) cudaFreeHost(e->snap_pin);
+    if (e->snap_actions_pin) cudaFreeHost(e->snap_actions_pin);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
     if (e->ev_host_copied) cudaEventDestroy(e->ev_host_copied);
@@ -1104,6 +1140,64 @@ int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host
         }
     }
     return pb_step_host_end(e, stream);
+}
+
+// The small-batch host round trip of the per-env drop-in (gym.py): what the reference's loop does
+// per env and step -- step(), is_done(), obs_numpy(), action_mask(), score() ...
+// (src/replay_buffer.py:107-137, src/algorithms/train_dqn.py:95-113) -- as ONE stream
+// synchronisation: k_step reads the actions in place from pinned host memory, k_snapshot and the
+// encoder fill one contiguous device block, one copy brings it to its pinned mirror.
+int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_reset,
+                          int32_t *reward_host, uint8_t *done_host, int32_t *info_host,
+                          uint8_t *mask_host, float *obs_host, void *stream) {
+    if (!e) return fail(PB_ERR_INVALID_ARG, "pb_step_snapshot_host: null engine");
+    if (e->n > PB_SNAPSHOT_MAX_ENVS)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_snapshot_host: engines of up to 1024 envs");
+    if (actions_host && (!reward_host || !done_host))
+        return fail(PB_ERR_INVALID_ARG, "pb_step_snapshot_host: a step needs reward / done outputs");
+    DeviceGuard g(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)e->n;
+    // block layout: bad u64 | info int32[n][8] | reward int32[n] | done u8[n] | mask u8[n][5] | pad | obs
+    const size_t off_bad = 0, off_info = 8, off_reward = off_info + 32 * n, off_done = off_reward + 4 * n;
+    const size_t off_mask = off_done + n, small = (off_mask + 5 * n + 15) & ~(size_t)15;
+    const size_t total = small + sizeof(float) * OBS_FLOATS * n;
+    if (!e->snap_dev) {
+        PB_CUDA(cudaMalloc(&e->snap_dev, total));
+        PB_CUDA(cudaMallocHost(&e->snap_pin, total));
+        PB_CUDA(cudaMallocHost(&e->snap_actions_pin, n));
+    }
+    unsigned char *d = e->snap_dev, *h = e->snap_pin;
+    if (actions_host) {
+        // the previous call synchronised the stream: the pinned actions are free to overwrite
+        memcpy(e->snap_actions_pin, actions_host, n);
+        k_step<<<grid_for(e->n), STEP_THREADS, 0, s>>>(
+            e->st, e->st, rng_params(e), e->snap_actions_pin,
+            reinterpret_cast<int32_t *>(d + off_reward), d + off_done, nullptr, auto_reset, e->bad_action, nullptr, 0ull, 0ll, e->n,
+            trace_slot(e, PB_TRACE_STEP));
+        PB_CUDA(cudaGetLastError());
+    }
+    k_snapshot<<<grid_for(e->n), STEP_THREADS, 0, s>>>(
+        e->st, reinterpret_cast<int32_t *>(d + off_info), d + off_mask, e->bad_action,
+        reinterpret_cast<unsigned long long *>(d + off_bad));
+    PB_CUDA(cudaGetLastError());
+    if (obs_host) {
+        int rc = launch_encode(e, reinterpret_cast<float *>(d + small), OBS_FLOATS, 0, e->n, s);
+        if (rc != PB_OK) return rc;
+    }
+    PB_CUDA(cudaMemcpyAsync(h, d, obs_host ? total : small, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    if (actions_host) {
+        memcpy(reward_host, h + off_reward, 4 * n);
+        memcpy(done_host, h + off_done, n);
+    }
+    if (info_host) memcpy(info_host, h + off_info, 32 * n);
+    if (mask_host) memcpy(mask_host, h + off_mask, 5 * n);
+    if (obs_host) memcpy(obs_host, h + small, sizeof(float) * OBS_FLOATS * n);
+    unsigned long long bad;
+    memcpy(&bad, h + off_bad, sizeof(bad));
+    if (bad != ~0ull) return fail(PB_ERR_INVALID_ACTION, "Invalid action");
+    return PB_OK;
 }
 
 // Observations straight to host memory, PCIe-bound instead of pageable-bound: the range is cut

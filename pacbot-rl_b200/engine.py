@@ -562,6 +562,32 @@ class BatchedPacmanGym:
             check(self._L.pb_step_host(*args, optr, OBS_FLOATS, self._stream()))
         return reward, done, mask
 
+    def step_snapshot(self, actions: Optional[np.ndarray] = None, want_obs: bool = True) -> dict:
+        """The per-env drop-in's round trip (pb_step_snapshot_host, engines of <= 1024 envs): step
+        every env with the uint8 [N] host `actions` (None: no step) and read back, in ONE stream
+        synchronisation, everything the reference's loop asks an env for afterwards.  Returns a
+        dict of host arrays owned by the engine and overwritten by the next call: `reward` int32
+        [N] / `done` bool [N] (only after a step), `info` int32 [N, 8] (score, lives, is_done,
+        first_ai_done, remaining_pellets, ticks_per_step, level, curr_ticks), `mask` bool [N, 5],
+        `obs` float32 [N, 17, 28, 31] (if want_obs)."""
+        b = getattr(self, "_snap_bufs", None)
+        if b is None:
+            n = self.num_envs
+            b = self._snap_bufs = {
+                "reward": np.zeros(n, np.int32), "done": np.zeros(n, np.bool_),
+                "info": np.zeros((n, 8), np.int32), "mask": np.zeros((n, NUM_ACTIONS), np.bool_),
+                "obs": np.zeros((n,) + OBS_SHAPE, np.float32), "actions": np.zeros(n, np.uint8)}
+            self._snap_ptrs = {k: v.ctypes.data_as(C.c_void_p) for k, v in b.items()}
+        p = self._snap_ptrs
+        aptr = None
+        if actions is not None:
+            b["actions"][:] = actions
+            aptr = p["actions"]
+        check(self._L.pb_step_snapshot_host(
+            self._h, aptr, int(self.auto_reset), p["reward"], p["done"], p["info"], p["mask"],
+            p["obs"] if want_obs else None, self._stream()))
+        return b
+
     def step_host_end(self):
         """Wait for the results of `step_host(..., begin_only=True)` -> (reward, done, mask)."""
         check(self._L.pb_step_host_end(self._h, self._stream()))

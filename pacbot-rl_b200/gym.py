@@ -113,6 +113,7 @@ class PacmanGym(_SingleEnvSurface):
             1, bool(random_start), bool(random_ticks), device=device, seed=int(seed),
             env_id_base=int(env_id))
         self._index = 0
+        self._snap = None
 
     @property
     def random_start(self) -> bool:  # #[pyo3(get, set)] env.rs:100-101
@@ -121,17 +122,56 @@ class PacmanGym(_SingleEnvSurface):
     @random_start.setter
     def random_start(self, value: bool) -> None:
         self._batch.random_start = bool(value)
+        self._snap = None
+
+    # ---- one device round trip per mutation --------------------------------------------------
+    # The reference's loop asks an env several questions between two mutations (`is_done()`,
+    # `obs_numpy()`, `action_mask()`, `score()` ...: src/replay_buffer.py:107-137,
+    # src/algorithms/train_dqn.py:95-113).  `step()` brings everything back with the step's own
+    # synchronisation (pb_step_snapshot_host: k_step, k_snapshot, k_encode_obs, one copy), and the
+    # getters answer from that snapshot until the env changes again.
+    def _snapshot(self) -> dict:
+        if self._snap is None:
+            self._snap = self._batch.step_snapshot(None, want_obs=True)
+        return self._snap
+
+    def invalidate(self) -> None:
+        """Forget the host snapshot (call after changing the env through `_batch` directly)."""
+        self._snap = None
 
     def reset(self) -> None:  # env.rs:140-212
         self._batch.reset()
+        self._snap = None
 
     def step(self, action: int) -> tuple[int, bool]:  # env.rs:216-267
         if not isinstance(action, (int, np.integer)):
             raise TypeError(f"'{type(action).__name__}' object cannot be interpreted as an integer")
         if not 0 <= int(action) <= 255:
             raise OverflowError("out of range integral type conversion attempted")
-        reward, done, _ = self._batch.step_host(np.array([int(action)], np.uint8), want_mask=False)
-        return int(reward[0]), bool(done[0])
+        self._snap = None
+        self._snap = snap = self._batch.step_snapshot(np.array([int(action)], np.uint8), want_obs=True)
+        return int(snap["reward"][0]), bool(snap["done"][0])
+
+    def score(self) -> int:  # env.rs:269-271
+        return int(self._snapshot()["info"][0, 0])
+
+    def lives(self) -> int:  # env.rs:273-275
+        return int(self._snapshot()["info"][0, 1])
+
+    def is_done(self) -> bool:  # env.rs:277-279
+        return bool(self._snapshot()["info"][0, 2])
+
+    def first_ai_done(self) -> bool:  # env.rs:281-285
+        return bool(self._snapshot()["info"][0, 3])
+
+    def remaining_pellets(self) -> int:  # env.rs:287-289
+        return int(self._snapshot()["info"][0, 4])
+
+    def action_mask(self) -> list[bool]:  # env.rs:293-302
+        return self._snapshot()["mask"][0].tolist()
+
+    def obs_numpy(self) -> np.ndarray:  # env.rs:305-307: fresh (17, 28, 31) float32 array
+        return self._snapshot()["obs"][0].copy()
 
     def clone(self) -> "PacmanGym":  # #[derive(Clone)] env.rs:96
         other = PacmanGym(False, False, device=self._batch.device, seed=self._batch.seed,

@@ -282,6 +282,7 @@ class MCTSContext:
 
     def reset(self) -> None:  # mcts.rs:138-145
         self._mcts.reset()
+        self._gym.invalidate()   # the tree engine changed the env behind the drop-in's snapshot
 
     def take_action(self, action: int) -> tuple[int, bool]:  # mcts.rs:153-170
         if self._gym.is_done():
@@ -289,6 +290,7 @@ class MCTSContext:
         if not 0 <= int(action) <= 4:
             raise ValueError("Invalid action")
         reward, done, _ = self._mcts.take_action(torch.tensor([int(action)], dtype=torch.uint8))
+        self._gym.invalidate()
         return int(reward[0]), bool(done[0])
 
     def best_action(self) -> int:  # mcts.rs:173-175

@@ -144,6 +144,24 @@ class HostEnv:
             raise ValueError("Invalid action")   # PB_ERR_INVALID_ACTION through _lib.check
         return reward, done.astype(bool), (mask.astype(bool) if want_mask else None)
 
+    def step_snapshot(self, actions=None, want_obs=True):   # pb_step_snapshot_host
+        n = self.num_envs
+        out = {}
+        if actions is not None:
+            r, d, _ = self.step_host(actions, want_mask=False)
+            out["reward"], out["done"] = r, d
+        st = self.get_state()
+        info = np.zeros((n, 8), np.int32)
+        info[:, 0], info[:, 1] = st["curr_score"], st["curr_lives"]
+        info[:, 2] = (st["curr_lives"] < 3) | (st["curr_level"] != 1)
+        info[:, 3] = self.first_ai_done().numpy()
+        info[:, 4] = st["num_pellets"]
+        out["info"] = info
+        out["mask"] = self.action_mask().numpy()
+        if want_obs:
+            out["obs"] = self.obs_numpy()
+        return out
+
     def obs_numpy(self, first=0, count=None):   # pb_obs_host
         count = self.num_envs - first if count is None else count
         out = torch.empty((count, 17, 28, 31), dtype=torch.float32)

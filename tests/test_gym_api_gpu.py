@@ -213,3 +213,79 @@ def test_step_random_equals_sample_then_step(pb):
         r_b, d_b = b_env.step(sampled)
         assert torch.equal(acts, sampled) and torch.equal(r_a, r_b) and torch.equal(d_a, d_b)
     assert np.array_equal(a_env.get_state(), b_env.get_state())
+
+
+def test_step_snapshot_matches_separate_calls(pb):
+    """pb_step_snapshot_host (the per-env drop-in's one round trip per step): reward / done / info /
+    mask / observation equal what the separate entry points return for the same envs and actions;
+    an invalid action raises like pb_step_host and leaves that env untouched; a snapshot without
+    a step changes nothing."""
+    import torch
+
+    n = 37
+    mk = lambda: pb.BatchedPacmanGym(n, np.arange(n) < n // 2, True, device="cuda:0", seed=3)  # noqa: E731
+    a, b = mk(), mk()
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        acts = rng.integers(0, 5, n, dtype=np.uint8)
+        r_a, d_a, m_a = a.step_host(acts)
+        snap = b.step_snapshot(acts)
+        assert np.array_equal(snap["reward"], r_a) and np.array_equal(snap["done"], d_a), t
+        assert np.array_equal(snap["mask"], m_a)
+        info = snap["info"]
+        assert np.array_equal(info[:, 0], a.score().cpu().numpy())
+        assert np.array_equal(info[:, 1], a.lives().cpu().numpy())
+        assert np.array_equal(info[:, 2].astype(bool), a.is_done().cpu().numpy())
+        assert np.array_equal(info[:, 3].astype(bool), a.first_ai_done().cpu().numpy())
+        assert np.array_equal(info[:, 4], a.remaining_pellets().cpu().numpy())
+        assert np.array_equal(info[:, 5], a.ticks_per_step().cpu().numpy())
+        assert np.array_equal(snap["obs"].view(np.uint32), a.obs().cpu().numpy().view(np.uint32))
+        if t % 9 == 8:
+            done = torch.from_numpy(d_a.copy()).to("cuda:0")
+            a.reset(done)
+            b.reset(done)
+    before = b.get_state()
+    again = b.step_snapshot(None, want_obs=False)          # no step: nothing moves
+    assert b.get_state().tobytes() == before.tobytes() == a.get_state().tobytes()
+    assert np.array_equal(again["info"][:, 0], a.score().cpu().numpy())
+    acts = rng.integers(0, 5, n, dtype=np.uint8)
+    acts[11] = 6
+    with pytest.raises(ValueError, match="Invalid action"):
+        b.step_snapshot(acts)
+    assert b.get_state()[11].tobytes() == before[11].tobytes()      # env.rs:83-88: env untouched
+    b.step_snapshot(np.zeros(n, np.uint8))                 # the record was cleared: works again
+    with pytest.raises(ValueError):
+        pb.BatchedPacmanGym(2000, False, False, device="cuda:0").step_snapshot(None)
+
+
+def test_pacman_gym_snapshot_follows_every_mutation(pb):
+    """The drop-in answers its getters from the snapshot of its last mutation: step / reset / the
+    random_start setter / clone / MCTSContext.take_action must all refresh it."""
+    gym = pb.PacmanGym(False, False, seed=5, env_id=0)
+    gym.reset()
+    p0, o0 = gym.remaining_pellets(), gym.obs_numpy()
+    for a in (3, 3, 3):
+        gym.step(a)
+    st = gym._batch.get_state()[0]
+    assert gym.score() == int(st["curr_score"]) and gym.remaining_pellets() == int(st["num_pellets"]) < p0
+    assert not np.array_equal(gym.obs_numpy(), o0)
+    twin = gym.clone()
+    assert twin.score() == gym.score() and np.array_equal(twin.obs_numpy(), gym.obs_numpy())
+    twin.step(3)
+    assert gym.remaining_pellets() == int(st["num_pellets"])        # the original did not move
+    gym.reset()
+    assert gym.remaining_pellets() == p0 and gym.score() == 0 and np.array_equal(gym.obs_numpy(), o0)
+
+    def evaluator(obs, mask):
+        return np.zeros(len(obs), np.float32), np.full((len(obs), 5), 0.2, np.float32)
+
+    ctx = pb.mcts.MCTSContext(gym, evaluator)
+    root0 = ctx.root_obs_numpy()
+    assert np.array_equal(root0, o0)
+    ctx.take_action(3)
+    assert not np.array_equal(ctx.root_obs_numpy(), root0)
+    assert np.array_equal(ctx.root_obs_numpy(), ctx.env.obs_numpy())
+    ctx.reset()
+    assert np.array_equal(ctx.root_obs_numpy(), ctx.env.obs_numpy())
