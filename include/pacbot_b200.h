@@ -406,6 +406,18 @@ int pb_bias_pool_silu_bwd(const float *dy_dev, const float *z_dev, const uint8_t
                           int64_t h, int64_t w, int64_t c, int pool, float *dx_out_dev,
                           float *dbias_out_dev, int device, void *stream);
 
+/* The head of QNetV2 / NetV2 (src/models.py:92-110, :139-141) for inference, one launch: global
+ * max over the map of the last convolution's output x (float32 [n][hw][128], channels-last,
+ * WITHOUT its bias) + conv_bias, SiLU, Linear 128 -> 256 (w1 [256][128], b1), SiLU, then
+ * dueling != 0: Q = V - mean(A) + A with wv [1][256], bv [1], wa [n_out][256], ba [n_out];
+ * dueling == 0: one plain linear layer wa / ba (wv / bv unused).  out float32 [n][n_out],
+ * n_out <= 7.  float32 arithmetic, summation order differs from cuBLAS (rtol 1e-5). */
+int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                     const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                     const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
+                     float *out_dev, int device, void *stream);
+
+
 /* ---- device timeline (diagnostics; no counterpart in the reference) --------------------------
  * Between pb_trace_begin and pb_trace_end every k_step / k_encode_obs launch of the engine
  * records, in nanoseconds of the GPU's %globaltimer: begin = first CTA started, ready = first CTA

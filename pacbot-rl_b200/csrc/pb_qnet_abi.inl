@@ -142,6 +142,105 @@ k_bias_pool_silu_bwd(const float4 *__restrict__ dy, const float4 *__restrict__ z
     }
 }
 
+
+// ---- the head of QNetV2 / NetV2 as one kernel (forward, inference) -----------------------------
+// reference models.py:92-110: `AdaptiveMaxPool2d((1, 1)) -> Flatten -> SiLU -> Linear(128, 256) ->
+// SiLU`, then the dueling combine `V - mean(A) + A` of two linear heads (QNetV2) or one plain
+// linear layer (NetV2, models.py:139-141).  torch runs this as ~11 launches per forward (max-pool,
+// silu, addmm + epilogue, silu, two addmm, mean, sub, add, the grouped convolution's bias add) on
+// [N, 128] / [N, 256] tensors: at batch 32 (the four policy forwards of an iteration, every
+// evaluation step) and 512 (the two target forwards) that is launch latency, not work.  Here:
+//   p[c] = max over the map of x[n, :, c] + conv_bias[c]   (fl(a + b) is monotone in a: equals
+//          the max of the biased map, with torch's NaN rule)
+//   a = SiLU(p); u = W1 a + b1; f = SiLU(u); head rows = Wh f + bh; Q = V - mean(A) + A
+// One CTA handles S samples: W1 (128 KB, L2 resident) is read once per CTA, row by row, a warp
+// per row with the 128 inputs split over the lanes (coalesced 512 B loads) and a shuffle tree.
+// float32 FMA throughout; the sums are ordered differently from cuBLAS (tests: rtol 1e-5).
+constexpr int HEAD_C = 128, HEAD_H = 256, HEAD_THREADS = 256, HEAD_MAX_OUT = 8;
+
+template <int S>
+__global__ void __launch_bounds__(HEAD_THREADS)
+k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ conv_bias,
+                const float *__restrict__ w1, const float *__restrict__ b1,
+                const float *__restrict__ wv, const float *__restrict__ bv,
+                const float *__restrict__ wa, const float *__restrict__ ba, int n_out, int dueling,
+                long long n, float *__restrict__ out) {
+    __shared__ __align__(16) float s_a[S][HEAD_C];
+    __shared__ float s_f[S][HEAD_H];
+    __shared__ float s_h[S][HEAD_MAX_OUT + 1];
+    const long long n0 = (long long)blockIdx.x * S;
+    for (int t = threadIdx.x; t < S * HEAD_C; t += HEAD_THREADS) {
+        const int smp = t / HEAD_C, c = t % HEAD_C;
+        const long long i = n0 + smp;
+        float a = 0.f;
+        if (i < n) {
+            const float *src = x + i * hw * HEAD_C + c;
+            float m = -INFINITY;
+            for (int p = 0; p < hw; p++) {
+                const float v = __ldg(src + (long long)p * HEAD_C);
+                if (v > m || v != v) m = v;
+            }
+            a = silu_f(m + __ldg(conv_bias + c));
+        }
+        s_a[smp][c] = a;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 av[S];
+#pragma unroll
+    for (int smp = 0; smp < S; smp++) av[smp] = *reinterpret_cast<const float4 *>(&s_a[smp][4 * lane]);
+#pragma unroll 4
+    for (int j = warp; j < HEAD_H; j += HEAD_THREADS / 32) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(w1 + (long long)j * HEAD_C) + lane);
+        float acc[S];
+#pragma unroll
+        for (int smp = 0; smp < S; smp++)
+            acc[smp] = fmaf(w.w, av[smp].w, fmaf(w.z, av[smp].z, fmaf(w.y, av[smp].y, w.x * av[smp].x)));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int smp = 0; smp < S; smp++) acc[smp] += __shfl_xor_sync(0xffffffffu, acc[smp], off);
+        if (lane == 0) {
+            const float b = __ldg(b1 + j);
+#pragma unroll
+            for (int smp = 0; smp < S; smp++) s_f[smp][j] = silu_f(acc[smp] + b);
+        }
+    }
+    __syncthreads();
+    // head rows: row 0 = the value head (dueling), rows 1.. = the advantage / output rows
+    const int rows = n_out + (dueling ? 1 : 0);
+    for (int r = warp; r < rows; r += HEAD_THREADS / 32) {
+        const bool is_v = dueling && r == 0;
+        const float *wr = is_v ? wv : wa + (long long)(r - (dueling ? 1 : 0)) * HEAD_H;
+        const float bias = is_v ? __ldg(bv) : __ldg(ba + r - (dueling ? 1 : 0));
+#pragma unroll
+        for (int smp = 0; smp < S; smp++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < HEAD_H / 32; t++) acc = fmaf(__ldg(wr + lane + 32 * t), s_f[smp][lane + 32 * t], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) s_h[smp][r] = acc + bias;
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < S * n_out) {
+        const int smp = threadIdx.x / n_out, k = threadIdx.x % n_out;
+        const long long i = n0 + smp;
+        if (i < n) {
+            float q;
+            if (dueling) {   // value - adv.mean(dim=1, keepdim=True) + adv  (models.py:108-110)
+                float sum = 0.f;
+                for (int t = 0; t < n_out; t++) sum += s_h[smp][1 + t];
+                q = (s_h[smp][0] - sum / (float)n_out) + s_h[smp][1 + k];
+            } else {
+                q = s_h[smp][k];
+            }
+            out[i * n_out + k] = q;
+        }
+    }
+}
+
 }  // namespace pb
 
 namespace {
@@ -216,6 +315,34 @@ int pb_bias_pool_silu_bwd(const float *dy_dev, const float *z_dev, const uint8_t
     else
         k_bias_pool_silu_bwd<false><<<grid, QN_THREADS, 0, (cudaStream_t)stream>>>(
             gs, zs, nullptr, n, (int)h, (int)w, c4, ds, dbias_out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                     const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                     const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
+                     float *out_dev, int device, void *stream) {
+    if (!x_dev || !conv_bias_dev || !w1_dev || !b1_dev || !wa_dev || !ba_dev || !out_dev || n <= 0 ||
+        hw <= 0 || hw > 4096 || n_out <= 0 || n_out > HEAD_MAX_OUT - (dueling ? 1 : 0) ||
+        (dueling && (!wv_dev || !bv_dev)) || !aligned16(w1_dev))
+        return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_fwd: bad arguments (x float32 [n][hw][128], "
+                                        "Linear 128 -> 256, up to 7 output rows)");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // samples per CTA: enough CTAs to cover the SMs at small batches, W1 amortised at large ones
+    const int sms = qnet_sms(device);
+#define PB_HEAD_LAUNCH(S)                                                                          \
+    k_qnet_head_fwd<S><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                   \
+        x_dev, (int)hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, (int)n_out,  \
+        dueling, n, out_dev)
+    if (n <= 2 * sms)
+        PB_HEAD_LAUNCH(1);
+    else if (n <= 4 * sms)
+        PB_HEAD_LAUNCH(2);
+    else
+        PB_HEAD_LAUNCH(4);
+#undef PB_HEAD_LAUNCH
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

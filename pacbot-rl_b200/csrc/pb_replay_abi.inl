@@ -95,34 +95,45 @@ k_replay_sample(const uint8_t *__restrict__ ring_valid, long long total, int bat
 }
 
 // One observation (17 x 868 floats, channel-major in the ring) to `dst`: a straight float4 copy,
-// or transposed to channels-last ([cell][17]) through a padded shared-memory tile.
-constexpr int TILE_STRIDE = CH_FLOATS + 1;   // 869: odd stride, conflict-free transposed reads
-constexpr int COLLATE_THREADS = 256;
-constexpr int COLLATE_SMEM = OBS_CH * TILE_STRIDE * 4;
+// or transposed to channels-last ([cell][cpad]) through a padded shared-memory tile.  An
+// observation is cut into OBS_SPLIT parts of 124 cells, one CTA each: a batch of 32 policy
+// observations is 224 CTAs instead of 32 (11 -> ~4 us per k_replay_slot call), a 512-sample
+// collate 7 168 small CTAs instead of 1 024 big ones that ran three to an SM in 2.3 waves.
+constexpr int OBS_SPLIT = 7;                          // 217 float4 per channel = 7 x 31
+constexpr int PART_VEC = CH_VEC / OBS_SPLIT;          // 31 float4 per channel and part
+constexpr int PART_CELLS = PART_VEC * 4;              // 124 cells
+constexpr int PART_STRIDE = PART_CELLS + 1;           // 125: odd stride, conflict-free transposed reads
+constexpr int COLLATE_THREADS = 128;
+static_assert(PART_VEC * OBS_SPLIT == CH_VEC, "the parts tile a channel");
 // `cpad`: 0 = channel-major copy (NCHW); otherwise the channel count of the channels-last output,
 // 17 (dense) or a multiple of 4 up to 64 whose channels >= 17 are written as zeros: cuDNN only has
 // tensor-core kernels for the first convolution when its input channels are a multiple of 8
 // (17 -> 32: 230 -> 140 us forward at batch 512, tools/experiments/pad_channels_probe.py).
-__device__ __forceinline__ void emit_obs(const float4 *__restrict__ src, float4 *__restrict__ dst,
-                                         bool zero, int cpad, float *tile) {
-    const int out_vec = (cpad ? CH_FLOATS * cpad : OBS_FLOATS) / 4;
+__device__ __forceinline__ void emit_obs_part(const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                              bool zero, int cpad, int part, float *tile) {
+    if (!cpad) {   // channel-major: the part's 31 float4 of every channel
+        for (int q = threadIdx.x; q < OBS_CH * PART_VEC; q += COLLATE_THREADS) {
+            const int ch = q / PART_VEC, v = q - ch * PART_VEC;
+            const int at = ch * CH_VEC + part * PART_VEC + v;
+            dst[at] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(src + at);
+        }
+        return;
+    }
+    // channels-last: the part's cells are one contiguous run of PART_CELLS * cpad floats
+    const int out_vec = PART_CELLS * cpad / 4;
+    float4 *o4 = dst + (long long)part * out_vec;
     if (zero) {
-        for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS)
-            dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
-    if (!cpad) {
-        for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) dst[q] = __ldg(src + q);
-        return;
-    }
-    for (int q = threadIdx.x; q < OBS_FLOATS / 4; q += COLLATE_THREADS) {
-        const float4 v = __ldg(src + q);
-        const int ch = q / (CH_FLOATS / 4), cell = (q - ch * (CH_FLOATS / 4)) * 4;
-        float *t = tile + ch * TILE_STRIDE + cell;
-        t[0] = v.x;
-        t[1] = v.y;
-        t[2] = v.z;
-        t[3] = v.w;
+    for (int q = threadIdx.x; q < OBS_CH * PART_VEC; q += COLLATE_THREADS) {
+        const int ch = q / PART_VEC, v = q - ch * PART_VEC;
+        const float4 x = __ldg(src + ch * CH_VEC + part * PART_VEC + v);
+        float *t = tile + ch * PART_STRIDE + 4 * v;
+        t[0] = x.x;
+        t[1] = x.y;
+        t[2] = x.z;
+        t[3] = x.w;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) {
@@ -130,12 +141,13 @@ __device__ __forceinline__ void emit_obs(const float4 *__restrict__ src, float4 
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = q * 4 + u, cell = j / cpad, ch = j - cell * cpad;
-            o[u] = ch < OBS_CH ? tile[ch * TILE_STRIDE + cell] : 0.0f;
+            o[u] = ch < OBS_CH ? tile[ch * PART_STRIDE + cell] : 0.0f;
         }
-        dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+        o4[q] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
+// grid: batch x {obs, next_obs} x OBS_SPLIT
 __global__ void __launch_bounds__(COLLATE_THREADS)
 k_replay_collate(const float4 *__restrict__ ring_obs, long long n, long long ring_slots,
                  const long long *__restrict__ idx, const uint8_t *__restrict__ ring_actions,
@@ -144,51 +156,47 @@ k_replay_collate(const float4 *__restrict__ ring_obs, long long n, long long rin
                  float4 *__restrict__ next_obs_out, int nhwc, long long *__restrict__ actions_out,
                  float *__restrict__ rewards_out, uint8_t *__restrict__ done_out,
                  uint8_t *__restrict__ next_mask_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);
-    const long long k = blockIdx.x >> 1;
-    const bool is_next = blockIdx.x & 1;
+    __shared__ float tile[OBS_CH * PART_STRIDE];
+    const int part = blockIdx.x % OBS_SPLIT;
+    const long long item = blockIdx.x / OBS_SPLIT;
+    const long long k = item >> 1;
+    const bool is_next = item & 1;
     const long long flat = idx[k];
     const long long slot = flat / n, env = flat - slot * n;
     const bool done = ring_done[flat] != 0;
     const long long out_vec = (nhwc ? CH_FLOATS * nhwc : OBS_FLOATS) / 4;   // float4 per output obs
     if (!is_next) {
-        emit_obs(ring_obs + flat * (OBS_FLOATS / 4), obs_out + k * out_vec, false, nhwc, tile);
-        if (threadIdx.x == 0) {
-            actions_out[k] = ring_actions[flat];
-            rewards_out[k] = (float)ring_rewards[flat];
-            done_out[k] = done ? 1 : 0;
+        emit_obs_part(ring_obs + flat * (OBS_FLOATS / 4), obs_out + k * out_vec, false, nhwc, part, tile);
+        if (part == 0) {
+            if (threadIdx.x == 0) {
+                actions_out[k] = ring_actions[flat];
+                rewards_out[k] = (float)ring_rewards[flat];
+                done_out[k] = done ? 1 : 0;
+            }
+            if (threadIdx.x < 5) next_mask_out[k * 5 + threadIdx.x] = ring_next_mask[flat * 5 + threadIdx.x];
         }
-        if (threadIdx.x < 5) next_mask_out[k * 5 + threadIdx.x] = ring_next_mask[flat * 5 + threadIdx.x];
     } else {
         // `next_obs is None` -> zeros (train_dqn.py:154-159); otherwise the next time slot
         const long long nflat = ((slot + 1) % ring_slots) * n + env;
-        emit_obs(ring_obs + nflat * (OBS_FLOATS / 4), next_obs_out + k * out_vec, done, nhwc, tile);
+        emit_obs_part(ring_obs + nflat * (OBS_FLOATS / 4), next_obs_out + k * out_vec, done, nhwc, part, tile);
     }
 }
 
+// grid: n envs x OBS_SPLIT
 __global__ void __launch_bounds__(COLLATE_THREADS)
 k_replay_slot(const float4 *__restrict__ ring_obs, long long n, long long ring_slots,
               const long long *__restrict__ t_dev, float4 *__restrict__ out, int nhwc) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const long long flat = (*t_dev % ring_slots) * n + blockIdx.x;
+    __shared__ float tile[OBS_CH * PART_STRIDE];
+    const int part = blockIdx.x % OBS_SPLIT;
+    const long long env = blockIdx.x / OBS_SPLIT;
+    const long long flat = (*t_dev % ring_slots) * n + env;
     const long long out_vec = (nhwc ? CH_FLOATS * nhwc : OBS_FLOATS) / 4;
-    emit_obs(ring_obs + flat * (OBS_FLOATS / 4), out + (long long)blockIdx.x * out_vec, false, nhwc,
-             reinterpret_cast<float *>(smem_raw));
+    emit_obs_part(ring_obs + flat * (OBS_FLOATS / 4), out + env * out_vec, false, nhwc, part, tile);
 }
 
 }  // namespace pb
 
 namespace {
-int collate_smem_attr(int device) {
-    static thread_local int set_for = -1;
-    if (set_for != device) {
-        PB_CUDA(cudaFuncSetAttribute(k_replay_collate, cudaFuncAttributeMaxDynamicSharedMemorySize, COLLATE_SMEM));
-        PB_CUDA(cudaFuncSetAttribute(k_replay_slot, cudaFuncAttributeMaxDynamicSharedMemorySize, COLLATE_SMEM));
-        set_for = device;
-    }
-    return PB_OK;
-}
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // channels_last argument of the ABI -> channel count of the channels-last output (0 = NCHW),
 // or -1 if it is not 0, 1 (= 17), 17, or a multiple of 4 in 20..64
@@ -262,10 +270,7 @@ int pb_replay_collate(const float *ring_obs_dev, int64_t n_envs, int64_t ring_sl
     channels_last = channels_arg(channels_last);
     if (batch == 0) return PB_OK;
     DeviceGuard g(device);
-    int rc = collate_smem_attr(device);
-    if (rc != PB_OK) return rc;
-    k_replay_collate<<<(unsigned)(2 * batch), COLLATE_THREADS, channels_last ? COLLATE_SMEM : 0,
-                       (cudaStream_t)stream>>>(
+    k_replay_collate<<<(unsigned)(2 * batch * OBS_SPLIT), COLLATE_THREADS, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(ring_obs_dev), n_envs, ring_slots,
         reinterpret_cast<const long long *>(idx_dev), ring_actions, ring_rewards, ring_done,
         ring_next_mask, reinterpret_cast<float4 *>(obs_out_dev),
@@ -284,10 +289,7 @@ int pb_replay_slot_obs(const float *ring_obs_dev, int64_t n_envs, int64_t ring_s
         return fail(PB_ERR_INVALID_ARG, "pb_replay_slot_obs: bad arguments");
     channels_last = channels_arg(channels_last);
     DeviceGuard g(device);
-    int rc = collate_smem_attr(device);
-    if (rc != PB_OK) return rc;
-    k_replay_slot<<<(unsigned)n_envs, COLLATE_THREADS, channels_last ? COLLATE_SMEM : 0,
-                    (cudaStream_t)stream>>>(
+    k_replay_slot<<<(unsigned)(n_envs * OBS_SPLIT), COLLATE_THREADS, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(ring_obs_dev), n_envs, ring_slots,
         reinterpret_cast<const long long *>(t_dev), reinterpret_cast<float4 *>(out_dev), channels_last);
     PB_CUDA(cudaGetLastError());

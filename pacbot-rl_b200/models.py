@@ -89,6 +89,31 @@ def bias_pool_silu(x: torch.Tensor, bias: torch.Tensor, pool: bool) -> torch.Ten
     return _BiasPoolSiLU.apply(x, bias, pool)
 
 
+def qnet_head(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.Linear,
+              value: "nn.Linear | None" = None) -> torch.Tensor:
+    """Inference-only head of QNetV2 / NetV2 as ONE launch (`pb_qnet_head_fwd`,
+    csrc/pb_qnet_abi.inl): global max of the last convolution's bias-free NHWC output `x`
+    [N, 128, H, W] + `conv_bias`, SiLU, `lin` (128 -> 256), SiLU, then `value` / `out` combined as
+    `V - mean(A) + A` (reference models.py:92-110) or, without `value`, the plain layer `out`
+    (models.py:139-141).  No autograd graph: callers use it under `torch.no_grad()`."""
+    import ctypes as C
+
+    from . import _lib
+
+    n, c, h, w = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and c == 128 and lin.in_features == 128
+            and lin.out_features == 256 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("qnet_head: channels-last float32 CUDA [N, 128, H, W] input and Linear(128, 256) expected")
+    q = torch.empty((n, out.out_features), dtype=torch.float32, device=x.device)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+    _lib.check(_lib.load().pb_qnet_head_fwd(
+        p(x), n, h * w, p(conv_bias), p(lin.weight), p(lin.bias),
+        p(value.weight if value is not None else None), p(value.bias if value is not None else None),
+        p(out.weight), p(out.bias), out.out_features, int(value is not None), p(q), x.device.index,
+        C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return q
+
+
 class GlobalMaxPool2d(nn.Module):
     """`nn.AdaptiveMaxPool2d((1, 1))` (reference models.py:96) computed as ONE max-pool window over
     the whole feature map: same values, same arg-max choice (first maximum in row-major order) and
@@ -156,6 +181,10 @@ class QNetV2(nn.Module):
         for i in (2, 5, 8):                     # Conv2d, MaxPool2d(2, ceil_mode=True), SiLU
             conv = bb[i]
             h = bias_pool_silu(nn.functional.conv2d(h, conv.weight, None, padding="same"), conv.bias, True)
+        if not torch.is_grad_enabled():         # policy / target / evaluation forwards: fused head
+            last = bb[11]
+            x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+            return qnet_head(x5, last.bias, bb[15], self.advantage_head[0], self.value_head[0])
         feat = bb[11:](h)                       # grouped conv, global max pool, SiLU, Linear, SiLU
         value = self.value_head(feat)
         adv = self.advantage_head(feat)
