@@ -865,7 +865,7 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
 
     from pacbot_rl_b200 import alphazero, models
 
-    model = models.NetV2((17, 28, 31), 6).to(dev).use_channels_last().eval()
+    model = models.NetV2((17, 28, 31), 6).to(dev).use_fused_blocks().eval()
 
     @torch.no_grad()
     def evaluator(obs, mask):  # train_alphazero.py:83-95 (reward_scale 1/100)
@@ -889,7 +889,7 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
     items = int(col.ep_len.sum()) + sum(int(f[0].numel()) for f in finished) - items0
     out = {"sims_per_sec": steps * num_envs / dt, "env_steps_per_sec": items / dt,
            "search_iterations": steps, "ms_per_iteration": 1e3 * dt / steps, "cuda_graph": graph,
-           "config": f"{num_envs} trees x tree_size {tree_size}, NetV2 fp32 evaluator (cuDNN, NHWC) on "
+           "config": f"{num_envs} trees x tree_size {tree_size}, NetV2 fp32 evaluator (cuDNN convolutions, NHWC, fused block tails and head) on "
                      "device-resident leaf observations, Dirichlet root noise, max_episode_length 1000"}
     if cpu_steps:
         import ctypes as C

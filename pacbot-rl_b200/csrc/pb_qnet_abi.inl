@@ -156,7 +156,9 @@ k_bias_pool_silu_bwd(const float4 *__restrict__ dy, const float4 *__restrict__ z
 // One CTA handles S samples: W1 (128 KB, L2 resident) is read once per CTA, row by row, a warp
 // per row with the 128 inputs split over the lanes (coalesced 512 B loads) and a shuffle tree.
 // float32 FMA throughout; the sums are ordered differently from cuBLAS (tests: rtol 1e-5).
-constexpr int HEAD_C = 128, HEAD_H = 256, HEAD_THREADS = 256, HEAD_MAX_OUT = 8;
+constexpr int HEAD_C = 128, HEAD_H = 256, HEAD_THREADS = 512, HEAD_MAX_OUT = 8;
+constexpr int HEAD_WARPS = HEAD_THREADS / 32, HEAD_RB = 8;      // rows of W1 in flight per warp
+constexpr int HEAD_PGROUPS = HEAD_THREADS / (HEAD_C / 4);   // 16 map positions in flight per sample
 
 template <int S>
 __global__ void __launch_bounds__(HEAD_THREADS)
@@ -166,44 +168,90 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
                 const float *__restrict__ wa, const float *__restrict__ ba, int n_out, int dueling,
                 long long n, float *__restrict__ out) {
     __shared__ __align__(16) float s_a[S][HEAD_C];
+    __shared__ __align__(16) float s_m[S][HEAD_PGROUPS][HEAD_C];
     __shared__ float s_f[S][HEAD_H];
     __shared__ float s_h[S][HEAD_MAX_OUT + 1];
+    __shared__ float s_b1[HEAD_H];
     const long long n0 = (long long)blockIdx.x * S;
-    for (int t = threadIdx.x; t < S * HEAD_C; t += HEAD_THREADS) {
-        const int smp = t / HEAD_C, c = t % HEAD_C;
-        const long long i = n0 + smp;
-        float a = 0.f;
-        if (i < n) {
-            const float *src = x + i * hw * HEAD_C + c;
-            float m = -INFINITY;
-            for (int p = 0; p < hw; p++) {
-                const float v = __ldg(src + (long long)p * HEAD_C);
-                if (v > m || v != v) m = v;
-            }
-            a = silu_f(m + __ldg(conv_bias + c));
-        }
-        s_a[smp][c] = a;
-    }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 wrow[HEAD_RB];
+#pragma unroll
+    for (int r = 0; r < HEAD_RB; r++)
+        wrow[r] = __ldg(reinterpret_cast<const float4 *>(w1 + (long long)(r * HEAD_WARPS + warp) * HEAD_C) + lane);
+    if (threadIdx.x < HEAD_H) s_b1[threadIdx.x] = __ldg(b1 + threadIdx.x);
+    // global max over the map: thread (g, c4) takes positions g, g + 16, ... of four channels
+    // (independent 16-byte loads, 512 B per position across a warp), then the 16 partial maxima
+    // of a channel meet in shared memory.  max is exact, so the grouping does not matter; a NaN
+    // anywhere in the map wins as in ATen's max_pool2d.
+    {
+        const int c4 = threadIdx.x % (HEAD_C / 4), g = threadIdx.x / (HEAD_C / 4);
+#pragma unroll
+        for (int smp = 0; smp < S; smp++) {
+            const long long i = n0 + smp;
+            float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (i < n) {
+                const float4 *src = reinterpret_cast<const float4 *>(x + i * hw * HEAD_C) + c4;
+#pragma unroll 4
+                for (int p = g; p < hw; p += HEAD_PGROUPS) {
+                    const float4 v = __ldg(src + (long long)p * (HEAD_C / 4));
+                    if (v.x > m.x || v.x != v.x) m.x = v.x;
+                    if (v.y > m.y || v.y != v.y) m.y = v.y;
+                    if (v.z > m.z || v.z != v.z) m.z = v.z;
+                    if (v.w > m.w || v.w != v.w) m.w = v.w;
+                }
+            }
+            *reinterpret_cast<float4 *>(&s_m[smp][g][4 * c4]) = m;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < S * HEAD_C; t += HEAD_THREADS) {
+            const int smp = t / HEAD_C, c = t % HEAD_C;
+            float best = s_m[smp][0][c];
+#pragma unroll
+            for (int k = 1; k < HEAD_PGROUPS; k++) {
+                const float v = s_m[smp][k][c];
+                if (best == best && (v > best || v != v)) best = v;
+            }
+            s_a[smp][c] = (n0 + smp < n) ? silu_f(best + __ldg(conv_bias + c)) : 0.f;
+        }
+        __syncthreads();
+    }
+    // Linear 128 -> 256: warp w owns rows w, w + 16, ...; the rows of a batch of HEAD_RB are all
+    // requested before any of them is used (their first batch was requested at the top of the
+    // kernel, under the max pooling), lanes split the 128 inputs, a butterfly sums them, and
+    // lane r finishes row r of the batch (bias, SiLU) so that the tail is not serialised either
     float4 av[S];
 #pragma unroll
     for (int smp = 0; smp < S; smp++) av[smp] = *reinterpret_cast<const float4 *>(&s_a[smp][4 * lane]);
-#pragma unroll 4
-    for (int j = warp; j < HEAD_H; j += HEAD_THREADS / 32) {
-        const float4 w = __ldg(reinterpret_cast<const float4 *>(w1 + (long long)j * HEAD_C) + lane);
-        float acc[S];
 #pragma unroll
-        for (int smp = 0; smp < S; smp++)
-            acc[smp] = fmaf(w.w, av[smp].w, fmaf(w.z, av[smp].z, fmaf(w.y, av[smp].y, w.x * av[smp].x)));
+    for (int jb = 0; jb < HEAD_H / (HEAD_WARPS * HEAD_RB); jb++) {
+        float acc[HEAD_RB][S];
+#pragma unroll
+        for (int r = 0; r < HEAD_RB; r++)
+#pragma unroll
+            for (int smp = 0; smp < S; smp++)
+                acc[r][smp] = fmaf(wrow[r].w, av[smp].w,
+                                   fmaf(wrow[r].z, av[smp].z, fmaf(wrow[r].y, av[smp].y, wrow[r].x * av[smp].x)));
+        if (jb + 1 < HEAD_H / (HEAD_WARPS * HEAD_RB)) {
+#pragma unroll
+            for (int r = 0; r < HEAD_RB; r++)
+                wrow[r] = __ldg(reinterpret_cast<const float4 *>(
+                                    w1 + (long long)(((jb + 1) * HEAD_RB + r) * HEAD_WARPS + warp) * HEAD_C) + lane);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-            for (int smp = 0; smp < S; smp++) acc[smp] += __shfl_xor_sync(0xffffffffu, acc[smp], off);
-        if (lane == 0) {
-            const float b = __ldg(b1 + j);
+            for (int r = 0; r < HEAD_RB; r++)
 #pragma unroll
-            for (int smp = 0; smp < S; smp++) s_f[smp][j] = silu_f(acc[smp] + b);
+                for (int smp = 0; smp < S; smp++)
+                    acc[r][smp] += __shfl_xor_sync(0xffffffffu, acc[r][smp], off);
+        const int row = (jb * HEAD_RB + (lane & (HEAD_RB - 1))) * HEAD_WARPS + warp;
+#pragma unroll
+        for (int smp = 0; smp < S; smp++) {
+            float v = acc[0][smp];
+#pragma unroll
+            for (int r = 1; r < HEAD_RB; r++)
+                if ((lane & (HEAD_RB - 1)) == r) v = acc[r][smp];
+            if (lane < HEAD_RB) s_f[smp][row] = silu_f(v + s_b1[row]);
         }
     }
     __syncthreads();
@@ -325,7 +373,7 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
                      float *out_dev, int device, void *stream) {
     if (!x_dev || !conv_bias_dev || !w1_dev || !b1_dev || !wa_dev || !ba_dev || !out_dev || n <= 0 ||
         hw <= 0 || hw > 4096 || n_out <= 0 || n_out > HEAD_MAX_OUT - (dueling ? 1 : 0) ||
-        (dueling && (!wv_dev || !bv_dev)) || !aligned16(w1_dev))
+        (dueling && (!wv_dev || !bv_dev)) || !aligned16(w1_dev) || !aligned16(x_dev))
         return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_fwd: bad arguments (x float32 [n][hw][128], "
                                         "Linear 128 -> 256, up to 7 output rows)");
     DeviceGuard g(device);
@@ -336,9 +384,9 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
     k_qnet_head_fwd<S><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                   \
         x_dev, (int)hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, (int)n_out,  \
         dueling, n, out_dev)
-    if (n <= 2 * sms)
+    if (n <= sms)
         PB_HEAD_LAUNCH(1);
-    else if (n <= 4 * sms)
+    else if (n <= 2 * sms)
         PB_HEAD_LAUNCH(2);
     else
         PB_HEAD_LAUNCH(4);

@@ -111,30 +111,47 @@ static_assert(PART_VEC * OBS_SPLIT == CH_VEC, "the parts tile a channel");
 // (17 -> 32: 230 -> 140 us forward at batch 512, tools/experiments/pad_channels_probe.py).
 __device__ __forceinline__ void emit_obs_part(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                               bool zero, int cpad, int part, float *tile) {
-    if (!cpad) {   // channel-major: the part's 31 float4 of every channel
-        for (int q = threadIdx.x; q < OBS_CH * PART_VEC; q += COLLATE_THREADS) {
-            const int ch = q / PART_VEC, v = q - ch * PART_VEC;
-            const int at = ch * CH_VEC + part * PART_VEC + v;
-            dst[at] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(src + at);
+    // the part's 17 x 31 float4 are requested up front (5 independent loads per thread), then used
+    constexpr int IN_VEC = OBS_CH * PART_VEC, IN_ITERS = (IN_VEC + COLLATE_THREADS - 1) / COLLATE_THREADS;
+    const int out_vec = cpad ? PART_CELLS * cpad / 4 : 0;
+    float4 *o4 = dst + (long long)part * out_vec;
+    if (zero) {
+        if (!cpad) {
+            for (int q = threadIdx.x; q < IN_VEC; q += COLLATE_THREADS) {
+                const int ch = q / PART_VEC, v = q - ch * PART_VEC;
+                dst[ch * CH_VEC + part * PART_VEC + v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         return;
     }
-    // channels-last: the part's cells are one contiguous run of PART_CELLS * cpad floats
-    const int out_vec = PART_CELLS * cpad / 4;
-    float4 *o4 = dst + (long long)part * out_vec;
-    if (zero) {
-        for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
+    float4 in[IN_ITERS];
+#pragma unroll
+    for (int u = 0; u < IN_ITERS; u++) {
+        const int q = threadIdx.x + u * COLLATE_THREADS;
+        if (q < IN_VEC) {
+            const int ch = q / PART_VEC, v = q - ch * PART_VEC;
+            in[u] = __ldg(src + ch * CH_VEC + part * PART_VEC + v);
+        }
     }
-    for (int q = threadIdx.x; q < OBS_CH * PART_VEC; q += COLLATE_THREADS) {
-        const int ch = q / PART_VEC, v = q - ch * PART_VEC;
-        const float4 x = __ldg(src + ch * CH_VEC + part * PART_VEC + v);
-        float *t = tile + ch * PART_STRIDE + 4 * v;
-        t[0] = x.x;
-        t[1] = x.y;
-        t[2] = x.z;
-        t[3] = x.w;
+#pragma unroll
+    for (int u = 0; u < IN_ITERS; u++) {
+        const int q = threadIdx.x + u * COLLATE_THREADS;
+        if (q < IN_VEC) {
+            const int ch = q / PART_VEC, v = q - ch * PART_VEC;
+            if (!cpad) {   // channel-major copy
+                dst[ch * CH_VEC + part * PART_VEC + v] = in[u];
+            } else {       // into the transposing tile
+                float *t = tile + ch * PART_STRIDE + 4 * v;
+                t[0] = in[u].x;
+                t[1] = in[u].y;
+                t[2] = in[u].z;
+                t[3] = in[u].w;
+            }
+        }
     }
+    if (!cpad) return;
     __syncthreads();
     for (int q = threadIdx.x; q < out_vec; q += COLLATE_THREADS) {
         float o[4];

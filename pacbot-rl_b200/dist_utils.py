@@ -27,19 +27,34 @@ def shard_env_ids(total_envs: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 @torch.no_grad()
-def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int) -> None:
+def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int, assign_views: bool = False) -> None:
     """Average gradients across ranks with ONE all-reduce of the flattened gradient
-    (156 934 floats = 628 KB for QNetV2: latency-bound, so a single bucket)."""
+    (156 934 floats = 628 KB for QNetV2: latency-bound, so a single bucket).  The gradients are
+    flattened in MEMORY order (the reduction is elementwise and every rank holds the same layouts),
+    so with `assign_views=True` each `p.grad` simply becomes a view of the reduced flat buffer with
+    the strides it had (NHWC weights keep NHWC gradients): one `cat`, the collective and one
+    `div_` instead of those plus a copy back per parameter."""
     if world <= 1:
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    params = [p for p in params if p.grad is not None]
+    if not params:
         return
-    flat = torch._utils._flatten_dense_tensors(grads)
+    grads = [p.grad for p in params]
+    dense = all(g.is_contiguous() or (g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last))
+                for g in grads)
+    raw = [g.as_strided((g.numel(),), (1,)) if dense else g.reshape(-1) for g in grads]
+    flat = torch.cat(raw)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(world)
-    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
+    offset = 0
+    for p, g, r in zip(params, grads, raw):
+        if assign_views and dense:
+            p.grad = flat.as_strided(g.size(), g.stride(), offset)
+        elif dense:
+            r.copy_(flat[offset:offset + g.numel()])
+        else:
+            g.copy_(flat[offset:offset + g.numel()].view_as(g))
+        offset += g.numel()
 
 
 def max_over_ranks(value: float, device: torch.device, world: int) -> float:

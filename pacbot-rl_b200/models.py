@@ -125,6 +125,21 @@ class GlobalMaxPool2d(nn.Module):
         return nn.functional.max_pool2d(x, kernel_size=tuple(x.shape[-2:]))
 
 
+def _fused_trunk(bb: nn.Sequential, obs: torch.Tensor) -> torch.Tensor:
+    """Blocks 0..8 of the QNetV2 / NetV2 layer list (conv5x5 + SiLU, 3 x [conv3x3, max pool, SiLU])
+    with every block tail as one `bias_pool_silu` launch; the convolutions run without bias."""
+    first = bb[0]
+    w = first.weight
+    if obs.shape[1] > first.in_channels:   # zero-padded observation channels, see QNetV2.forward()
+        w = nn.functional.pad(w, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels))
+    w = w.contiguous(memory_format=torch.channels_last)
+    h = bias_pool_silu(nn.functional.conv2d(obs, w, None, padding="same"), first.bias, False)
+    for i in (2, 5, 8):                     # Conv2d, MaxPool2d(2, ceil_mode=True), SiLU
+        conv = bb[i]
+        h = bias_pool_silu(nn.functional.conv2d(h, conv.weight, None, padding="same"), conv.bias, True)
+    return h
+
+
 class QNetV2(nn.Module):
     """conv5x5(C->16) SiLU, 3 x [conv3x3, maxpool2(ceil), SiLU] (32, 64, 128), grouped conv3x3
     (128, 8 groups), global max, SiLU, Linear 128->256, SiLU, dueling heads V(1) / A(actions);
@@ -172,15 +187,7 @@ class QNetV2(nn.Module):
 
     def _forward_fused(self, obs: torch.Tensor) -> torch.Tensor:
         bb = self.backbone
-        first = bb[0]
-        w = first.weight
-        if obs.shape[1] > first.in_channels:   # zero-padded observation channels, see forward()
-            w = nn.functional.pad(w, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels))
-        w = w.contiguous(memory_format=torch.channels_last)
-        h = bias_pool_silu(nn.functional.conv2d(obs, w, None, padding="same"), first.bias, False)
-        for i in (2, 5, 8):                     # Conv2d, MaxPool2d(2, ceil_mode=True), SiLU
-            conv = bb[i]
-            h = bias_pool_silu(nn.functional.conv2d(h, conv.weight, None, padding="same"), conv.bias, True)
+        h = _fused_trunk(bb, obs)
         if not torch.is_grad_enabled():         # policy / target / evaluation forwards: fused head
             last = bb[11]
             x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
@@ -298,7 +305,23 @@ class NetV2(nn.Module):
         self._channels_last = True
         return self
 
+    def use_fused_blocks(self, enabled: bool = True) -> "NetV2":
+        """As QNetV2.use_fused_blocks: block tails as `bias_pool_silu`, and under `torch.no_grad()`
+        (the MCTS evaluator) the whole head as one `qnet_head` launch."""
+        if enabled and not getattr(self, "_channels_last", False):
+            self.use_channels_last()
+        self._fused_blocks = bool(enabled)
+        return self
+
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_channels_last", False):
             obs = obs.contiguous(memory_format=torch.channels_last)
+        if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:
+            net = self.network
+            h = _fused_trunk(net, obs)
+            if not torch.is_grad_enabled():
+                last = net[11]
+                x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+                return qnet_head(x5, last.bias, net[15], net[17])
+            return net[11:](h)
         return self.network(obs)

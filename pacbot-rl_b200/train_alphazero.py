@@ -130,6 +130,8 @@ class AlphaZeroTrainer:
         torch.manual_seed(args.seed)  # identical initial weights on every rank
         model_class = getattr(models, args.model)
         self.model = model_class(OBS_SHAPE, NUM_ACTIONS + 1).to(self.device)
+        if hasattr(self.model, "use_fused_blocks"):   # NHWC weights, fused block tails / inference head
+            self.model.use_fused_blocks()
         torch.manual_seed(args.seed + 7919 * (self.rank + 1))  # per-rank batch sampling / root noise
         self.has_model_updated = False
         self.collector = BatchedExperienceCollector(

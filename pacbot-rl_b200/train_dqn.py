@@ -317,7 +317,10 @@ class DQNTrainer:
         cfg = self.cfg
         batch = self.replay.sample_batch(cfg.batch_size)
         target_q = dqn_targets(batch, self.q_net, self.target_q_net, cfg.discount_factor, cfg.reward_scale)
-        self.optimizer.zero_grad(set_to_none=False)
+        # set_to_none: backward then WRITES each gradient instead of adding it to a zeroed one (16
+        # accumulation launches and the zero fill per iteration); inside the captured graph the
+        # gradients come from the graph's private pool, i.e. the same addresses at every replay
+        self.optimizer.zero_grad(set_to_none=True)
         loss, all_q = dqn_loss(batch, self.q_net, target_q)
         loss.backward()
         if self.world > 1:
@@ -379,7 +382,7 @@ class DQNTrainer:
     def _allreduce_grads(self) -> None:
         from .dist_utils import allreduce_mean_grads
 
-        allreduce_mean_grads(self.params, self.world)
+        allreduce_mean_grads(self.params, self.world, assign_views=True)
 
     def pop_metrics(self) -> dict:
         vals = (self._acc / max(1, self._acc_n)).tolist()   # the only host sync of the loop

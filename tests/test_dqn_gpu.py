@@ -750,6 +750,40 @@ def test_qnet_head_matches_torch_composition(pb, n):
         qnet_head(torch.randn((2, 64, 4, 4), device=dev), conv_bias, lin, adv, val)
 
 
+def test_netv2_fused_blocks_match_the_plain_network(pb):
+    """NetV2.use_fused_blocks() (the MCTS evaluator's network): inference through the fused block
+    tails + `qnet_head` and training through the fused tails agree with the plain module."""
+    import copy
+
+    import torch
+    from pacbot_rl_b200.models import NetV2
+
+    dev = torch.device("cuda:0")
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(5)
+        plain = NetV2(pb.OBS_SHAPE, 6).to(dev).use_channels_last()
+        with torch.no_grad():
+            for p in plain.parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.3)
+            plain.network[-1].weight.normal_(0, 0.3)
+        fused = copy.deepcopy(plain).use_fused_blocks()
+        x = (torch.rand((40,) + pb.OBS_SHAPE, device=dev) < 0.15).float() * torch.rand((40,) + pb.OBS_SHAPE, device=dev)
+        with torch.no_grad():
+            torch.testing.assert_close(fused(x), plain(x), rtol=1e-5, atol=1e-6)
+        qa, qb = plain(x), fused(x)
+        assert torch.equal(qa, qb)                 # with grad: same cuDNN / cuBLAS calls, fused tails
+        (qa ** 2).sum().backward()
+        (qb ** 2).sum().backward()
+        for (name, pa), pf in zip(plain.named_parameters(), fused.parameters()):
+            scale = float(pa.grad.abs().max())
+            assert float((pf.grad - pa.grad).abs().max()) <= 5e-3 * scale, name
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+
 def test_qnetv2_fused_blocks_match_the_plain_network(pb):
     """QNetV2.use_fused_blocks(): same Q-values (bit for bit with TF32 off: the same cuDNN
     convolutions, the tail arithmetic is identical) and the same gradients as the plain torch

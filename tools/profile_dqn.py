@@ -46,10 +46,11 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(10): tr.train_iteration()
     torch.cuda.synchronize()
-rows = [e for e in prof.key_averages() if e.self_device_time_total > 0]
+from torch.autograd import DeviceType
+rows = [e for e in prof.key_averages() if e.self_device_time_total > 0 and e.device_type == DeviceType.CUDA]
 rows.sort(key=lambda e: -e.self_device_time_total)
 total = sum(e.self_device_time_total for e in rows)
-print(f"GPU time per iteration: {total / 10 / 1e3:.3f} ms ({len(rows)} kernel / op rows with device time)")
+print(f"GPU time per iteration: {total / 10 / 1e3:.3f} ms ({len(rows)} kernel rows)")
 print(f"{'self device us / iter':>22s} {'%':>6s} {'calls / iter':>13s}  name")
-for e in rows[:60]:
+for e in rows[:90]:
     print(f"{e.self_device_time_total / 10:22.1f} {100 * e.self_device_time_total / total:6.2f} {e.count / 10:13.1f}  {e.key[:110]}")
