@@ -355,6 +355,10 @@ int pb_replay_record(int64_t n_envs, int64_t ring_slots, const int64_t *t_dev,
  * replacement over the m entries (index 0 if m == 0) -- check m before training.
  * Limits: batch <= 4 096, total = R * n <= pb_replay_sample_capacity() (the list lives in
  * shared memory). */
+/* The ring advances by one step: *t_dev += 1, *next_slot_dev = (*t_dev + 1) % ring_slots (the slot
+ * pb_encode_obs_ring writes the next observation to); device-side so that a captured graph keeps
+ * working (the deque append of replay_buffer.py:130 moving on). */
+int pb_replay_advance(int64_t *t_dev, int64_t *next_slot_dev, int64_t ring_slots, int device, void *stream);
 uint32_t pb_replay_raw(uint64_t seed, uint64_t call_idx, uint32_t j);
 int64_t pb_replay_sample_capacity(void);
 int pb_replay_sample(const uint8_t *ring_valid_dev, int64_t total, int64_t batch, uint64_t seed,

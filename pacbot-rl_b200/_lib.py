@@ -108,6 +108,7 @@ SIGNATURES = {
     "pb_rollout_host_sync": (_int, [_vp]),
     "pb_rollout_join": (_int, [_vp, _vp]),
     "pb_qnet_head_fwd": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _int, _vp]),
+    "pb_replay_advance": (_int, [_vp, _vp, _i64, _int, _vp]),
     "pb_step_snapshot_host": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_rollout_streams": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "pb_check_actions": (_int, [_vp, C.POINTER(_i64), _vp]),

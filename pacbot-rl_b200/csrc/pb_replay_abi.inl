@@ -42,6 +42,15 @@ k_replay_record(long long n, long long ring_slots, const long long *__restrict__
     ring_valid[nx] = 0;  // slot t + 1 holds the current observation only
 }
 
+// the ring moves on by one step: t += 1 and the slot the next observation goes to, (t + 1) % R
+// (one launch instead of three tiny torch kernels per experience step)
+__global__ void k_replay_advance(long long *__restrict__ t_dev, long long *__restrict__ next_slot_dev,
+                                 long long ring_slots) {
+    const long long t = *t_dev + 1;
+    *t_dev = t;
+    *next_slot_dev = (t + 1) % ring_slots;
+}
+
 constexpr int SAMPLE_THREADS = 1024;
 constexpr int SAMPLE_SMEM_MAX = 227 * 1024 - SAMPLE_THREADS * 4;  // dynamic part
 // dynamic shared memory: int32 list[total] + uint32 raw[batch]
@@ -247,6 +256,16 @@ int pb_replay_record(int64_t n_envs, int64_t ring_slots, const int64_t *t_dev,
         n_envs, ring_slots, reinterpret_cast<const long long *>(t_dev), actions_dev, reward_dev,
         done_dev, mask_dev, in_phase1_dev, ring_actions, ring_rewards, ring_done, ring_next_mask,
         ring_valid);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_replay_advance(int64_t *t_dev, int64_t *next_slot_dev, int64_t ring_slots, int device, void *stream) {
+    if (!t_dev || !next_slot_dev || ring_slots < 1)
+        return fail(PB_ERR_INVALID_ARG, "pb_replay_advance: bad arguments");
+    DeviceGuard g(device);
+    k_replay_advance<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(t_dev),
+                                                       reinterpret_cast<long long *>(next_slot_dev), ring_slots);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

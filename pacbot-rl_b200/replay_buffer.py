@@ -251,8 +251,8 @@ class ReplayBuffer:
                                  C.c_void_p(self._valid.data_ptr()), dev, stream))
         if self.phase1_policy is not None:
             self._in_phase1.copy_((self._in_phase1 | self._done_step) & ~self.envs.first_ai_done())
-        self._t_dev += 1
-        torch.remainder(self._t_dev + 1, r, out=self._nxt_dev)
+        check(L.pb_replay_advance(C.c_void_p(self._t_dev.data_ptr()), C.c_void_p(self._nxt_dev.data_ptr()),
+                                  r, dev, stream))
         if count_on_host:
             self._t += 1
 
