@@ -125,6 +125,36 @@ class GlobalMaxPool2d(nn.Module):
         return nn.functional.max_pool2d(x, kernel_size=tuple(x.shape[-2:]))
 
 
+_ZERO_I64: dict = {}
+
+
+def obs_to_padded_nhwc(obs: torch.Tensor, channels: int = 32) -> torch.Tensor:
+    """A channel-major observation batch [N, 17, 28, 31] (what the encoder writes) as a
+    channels-last batch zero-padded to `channels` channels, in ONE launch (`pb_replay_slot_obs`, the
+    transposing copy of the replay ring): torch would run a layout-conversion kernel and cuDNN its
+    own channel-padding kernel before a first convolution that, with 17 input channels, has no
+    tensor-core kernel.  The networks pad their first weight to match (see `_fused_trunk`)."""
+    import ctypes as C
+
+    from . import _lib
+
+    n, dev = obs.shape[0], obs.device
+    out = torch.empty((n, channels) + tuple(obs.shape[2:]), dtype=torch.float32, device=dev,
+                      memory_format=torch.channels_last)
+    zero = _ZERO_I64.get(dev)
+    if zero is None:
+        zero = _ZERO_I64[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().pb_replay_slot_obs(
+        C.c_void_p(obs.data_ptr()), n, 1, C.c_void_p(zero.data_ptr()), C.c_void_p(out.data_ptr()), channels,
+        dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
+def _is_raw_obs(obs: torch.Tensor) -> bool:
+    return (obs.is_cuda and obs.dtype == torch.float32 and obs.dim() == 4 and tuple(obs.shape[1:]) == (17, 28, 31)
+            and obs.is_contiguous() and not obs.requires_grad and obs.shape[0] > 0)
+
+
 def _fused_trunk(bb: nn.Sequential, obs: torch.Tensor) -> torch.Tensor:
     """Blocks 0..8 of the QNetV2 / NetV2 layer list (conv5x5 + SiLU, 3 x [conv3x3, max pool, SiLU])
     with every block tail as one `bias_pool_silu` launch; the convolutions run without bias."""
@@ -198,6 +228,8 @@ class QNetV2(nn.Module):
         return value - adv.mean(dim=1, keepdim=True) + adv
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_fused_blocks", False) and _is_raw_obs(obs):
+            obs = obs_to_padded_nhwc(obs)          # encoder output -> NHWC, 32 channels, one launch
         if getattr(self, "_channels_last", False):
             obs = obs.contiguous(memory_format=torch.channels_last)
         if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:
@@ -314,6 +346,8 @@ class NetV2(nn.Module):
         return self
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_fused_blocks", False) and _is_raw_obs(obs):
+            obs = obs_to_padded_nhwc(obs)          # encoder output -> NHWC, 32 channels, one launch
         if getattr(self, "_channels_last", False):
             obs = obs.contiguous(memory_format=torch.channels_last)
         if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:

@@ -9,7 +9,7 @@ from pacbot_rl_b200 import alphazero, models
 
 dev = torch.device("cuda:0")
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-model = models.NetV2((17, 28, 31), 6).to(dev).use_channels_last().eval()
+model = models.NetV2((17, 28, 31), 6).to(dev).use_fused_blocks().eval()
 
 @torch.no_grad()
 def evaluator(obs, mask):
@@ -42,7 +42,13 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(50):
         col.generate_experience_step(fin)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
+from torch.autograd import DeviceType
+rows = [e for e in prof.key_averages() if e.self_device_time_total > 0 and e.device_type == DeviceType.CUDA]
+rows.sort(key=lambda e: -e.self_device_time_total)
+total = sum(e.self_device_time_total for e in rows)
+print(f"GPU time per collector step: {total / 50:.1f} us ({len(rows)} kernel rows)")
+for e in rows[:40]:
+    print(f"{e.self_device_time_total / 50:10.1f} us {e.count / 50:6.1f} calls  {e.key[:120]}")
 colg = make(); colg.enable_cuda_graph()
 print(f"{P} trees, graph step: {wall(colg):.3f} ms")
 # the search iteration alone (no env steps, no host read)
