@@ -421,6 +421,27 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
                      const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
                      float *out_dev, int device, void *stream);
 
+/* Training form of the head: the same forward that also keeps p_out float32 [n][128] (pooled
+ * maximum + bias), idx_out uint8 [n][128] (map position of the maximum, first one in row-major
+ * order as torch chooses; hw <= 255) and u_out float32 [n][256] (input of the second SiLU) ... */
+int pb_qnet_head_fwd_train(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                           const float *w1_dev, const float *b1_dev, const float *wv_dev,
+                           const float *bv_dev, const float *wa_dev, const float *ba_dev, int64_t n_out,
+                           int dueling, float *out_dev, float *p_out_dev, uint8_t *idx_out_dev,
+                           float *u_out_dev, int device, void *stream);
+/* ... and its backward, two launches: dq float32 [n][n_out] in; dx float32 [n][hw][128] (every
+ * cell written: the gradient at the arg-max position, 0 elsewhere), the convolution bias gradient
+ * [128], dW1 [256][128], db1 [256], dWv [256] / dbv [1] (dueling only), dWa [n_out][256], dba
+ * [n_out] out.  scratch_dev: pb_qnet_head_bwd_scratch_floats(n) floats of device memory.  The
+ * arithmetic is the chain rule of src/models.py:92-110 in float32; batch sums in sample order. */
+int pb_qnet_head_bwd(const float *dq_dev, const float *p_dev, const uint8_t *idx_dev, const float *u_dev,
+                     const float *w1_dev, const float *wv_dev, const float *wa_dev, int64_t n, int64_t hw,
+                     int64_t n_out, int dueling, float *dx_dev, float *dconv_bias_dev, float *dw1_dev,
+                     float *db1_dev, float *dwv_dev, float *dbv_dev, float *dwa_dev, float *dba_dev,
+                     float *scratch_dev, int device, void *stream);
+int64_t pb_qnet_head_bwd_scratch_floats(int64_t n);
+
+
 
 /* ---- device timeline (diagnostics; no counterpart in the reference) --------------------------
  * Between pb_trace_begin and pb_trace_end every k_step / k_encode_obs launch of the engine

@@ -108,6 +108,11 @@ SIGNATURES = {
     "pb_rollout_host_sync": (_int, [_vp]),
     "pb_rollout_join": (_int, [_vp, _vp]),
     "pb_qnet_head_fwd": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _int, _vp]),
+    "pb_qnet_head_fwd_train": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp,
+                               _vp, _vp, _int, _vp]),
+    "pb_qnet_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp,
+                         _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "pb_qnet_head_bwd_scratch_floats": (_i64, [_i64]),
     "pb_replay_advance": (_int, [_vp, _vp, _i64, _int, _vp]),
     "pb_step_snapshot_host": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_rollout_streams": (_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),

@@ -160,15 +160,20 @@ constexpr int HEAD_C = 128, HEAD_H = 256, HEAD_THREADS = 512, HEAD_MAX_OUT = 8;
 constexpr int HEAD_WARPS = HEAD_THREADS / 32, HEAD_RB = 8;      // rows of W1 in flight per warp
 constexpr int HEAD_PGROUPS = HEAD_THREADS / (HEAD_C / 4);   // 16 map positions in flight per sample
 
-template <int S>
+// TRAIN: additionally keeps what the backward kernels need -- p_out [n][128] (the pooled maximum +
+// bias, i.e. the first SiLU's input), idx_out [n][128] (map position of the maximum: the first
+// one in row-major order, torch's choice), u_out [n][256] (the second SiLU's input).
+template <int S, bool TRAIN>
 __global__ void __launch_bounds__(HEAD_THREADS)
 k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ conv_bias,
                 const float *__restrict__ w1, const float *__restrict__ b1,
                 const float *__restrict__ wv, const float *__restrict__ bv,
                 const float *__restrict__ wa, const float *__restrict__ ba, int n_out, int dueling,
-                long long n, float *__restrict__ out) {
+                long long n, float *__restrict__ out, float *__restrict__ p_out,
+                unsigned char *__restrict__ idx_out, float *__restrict__ u_out) {
     __shared__ __align__(16) float s_a[S][HEAD_C];
     __shared__ __align__(16) float s_m[S][HEAD_PGROUPS][HEAD_C];
+    __shared__ unsigned char s_pos[TRAIN ? S : 1][HEAD_PGROUPS][HEAD_C];
     __shared__ float s_f[S][HEAD_H];
     __shared__ float s_h[S][HEAD_MAX_OUT + 1];
     __shared__ float s_b1[HEAD_H];
@@ -189,29 +194,48 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
         for (int smp = 0; smp < S; smp++) {
             const long long i = n0 + smp;
             float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            int ax = g, ay = g, az = g, aw = g;   // TRAIN: position of each channel's maximum so far
             if (i < n) {
                 const float4 *src = reinterpret_cast<const float4 *>(x + i * hw * HEAD_C) + c4;
 #pragma unroll 4
                 for (int p = g; p < hw; p += HEAD_PGROUPS) {
                     const float4 v = __ldg(src + (long long)p * (HEAD_C / 4));
-                    if (v.x > m.x || v.x != v.x) m.x = v.x;
-                    if (v.y > m.y || v.y != v.y) m.y = v.y;
-                    if (v.z > m.z || v.z != v.z) m.z = v.z;
-                    if (v.w > m.w || v.w != v.w) m.w = v.w;
+                    if (v.x > m.x || v.x != v.x) { m.x = v.x; ax = p; }
+                    if (v.y > m.y || v.y != v.y) { m.y = v.y; ay = p; }
+                    if (v.z > m.z || v.z != v.z) { m.z = v.z; az = p; }
+                    if (v.w > m.w || v.w != v.w) { m.w = v.w; aw = p; }
                 }
             }
             *reinterpret_cast<float4 *>(&s_m[smp][g][4 * c4]) = m;
+            if (TRAIN)
+                *reinterpret_cast<uchar4 *>(&s_pos[smp][g][4 * c4]) =
+                    make_uchar4((unsigned char)ax, (unsigned char)ay, (unsigned char)az, (unsigned char)aw);
         }
         __syncthreads();
         for (int t = threadIdx.x; t < S * HEAD_C; t += HEAD_THREADS) {
             const int smp = t / HEAD_C, c = t % HEAD_C;
             float best = s_m[smp][0][c];
+            int bpos = TRAIN ? s_pos[smp][0][c] : 0;
 #pragma unroll
             for (int k = 1; k < HEAD_PGROUPS; k++) {
                 const float v = s_m[smp][k][c];
-                if (best == best && (v > best || v != v)) best = v;
+                if (TRAIN) {   // equal maxima: the smaller map position (first in row-major order)
+                    const int vp = s_pos[smp][k][c];
+                    if (best == best && (v > best || v != v || (v == best && vp < bpos))) {
+                        best = v;
+                        bpos = vp;
+                    }
+                } else if (best == best && (v > best || v != v)) {
+                    best = v;
+                }
             }
-            s_a[smp][c] = (n0 + smp < n) ? silu_f(best + __ldg(conv_bias + c)) : 0.f;
+            const bool live = n0 + smp < n;
+            const float pre = best + __ldg(conv_bias + c);
+            s_a[smp][c] = live ? silu_f(pre) : 0.f;
+            if (TRAIN && live) {
+                p_out[(n0 + smp) * HEAD_C + c] = pre;
+                idx_out[(n0 + smp) * HEAD_C + c] = (unsigned char)bpos;
+            }
         }
         __syncthreads();
     }
@@ -251,7 +275,11 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
 #pragma unroll
             for (int r = 1; r < HEAD_RB; r++)
                 if ((lane & (HEAD_RB - 1)) == r) v = acc[r][smp];
-            if (lane < HEAD_RB) s_f[smp][row] = silu_f(v + s_b1[row]);
+            if (lane < HEAD_RB) {
+                const float pre = v + s_b1[row];
+                s_f[smp][row] = silu_f(pre);
+                if (TRAIN && n0 + smp < n) u_out[(n0 + smp) * HEAD_H + row] = pre;
+            }
         }
     }
     __syncthreads();
@@ -286,6 +314,209 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
             }
             out[i * n_out + k] = q;
         }
+    }
+}
+
+// ---- backward of the head (training forward = k_qnet_head_fwd<S, true>) ------------------------
+// k_qnet_head_bwd: the per-sample chain, one CTA per S samples like the forward:
+//   dh   = d(head rows): dueling  dV = sum_k dq_k, dA_k = dq_k - (sum_j dq_j) / A; plain  dq
+//   df_j = sum_r Wh[r][j] dh_r;  du_j = df_j SiLU'(u_j)
+//   da_c = sum_j W1[j][c] du_j   (column walk of W1: row j is one coalesced 512 B load, four
+//          groups of 64 rows in flight over the CTA, partial sums meet in shared memory)
+//   dp_c = da_c SiLU'(p_c);  dx[pos][c] = dp_c at the arg-max position, 0 elsewhere -- every
+//          cell of dx is written exactly once, no zero fill
+// and it leaves du, dh, dp plus the recomputed activations a = SiLU(p), f = SiLU(u) for
+// k_qnet_head_wgrad, which reduces over the batch: dW1 = du^T a (32 x 32 tiles, shared-memory
+// staged), db1, dWh = dh^T f, dbh, and the convolution bias gradient sum_n dp.
+constexpr int HEAD_R = HEAD_MAX_OUT;   // head rows incl. the value row (padded to 8)
+
+template <int S>
+__global__ void __launch_bounds__(HEAD_THREADS)
+k_qnet_head_bwd(const float *__restrict__ dq, const float *__restrict__ p, const unsigned char *__restrict__ idx,
+                const float *__restrict__ u, const float *__restrict__ w1, const float *__restrict__ wv,
+                const float *__restrict__ wa, int hw, int n_out, int dueling, long long n,
+                float *__restrict__ dx, float *__restrict__ dp_out, float *__restrict__ du_out,
+                float *__restrict__ a_out, float *__restrict__ f_out, float *__restrict__ dh_out) {
+    __shared__ float s_dh[S][HEAD_R];
+    __shared__ float s_du[S][HEAD_H];
+    __shared__ float s_part[HEAD_THREADS / HEAD_C][S][HEAD_C];
+    __shared__ float s_dp[S][HEAD_C];
+    __shared__ unsigned char s_idx[S][HEAD_C];
+    const long long n0 = (long long)blockIdx.x * S;
+    const int rows = n_out + (dueling ? 1 : 0);
+    if ((int)threadIdx.x < S * HEAD_R) {
+        const int smp = threadIdx.x / HEAD_R, r = threadIdx.x % HEAD_R;
+        const long long i = n0 + smp;
+        float v = 0.f;
+        if (i < n && r < rows) {
+            const float *g = dq + i * n_out;
+            if (dueling) {
+                float sum = 0.f;
+                for (int k = 0; k < n_out; k++) sum += g[k];
+                v = r == 0 ? sum : g[r - 1] - sum / (float)n_out;
+            } else {
+                v = g[r];
+            }
+        }
+        s_dh[smp][r] = v;
+        if (i < n) dh_out[i * HEAD_R + r] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < S * HEAD_H; t += HEAD_THREADS) {
+        const int smp = t / HEAD_H, j = t % HEAD_H;
+        const long long i = n0 + smp;
+        float du = 0.f;
+        if (i < n) {
+            float df = 0.f;
+            for (int r = 0; r < rows; r++) {
+                const float w = (dueling && r == 0) ? __ldg(wv + j) : __ldg(wa + (long long)(r - (dueling ? 1 : 0)) * HEAD_H + j);
+                df = fmaf(w, s_dh[smp][r], df);
+            }
+            const float uu = __ldg(u + i * HEAD_H + j);
+            du = silu_grad_f(df, uu);
+            du_out[i * HEAD_H + j] = du;
+            f_out[i * HEAD_H + j] = silu_f(uu);
+        }
+        s_du[smp][j] = du;
+    }
+    __syncthreads();
+    {
+        const int c = threadIdx.x % HEAD_C, jg = threadIdx.x / HEAD_C;   // 4 groups of 64 rows
+        constexpr int ROWS_PER = HEAD_H / (HEAD_THREADS / HEAD_C);
+        float acc[S];
+#pragma unroll
+        for (int smp = 0; smp < S; smp++) acc[smp] = 0.f;
+#pragma unroll 8
+        for (int jj = 0; jj < ROWS_PER; jj++) {
+            const int j = jg * ROWS_PER + jj;
+            const float w = __ldg(w1 + (long long)j * HEAD_C + c);
+#pragma unroll
+            for (int smp = 0; smp < S; smp++) acc[smp] = fmaf(w, s_du[smp][j], acc[smp]);
+        }
+#pragma unroll
+        for (int smp = 0; smp < S; smp++) s_part[jg][smp][c] = acc[smp];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < S * HEAD_C; t += HEAD_THREADS) {
+        const int smp = t / HEAD_C, c = t % HEAD_C;
+        const long long i = n0 + smp;
+        float dp = 0.f;
+        unsigned char pos = 0;
+        if (i < n) {
+            float da = 0.f;
+#pragma unroll
+            for (int k = 0; k < HEAD_THREADS / HEAD_C; k++) da += s_part[k][smp][c];
+            const float pp = __ldg(p + i * HEAD_C + c);
+            dp = silu_grad_f(da, pp);
+            dp_out[i * HEAD_C + c] = dp;
+            a_out[i * HEAD_C + c] = silu_f(pp);
+            pos = idx[i * HEAD_C + c];
+        }
+        s_dp[smp][c] = dp;
+        s_idx[smp][c] = pos;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < S * hw * (HEAD_C / 4); t += HEAD_THREADS) {
+        const int c4 = t % (HEAD_C / 4);
+        const int r = t / (HEAD_C / 4);
+        const int pos = r % hw, smp = r / hw;
+        const long long i = n0 + smp;
+        if (i >= n) continue;
+        const int c = 4 * c4;
+        const float4 v = make_float4(s_idx[smp][c] == pos ? s_dp[smp][c] : 0.f,
+                                     s_idx[smp][c + 1] == pos ? s_dp[smp][c + 1] : 0.f,
+                                     s_idx[smp][c + 2] == pos ? s_dp[smp][c + 2] : 0.f,
+                                     s_idx[smp][c + 3] == pos ? s_dp[smp][c + 3] : 0.f);
+        reinterpret_cast<float4 *>(dx + (i * hw + pos) * HEAD_C)[c4] = v;
+    }
+}
+
+constexpr int WG_THREADS = 256, WG_T = 32;   // 32 x 32 output tile, 32 samples per stage
+constexpr int WG_TILES = (HEAD_H / WG_T) * (HEAD_C / WG_T);   // 32 tiles of dW1
+// blocks [0, WG_TILES): dW1 tiles (+ db1 in the tiles of the first column block);
+// block WG_TILES: dWh / dbh; block WG_TILES + 1: the convolution bias gradient
+__global__ void __launch_bounds__(WG_THREADS)
+k_qnet_head_wgrad(const float *__restrict__ du, const float *__restrict__ a, const float *__restrict__ f,
+                  const float *__restrict__ dh, const float *__restrict__ dp, long long n, int n_out,
+                  int dueling, float *__restrict__ dw1, float *__restrict__ db1, float *__restrict__ dwv,
+                  float *__restrict__ dbv, float *__restrict__ dwa, float *__restrict__ dba,
+                  float *__restrict__ dconv_bias) {
+    __shared__ float s_x[WG_T][WG_T + 1];
+    __shared__ float s_y[WG_T][WG_T + 1];
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < WG_TILES) {
+        const int jt = blockIdx.x / (HEAD_C / WG_T), ct = blockIdx.x % (HEAD_C / WG_T);
+        const int c = tid % WG_T, tj = tid / WG_T;   // rows tj, tj + 8, tj + 16, tj + 24 of the tile
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (long long nb = 0; nb < n; nb += WG_T) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {   // 32 samples x 32 columns of du and of a
+                const int nn = tj + 8 * k;
+                const long long i = nb + nn;
+                s_x[nn][c] = i < n ? __ldg(du + i * HEAD_H + jt * WG_T + c) : 0.f;
+                s_y[nn][c] = i < n ? __ldg(a + i * HEAD_C + ct * WG_T + c) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int nn = 0; nn < WG_T; nn++) {
+                const float y = s_y[nn][c];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float x = s_x[nn][tj + 8 * k];
+                    acc[k] = fmaf(x, y, acc[k]);
+                    accb[k] += x;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int j = jt * WG_T + tj + 8 * k;
+            dw1[(long long)j * HEAD_C + ct * WG_T + c] = acc[k];
+            if (ct == 0 && c == 0) db1[j] = accb[k];
+        }
+        return;
+    }
+    if ((int)blockIdx.x == WG_TILES) {   // head rows: thread j owns column j of every row
+        const int rows = n_out + (dueling ? 1 : 0);
+        float acc[HEAD_R], accb = 0.f;
+#pragma unroll
+        for (int r = 0; r < HEAD_R; r++) acc[r] = 0.f;
+        float *s_dh = &s_x[0][0];   // 32 samples x 8 rows per stage
+        for (long long nb = 0; nb < n; nb += WG_T) {
+            {
+                const long long i = nb + tid / HEAD_R;
+                s_dh[tid] = i < n ? __ldg(dh + i * HEAD_R + tid % HEAD_R) : 0.f;
+            }
+            __syncthreads();
+            float fv[WG_T];
+#pragma unroll
+            for (int nn = 0; nn < WG_T; nn++) fv[nn] = (nb + nn < n) ? __ldg(f + (nb + nn) * HEAD_H + tid) : 0.f;
+#pragma unroll
+            for (int nn = 0; nn < WG_T; nn++) {
+#pragma unroll
+                for (int r = 0; r < HEAD_R; r++) acc[r] = fmaf(s_dh[nn * HEAD_R + r], fv[nn], acc[r]);
+                if (tid < HEAD_R) accb += s_dh[nn * HEAD_R + tid];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < HEAD_R; r++) {
+            if (r >= rows) break;
+            if (dueling && r == 0) dwv[tid] = acc[r];
+            else dwa[(long long)(r - (dueling ? 1 : 0)) * HEAD_H + tid] = acc[r];
+        }
+        if (tid < rows) {
+            if (dueling && tid == 0) dbv[0] = accb;
+            else dba[tid - (dueling ? 1 : 0)] = accb;
+        }
+        return;
+    }
+    if (tid < HEAD_C) {   // convolution bias gradient
+        float acc = 0.f;
+#pragma unroll 8
+        for (long long i = 0; i < n; i++) acc += __ldg(dp + i * HEAD_C + tid);
+        dconv_bias[tid] = acc;
     }
 }
 
@@ -371,6 +602,18 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
                      const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
                      const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
                      float *out_dev, int device, void *stream) {
+    return pb_qnet_head_fwd_train(x_dev, n, hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev,
+                                  ba_dev, n_out, dueling, out_dev, nullptr, nullptr, nullptr, device, stream);
+}
+
+int pb_qnet_head_fwd_train(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                           const float *w1_dev, const float *b1_dev, const float *wv_dev,
+                           const float *bv_dev, const float *wa_dev, const float *ba_dev, int64_t n_out,
+                           int dueling, float *out_dev, float *p_out_dev, uint8_t *idx_out_dev,
+                           float *u_out_dev, int device, void *stream) {
+    const bool train = p_out_dev || idx_out_dev || u_out_dev;
+    if (train && (!p_out_dev || !idx_out_dev || !u_out_dev || hw > 255))
+        return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_fwd_train: p / idx / u outputs come together, map of <= 255 cells");
     if (!x_dev || !conv_bias_dev || !w1_dev || !b1_dev || !wa_dev || !ba_dev || !out_dev || n <= 0 ||
         hw <= 0 || hw > 4096 || n_out <= 0 || n_out > HEAD_MAX_OUT - (dueling ? 1 : 0) ||
         (dueling && (!wv_dev || !bv_dev)) || !aligned16(w1_dev) || !aligned16(x_dev))
@@ -380,19 +623,64 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
     cudaStream_t s = (cudaStream_t)stream;
     // samples per CTA: enough CTAs to cover the SMs at small batches, W1 amortised at large ones
     const int sms = qnet_sms(device);
-#define PB_HEAD_LAUNCH(S)                                                                          \
-    k_qnet_head_fwd<S><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                   \
+#define PB_HEAD_LAUNCH(S, T)                                                                       \
+    k_qnet_head_fwd<S, T><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                \
         x_dev, (int)hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, (int)n_out,  \
-        dueling, n, out_dev)
-    if (n <= sms)
-        PB_HEAD_LAUNCH(1);
-    else if (n <= 2 * sms)
-        PB_HEAD_LAUNCH(2);
-    else
-        PB_HEAD_LAUNCH(4);
+        dueling, n, out_dev, p_out_dev, idx_out_dev, u_out_dev)
+    if (train) {
+        if (n <= sms)
+            PB_HEAD_LAUNCH(1, true);
+        else if (n <= 2 * sms)
+            PB_HEAD_LAUNCH(2, true);
+        else
+            PB_HEAD_LAUNCH(4, true);
+    } else if (n <= sms) {
+        PB_HEAD_LAUNCH(1, false);
+    } else if (n <= 2 * sms) {
+        PB_HEAD_LAUNCH(2, false);
+    } else {
+        PB_HEAD_LAUNCH(4, false);
+    }
 #undef PB_HEAD_LAUNCH
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
+
+int pb_qnet_head_bwd(const float *dq_dev, const float *p_dev, const uint8_t *idx_dev, const float *u_dev,
+                     const float *w1_dev, const float *wv_dev, const float *wa_dev, int64_t n, int64_t hw,
+                     int64_t n_out, int dueling, float *dx_dev, float *dconv_bias_dev, float *dw1_dev,
+                     float *db1_dev, float *dwv_dev, float *dbv_dev, float *dwa_dev, float *dba_dev,
+                     float *scratch_dev, int device, void *stream) {
+    if (!dq_dev || !p_dev || !idx_dev || !u_dev || !w1_dev || !wa_dev || !dx_dev || !dconv_bias_dev ||
+        !dw1_dev || !db1_dev || !dwa_dev || !dba_dev || !scratch_dev || n <= 0 || hw <= 0 || hw > 255 ||
+        n_out <= 0 || n_out > HEAD_MAX_OUT - (dueling ? 1 : 0) || (dueling && (!wv_dev || !dwv_dev || !dbv_dev)) ||
+        !aligned16(dx_dev))
+        return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_bwd: bad arguments");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // scratch: dp [n][128] | du [n][256] | a [n][128] | f [n][256] | dh [n][8]
+    float *dp = scratch_dev, *du = dp + n * HEAD_C, *a = du + n * HEAD_H, *f = a + n * HEAD_C,
+          *dh = f + n * HEAD_H;
+    const int sms = qnet_sms(device);
+#define PB_HEAD_BWD(S)                                                                             \
+    k_qnet_head_bwd<S><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                   \
+        dq_dev, p_dev, idx_dev, u_dev, w1_dev, wv_dev, wa_dev, (int)hw, (int)n_out, dueling, n,    \
+        dx_dev, dp, du, a, f, dh)
+    if (n <= sms)
+        PB_HEAD_BWD(1);
+    else if (n <= 2 * sms)
+        PB_HEAD_BWD(2);
+    else
+        PB_HEAD_BWD(4);
+#undef PB_HEAD_BWD
+    PB_CUDA(cudaGetLastError());
+    k_qnet_head_wgrad<<<WG_TILES + 2, WG_THREADS, 0, s>>>(du, a, f, dh, dp, n, (int)n_out, dueling, dw1_dev,
+                                                         db1_dev, dwv_dev, dbv_dev, dwa_dev, dba_dev,
+                                                         dconv_bias_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int64_t pb_qnet_head_bwd_scratch_floats(int64_t n) { return n * (2 * HEAD_C + 2 * HEAD_H + HEAD_R); }
 
 }  // extern "C"

@@ -114,6 +114,77 @@ def qnet_head(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.
     return q
 
 
+class _QNetHead(torch.autograd.Function):
+    """`qnet_head` with gradients: forward = `pb_qnet_head_fwd_train` (one launch; keeps the two
+    SiLU inputs and the arg-max positions), backward = `pb_qnet_head_bwd` (two launches: the
+    per-sample chain incl. the scatter to the arg-max cells, and the batch reductions for the
+    weight / bias gradients) instead of ~25 torch launches (max-pool, SiLU, three `addmm` and their
+    backward GEMMs, reductions, the convolution's bias add and bias-gradient sum)."""
+
+    @staticmethod
+    def forward(ctx, x, conv_bias, w1, b1, wv, bv, wa, ba):
+        import ctypes as C
+
+        from . import _lib
+
+        n, c, h, w = x.shape
+        dev = x.device
+        dueling = wv is not None
+        n_out = wa.shape[0]
+        q = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+        pre = torch.empty((n, 128), dtype=torch.float32, device=dev)
+        idx = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+        u = torch.empty((n, 256), dtype=torch.float32, device=dev)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        _lib.check(_lib.load().pb_qnet_head_fwd_train(
+            p(x), n, h * w, p(conv_bias), p(w1), p(b1), p(wv), p(bv), p(wa), p(ba), n_out, int(dueling),
+            p(q), p(pre), p(idx), p(u), dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        ctx.save_for_backward(pre, idx, u, w1, wv, wa)
+        ctx.shape = (n, c, h, w)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        import ctypes as C
+
+        from . import _lib
+
+        pre, idx, u, w1, wv, wa = ctx.saved_tensors
+        n, c, h, w = ctx.shape
+        dev = dq.device
+        L = _lib.load()
+        dueling = wv is not None
+        n_out = wa.shape[0]
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)   # noqa: E731
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        dcb, dw1, db1, dwa, dba = new(128), new(256, 128), new(256), new(n_out, 256), new(n_out)
+        dwv, dbv = (new(1, 256), new(1)) if dueling else (None, None)
+        scratch = new(int(L.pb_qnet_head_bwd_scratch_floats(n)))
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        _lib.check(L.pb_qnet_head_bwd(
+            p(dq.contiguous()), p(pre), p(idx), p(u), p(w1), p(wv), p(wa), n, h * w, n_out, int(dueling),
+            p(dx), p(dcb), p(dw1), p(db1), p(dwv), p(dbv), p(dwa), p(dba), p(scratch), dev.index,
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return dx, dcb, dw1, db1, dwv, dbv, dwa, dba
+
+
+def _head_args_ok(x: torch.Tensor, lin: nn.Linear) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 128
+            and lin.in_features == 128 and lin.out_features == 256 and x.shape[2] * x.shape[3] <= 255
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def qnet_head_train(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.Linear,
+                    value: "nn.Linear | None" = None) -> torch.Tensor:
+    """`qnet_head` for the forward that needs gradients (`_QNetHead`): same arguments."""
+    if not _head_args_ok(x, lin):
+        raise ValueError("qnet_head_train: channels-last float32 CUDA [N, 128, H, W] input (H*W <= 255) and "
+                         "Linear(128, 256) expected")
+    return _QNetHead.apply(x.contiguous(memory_format=torch.channels_last), conv_bias, lin.weight, lin.bias,
+                           None if value is None else value.weight, None if value is None else value.bias,
+                           out.weight, out.bias)
+
+
 class GlobalMaxPool2d(nn.Module):
     """`nn.AdaptiveMaxPool2d((1, 1))` (reference models.py:96) computed as ONE max-pool window over
     the whole feature map: same values, same arg-max choice (first maximum in row-major order) and
@@ -222,10 +293,9 @@ class QNetV2(nn.Module):
             last = bb[11]
             x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
             return qnet_head(x5, last.bias, bb[15], self.advantage_head[0], self.value_head[0])
-        feat = bb[11:](h)                       # grouped conv, global max pool, SiLU, Linear, SiLU
-        value = self.value_head(feat)
-        adv = self.advantage_head(feat)
-        return value - adv.mean(dim=1, keepdim=True) + adv
+        last = bb[11]                            # the forward that needs gradients: fused head + backward
+        x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+        return qnet_head_train(x5, last.bias, bb[15], self.advantage_head[0], self.value_head[0])
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_fused_blocks", False) and _is_raw_obs(obs):
@@ -357,5 +427,7 @@ class NetV2(nn.Module):
                 last = net[11]
                 x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
                 return qnet_head(x5, last.bias, net[15], net[17])
-            return net[11:](h)
+            last = net[11]
+            x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+            return qnet_head_train(x5, last.bias, net[15], net[17])
         return self.network(obs)

@@ -750,6 +750,58 @@ def test_qnet_head_matches_torch_composition(pb, n):
         qnet_head(torch.randn((2, 64, 4, 4), device=dev), conv_bias, lin, adv, val)
 
 
+@pytest.mark.parametrize("n,dueling", [(32, True), (300, True), (512, True), (1100, True), (40, False)])
+def test_qnet_head_train_matches_torch_autograd(pb, n, dueling):
+    """`qnet_head_train` (pb_qnet_head_fwd_train + pb_qnet_head_bwd): Q-values and EVERY gradient
+    (the convolution output incl. the routing to the arg-max cells, the convolution bias, both
+    linear layers, the dueling heads) against autograd through the torch modules it replaces
+    (reference models.py:92-110 / :139-141).  float32 both ways; the batch reductions run in
+    another order than cuBLAS: rtol 1e-4, atol 1e-5 of each tensor's largest entry."""
+    import torch
+    from torch import nn
+    from pacbot_rl_b200.models import GlobalMaxPool2d, qnet_head_train
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(100 + n)
+    x0 = torch.randn((n, 128, 4, 4), device=dev)
+    x0[:, 7] = x0[:, 7].round()            # ties inside a map: the first maximum must get the gradient
+    lin, out = nn.Linear(128, 256).to(dev), nn.Linear(256, 5 if dueling else 6).to(dev)
+    val = nn.Linear(256, 1).to(dev) if dueling else None
+    conv_bias = (torch.randn(128, device=dev) * 0.5).requires_grad_()
+    weight = torch.randn((n, out.out_features), device=dev)      # d(loss)/dq
+
+    def run(fused: bool):
+        for m in (lin, out, val):
+            if m is not None:
+                m.zero_grad()
+        conv_bias.grad = None
+        x = x0.clone().contiguous(memory_format=torch.channels_last).requires_grad_()
+        if fused:
+            q = qnet_head_train(x, conv_bias, lin, out, val)
+        else:
+            feat = nn.SiLU()(lin(nn.SiLU()(nn.Flatten()(GlobalMaxPool2d()(x + conv_bias.view(1, -1, 1, 1))))))
+            a = out(feat)
+            q = a if val is None else val(feat) - a.mean(dim=1, keepdim=True) + a
+        (q * weight).sum().backward()
+        grads = {"x": x.grad, "conv_bias": conv_bias.grad, "w1": lin.weight.grad, "b1": lin.bias.grad,
+                 "wa": out.weight.grad, "ba": out.bias.grad}
+        if val is not None:
+            grads.update(wv=val.weight.grad, bv=val.bias.grad)
+        return q.detach().clone(), {k: v.detach().clone() for k, v in grads.items()}
+
+    q_ref, g_ref = run(False)
+    q_got, g_got = run(True)
+    torch.testing.assert_close(q_got, q_ref, rtol=1e-5, atol=1e-6)
+    for name, ref in g_ref.items():
+        got = g_got[name]
+        assert got.shape == ref.shape, name
+        scale = float(ref.abs().max())
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5 * scale, msg=lambda m, name=name: f"{name}: {m}")
+    # the gradient of the map is non-zero in exactly one cell per (sample, channel): the arg-max
+    nz = (g_got["x"] != 0).sum(dim=(2, 3))
+    assert int(nz.max()) <= 1 and torch.equal(g_got["x"] != 0, g_ref["x"] != 0)
+
+
 def test_obs_to_padded_nhwc_is_a_pure_layout_change(pb):
     import torch
     from pacbot_rl_b200.models import obs_to_padded_nhwc
@@ -798,8 +850,8 @@ def test_netv2_fused_blocks_match_the_plain_network(pb):
 
 
 def test_qnetv2_fused_blocks_match_the_plain_network(pb):
-    """QNetV2.use_fused_blocks(): same Q-values (bit for bit with TF32 off: the same cuDNN
-    convolutions, the tail arithmetic is identical) and the same gradients as the plain torch
+    """QNetV2.use_fused_blocks(): same Q-values (TF32 off: the same cuDNN convolutions, the block
+    tails bit-identical, the head to float32 rounding) and the same gradients as the plain torch
     module, for the 17-channel and the zero-padded 32-channel input, train and no_grad."""
     import copy
 
@@ -831,18 +883,16 @@ def test_qnetv2_fused_blocks_match_the_plain_network(pb):
             for net in (plain, fused, twin):
                 net.zero_grad()
             qa, qb = plain(x), fused(x)
-            if x is obs:   # raw encoder layout: the fused network pads it to 32 channels itself, so
-                # cuDNN may pick another first-convolution kernel than for the 17-channel input
-                torch.testing.assert_close(qb, qa, rtol=1e-5, atol=1e-6)
-            else:
-                assert torch.equal(qa, qb)
+            # the head is one kernel with gradients too (float32 sums in another order than cuBLAS);
+            # for the raw encoder layout the fused network also pads the batch to 32 channels itself
+            torch.testing.assert_close(qb, qa, rtol=1e-5, atol=1e-6)
             (qa ** 2).sum().backward()
             (qb ** 2).sum().backward()
             # the reference for "noise": the PLAIN module once more -- on the 32-channel padded batch
             # when the fused network pads the raw layout itself (another cuDNN weight-gradient
             # kernel for the first convolution than for the 17-channel input)
             (twin(torch.nn.functional.pad(obs, (0, 0, 0, 0, 0, 15)) if x is obs else x) ** 2).sum().backward()
-            # gradients, relative to each tensor's largest entry: 1e-6 (the bias gradients are
+            # gradients, relative to each tensor's largest entry: 5e-6 (bias and head gradients are
             # summed in another order), or the difference between two runs of the PLAIN module
             # where that is larger (cuDNN's fp32 weight-gradient kernel for the first convolution
             # is not run-to-run deterministic: 1.5e-3 between identical plain networks)
@@ -850,7 +900,7 @@ def test_qnetv2_fused_blocks_match_the_plain_network(pb):
                 scale = float(pa.grad.abs().max())
                 err = float((pf.grad - pa.grad).abs().max()) / scale
                 noise = float((pt.grad - pa.grad).abs().max()) / scale
-                assert err <= max(1e-6, 3 * noise), (name, err, noise)
+                assert err <= max(5e-6, 3 * noise), (name, err, noise)
         # checkpoints are written from a plain copy
         from pacbot_rl_b200.models import portable_copy
 
