@@ -30,6 +30,8 @@ def portable_copy(net: nn.Module) -> nn.Module:
         out._channels_last = False
     if getattr(out, "_fused_blocks", False):
         out._fused_blocks = False
+    for m in out.modules():          # scratch buffers of the fused forward do not belong in a checkpoint
+        m.__dict__.pop("_pb_pad_buffers", None)
     return out
 
 
@@ -226,14 +228,36 @@ def _is_raw_obs(obs: torch.Tensor) -> bool:
             and obs.is_contiguous() and not obs.requires_grad and obs.shape[0] > 0)
 
 
+def _pad_buffer(conv: nn.Conv2d, channels: int) -> torch.Tensor:
+    """Persistent channels-last weight buffer [out, channels, kh, kw] of `conv`, zero where the
+    input channels are padding (allocated once per module and channel count; not a parameter, not
+    in the state dict).  The no-grad forwards refresh its live part with ONE strided copy
+    (`F.pad` + `.contiguous(channels_last)` are a fill and two copies, six times per DQN
+    iteration)."""
+    bufs = conv.__dict__.setdefault("_pb_pad_buffers", {})
+    w = conv.weight
+    key = (channels, w.device)
+    buf = bufs.get(key)
+    if buf is None:
+        buf = bufs[key] = torch.zeros((w.shape[0], channels) + tuple(w.shape[2:]), dtype=w.dtype,
+                                      device=w.device).contiguous(memory_format=torch.channels_last)
+    return buf
+
+
 def _fused_trunk(bb: nn.Sequential, obs: torch.Tensor) -> torch.Tensor:
     """Blocks 0..8 of the QNetV2 / NetV2 layer list (conv5x5 + SiLU, 3 x [conv3x3, max pool, SiLU])
     with every block tail as one `bias_pool_silu` launch; the convolutions run without bias."""
     first = bb[0]
     w = first.weight
     if obs.shape[1] > first.in_channels:   # zero-padded observation channels, see QNetV2.forward()
-        w = nn.functional.pad(w, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels))
-    w = w.contiguous(memory_format=torch.channels_last)
+        if torch.is_grad_enabled():        # a fresh tensor: autograd may keep it for a later backward
+            w = nn.functional.pad(w, (0, 0, 0, 0, 0, obs.shape[1] - first.in_channels)).contiguous(
+                memory_format=torch.channels_last)
+        else:                              # one strided copy into the module's persistent buffer
+            w = _pad_buffer(first, obs.shape[1])
+            w[:, :first.in_channels].copy_(first.weight)
+    else:
+        w = w.contiguous(memory_format=torch.channels_last)
     h = bias_pool_silu(nn.functional.conv2d(obs, w, None, padding="same"), first.bias, False)
     for i in (2, 5, 8):                     # Conv2d, MaxPool2d(2, ceil_mode=True), SiLU
         conv = bb[i]
