@@ -421,6 +421,14 @@ int pb_qnet_head_fwd(const float *x_dev, int64_t n, int64_t hw, const float *con
                      const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
                      float *out_dev, int device, void *stream);
 
+/* pb_qnet_head_fwd + MaxQPolicy (src/policies.py:44-59) in the same launch: actions_out uint8 [n] =
+ * argmax over the actions with mask_dev uint8 [n][n_out] != 0 (first maximum; 0 if none), q_out
+ * float32 [n][n_out] as above.  One launch per greedy evaluation step instead of four more. */
+int pb_qnet_head_greedy(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                        const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                        const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
+                        float *q_out_dev, const uint8_t *mask_dev, uint8_t *actions_out_dev, int device,
+                        void *stream);
 /* Training form of the head: the same forward that also keeps p_out float32 [n][128] (pooled
  * maximum + bias), idx_out uint8 [n][128] (map position of the maximum, first one in row-major
  * order as torch chooses; hw <= 255) and u_out float32 [n][256] (input of the second SiLU) ... */

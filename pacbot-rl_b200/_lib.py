@@ -110,6 +110,8 @@ SIGNATURES = {
     "pb_qnet_head_fwd": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _int, _vp]),
     "pb_qnet_head_fwd_train": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp,
                                _vp, _vp, _int, _vp]),
+    "pb_qnet_head_greedy": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp,
+                            _int, _vp]),
     "pb_qnet_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp,
                          _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "pb_qnet_head_bwd_scratch_floats": (_i64, [_i64]),

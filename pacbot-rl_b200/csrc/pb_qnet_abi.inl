@@ -170,7 +170,8 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
                 const float *__restrict__ wv, const float *__restrict__ bv,
                 const float *__restrict__ wa, const float *__restrict__ ba, int n_out, int dueling,
                 long long n, float *__restrict__ out, float *__restrict__ p_out,
-                unsigned char *__restrict__ idx_out, float *__restrict__ u_out) {
+                unsigned char *__restrict__ idx_out, float *__restrict__ u_out,
+                const unsigned char *__restrict__ act_mask, unsigned char *__restrict__ act_out) {
     __shared__ __align__(16) float s_a[S][HEAD_C];
     __shared__ __align__(16) float s_m[S][HEAD_PGROUPS][HEAD_C];
     __shared__ unsigned char s_pos[TRAIN ? S : 1][HEAD_PGROUPS][HEAD_C];
@@ -300,19 +301,40 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
         }
     }
     __syncthreads();
-    if ((int)threadIdx.x < S * n_out) {
+    float q = 0.f;
+    const bool q_thread = (int)threadIdx.x < S * n_out && n0 + threadIdx.x / n_out < n;
+    if (q_thread) {
         const int smp = threadIdx.x / n_out, k = threadIdx.x % n_out;
-        const long long i = n0 + smp;
-        if (i < n) {
-            float q;
-            if (dueling) {   // value - adv.mean(dim=1, keepdim=True) + adv  (models.py:108-110)
-                float sum = 0.f;
-                for (int t = 0; t < n_out; t++) sum += s_h[smp][1 + t];
-                q = (s_h[smp][0] - sum / (float)n_out) + s_h[smp][1 + k];
-            } else {
-                q = s_h[smp][k];
+        if (dueling) {   // value - adv.mean(dim=1, keepdim=True) + adv  (models.py:108-110)
+            float sum = 0.f;
+            for (int t = 0; t < n_out; t++) sum += s_h[smp][1 + t];
+            q = (s_h[smp][0] - sum / (float)n_out) + s_h[smp][1 + k];
+        } else {
+            q = s_h[smp][k];
+        }
+        out[(n0 + smp) * n_out + k] = q;
+    }
+    if (act_out) {   // the Q-values take the place of the advantage rows for the arg-max below
+        __syncthreads();
+        if (q_thread) s_h[threadIdx.x / n_out][(dueling ? 1 : 0) + threadIdx.x % n_out] = q;
+    }
+    // MaxQPolicy (src/policies.py:44-59) in the same launch: q.masked_fill(~mask, -inf).argmax(1),
+    // first maximum, a NaN counts as the maximum, 0 when every action is masked
+    if (act_out) {
+        __syncthreads();
+        if ((int)threadIdx.x < S && n0 + threadIdx.x < n) {
+            const int smp = threadIdx.x;
+            const long long i = n0 + smp;
+            float best = -INFINITY;
+            int arg = 0;
+            for (int k = 0; k < n_out; k++) {
+                const float v = act_mask[i * n_out + k] ? s_h[smp][(dueling ? 1 : 0) + k] : -INFINITY;
+                if (best == best && (v > best || v != v)) {
+                    best = v;
+                    arg = k;
+                }
             }
-            out[i * n_out + k] = q;
+            act_out[i] = (unsigned char)arg;
         }
     }
 }
@@ -535,6 +557,11 @@ unsigned qnet_grid(long long total, int num_sms) {
     const long long cap = (long long)num_sms * 8;
     return (unsigned)(need < cap ? need : cap);
 }
+int qnet_head_launch(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                     const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                     const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling, float *out_dev,
+                     float *p_out_dev, uint8_t *idx_out_dev, float *u_out_dev, const uint8_t *mask_dev,
+                     uint8_t *actions_out_dev, int device, void *stream);
 int qnet_sms(int device) {
     static thread_local int cached_dev = -1, sms = 148;
     if (cached_dev != device) {
@@ -611,6 +638,29 @@ int pb_qnet_head_fwd_train(const float *x_dev, int64_t n, int64_t hw, const floa
                            const float *bv_dev, const float *wa_dev, const float *ba_dev, int64_t n_out,
                            int dueling, float *out_dev, float *p_out_dev, uint8_t *idx_out_dev,
                            float *u_out_dev, int device, void *stream) {
+    return qnet_head_launch(x_dev, n, hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, n_out,
+                            dueling, out_dev, p_out_dev, idx_out_dev, u_out_dev, nullptr, nullptr, device, stream);
+}
+
+int pb_qnet_head_greedy(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                        const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                        const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
+                        float *q_out_dev, const uint8_t *mask_dev, uint8_t *actions_out_dev, int device,
+                        void *stream) {
+    if (!mask_dev || !actions_out_dev) return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_greedy: null argument");
+    return qnet_head_launch(x_dev, n, hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, n_out,
+                            dueling, q_out_dev, nullptr, nullptr, nullptr, mask_dev, actions_out_dev, device,
+                            stream);
+}
+
+}  // extern "C"
+
+namespace {
+int qnet_head_launch(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                     const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
+                     const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling, float *out_dev,
+                     float *p_out_dev, uint8_t *idx_out_dev, float *u_out_dev, const uint8_t *mask_dev,
+                     uint8_t *actions_out_dev, int device, void *stream) {
     const bool train = p_out_dev || idx_out_dev || u_out_dev;
     if (train && (!p_out_dev || !idx_out_dev || !u_out_dev || hw > 255))
         return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_fwd_train: p / idx / u outputs come together, map of <= 255 cells");
@@ -626,7 +676,7 @@ int pb_qnet_head_fwd_train(const float *x_dev, int64_t n, int64_t hw, const floa
 #define PB_HEAD_LAUNCH(S, T)                                                                       \
     k_qnet_head_fwd<S, T><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                \
         x_dev, (int)hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, (int)n_out,  \
-        dueling, n, out_dev, p_out_dev, idx_out_dev, u_out_dev)
+        dueling, n, out_dev, p_out_dev, idx_out_dev, u_out_dev, mask_dev, actions_out_dev)
     if (train) {
         if (n <= sms)
             PB_HEAD_LAUNCH(1, true);
@@ -645,6 +695,9 @@ int pb_qnet_head_fwd_train(const float *x_dev, int64_t n, int64_t hw, const floa
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int pb_qnet_head_bwd(const float *dq_dev, const float *p_dev, const uint8_t *idx_dev, const float *u_dev,
                      const float *w1_dev, const float *wv_dev, const float *wa_dev, int64_t n, int64_t hw,

@@ -92,12 +92,14 @@ def bias_pool_silu(x: torch.Tensor, bias: torch.Tensor, pool: bool) -> torch.Ten
 
 
 def qnet_head(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.Linear,
-              value: "nn.Linear | None" = None) -> torch.Tensor:
+              value: "nn.Linear | None" = None, greedy_mask: "torch.Tensor | None" = None):
     """Inference-only head of QNetV2 / NetV2 as ONE launch (`pb_qnet_head_fwd`,
     csrc/pb_qnet_abi.inl): global max of the last convolution's bias-free NHWC output `x`
     [N, 128, H, W] + `conv_bias`, SiLU, `lin` (128 -> 256), SiLU, then `value` / `out` combined as
     `V - mean(A) + A` (reference models.py:92-110) or, without `value`, the plain layer `out`
-    (models.py:139-141).  No autograd graph: callers use it under `torch.no_grad()`."""
+    (models.py:139-141).  No autograd graph: callers use it under `torch.no_grad()`.
+    With `greedy_mask` (bool / uint8 [N, actions]) the same launch also takes the masked arg-max
+    (`MaxQPolicy`, policies.py:44-59) and the result is `(q, actions uint8 [N])`."""
     import ctypes as C
 
     from . import _lib
@@ -108,12 +110,19 @@ def qnet_head(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.
         raise ValueError("qnet_head: channels-last float32 CUDA [N, 128, H, W] input and Linear(128, 256) expected")
     q = torch.empty((n, out.out_features), dtype=torch.float32, device=x.device)
     p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
-    _lib.check(_lib.load().pb_qnet_head_fwd(
-        p(x), n, h * w, p(conv_bias), p(lin.weight), p(lin.bias),
-        p(value.weight if value is not None else None), p(value.bias if value is not None else None),
-        p(out.weight), p(out.bias), out.out_features, int(value is not None), p(q), x.device.index,
-        C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
-    return q
+    head = (p(x), n, h * w, p(conv_bias), p(lin.weight), p(lin.bias),
+            p(value.weight if value is not None else None), p(value.bias if value is not None else None),
+            p(out.weight), p(out.bias), out.out_features, int(value is not None), p(q))
+    tail = (x.device.index, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if greedy_mask is None:
+        _lib.check(_lib.load().pb_qnet_head_fwd(*head, *tail))
+        return q
+    m = greedy_mask.contiguous().view(torch.uint8)
+    if tuple(m.shape) != (n, out.out_features) or m.device != x.device:
+        raise ValueError("qnet_head: greedy_mask must be [N, actions] on the input's device")
+    actions = torch.empty(n, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.load().pb_qnet_head_greedy(*head, p(m), p(actions), *tail))
+    return q, actions
 
 
 class _QNetHead(torch.autograd.Function):
@@ -320,6 +329,22 @@ class QNetV2(nn.Module):
         last = bb[11]                            # the forward that needs gradients: fused head + backward
         x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
         return qnet_head_train(x5, last.bias, bb[15], self.advantage_head[0], self.value_head[0])
+
+    @torch.no_grad()
+    def greedy_actions(self, obs: torch.Tensor, action_masks: torch.Tensor) -> torch.Tensor:
+        """`MaxQPolicy(self)(obs, action_masks)` as uint8 [N]: with the fused blocks on, the masked
+        arg-max comes out of the head's own launch (no masked_fill / argmax / cast kernels)."""
+        if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:
+            if _is_raw_obs(obs):
+                obs = obs_to_padded_nhwc(obs)
+            obs = obs.contiguous(memory_format=torch.channels_last)
+            bb = self.backbone
+            h = _fused_trunk(bb, obs)
+            last = bb[11]
+            x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+            return qnet_head(x5, last.bias, bb[15], self.advantage_head[0], self.value_head[0],
+                             greedy_mask=action_masks)[1]
+        return self(obs).masked_fill(~action_masks, -torch.inf).argmax(dim=1).to(torch.uint8)
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_fused_blocks", False) and _is_raw_obs(obs):

@@ -26,6 +26,15 @@ class MaxQPolicy:
         q = self.q_net(obs)
         return q.masked_fill(~action_masks, -torch.inf).argmax(dim=1)
 
+    @torch.no_grad()
+    def actions_u8(self, obs: torch.Tensor, action_masks: torch.Tensor) -> torch.Tensor:
+        """The same choice as uint8 [B] (what the env engine steps with); a network with a fused
+        head (`QNetV2.greedy_actions`) takes the masked arg-max inside its last launch."""
+        greedy = getattr(self.q_net, "greedy_actions", None)
+        if greedy is not None:
+            return greedy(obs, action_masks)
+        return self(obs, action_masks).to(torch.uint8)
+
 
 class EpsilonGreedy:
     """epsilon-greedy wrapper (policies.py:16-41): greedy iff rand > epsilon, otherwise a

@@ -173,7 +173,8 @@ class EpisodeEvaluator:
         """One greedy step of every env (train_dqn.py:99-105) + its bookkeeping: forward, step,
         observation encode (one C call) and pb_eval_track."""
         env = self.env
-        actions = self.policy(self.obs, self.mask)
+        pol = self.policy
+        actions = pol.actions_u8(self.obs, self.mask) if hasattr(pol, "actions_u8") else pol(self.obs, self.mask)
         _, done = env.step_obs(actions, self.obs, mask_out=self.mask)
         check(env._L.pb_eval_track(env._h, C.c_void_p(done.data_ptr()), C.c_void_p(self.track.data_ptr()),
                                    env._stream()))

@@ -802,6 +802,47 @@ def test_qnet_head_train_matches_torch_autograd(pb, n, dueling):
     assert int(nz.max()) <= 1 and torch.equal(g_got["x"] != 0, g_ref["x"] != 0)
 
 
+def test_greedy_head_matches_max_q_policy(pb):
+    """`QNetV2.greedy_actions` / `MaxQPolicy.actions_u8` (the masked arg-max taken inside the head
+    launch, pb_qnet_head_greedy) == `q.masked_fill(~mask, -inf).argmax(1)` on the SAME Q-values
+    (reference policies.py:44-59), incl. rows with a single valid action and rows with none."""
+    import copy
+
+    import torch
+    from pacbot_rl_b200.models import QNetV2
+    from pacbot_rl_b200.policies import MaxQPolicy
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(9)
+    net = QNetV2(pb.OBS_SHAPE, 5).to(dev)
+    with torch.no_grad():
+        for head in (net.value_head, net.advantage_head):
+            head[0].weight.normal_(0, 0.3)
+            head[0].bias.normal_(0, 0.3)
+    plain = copy.deepcopy(net).use_channels_last().eval()
+    net.use_fused_blocks().eval()
+    for n in (1, 32, 200, 700):
+        obs = (torch.rand((n,) + pb.OBS_SHAPE, device=dev) < 0.15).float()
+        mask = torch.rand((n, 5), device=dev) < 0.6
+        mask[:, 0] = True
+        if n > 2:
+            mask[1] = False              # no valid action: argmax of all -inf is 0
+            mask[2] = False
+            mask[2, 3] = True            # exactly one
+        with torch.no_grad():
+            q = net(obs)                                                      # the fused head's own Q-values
+            want = q.masked_fill(~mask, -torch.inf).argmax(dim=1)
+            got = net.greedy_actions(obs, mask)
+            assert got.dtype == torch.uint8 and torch.equal(got.long(), want)
+            assert torch.equal(MaxQPolicy(net).actions_u8(obs, mask), got)
+            # and the plain network's policy agrees wherever its two best valid Q-values are not within rounding
+            qp = plain(obs).masked_fill(~mask, -torch.inf)
+            top2 = qp.topk(2, dim=1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+            assert torch.equal(MaxQPolicy(plain)(obs, mask)[clear], want[clear])
+            assert torch.equal(MaxQPolicy(plain).actions_u8(obs, mask).long(), MaxQPolicy(plain)(obs, mask))
+
+
 def test_obs_to_padded_nhwc_is_a_pure_layout_change(pb):
     import torch
     from pacbot_rl_b200.models import obs_to_padded_nhwc
