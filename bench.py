@@ -869,8 +869,7 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
 
     @torch.no_grad()
     def evaluator(obs, mask):  # train_alphazero.py:83-95 (reward_scale 1/100)
-        pred = model(obs)
-        return pred[:, -1] * 100.0, torch.softmax(pred[:, :-1].masked_fill(~mask, -torch.inf), dim=-1)
+        return model.policy_value(obs, mask, 100.0)
 
     cfg = alphazero.AlphaZeroConfig(tree_size, 1000, 0.99, num_envs)
     col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=seed)

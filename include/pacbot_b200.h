@@ -429,6 +429,15 @@ int pb_qnet_head_greedy(const float *x_dev, int64_t n, int64_t hw, const float *
                         const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling,
                         float *q_out_dev, const uint8_t *mask_dev, uint8_t *actions_out_dev, int device,
                         void *stream);
+/* pb_qnet_head_fwd (plain head, n_out = actions + 1 rows) + the AlphaZero evaluator's
+ * post-processing (src/algorithms/train_alphazero.py:83-95) in the same launch: value_out float32
+ * [n] = last row * value_scale, policy_out float32 [n][n_out - 1] = softmax of the other rows with
+ * the actions whose mask_dev uint8 [n][n_out - 1] is 0 at -inf; out float32 [n][n_out] as above. */
+int pb_qnet_head_policy_value(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                              const float *w1_dev, const float *b1_dev, const float *wo_dev,
+                              const float *bo_dev, int64_t n_out, const uint8_t *mask_dev, float value_scale,
+                              float *out_dev, float *value_out_dev, float *policy_out_dev, int device,
+                              void *stream);
 /* Training form of the head: the same forward that also keeps p_out float32 [n][128] (pooled
  * maximum + bias), idx_out uint8 [n][128] (map position of the maximum, first one in row-major
  * order as torch chooses; hw <= 255) and u_out float32 [n][256] (input of the second SiLU) ... */
@@ -504,6 +513,10 @@ int pb_mcts_reset_root(pb_mcts *m, const uint8_t *mask_dev, const float *value_d
  * valid actions of the real env; the k-th valid action takes noise_dev[i][k] (float32 [n][5]). */
 int pb_mcts_root_noise(pb_mcts *m, const uint8_t *mask_dev, const float *noise_dev, float mix,
                        void *stream);
+/* The same with the noise drawn on the device: Dirichlet(alpha / num_valid) over the valid actions
+ * (mcts.rs:263-271; the reference draws from thread_rng, so only the distribution is defined) from
+ * the engine's counter RNG, keyed by (seed, tree id, number of draws that tree has taken). */
+int pb_mcts_root_noise_dirichlet(pb_mcts *m, const uint8_t *mask_dev, float alpha, float mix, void *stream);
 /* select_trajectory (mcts.rs:290-321) for every env with active_dev[i] != 0 (NULL = all).
  * leaf_kind_dev uint8 [n] (may be NULL): 0 inactive, 1 trajectory ended in a terminal state,
  * 2 unexpanded leaf (its state is slot i of `sim`: encode + evaluate it);

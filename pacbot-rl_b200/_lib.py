@@ -112,6 +112,8 @@ SIGNATURES = {
                                _vp, _vp, _int, _vp]),
     "pb_qnet_head_greedy": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp,
                             _int, _vp]),
+    "pb_qnet_head_policy_value": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, _vp, _vp,
+                                  _vp, _int, _vp]),
     "pb_qnet_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp,
                          _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "pb_qnet_head_bwd_scratch_floats": (_i64, [_i64]),
@@ -151,6 +153,7 @@ SIGNATURES = {
     "pb_mcts_max_nodes": (_int, [_vp]),
     "pb_mcts_reset_root": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_mcts_root_noise": (_int, [_vp, _vp, _vp, C.c_float, _vp]),
+    "pb_mcts_root_noise_dirichlet": (_int, [_vp, _vp, C.c_float, C.c_float, _vp]),
     "pb_mcts_select": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_mcts_backprop": (_int, [_vp, _vp, _vp, _vp]),
     "pb_mcts_take_action": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -72,6 +72,7 @@ struct MctsView {
     uint8_t *leaf_kind;        // [n]
     int32_t *stack;            // [n][L] scratch (compaction, max_depth)
     unsigned long long *epoch; // number of completed search iterations
+    int32_t *noise_calls;      // [n] built-in root-noise draws taken so far (RNG counter)
     unsigned int *error;       // sticky error bits
     long long n;
     int M;                     // physical slots per tree and pool
@@ -135,6 +136,64 @@ k_mcts_root_noise(MctsView v, StateView root, const uint8_t *__restrict__ mask,
     for (int a = 0; a < 5; a++) {
         if (!((m >> a) & 1u)) continue;
         nd->prior[a] = __fadd_rn(__fmul_rn(keep, nd->prior[a]), __fmul_rn(mix, noise[i * 5 + k]));
+        k++;
+    }
+}
+
+// add_root_policy_noise with the noise drawn on the device (mcts.rs:259-281: Dirichlet with
+// concentration alpha / num_valid over the valid actions, mixed into the root prior).  The
+// reference draws from rand_distr::Dirichlet on thread_rng, so there is no stream to reproduce:
+// this is the same distribution from the engine's counter RNG, keyed (seed, tree id, call number
+// of that tree), one launch instead of the ~14 of the torch formulation (mask, sum, arange,
+// _standard_gamma, normalise ...).  gamma(a), a >= 1 (alpha = 11, at most 5 valid actions):
+// Marsaglia-Tsang, normals by Box-Muller.
+__device__ __forceinline__ float noise_uniform(uint64_t key, uint32_t &ctr) {
+    const uint32_t raw = (uint32_t)(mix64(key + (uint64_t)(ctr++) * 0x9e3779b97f4a7c15ull) >> 32);
+    return ((float)raw + 0.5f) * (1.0f / 4294967296.0f);   // (0, 1)
+}
+__device__ __forceinline__ float noise_gamma(float a, uint64_t key, uint32_t &ctr) {
+    const float boost = a < 1.0f ? powf(noise_uniform(key, ctr), 1.0f / a) : 1.0f;   // gamma(a) = gamma(a+1) U^(1/a)
+    if (a < 1.0f) a += 1.0f;
+    const float d = a - 1.0f / 3.0f, c = 1.0f / sqrtf(9.0f * d);
+    for (int tries = 0; tries < 64; tries++) {
+        const float u1 = noise_uniform(key, ctr), u2 = noise_uniform(key, ctr);
+        const float x = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+        float v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
+        v = v * v * v;
+        const float u = noise_uniform(key, ctr);
+        if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return d * v * boost;
+    }
+    return d * boost;   // (the mean; 64 rejections in a row do not happen)
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_root_noise_dirichlet(MctsView v, StateView root, const uint8_t *__restrict__ mask, float alpha,
+                            float keep, float mix, unsigned long long seed, long long gid_base) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = mcts_tree_of_thread(v);
+    if (i >= v.n || (mask && !mask[i])) return;
+    EnvR s;
+    load_env(root, i, s);
+    const uint32_t m = action_mask_bits(s, s_walls);
+    const int nv = __popc(m);
+    const uint32_t call = (uint32_t)v.noise_calls[i];
+    v.noise_calls[i] = (int32_t)(call + 1u);
+    const uint64_t key = mix64(env_key(seed ^ 0xd1b54a32d192ed03ull, (uint64_t)(gid_base + i)) +
+                               (uint64_t)call * 0xd6e8feb86659fd93ull);
+    uint32_t ctr = 0;
+    float g[5], sum = 0.0f;
+    for (int k = 0; k < nv; k++) {
+        g[k] = noise_gamma(alpha / (float)nv, key, ctr);
+        sum += g[k];
+    }
+    MctsNode *nd = v.nodes(i, v.cur[i]) + v.root[i];
+    int k = 0;
+    for (int a = 0; a < 5; a++) {
+        if (!((m >> a) & 1u)) continue;
+        const float noise = sum > 0.0f ? g[k] / sum : 1.0f / (float)nv;
+        nd->prior[a] = __fadd_rn(__fmul_rn(keep, nd->prior[a]), __fmul_rn(mix, noise));
         k++;
     }
 }

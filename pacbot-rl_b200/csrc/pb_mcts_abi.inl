@@ -63,6 +63,7 @@ int pb_mcts_create(pb_mcts **out, pb_engine *root, pb_engine *sim, int max_nodes
     alloc(&v.leaf_kind, n, 0);
     alloc(&v.stack, sizeof(int32_t) * n * L, 0);
     alloc(&v.epoch, sizeof(unsigned long long), 0);
+    alloc(&v.noise_calls, sizeof(int32_t) * n, 0);
     alloc(&v.error, sizeof(unsigned int), 0);
     if (err != cudaSuccess) {
         std::string msg = std::string("pb_mcts_create: ") + cudaGetErrorString(err);
@@ -88,6 +89,7 @@ int pb_mcts_destroy(pb_mcts *m) {
     cudaFree(v.leaf_kind);
     cudaFree(v.stack);
     cudaFree(v.epoch);
+    cudaFree(v.noise_calls);
     cudaFree(v.error);
     delete m;
     return PB_OK;
@@ -113,6 +115,15 @@ int pb_mcts_root_noise(pb_mcts *m, const uint8_t *mask_dev, const float *noise_d
     DeviceGuard g(m->device);
     k_mcts_root_noise<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, m->root->st, mask_dev, noise_dev, 1.0f - mix, mix);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_mcts_root_noise_dirichlet(pb_mcts *m, const uint8_t *mask_dev, float alpha, float mix, void *stream) {
+    if (!m || !(alpha > 0.0f)) return fail(PB_ERR_INVALID_ARG, "pb_mcts_root_noise_dirichlet: bad arguments");
+    DeviceGuard g(m->device);
+    k_mcts_root_noise_dirichlet<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, m->root->st, mask_dev, alpha, 1.0f - mix, mix, m->root->seed, m->root->gid_base);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

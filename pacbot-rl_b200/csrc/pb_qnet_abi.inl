@@ -171,7 +171,8 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
                 const float *__restrict__ wa, const float *__restrict__ ba, int n_out, int dueling,
                 long long n, float *__restrict__ out, float *__restrict__ p_out,
                 unsigned char *__restrict__ idx_out, float *__restrict__ u_out,
-                const unsigned char *__restrict__ act_mask, unsigned char *__restrict__ act_out) {
+                const unsigned char *__restrict__ act_mask, unsigned char *__restrict__ act_out,
+                float *__restrict__ pv_value, float *__restrict__ pv_policy, float value_scale) {
     __shared__ __align__(16) float s_a[S][HEAD_C];
     __shared__ __align__(16) float s_m[S][HEAD_PGROUPS][HEAD_C];
     __shared__ unsigned char s_pos[TRAIN ? S : 1][HEAD_PGROUPS][HEAD_C];
@@ -317,6 +318,26 @@ k_qnet_head_fwd(const float *__restrict__ x, int hw, const float *__restrict__ c
     if (act_out) {   // the Q-values take the place of the advantage rows for the arg-max below
         __syncthreads();
         if (q_thread) s_h[threadIdx.x / n_out][(dueling ? 1 : 0) + threadIdx.x % n_out] = q;
+    }
+    // The AlphaZero evaluator's post-processing (src/algorithms/train_alphazero.py:83-95) in the same
+    // launch, plain head only: value = last row * value_scale, policy = softmax over the other
+    // rows with invalid actions at -inf (exp(x - max) / sum, as torch.softmax).
+    if (pv_policy) {
+        if ((int)threadIdx.x < S && n0 + threadIdx.x < n) {
+            const int smp = threadIdx.x, na = n_out - 1;
+            const long long i = n0 + smp;
+            float mx = -INFINITY;
+            for (int k = 0; k < na; k++)
+                if (act_mask[i * na + k]) mx = fmaxf(mx, s_h[smp][k]);
+            float e[HEAD_MAX_OUT], sum = 0.f;
+            for (int k = 0; k < na; k++) {
+                e[k] = act_mask[i * na + k] ? expf(s_h[smp][k] - mx) : 0.f;
+                sum += e[k];
+            }
+            for (int k = 0; k < na; k++) pv_policy[i * na + k] = e[k] / sum;
+            pv_value[i] = s_h[smp][na] * value_scale;
+        }
+        return;
     }
     // MaxQPolicy (src/policies.py:44-59) in the same launch: q.masked_fill(~mask, -inf).argmax(1),
     // first maximum, a NaN counts as the maximum, 0 when every action is masked
@@ -561,7 +582,8 @@ int qnet_head_launch(const float *x_dev, int64_t n, int64_t hw, const float *con
                      const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
                      const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling, float *out_dev,
                      float *p_out_dev, uint8_t *idx_out_dev, float *u_out_dev, const uint8_t *mask_dev,
-                     uint8_t *actions_out_dev, int device, void *stream);
+                     uint8_t *actions_out_dev, int device, void *stream, float *pv_value_dev = nullptr,
+                     float *pv_policy_dev = nullptr, float value_scale = 1.0f);
 int qnet_sms(int device) {
     static thread_local int cached_dev = -1, sms = 148;
     if (cached_dev != device) {
@@ -653,6 +675,18 @@ int pb_qnet_head_greedy(const float *x_dev, int64_t n, int64_t hw, const float *
                             stream);
 }
 
+int pb_qnet_head_policy_value(const float *x_dev, int64_t n, int64_t hw, const float *conv_bias_dev,
+                              const float *w1_dev, const float *b1_dev, const float *wo_dev,
+                              const float *bo_dev, int64_t n_out, const uint8_t *mask_dev, float value_scale,
+                              float *out_dev, float *value_out_dev, float *policy_out_dev, int device,
+                              void *stream) {
+    if (!mask_dev || !value_out_dev || !policy_out_dev || n_out < 2)
+        return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_policy_value: bad arguments");
+    return qnet_head_launch(x_dev, n, hw, conv_bias_dev, w1_dev, b1_dev, nullptr, nullptr, wo_dev, bo_dev, n_out, 0,
+                            out_dev, nullptr, nullptr, nullptr, mask_dev, nullptr, device, stream,
+                            value_out_dev, policy_out_dev, value_scale);
+}
+
 }  // extern "C"
 
 namespace {
@@ -660,7 +694,8 @@ int qnet_head_launch(const float *x_dev, int64_t n, int64_t hw, const float *con
                      const float *w1_dev, const float *b1_dev, const float *wv_dev, const float *bv_dev,
                      const float *wa_dev, const float *ba_dev, int64_t n_out, int dueling, float *out_dev,
                      float *p_out_dev, uint8_t *idx_out_dev, float *u_out_dev, const uint8_t *mask_dev,
-                     uint8_t *actions_out_dev, int device, void *stream) {
+                     uint8_t *actions_out_dev, int device, void *stream, float *pv_value_dev,
+                     float *pv_policy_dev, float value_scale) {
     const bool train = p_out_dev || idx_out_dev || u_out_dev;
     if (train && (!p_out_dev || !idx_out_dev || !u_out_dev || hw > 255))
         return fail(PB_ERR_INVALID_ARG, "pb_qnet_head_fwd_train: p / idx / u outputs come together, map of <= 255 cells");
@@ -676,7 +711,8 @@ int qnet_head_launch(const float *x_dev, int64_t n, int64_t hw, const float *con
 #define PB_HEAD_LAUNCH(S, T)                                                                       \
     k_qnet_head_fwd<S, T><<<(unsigned)((n + (S) - 1) / (S)), HEAD_THREADS, 0, s>>>(                \
         x_dev, (int)hw, conv_bias_dev, w1_dev, b1_dev, wv_dev, bv_dev, wa_dev, ba_dev, (int)n_out,  \
-        dueling, n, out_dev, p_out_dev, idx_out_dev, u_out_dev, mask_dev, actions_out_dev)
+        dueling, n, out_dev, p_out_dev, idx_out_dev, u_out_dev, mask_dev, actions_out_dev, pv_value_dev,     \
+        pv_policy_dev, value_scale)
     if (train) {
         if (n <= sms)
             PB_HEAD_LAUNCH(1, true);

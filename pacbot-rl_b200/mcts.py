@@ -34,7 +34,9 @@ ST_UNTOUCHED, ST_DONE, ST_REROOTED, ST_NEEDS_ROOT, ST_WAS_DONE, ST_BAD_ACTION = 
 
 def dirichlet_root_noise(num_valid: torch.Tensor, alpha: float = DIRICHLET_ALPHA) -> torch.Tensor:
     """Dirichlet(alpha / num_valid) samples of size num_valid per row (mcts.rs:266-271), laid out
-    compactly: the k-th valid action takes column k; columns >= num_valid are zero."""
+    compactly: the k-th valid action takes column k; columns >= num_valid are zero.  A torch
+    formulation usable as `noise_fn=lambda nv, mask: dirichlet_root_noise(nv)`; the built-in noise
+    (`noise_fn=None`) is drawn by the device kernel `pb_mcts_root_noise_dirichlet` instead."""
     n = num_valid.shape[0]
     cols = torch.arange(NUM_ACTIONS, device=num_valid.device)[None, :] < num_valid[:, None]
     conc = (alpha / num_valid.clamp(min=1).to(torch.float32))[:, None].expand(n, NUM_ACTIONS)
@@ -120,11 +122,12 @@ class BatchedMCTS:
     def add_root_noise(self, mask: Optional[torch.Tensor] = None) -> None:
         """add_root_policy_noise (mcts.rs:259-281) for the masked trees."""
         m = self._mask_u8(mask)
+        if self.noise_fn is None:   # built-in: drawn on the device, one launch
+            check(self._L.pb_mcts_root_noise_dirichlet(self._h, self._p(m), self.dirichlet_alpha,
+                                                       self.noise_mix, self._stream()))
+            return
         num_valid = self.env.action_mask().sum(dim=1)
-        if self.noise_fn is not None:
-            noise = self.noise_fn(num_valid, m)
-        else:
-            noise = dirichlet_root_noise(num_valid, self.dirichlet_alpha)
+        noise = self.noise_fn(num_valid, m)
         noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
         check(self._L.pb_mcts_root_noise(self._h, self._p(m), self._p(noise), self.noise_mix,
                                          self._stream()))

@@ -464,6 +464,41 @@ class NetV2(nn.Module):
         self._fused_blocks = bool(enabled)
         return self
 
+    @torch.no_grad()
+    def policy_value(self, obs: torch.Tensor, action_masks: torch.Tensor, value_scale: float = 1.0):
+        """The evaluator of the AlphaZero loop (reference train_alphazero.py:83-95): `(value [N],
+        policy [N, actions])` with `value = out[:, -1] * value_scale` and `policy =
+        softmax(out[:, :-1] masked with -inf)`.  With the fused blocks on, both come out of the
+        head's own launch (`pb_qnet_head_policy_value`)."""
+        if getattr(self, "_fused_blocks", False) and obs.is_cuda and obs.dtype == torch.float32:
+            import ctypes as C
+
+            from . import _lib
+
+            if _is_raw_obs(obs):
+                obs = obs_to_padded_nhwc(obs)
+            obs = obs.contiguous(memory_format=torch.channels_last)
+            net = self.network
+            h = _fused_trunk(net, obs)
+            last, lin, out = net[11], net[15], net[17]
+            x5 = nn.functional.conv2d(h, last.weight, None, padding="same", groups=last.groups)
+            n, dev, rows = x5.shape[0], x5.device, out.out_features
+            m = action_masks.contiguous().view(torch.uint8)
+            if tuple(m.shape) != (n, rows - 1):
+                raise ValueError("policy_value: action_masks must be [N, actions]")
+            raw = torch.empty((n, rows), dtype=torch.float32, device=dev)
+            value = torch.empty(n, dtype=torch.float32, device=dev)
+            policy = torch.empty((n, rows - 1), dtype=torch.float32, device=dev)
+            p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+            _lib.check(_lib.load().pb_qnet_head_policy_value(
+                p(x5), n, x5.shape[2] * x5.shape[3], p(last.bias), p(lin.weight), p(lin.bias), p(out.weight),
+                p(out.bias), rows, p(m), float(value_scale), p(raw), p(value), p(policy), dev.index,
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            return value, policy
+        pred = self(obs)
+        return (pred[:, -1] * value_scale,
+                torch.softmax(pred[:, :-1].masked_fill(~action_masks.bool(), -torch.inf), dim=-1))
+
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_fused_blocks", False) and _is_raw_obs(obs):
             obs = obs_to_padded_nhwc(obs)          # encoder output -> NHWC, 32 channels, one launch

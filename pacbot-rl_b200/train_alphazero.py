@@ -149,6 +149,8 @@ class AlphaZeroTrainer:
     @torch.no_grad()
     def model_evaluator(self, obs: torch.Tensor, action_mask: torch.Tensor):
         if self.has_model_updated:
+            if hasattr(self.model, "policy_value"):   # value scaling + masked softmax inside the head's launch
+                return self.model.policy_value(obs, action_mask, 1.0 / self.args.reward_scale)
             predictions = self.model(obs)
             values = predictions[:, -1] / self.args.reward_scale
             policy_logits = predictions[:, :-1].masked_fill(~action_mask, -torch.inf)

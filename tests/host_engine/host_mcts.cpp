@@ -95,7 +95,7 @@ struct HMcts {
     HEngine *root = nullptr, *sim = nullptr;
     MctsView v{};
     std::vector<MctsNode> pool;
-    std::vector<int32_t> cur, rootv, n_alloc, traj_len, path, traj_rew, stack;
+    std::vector<int32_t> cur, rootv, n_alloc, traj_len, path, traj_rew, stack, noise_calls;
     std::vector<uint8_t> traj_act, leaf_kind;
     unsigned long long epoch = 0;
     unsigned int error = 0;
@@ -249,6 +249,7 @@ void *hm_mcts_create(void *root_h, void *sim_h, int max_nodes, int pool_factor, 
     m->traj_rew.assign(n * L, 0);
     m->leaf_kind.assign(n, 0);
     m->stack.assign(n * L, 0);
+    m->noise_calls.assign(n, 0);
     v.pool = m->pool.data();
     v.cur = m->cur.data();
     v.root = m->rootv.data();
@@ -260,6 +261,7 @@ void *hm_mcts_create(void *root_h, void *sim_h, int max_nodes, int pool_factor, 
     v.leaf_kind = m->leaf_kind.data();
     v.stack = m->stack.data();
     v.epoch = &m->epoch;
+    v.noise_calls = m->noise_calls.data();
     v.error = &m->error;
     return m;
 }
@@ -272,6 +274,13 @@ void hm_mcts_reset_root(void *h, const uint8_t *mask, const float *value, const 
 void hm_mcts_root_noise(void *h, const uint8_t *mask, const float *noise, float mix) {
     HMcts *m = static_cast<HMcts *>(h);
     launch(m->v, [&] { k_mcts_root_noise(m->v, m->root->st, mask, noise, 1.0f - mix, mix); });
+}
+void hm_mcts_root_noise_dirichlet(void *h, const uint8_t *mask, float alpha, float mix) {
+    HMcts *m = static_cast<HMcts *>(h);
+    launch(m->v, [&] {
+        k_mcts_root_noise_dirichlet(m->v, m->root->st, mask, alpha, 1.0f - mix, mix, m->root->seed,
+                                    m->root->gid_base);
+    });
 }
 void hm_mcts_select(void *h, const uint8_t *active, uint8_t *leaf_kind_out, uint8_t *leaf_mask_out) {
     HMcts *m = static_cast<HMcts *>(h);

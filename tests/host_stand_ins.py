@@ -57,6 +57,7 @@ def hm(pb):
             hm_engine_destroy=[vp], hm_engine_reset=[vp, vp], hm_engine_get_state=[vp, vp],
             hm_engine_set_state=[vp, vp], hm_engine_action_mask=[vp, vp], hm_mcts_destroy=[vp],
             hm_mcts_reset_root=[vp, vp, vp, vp], hm_mcts_root_noise=[vp, vp, vp, C.c_float],
+            hm_mcts_root_noise_dirichlet=[vp, vp, C.c_float, C.c_float],
             hm_mcts_select=[vp, vp, vp, vp], hm_mcts_backprop=[vp, vp, vp],
             hm_mcts_take_action=[vp, vp, vp, vp, vp, vp], hm_mcts_query=[vp, C.c_int, vp]).items():
         getattr(L, name).restype = None
@@ -282,6 +283,10 @@ class HostABI:
 
     def pb_mcts_root_noise(self, h, mask, noise, mix, stream):
         self._lib.hm_mcts_root_noise(h, mask, noise, mix)
+        return 0
+
+    def pb_mcts_root_noise_dirichlet(self, h, mask, alpha, mix, stream):
+        self._lib.hm_mcts_root_noise_dirichlet(h, mask, alpha, mix)
         return 0
 
     def pb_mcts_select(self, h, active, leaf_kind, leaf_mask, stream):

@@ -843,6 +843,43 @@ def test_greedy_head_matches_max_q_policy(pb):
             assert torch.equal(MaxQPolicy(plain).actions_u8(obs, mask).long(), MaxQPolicy(plain)(obs, mask))
 
 
+def test_netv2_policy_value_matches_the_evaluator_expressions(pb):
+    """`NetV2.policy_value` with the fused blocks on (value scaling + masked softmax inside the head
+    launch, pb_qnet_head_policy_value) against the evaluator of train_alphazero.py:83-95 written
+    with torch ops on the plain network: rtol 1e-5 / atol 1e-6; invalid actions get exactly 0."""
+    import copy
+
+    import torch
+    from pacbot_rl_b200.models import NetV2
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(12)
+    plain = NetV2(pb.OBS_SHAPE, 6).to(dev).use_channels_last().eval()
+    with torch.no_grad():
+        plain.network[-1].weight.normal_(0, 0.5)
+        plain.network[-1].bias.normal_(0, 0.5)
+    fused = copy.deepcopy(plain).use_fused_blocks().eval()
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for n in (1, 128, 500):
+            obs = (torch.rand((n,) + pb.OBS_SHAPE, device=dev) < 0.15).float()
+            mask = torch.rand((n, 5), device=dev) < 0.6
+            mask[:, 0] = True
+            with torch.no_grad():
+                pred = plain(obs)
+                want_v = pred[:, -1] * 100.0
+                want_p = torch.softmax(pred[:, :-1].masked_fill(~mask, -torch.inf), dim=-1)
+                got_v, got_p = fused.policy_value(obs, mask, 100.0)
+                ref_v, ref_p = plain.policy_value(obs, mask, 100.0)       # the unfused route of the same method
+            torch.testing.assert_close(got_v, want_v, rtol=1e-5, atol=1e-4)
+            torch.testing.assert_close(got_p, want_p, rtol=1e-5, atol=1e-6)
+            assert torch.equal(ref_v, want_v) and torch.equal(ref_p, want_p)
+            assert not bool(got_p[~mask].any()) and torch.allclose(got_p.sum(1), torch.ones(n, device=dev), atol=1e-6)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+
 def test_obs_to_padded_nhwc_is_a_pure_layout_change(pb):
     import torch
     from pacbot_rl_b200.models import obs_to_padded_nhwc

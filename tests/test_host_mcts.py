@@ -40,6 +40,13 @@ def test_device_mcts_ponder_on_cpu(host_pb, pymcts):
     tg.test_ponder_grows_each_tree_to_the_requested_size(host_pb, pymcts)
 
 
+def test_builtin_root_noise_is_dirichlet_on_cpu(host_pb):
+    """k_mcts_root_noise_dirichlet (counter-RNG gamma sampling on the device) executed on the host."""
+    import test_mcts_gpu as tg
+
+    tg.test_builtin_root_noise_is_dirichlet(host_pb, n=3000)
+
+
 def test_device_mcts_reports_search_from_finished_env(host_pb):
     import test_mcts_gpu as tg
 

@@ -124,6 +124,43 @@ def test_ponder_grows_each_tree_to_the_requested_size(pb, pymcts):
         gm.ponder(size + 1)
 
 
+def test_builtin_root_noise_is_dirichlet(pb, n=6000):
+    """pb_mcts_root_noise_dirichlet (the built-in root noise, drawn on the device): what reaches the
+    root prior is `0.75 prior + 0.25 noise` with noise ~ Dirichlet(11 / num_valid) over the valid
+    actions (mcts.rs:259-281): on the simplex, zero on invalid actions, component mean 1 / k and
+    variance (1/k)(1 - 1/k) / (alpha + 1); different per tree and per call."""
+    env = pb.BatchedPacmanGym(n, True, False, device="cuda:0", seed=21, env_id_base=5)
+    gm = pb.mcts.BatchedMCTS(env, torch_eval(uniform_evaluator), 8)        # noise_fn=None: built in
+    gm.reset()                                                             # reset_root -> prior + noise
+    mask = env.action_mask().cpu().numpy().astype(bool)
+    nv = mask.sum(1)
+    uniform = mask / nv[:, None]
+    prior1 = gm.policy_prior().cpu().numpy().astype(np.float64)
+    noise1 = (prior1 - 0.75 * uniform) / 0.25
+    gm.add_root_noise()                                                    # a second draw on top
+    prior2 = gm.policy_prior().cpu().numpy().astype(np.float64)
+    noise2 = (prior2 - 0.75 * prior1) / 0.25
+    for noise in (noise1, noise2):
+        assert np.abs(noise[~mask]).max() < 1e-6 and noise.min() > -1e-6
+        assert np.abs(noise.sum(1) - 1.0).max() < 1e-5
+    assert np.abs(noise1 - noise2)[mask & (nv[:, None] > 1)].mean() > 0.05   # per call
+    alpha = 11.0
+    checked = 0
+    for k in range(3, 6):                 # Stay is always valid: 3 (corridor) .. 5 (crossing)
+        rows = np.nonzero(nv == k)[0]
+        if len(rows) < 300:
+            continue
+        comp = np.concatenate([noise1[rows][mask[rows]].reshape(len(rows), k),
+                               noise2[rows][mask[rows]].reshape(len(rows), k)])
+        var = (1 / k) * (1 - 1 / k) / (alpha + 1)
+        sem = (var / len(comp)) ** 0.5
+        assert np.abs(comp.mean(0) - 1 / k).max() < 5 * sem, (k, comp.mean(0))
+        assert np.abs(comp.var(0) / var - 1).max() < 0.2, (k, comp.var(0), var)
+        assert len(np.unique(np.round(comp[:, 0], 6))) > 0.95 * len(comp)     # per tree
+        checked += 1
+    assert checked >= 1 and (nv == 3).sum() >= 300      # corridors dominate the maze
+
+
 def test_search_from_a_finished_env_is_reported(pb):
     env = pb.BatchedPacmanGym(2, False, False, device="cuda:0")
     gm = pb.mcts.BatchedMCTS(env, torch_eval(uniform_evaluator), 8)
@@ -240,19 +277,11 @@ def test_experience_collector_drop_in_surface(pb):
     assert isinstance(it.value, float) and len(it.action_distribution) == 5
 
 
-def test_collector_cuda_graph_matches_eager(pb, monkeypatch):
+def test_collector_cuda_graph_matches_eager(pb):
     """The captured collector step (search iteration + env steps + root noise in one CUDA graph)
     must leave envs, trees and episode buffers exactly where eager execution leaves them."""
-    from pacbot_rl_b200 import mcts as M
-
-    def flat_noise(num_valid, alpha=None):   # capturable, deterministic stand-in for the Dirichlet
-        k = num_valid.to(torch.float32)[:, None]
-        w = (torch.arange(5, device=k.device)[None, :] < k).to(torch.float32) * (
-            1.0 + torch.arange(5, device=k.device)[None, :].to(torch.float32))
-        return w / w.sum(dim=1, keepdim=True)
-
-    monkeypatch.setattr(M, "dirichlet_root_noise", flat_noise)
-
+    # the built-in root noise is drawn on the device from the counter RNG, keyed by (seed, tree,
+    # draws taken by that tree): both collectors see the same Dirichlet samples
     def evaluator(obs, mask):
         value = (obs[:, 1] != 0).sum(dim=(1, 2)).to(torch.float32) * 0.25 - obs[:, 2].flatten(1).argmax(1) % 7
         m = mask.to(torch.float32) * (1.0 + obs[:, 2].flatten(1).argmax(1)[:, None] % 3)
@@ -265,7 +294,7 @@ def test_collector_cuda_graph_matches_eager(pb, monkeypatch):
     fin = [[], cols[1]._pending]
     for _ in range(3):
         cols[0].generate_experience_step(fin[0])
-    for step in range(150):
+    for step in range(330):
         for c, f in zip(cols, fin):
             c.generate_experience_step(f)
         if step % 30 == 29:

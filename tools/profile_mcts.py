@@ -13,8 +13,7 @@ model = models.NetV2((17, 28, 31), 6).to(dev).use_fused_blocks().eval()
 
 @torch.no_grad()
 def evaluator(obs, mask):
-    pred = model(obs)
-    return pred[:, -1] * 100.0, torch.softmax(pred[:, :-1].masked_fill(~mask, -torch.inf), dim=-1)
+    return model.policy_value(obs, mask, 100.0)
 
 def make():
     return alphazero.BatchedExperienceCollector(evaluator, alphazero.AlphaZeroConfig(100, 1000, 0.99, P), device=dev)
