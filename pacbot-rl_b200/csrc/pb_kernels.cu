@@ -1162,11 +1162,9 @@ int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_re
     const size_t off_bad = 0, off_info = 8, off_reward = off_info + 32 * n, off_done = off_reward + 4 * n;
     const size_t off_mask = off_done + n, small = (off_mask + 5 * n + 15) & ~(size_t)15;
     const size_t total = small + sizeof(float) * OBS_FLOATS * n;
-    if (!e->snap_dev) {
-        PB_CUDA(cudaMalloc(&e->snap_dev, total));
-        PB_CUDA(cudaMallocHost(&e->snap_pin, total));
-        PB_CUDA(cudaMallocHost(&e->snap_actions_pin, n));
-    }
+    if (!e->snap_dev) PB_CUDA(cudaMalloc(&e->snap_dev, total));
+    if (!e->snap_pin) PB_CUDA(cudaMallocHost(&e->snap_pin, total));
+    if (!e->snap_actions_pin) PB_CUDA(cudaMallocHost(&e->snap_actions_pin, n));
     unsigned char *d = e->snap_dev, *h = e->snap_pin;
     if (actions_host) {
         // the previous call synchronised the stream: the pinned actions are free to overwrite
