@@ -410,12 +410,16 @@ k_qnet_head_bwd(const float *__restrict__ dq, const float *__restrict__ p, const
         const long long i = n0 + smp;
         float du = 0.f;
         if (i < n) {
-            float df = 0.f;
-            for (int r = 0; r < rows; r++) {
-                const float w = (dueling && r == 0) ? __ldg(wv + j) : __ldg(wa + (long long)(r - (dueling ? 1 : 0)) * HEAD_H + j);
-                df = fmaf(w, s_dh[smp][r], df);
-            }
             const float uu = __ldg(u + i * HEAD_H + j);
+            float w[HEAD_R];
+#pragma unroll
+            for (int r = 0; r < HEAD_R; r++)   // independent loads, requested together
+                w[r] = r >= rows ? 0.f
+                       : (dueling && r == 0) ? __ldg(wv + j)
+                                             : __ldg(wa + (long long)(r - (dueling ? 1 : 0)) * HEAD_H + j);
+            float df = 0.f;
+#pragma unroll
+            for (int r = 0; r < HEAD_R; r++) df = fmaf(w[r], s_dh[smp][r], df);
             du = silu_grad_f(df, uu);
             du_out[i * HEAD_H + j] = du;
             f_out[i * HEAD_H + j] = silu_f(uu);
@@ -474,34 +478,42 @@ k_qnet_head_bwd(const float *__restrict__ dq, const float *__restrict__ p, const
     }
 }
 
-constexpr int WG_THREADS = 256, WG_T = 32;   // 32 x 32 output tile, 32 samples per stage
+constexpr int WG_THREADS = 256, WG_T = 32, WG_NS = 64;   // 32 x 32 output tile, 64 samples per stage
 constexpr int WG_TILES = (HEAD_H / WG_T) * (HEAD_C / WG_T);   // 32 tiles of dW1
 // blocks [0, WG_TILES): dW1 tiles (+ db1 in the tiles of the first column block);
-// block WG_TILES: dWh / dbh; block WG_TILES + 1: the convolution bias gradient
+// block WG_TILES: dWh / dbh; block WG_TILES + 1: the convolution bias gradient.
+// Every block walks the batch in stages whose global loads are all requested before the first one
+// is used (16 per thread in the tile blocks, 32 in the head-row block, 16 in the bias block): the
+// kernel is a chain of L2 round trips, so the number of stages is what it costs.
 __global__ void __launch_bounds__(WG_THREADS)
 k_qnet_head_wgrad(const float *__restrict__ du, const float *__restrict__ a, const float *__restrict__ f,
                   const float *__restrict__ dh, const float *__restrict__ dp, long long n, int n_out,
                   int dueling, float *__restrict__ dw1, float *__restrict__ db1, float *__restrict__ dwv,
                   float *__restrict__ dbv, float *__restrict__ dwa, float *__restrict__ dba,
                   float *__restrict__ dconv_bias) {
-    __shared__ float s_x[WG_T][WG_T + 1];
-    __shared__ float s_y[WG_T][WG_T + 1];
+    __shared__ float s_x[WG_NS][WG_T + 1];
+    __shared__ float s_y[WG_NS][WG_T + 1];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < WG_TILES) {
         const int jt = blockIdx.x / (HEAD_C / WG_T), ct = blockIdx.x % (HEAD_C / WG_T);
         const int c = tid % WG_T, tj = tid / WG_T;   // rows tj, tj + 8, tj + 16, tj + 24 of the tile
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-        for (long long nb = 0; nb < n; nb += WG_T) {
+        for (long long nb = 0; nb < n; nb += WG_NS) {
+            float vx[WG_NS / 8], vy[WG_NS / 8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {   // 32 samples x 32 columns of du and of a
-                const int nn = tj + 8 * k;
-                const long long i = nb + nn;
-                s_x[nn][c] = i < n ? __ldg(du + i * HEAD_H + jt * WG_T + c) : 0.f;
-                s_y[nn][c] = i < n ? __ldg(a + i * HEAD_C + ct * WG_T + c) : 0.f;
+            for (int k = 0; k < WG_NS / 8; k++) {   // 64 samples x 32 columns of du and of a
+                const long long i = nb + tj + 8 * k;
+                vx[k] = i < n ? __ldg(du + i * HEAD_H + jt * WG_T + c) : 0.f;
+                vy[k] = i < n ? __ldg(a + i * HEAD_C + ct * WG_T + c) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < WG_NS / 8; k++) {
+                s_x[tj + 8 * k][c] = vx[k];
+                s_y[tj + 8 * k][c] = vy[k];
             }
             __syncthreads();
 #pragma unroll 8
-            for (int nn = 0; nn < WG_T; nn++) {
+            for (int nn = 0; nn < WG_NS; nn++) {
                 const float y = s_y[nn][c];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -525,18 +537,20 @@ k_qnet_head_wgrad(const float *__restrict__ du, const float *__restrict__ a, con
         float acc[HEAD_R], accb = 0.f;
 #pragma unroll
         for (int r = 0; r < HEAD_R; r++) acc[r] = 0.f;
-        float *s_dh = &s_x[0][0];   // 32 samples x 8 rows per stage
-        for (long long nb = 0; nb < n; nb += WG_T) {
-            {
-                const long long i = nb + tid / HEAD_R;
-                s_dh[tid] = i < n ? __ldg(dh + i * HEAD_R + tid % HEAD_R) : 0.f;
+        float *s_dh = &s_x[0][0];   // 64 samples x 8 rows per stage
+        for (long long nb = 0; nb < n; nb += WG_NS) {
+            float fv[WG_NS];
+#pragma unroll
+            for (int nn = 0; nn < WG_NS; nn++) fv[nn] = (nb + nn < n) ? __ldg(f + (nb + nn) * HEAD_H + tid) : 0.f;
+#pragma unroll
+            for (int k = 0; k < WG_NS * HEAD_R / WG_THREADS; k++) {
+                const int t = tid + k * WG_THREADS;
+                const long long i = nb + t / HEAD_R;
+                s_dh[t] = i < n ? __ldg(dh + i * HEAD_R + t % HEAD_R) : 0.f;
             }
             __syncthreads();
-            float fv[WG_T];
 #pragma unroll
-            for (int nn = 0; nn < WG_T; nn++) fv[nn] = (nb + nn < n) ? __ldg(f + (nb + nn) * HEAD_H + tid) : 0.f;
-#pragma unroll
-            for (int nn = 0; nn < WG_T; nn++) {
+            for (int nn = 0; nn < WG_NS; nn++) {
 #pragma unroll
                 for (int r = 0; r < HEAD_R; r++) acc[r] = fmaf(s_dh[nn * HEAD_R + r], fv[nn], acc[r]);
                 if (tid < HEAD_R) accb += s_dh[nn * HEAD_R + tid];
@@ -555,11 +569,20 @@ k_qnet_head_wgrad(const float *__restrict__ du, const float *__restrict__ a, con
         }
         return;
     }
-    if (tid < HEAD_C) {   // convolution bias gradient
+    {   // convolution bias gradient: two halves of the batch per channel, 16 loads in flight each
+        const int c = tid % HEAD_C, half = tid / HEAD_C;
         float acc = 0.f;
-#pragma unroll 8
-        for (long long i = 0; i < n; i++) acc += __ldg(dp + i * HEAD_C + tid);
-        dconv_bias[tid] = acc;
+        for (long long i0 = half; i0 < n; i0 += 32) {
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = (i0 + 2 * k < n) ? __ldg(dp + (i0 + 2 * k) * HEAD_C + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc += v[k];
+        }
+        float *s_half = &s_x[0][0];
+        if (half == 1) s_half[c] = acc;
+        __syncthreads();
+        if (half == 0) dconv_bias[c] = acc + s_half[c];
     }
 }
 
