@@ -258,8 +258,10 @@ int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream);
 
 /* ---- the per-env drop-in's round trip (engines of up to PB_SNAPSHOT_MAX_ENVS envs) ------------ */
 /* What the reference's loop reads per env and step (src/replay_buffer.py:107-137,
- * src/algorithms/train_dqn.py:95-113) in ONE stream synchronisation: optionally step every env
- * with `actions_host` (uint8 [n]; NULL = no step; pb_step semantics, reward int32 [n] / done
+ * src/algorithms/train_dqn.py:95-113) in ONE kernel launch and no copy operation (the kernel
+ * reads the actions from, and writes every answer to, pinned host memory; the call returns when
+ * its last CTA has published the results, with `stream` drained up to it): optionally step every
+ * env with `actions_host` (uint8 [n]; NULL = no step; pb_step semantics, reward int32 [n] / done
  * uint8 [n] returned), then info_host int32 [n][8] = score, lives, is_done, first_ai_done,
  * remaining_pellets, ticks_per_step, level, curr_ticks (env.rs:269-289), mask_host uint8 [n][5]
  * (env.rs:293-302) and obs_host float [n][17][28][31] (env.rs:305-307); any output may be NULL.
@@ -268,6 +270,12 @@ int pb_rollout_streams(pb_engine *e, void **step_stream, void **encode_stream);
 int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_reset,
                           int32_t *reward_host, uint8_t *done_host, int32_t *info_host,
                           uint8_t *mask_host, float *obs_host, void *stream);
+/* Zero-copy form: the engine's own pinned buffers.  *block_host receives the block the kernel
+ * fills and offsets[0..5] the byte offsets of info, reward, done, mask, obs inside it and its
+ * total size; *actions_host the pinned uint8 [n] the kernel reads.  Passing exactly these
+ * addresses to pb_step_snapshot_host means "in place": nothing is copied on the host, and the
+ * contents are valid until the next pb_step_snapshot_host call of this engine. */
+int pb_snapshot_block(pb_engine *e, void **block_host, uint8_t **actions_host, size_t *offsets);
 
 /* Synchronises `stream`, then returns PB_ERR_INVALID_ACTION (and the lowest offending env index
  * in *first_bad_env) if any pb_step since the last check saw an action > 4; clears the record. */
@@ -457,6 +465,21 @@ int pb_qnet_head_bwd(const float *dq_dev, const float *p_dev, const uint8_t *idx
                      float *db1_dev, float *dwv_dev, float *dbv_dev, float *dwa_dev, float *dba_dev,
                      float *scratch_dev, int device, void *stream);
 int64_t pb_qnet_head_bwd_scratch_floats(int64_t n);
+
+/* ---- end of a DQN iteration (src/algorithms/train_dqn.py:200-206) -----------------------------
+ * torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by torch.optim.Adam.step()
+ * (default Adam: no weight decay, no amsgrad) over `count` <= 32 float32 tensors, two launches.
+ * params_dev / grads_dev: HOST arrays of `count` device pointers; sizes[t] = elements of tensor t;
+ * a parameter and its gradient share one memory layout (storage order is what is paired).
+ * exp_avg_dev / exp_avg_sq_dev: float32 [sum sizes], the moments in tensor order (zero at start);
+ * step_dev: int64 [1] device step counter, advanced by the call (zero at start);
+ * partials_dev: float32 [count * 8] scratch; grad_norm_out_dev: float32 [1], the total norm BEFORE
+ * clipping, what clip_grad_norm_ returns (may be NULL).  The gradients are read, not rewritten.
+ * The hyper-parameters are doubles, as torch takes them (1 - beta is rounded to float32 once). */
+int pb_clip_adam(int count, float *const *params_dev, const float *const *grads_dev,
+                 const int64_t *sizes, float *exp_avg_dev, float *exp_avg_sq_dev, int64_t *step_dev,
+                 float *partials_dev, double max_norm, double lr, double beta1, double beta2, double eps,
+                 float *grad_norm_out_dev, int device, void *stream);
 
 
 

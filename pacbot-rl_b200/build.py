@@ -16,11 +16,13 @@ HEADERS = [
     os.path.join(CSRC, "pb_state.cuh"),
     os.path.join(CSRC, "pb_engine.cuh"),
     os.path.join(CSRC, "pb_encode.cuh"),
+    os.path.join(CSRC, "pb_encode_small.cuh"),
     os.path.join(CSRC, "pb_mcts.cuh"),
     os.path.join(CSRC, "pb_mcts_abi.inl"),
     os.path.join(CSRC, "pb_rollout_abi.inl"),
     os.path.join(CSRC, "pb_replay_abi.inl"),
     os.path.join(CSRC, "pb_qnet_abi.inl"),
+    os.path.join(CSRC, "pb_optim_abi.inl"),
     os.path.join(os.path.dirname(HERE), "include", "pacbot_b200.h"),
 ]
 NVCC_FLAGS = [

@@ -218,6 +218,107 @@ __device__ __forceinline__ bool warp_arrived(unsigned int v) {
 // offset of (channel, cell) inside the private image (channel 0 is not part of it)
 __device__ __forceinline__ int img_off(int ch, int cell) { return (ch - 1) * CH_FLOATS + cell; }
 
+// The single cells of one env's observation as per-lane roles: pure register work, branch free.
+// Called by all 32 lanes of a warp; lane l < PEL_WORDS holds word l of the observation-ordered
+// pellet bitboard in F.  Every lane ends up with at most ONE store into the image of channels
+// 1..16 (`off` floats from the start of channel 1); `unpatch`: the cell belongs to a sparse
+// channel and has to be cleared again before the image is reused for another env.  Also hands
+// back the two fill values of the env: pv (a plain pellet's channel-1 value) and sp (channel 15).
+struct CellRole {
+    bool do_store, unpatch;
+    int off;
+    float val, pv, sp;
+};
+__device__ __forceinline__ CellRole cell_role(const EnvR &s, const uint32_t F, const int lane) {
+    // Every lane ends up with at most ONE store (offset, value, needs-un-patch):
+    //   lane 0,1    Pac-Man, ch 2 / 3                       (env.rs:452-457)
+    //   lane 4..7   ghost g = lane & 3, ch 4+g              (env.rs:461)
+    //   lane 8..11  ghost g, ch 8+g                         (env.rs:476-480)
+    //   lane 12..15 ghost g timer, ch 12 / 13 / 14          (env.rs:462-469)
+    //   lane 16..19 ghost g frightened bonus, ch 1          (env.rs:464)
+    //   lane 20..23 super pellet k = lane & 3, ch 16        (env.rs:487-497)
+    //   lane 24..27 super pellet k value, ch 1              (env.rs:428-432)
+    //   lane 28     fruit value, ch 1                       (env.rs:433-437)
+    const int grp = lane >> 2, gi = lane & 3;
+    int grow = s.g[0].row, gcol = s.g[0].col, gfr = s.g[0].fright;
+#pragma unroll
+    for (int g = 1; g < 4; g++) {
+        grow = (g == gi) ? s.g[g].row : grow;
+        gcol = (g == gi) ? s.g[g].col : gcol;
+        gfr = (g == gi) ? s.g[g].fright : gfr;
+    }
+    const bool g_on = on_board(grow, gcol);
+    const int g_cell = g_on ? obs_cell(grow, gcol) : 0;
+    const int sup_cell = obs_cell(gi < 2 ? 3 : 23, (gi & 1) ? 26 : 1);
+    const bool pac_on = on_board(s.prow, s.pcol);
+    const int pac_cell = pac_on ? obs_cell(s.prow, s.pcol) : 0;
+    // the cell whose pellet bit / frightened occupants this lane needs (ch-1 finalisers)
+    const int cell = (grp == 4) ? g_cell : ((grp == 5 || grp == 6) ? sup_cell
+                                           : obs_cell(FRUIT_ROW, FRUIT_COL));
+    const uint32_t cell_word = __shfl_sync(0xffffffffu, F, cell >> 5);
+    const bool cell_pellet = (cell_word >> (cell & 31)) & 1u;
+    bool fright_here = false, earlier_fright_here = false, later_same_timer = false;
+    const int my_timer_ch = gfr > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
+    float bonus_sum_v = 0.0f;  // filled below for the bonus lanes
+    {
+        // base value under a frightened ghost (env.rs:427-441), then one IEEE add per
+        // frightened ghost on that cell, in ghost order, starting with this lane's ghost
+        const bool last_pellet0 = s.num_pellets == 1;
+        const float pv0 = last_pellet0 ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
+                                       : (float)PELLET_POINTS / 200.0f;
+        const float sv0 = last_pellet0 ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
+                                       : (float)SUPER_PELLET_POINTS / 200.0f;
+        const bool is_sup = (grow == 3 || grow == 23) && (gcol == 1 || gcol == 26);
+        const bool is_fruit = s.fruit_steps > 0 && grow == FRUIT_ROW && gcol == FRUIT_COL;
+        float v = cell_pellet ? (is_sup ? sv0 : pv0)
+                              : (is_fruit ? (float)FRUIT_POINTS / 200.0f : 0.0f);
+        const float bonus = (float)(1 << (s.combo & 31));
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const bool on = on_board(s.g[g].row, s.g[g].col);
+            const bool f_here = s.g[g].fright > 0 && on && obs_cell(s.g[g].row, s.g[g].col) == cell;
+            fright_here |= f_here;
+            earlier_fright_here |= f_here && g < gi;
+            const int gch = s.g[g].fright > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
+            later_same_timer |= g > gi && on && s.g[g].row == grow && s.g[g].col == gcol &&
+                                gch == my_timer_ch;
+            const bool add = g >= gi && s.g[g].fright > 0 && s.g[g].row == grow && s.g[g].col == gcol;
+            v = add ? __fadd_rn(v, bonus) : v;
+        }
+        bonus_sum_v = v;
+    }
+    // env.rs:427-441: (points + LAST_REWARD if this is the last pellet) as f32 / 200.0; the
+    // four possible quotients are IEEE-rounded compile-time constants
+    const bool last_pellet = s.num_pellets == 1;
+    const float pv = last_pellet ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
+                                 : (float)PELLET_POINTS / 200.0f;
+    const float sv = last_pellet ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
+                                 : (float)SUPER_PELLET_POINTS / 200.0f;
+    const float sp = __fdiv_rn((float)s.tps, (float)s.period);      // env.rs:484
+    const float timer_v = gfr > 0 ? c_tab.fright_q[gfr & 0xff] : c_tab.mode_q[s.mode_steps & 0xff];
+    // one store per lane
+    bool do_store, unpatch;
+    int off;
+    float val;
+    if (grp == 0) {             // Pac-Man (lanes 0, 1; lanes 2, 3 idle)
+        do_store = pac_on && lane < 2; unpatch = true; off = img_off(2 + lane, pac_cell); val = 1.0f;
+    } else if (grp <= 2) {      // ghost position, ch 4+g (lanes 4..7) and 8+g (lanes 8..11)
+        do_store = g_on; unpatch = true; off = img_off(lane, g_cell); val = 1.0f;
+    } else if (grp == 3) {      // timers; "last ghost wins" on a shared cell of one channel
+        do_store = g_on && !later_same_timer; unpatch = true; off = img_off(my_timer_ch, g_cell); val = timer_v;
+    } else if (grp == 4) {      // bonus: the FIRST frightened ghost on a cell finalises ch 1 there
+        do_store = g_on && gfr > 0 && !earlier_fright_here; unpatch = false; off = g_cell; val = bonus_sum_v;
+    } else if (grp == 5) {      // super pellet still there: ch 16
+        do_store = cell_pellet; unpatch = true; off = img_off(16, sup_cell); val = 1.0f;
+    } else if (grp == 6) {      // ... and its ch-1 value unless a frightened ghost owns the cell
+        do_store = cell_pellet && !fright_here; unpatch = false; off = sup_cell; val = sv;
+    } else {                    // fruit (lane 28): only where there is no pellet
+        do_store = lane == 28 && s.fruit_steps > 0 && !cell_pellet && !fright_here;
+        unpatch = false; off = cell; val = (float)FRUIT_POINTS / 200.0f;
+    }
+    return CellRole{do_store, unpatch, off, val, pv, sp};
+}
+
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 k_encode_obs(StateView st, float *__restrict__ out,
              long long env_stride, long long env_first, long long env_count,
@@ -305,93 +406,11 @@ k_encode_obs(StateView st, float *__restrict__ out,
         EnvR s;
         unpack_env(c0, c1, ga, gb, s);
 
-        // ---- per-lane role for the single cells: pure register work, branch free.
-        // Every lane ends up with at most ONE store (offset, value, needs-un-patch):
-        //   lane 0,1    Pac-Man, ch 2 / 3                       (env.rs:452-457)
-        //   lane 4..7   ghost g = lane & 3, ch 4+g              (env.rs:461)
-        //   lane 8..11  ghost g, ch 8+g                         (env.rs:476-480)
-        //   lane 12..15 ghost g timer, ch 12 / 13 / 14          (env.rs:462-469)
-        //   lane 16..19 ghost g frightened bonus, ch 1          (env.rs:464)
-        //   lane 20..23 super pellet k = lane & 3, ch 16        (env.rs:487-497)
-        //   lane 24..27 super pellet k value, ch 1              (env.rs:428-432)
-        //   lane 28     fruit value, ch 1                       (env.rs:433-437)
-        const int grp = lane >> 2, gi = lane & 3;
-        int grow = s.g[0].row, gcol = s.g[0].col, gfr = s.g[0].fright;
-#pragma unroll
-        for (int g = 1; g < 4; g++) {
-            grow = (g == gi) ? s.g[g].row : grow;
-            gcol = (g == gi) ? s.g[g].col : gcol;
-            gfr = (g == gi) ? s.g[g].fright : gfr;
-        }
-        const bool g_on = on_board(grow, gcol);
-        const int g_cell = g_on ? obs_cell(grow, gcol) : 0;
-        const int sup_cell = obs_cell(gi < 2 ? 3 : 23, (gi & 1) ? 26 : 1);
-        const bool pac_on = on_board(s.prow, s.pcol);
-        const int pac_cell = pac_on ? obs_cell(s.prow, s.pcol) : 0;
-        // the cell whose pellet bit / frightened occupants this lane needs (ch-1 finalisers)
-        const int cell = (grp == 4) ? g_cell : ((grp == 5 || grp == 6) ? sup_cell
-                                               : obs_cell(FRUIT_ROW, FRUIT_COL));
-        const uint32_t cell_word = __shfl_sync(0xffffffffu, F, cell >> 5);
-        const bool cell_pellet = (cell_word >> (cell & 31)) & 1u;
-        bool fright_here = false, earlier_fright_here = false, later_same_timer = false;
-        const int my_timer_ch = gfr > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
-        float bonus_sum_v = 0.0f;  // filled below for the bonus lanes
-        {
-            // base value under a frightened ghost (env.rs:427-441), then one IEEE add per
-            // frightened ghost on that cell, in ghost order, starting with this lane's ghost
-            const bool last_pellet0 = s.num_pellets == 1;
-            const float pv0 = last_pellet0 ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
-                                           : (float)PELLET_POINTS / 200.0f;
-            const float sv0 = last_pellet0 ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
-                                           : (float)SUPER_PELLET_POINTS / 200.0f;
-            const bool is_sup = (grow == 3 || grow == 23) && (gcol == 1 || gcol == 26);
-            const bool is_fruit = s.fruit_steps > 0 && grow == FRUIT_ROW && gcol == FRUIT_COL;
-            float v = cell_pellet ? (is_sup ? sv0 : pv0)
-                                  : (is_fruit ? (float)FRUIT_POINTS / 200.0f : 0.0f);
-            const float bonus = (float)(1 << (s.combo & 31));
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const bool on = on_board(s.g[g].row, s.g[g].col);
-                const bool f_here = s.g[g].fright > 0 && on && obs_cell(s.g[g].row, s.g[g].col) == cell;
-                fright_here |= f_here;
-                earlier_fright_here |= f_here && g < gi;
-                const int gch = s.g[g].fright > 0 ? 14 : (s.mode == CHASE ? 13 : 12);
-                later_same_timer |= g > gi && on && s.g[g].row == grow && s.g[g].col == gcol &&
-                                    gch == my_timer_ch;
-                const bool add = g >= gi && s.g[g].fright > 0 && s.g[g].row == grow && s.g[g].col == gcol;
-                v = add ? __fadd_rn(v, bonus) : v;
-            }
-            bonus_sum_v = v;
-        }
-        // env.rs:427-441: (points + LAST_REWARD if this is the last pellet) as f32 / 200.0; the
-        // four possible quotients are IEEE-rounded compile-time constants
-        const bool last_pellet = s.num_pellets == 1;
-        const float pv = last_pellet ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
-                                     : (float)PELLET_POINTS / 200.0f;
-        const float sv = last_pellet ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
-                                     : (float)SUPER_PELLET_POINTS / 200.0f;
-        const float sp = __fdiv_rn((float)s.tps, (float)s.period);      // env.rs:484
-        const float timer_v = gfr > 0 ? c_tab.fright_q[gfr & 0xff] : c_tab.mode_q[s.mode_steps & 0xff];
-        // one store per lane
-        bool do_store, unpatch;
-        int off;
-        float val;
-        if (grp == 0) {             // Pac-Man (lanes 0, 1; lanes 2, 3 idle)
-            do_store = pac_on && lane < 2; unpatch = true; off = img_off(2 + lane, pac_cell); val = 1.0f;
-        } else if (grp <= 2) {      // ghost position, ch 4+g (lanes 4..7) and 8+g (lanes 8..11)
-            do_store = g_on; unpatch = true; off = img_off(lane, g_cell); val = 1.0f;
-        } else if (grp == 3) {      // timers; "last ghost wins" on a shared cell of one channel
-            do_store = g_on && !later_same_timer; unpatch = true; off = img_off(my_timer_ch, g_cell); val = timer_v;
-        } else if (grp == 4) {      // bonus: the FIRST frightened ghost on a cell finalises ch 1 there
-            do_store = g_on && gfr > 0 && !earlier_fright_here; unpatch = false; off = g_cell; val = bonus_sum_v;
-        } else if (grp == 5) {      // super pellet still there: ch 16
-            do_store = cell_pellet; unpatch = true; off = img_off(16, sup_cell); val = 1.0f;
-        } else if (grp == 6) {      // ... and its ch-1 value unless a frightened ghost owns the cell
-            do_store = cell_pellet && !fright_here; unpatch = false; off = sup_cell; val = sv;
-        } else {                    // fruit (lane 28): only where there is no pellet
-            do_store = lane == 28 && s.fruit_steps > 0 && !cell_pellet && !fright_here;
-            unpatch = false; off = cell; val = (float)FRUIT_POINTS / 200.0f;
-        }
+        // ---- per-lane role for the single cells (cell_role above): at most one store per lane
+        const CellRole role = cell_role(s, F, lane);
+        const bool do_store = role.do_store, unpatch = role.unpatch;
+        const int off = role.off;
+        const float val = role.val, pv = role.pv, sp = role.sp;
 
         // ---- rebuild the image (it is free: the ticket was only taken after the previous copy
         // had finished reading it).  Clear last env's single cell, then channel 1 base values (a

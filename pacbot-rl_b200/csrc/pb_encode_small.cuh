@@ -1,0 +1,210 @@
+// pb_encode_small.cuh -- the small-batch forms of the hot path: one CTA per env.
+//
+// k_encode_obs (pb_encode.cuh) is a persistent kernel sized for the 65 536-env shard: every one of
+// its 148 CTAs zeroes 222 KB of shared memory and builds the wall template before the first ticket
+// is taken, ~10 us that a 3.9 GB write stream hides and a 32-env launch does not.  The DQN loop
+// (32 envs per experience step, 1 env per evaluation step), the MCTS collector (one leaf per tree)
+// and the per-env drop-in (gym.py, ONE env) only ever launch small batches, so they get:
+//
+//   k_obs_small   PacmanGym::obs (env.rs:410-500) for <= SMALL_ENC_MAX envs: one 256-thread CTA
+//                 per env assembles the whole 59 024 B observation in shared memory (base values
+//                 with 128-bit stores, then the <= 29 single cells of cell_role(), the SAME
+//                 per-lane roles as the persistent kernel) and copies it out with coalesced
+//                 128-bit stores;
+//   k_gym_call    the per-env drop-in's whole round trip in ONE launch and NO copy operation:
+//                 thread 0 of the env's CTA steps it (env.rs:216-267, auto reset as k_step) and
+//                 answers every getter of env.rs:269-302, the CTA encodes the observation, and
+//                 all of it is written straight into the caller's block of pinned host memory;
+//                 the last CTA to finish publishes a sequence number there, which is what the
+//                 host waits for (pb_step_snapshot_host).
+//
+// Bit-exactness: the values are cell_role()'s and the fills of k_encode_obs (pv nibbles for
+// channel 1, tps / period for channel 15, the wall bits for channel 0); tests diff both kernels
+// against the oracle and against each other.
+#pragma once
+
+namespace pb {
+
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_IMG_BYTES = OBS_FLOATS * 4;                      // 59 024: all 17 channels
+constexpr int SMALL_SMEM = SMALL_IMG_BYTES + 32 * 4;                 // + the pellet words
+static_assert(SMALL_IMG_BYTES % 16 == 0, "the image is copied out as float4");
+// launches of up to this many envs go to k_obs_small (three 59 KB CTAs fit an SM: 444 resident
+// CTAs, so up to about one wave); larger ones to the persistent k_encode_obs
+constexpr long long SMALL_ENC_MAX = 512;
+
+// One env's observation into `img` (shared memory, OBS_FLOATS floats), by all SMALL_THREADS
+// threads of the CTA; `words` (shared, 32 words) receives the pellet bitboard.  Ends with a
+// __syncthreads(): the image is complete and visible to the whole CTA on return.
+__device__ __forceinline__ void build_obs_image(const StateView &st, long long env, float *img,
+                                                uint32_t *words) {
+    const int t = threadIdx.x, lane = t & 31;
+    if (t < 32) words[t] = (t < PEL_WORDS) ? st.pel[(long long)t * st.npad + env] : 0u;
+    EnvR s;
+    load_env(st, env, s);
+    __syncthreads();
+    // every warp evaluates the roles (register work); warp 0 does the stores after the fill
+    const CellRole role = cell_role(s, words[lane], lane);
+    float4 *img4 = reinterpret_cast<float4 *>(img);
+    for (int j = t; j < OBS_CH * CH_VEC; j += SMALL_THREADS) {
+        const int ch = j / CH_VEC, q = j - ch * CH_VEC;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch == 0) {                      // walls (env.rs:426), cell c = col * ROWS + (30 - row)
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = 4 * q + u;
+                const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
+                w[u] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
+            }
+            v = make_float4(w[0], w[1], w[2], w[3]);
+        } else if (ch == 1) {               // pellet values: one nibble of the bitboard
+            const uint32_t nib = words[q >> 3] >> (4 * (q & 7));
+            v.x = (nib & 1u) ? role.pv : 0.0f;
+            v.y = (nib & 2u) ? role.pv : 0.0f;
+            v.z = (nib & 4u) ? role.pv : 0.0f;
+            v.w = (nib & 8u) ? role.pv : 0.0f;
+        } else if (ch == 15) {              // ticks per step / update period (env.rs:484)
+            v = make_float4(role.sp, role.sp, role.sp, role.sp);
+        }
+        img4[j] = v;
+    }
+    __syncthreads();
+    if (t < 32 && role.do_store) img[CH_FLOATS + role.off] = role.val;   // disjoint cells
+    __syncthreads();
+}
+
+__device__ __forceinline__ void copy_obs_image(const float *img, float *dst) {
+    const float4 *src4 = reinterpret_cast<const float4 *>(img);
+    float4 *dst4 = reinterpret_cast<float4 *>(dst);
+    for (int j = threadIdx.x; j < OBS_CH * CH_VEC; j += SMALL_THREADS) dst4[j] = src4[j];
+}
+
+// Same contract as k_encode_obs for envs [env_first, env_first + gridDim.x): out + k * env_stride,
+// optional ring-slot indirection read from device memory (CUDA-graph replays while the ring
+// advances), optional device-timeline record.
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
+            const long long *__restrict__ slot_index, long long slot_stride,
+            TraceRec *__restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *img = reinterpret_cast<float *>(smem_raw);
+    uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw + SMALL_IMG_BYTES);
+    if (trace && threadIdx.x == 0) {
+        const unsigned long long t = global_timer_ns();
+        stamp_min(&trace->begin, t);
+        stamp_min(&trace->ready, t);
+    }
+    if (slot_index) out += *slot_index * slot_stride;
+    const long long k = blockIdx.x;
+    build_obs_image(st, env_first + k, img, words);
+    copy_obs_image(img, out + k * env_stride);
+    if (trace && threadIdx.x == 0) stamp_max(&trace->end, global_timer_ns());
+}
+
+// Layout of the block k_gym_call fills (pb_step_snapshot_host computes the same offsets):
+//   seq u64 | bad u64 | info int32[n][8] | reward int32[n] | done u8[n] | mask u8[n][5] | pad to 16
+//   | obs float32[n][17][28][31]
+struct GymCallLayout {
+    size_t off_seq, off_bad, off_info, off_reward, off_done, off_mask, off_obs, total;
+};
+__host__ __device__ inline GymCallLayout gym_call_layout(size_t n) {
+    GymCallLayout l;
+    l.off_seq = 0;
+    l.off_bad = 8;
+    l.off_info = 16;
+    l.off_reward = l.off_info + 32 * n;
+    l.off_done = l.off_reward + 4 * n;
+    l.off_mask = l.off_done + n;
+    l.off_obs = (l.off_mask + 5 * n + 15) & ~(size_t)15;
+    l.total = l.off_obs + sizeof(float) * (size_t)OBS_FLOATS * n;
+    return l;
+}
+
+// One CTA per env of a small engine.  `actions` (pinned host memory, read in place) may be null:
+// no step, only the answers.  `blk` is the caller's pinned block (GymCallLayout); `arrive` a
+// device counter that is zero between launches; `seq` the number to publish when the whole block
+// is in host memory.
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int auto_reset,
+           unsigned long long *bad_action, unsigned char *__restrict__ blk, int want_obs,
+           unsigned int *arrive, unsigned long long seq, TraceRec *__restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *img = reinterpret_cast<float *>(smem_raw);
+    uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw + SMALL_IMG_BYTES);
+    __shared__ uint32_t s_walls[32];
+    if (trace && threadIdx.x == 0) {
+        const unsigned long long t = global_timer_ns();
+        stamp_min(&trace->begin, t);
+        stamp_min(&trace->ready, t);
+    }
+    load_walls(s_walls);
+    const long long i = blockIdx.x;
+    const GymCallLayout l = gym_call_layout((size_t)st.n);
+    if (threadIdx.x == 0) {
+        EnvR s;
+        load_env(st, i, s);
+        int32_t *reward = reinterpret_cast<int32_t *>(blk + l.off_reward);
+        uint8_t *done_out = blk + l.off_done;
+        if (actions) {
+            const int action = actions[i];
+            if (action > 4) {  // env.rs:83-88: "Invalid action" -- env untouched
+                atomicMin(bad_action, (unsigned long long)i);
+                reward[i] = 0;
+                done_out[i] = 0;
+            } else {
+                const PelRef pel{st.pel + i, st.npad};
+                const RngCtx rng = make_rng(rp, i);
+                int rew;
+                bool done;
+                gym_step(s, pel, c_tab, s_walls, rng, action, rew, done);
+                if (done && auto_reset) gym_reset(s, pel, c_tab, s_walls, rng, true);
+                store_env(st, i, s);
+                reward[i] = rew;
+                done_out[i] = done ? 1 : 0;
+            }
+        }
+        int32_t *o = reinterpret_cast<int32_t *>(blk + l.off_info) + i * 8;   // env.rs:269-289
+        o[0] = s.score;
+        o[1] = s.lives;
+        o[2] = is_done(s);
+        o[3] = first_ai_done(st, i, s);
+        o[4] = s.num_pellets;
+        o[5] = s.tps;
+        o[6] = s.level;
+        o[7] = (int)s.ticks;
+        write_mask(blk + l.off_mask, i, action_mask_bits(s, s_walls));          // env.rs:293-302
+    }
+    __syncthreads();   // thread 0's state (global memory) is what the CTA encodes
+    if (want_obs) {
+        build_obs_image(st, i, img, words);
+        copy_obs_image(img, reinterpret_cast<float *>(blk + l.off_obs) + i * (long long)OBS_FLOATS);
+    }
+    // The CTA's stores to host memory (all threads', made visible to thread 0 by the barrier; the
+    // fence is cumulative) are performed before thread 0 counts the CTA in; the last CTA hands the
+    // invalid-action record over and publishes the sequence number.  A one-env engine -- the
+    // drop-in's case -- is its own last CTA and needs a single system fence.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (trace) stamp_max(&trace->end, global_timer_ns());
+        volatile unsigned long long *bad_word = reinterpret_cast<volatile unsigned long long *>(blk + l.off_bad);
+        volatile unsigned long long *seq_word = reinterpret_cast<volatile unsigned long long *>(blk + l.off_seq);
+        if (gridDim.x == 1) {
+            *bad_word = atomicExch(bad_action, ~0ull);
+            __threadfence_system();
+            *seq_word = seq;
+        } else {
+            __threadfence_system();
+            const unsigned int before = atomicAdd(arrive, 1u);
+            if (before == gridDim.x - 1) {
+                __threadfence();
+                *bad_word = atomicExch(bad_action, ~0ull);
+                atomicExch(arrive, 0u);
+                __threadfence_system();
+                *seq_word = seq;
+            }
+        }
+    }
+}
+
+}  // namespace pb

@@ -7,6 +7,7 @@
 //   k_encode_obs (pb_encode.cuh) one env per warp; the observation image is assembled in shared
 //                memory and shipped to HBM by the TMA engine with cp.async.bulk (SASS UBLKCP)
 //   k_mask / k_query / k_sample_actions / k_select_actions / k_gather_obs / k_clone
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -221,34 +222,13 @@ k_query(StateView st, int what, int32_t *__restrict__ out) {
     out[i] = v;
 }
 
-// Everything the reference's per-env loop reads besides the observation (env.rs:269-302), for a
-// small engine, in one launch: info[i][0..7] = score, lives, is_done, first_ai_done,
-// remaining_pellets, ticks_per_step, level, curr_ticks; the action mask; and the engine's
-// invalid-action record, which is handed over and cleared.
-__global__ void __launch_bounds__(STEP_THREADS)
-k_snapshot(StateView st, int32_t *__restrict__ info, uint8_t *__restrict__ mask_out,
-           unsigned long long *bad_action, unsigned long long *__restrict__ bad_out) {
-    __shared__ uint32_t s_walls[32];
-    load_walls(s_walls);
-    const long long i = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
-    if (i == 0) {
-        *bad_out = *bad_action;
-        *bad_action = ~0ull;
-    }
-    if (i >= st.n) return;
-    EnvR s;
-    load_env(st, i, s);
-    int32_t *o = info + i * 8;
-    o[0] = s.score;
-    o[1] = s.lives;
-    o[2] = is_done(s);
-    o[3] = first_ai_done(st, i, s);
-    o[4] = s.num_pellets;
-    o[5] = s.tps;
-    o[6] = s.level;
-    o[7] = (int)s.ticks;
-    write_mask(mask_out, i, action_mask_bits(s, s_walls));
-}
+}  // namespace pb
+
+// the small-batch forms: k_obs_small (one CTA per env) and k_gym_call (the per-env drop-in's whole
+// round trip in one launch); they use load_env / store_env / first_ai_done / write_mask above
+#include "pb_encode_small.cuh"
+
+namespace pb {
 
 // =============================================================================================
 // k_sample_actions / k_select_actions (policies.py:16-59)
@@ -445,10 +425,12 @@ struct pb_engine {
     int roll_last_enc = 0;                   // roll_enc index of the most recent encoder launch
     cudaEvent_t ev_roll_copied = nullptr;    // last result copy of a host chunk
     bool roll_host_pending = false;
-    // pb_step_snapshot_host: one contiguous device block + its pinned mirror, and pinned actions
-    // that k_step reads in place (zero copy)
-    unsigned char *snap_dev = nullptr, *snap_pin = nullptr;
+    // pb_step_snapshot_host: the pinned block k_gym_call fills in place, pinned actions it reads
+    // in place (zero copy both ways), the device counter its CTAs arrive at, the call number
+    unsigned char *snap_pin = nullptr;
     uint8_t *snap_actions_pin = nullptr;
+    unsigned int *snap_arrive = nullptr;
+    unsigned long long snap_seq = 0;
     // pb_trace_*: device timeline of this engine's k_step / k_encode_obs launches
     TraceRec *trace = nullptr;
     long long trace_cap = 0, trace_n = 0;
@@ -457,6 +439,13 @@ struct pb_engine {
 constexpr unsigned int TICKET_RING = 64;
 
 namespace {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -507,7 +496,24 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     static thread_local int attr_set_for = -1;
     if (attr_set_for != e->device) {
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         attr_set_for = e->device;
+    }
+    // Small batches (the DQN loop's 32 envs, an evaluation env, the leaves of a few hundred MCTS
+    // trees): one CTA per env instead of the persistent kernel, whose prologue alone costs more
+    // than these launches (pb_encode_small.cuh).  PB_SMALL_ENC_MAX overrides the switch-over
+    // count for A/B runs (0: always the persistent kernel).
+    static const long long small_max = [] {
+        const char *v = getenv("PB_SMALL_ENC_MAX");
+        return v ? atoll(v) : (long long)SMALL_ENC_MAX;
+    }();
+    if (count <= small_max) {
+        TraceRec *trace = trace_slot(e, PB_TRACE_ENCODE);
+        k_obs_small<<<(unsigned)count, SMALL_THREADS, SMALL_SMEM, s>>>(
+            e->st, out_dev, stride, first, slot_index, slot_stride, trace);
+        PB_CUDA(cudaGetLastError());
+        return PB_OK;
     }
     long long blocks = (count + ENC_WARPS - 1) / ENC_WARPS;
     if (blocks > e->num_sms) blocks = e->num_sms;
@@ -591,7 +597,7 @@ int pb_destroy(pb_engine *e) {
     }
     cudaFree(e->tickets);
     cudaFree(e->trace);
-    cudaFree(e->snap_dev);
+    cudaFree(e->snap_arrive);
     if (e->snap_pin) cudaFreeHost(e->snap_pin);
     if (e->snap_actions_pin) cudaFreeHost(e->snap_actions_pin);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -1144,9 +1150,54 @@ int pb_step_host(pb_engine *e, const uint8_t *actions_host, int32_t *reward_host
 
 // The small-batch host round trip of the per-env drop-in (gym.py): what the reference's loop does
 // per env and step -- step(), is_done(), obs_numpy(), action_mask(), score() ...
-// (src/replay_buffer.py:107-137, src/algorithms/train_dqn.py:95-113) -- as ONE stream
-// synchronisation: k_step reads the actions in place from pinned host memory, k_snapshot and the
-// encoder fill one contiguous device block, one copy brings it to its pinned mirror.
+// (src/replay_buffer.py:107-137, src/algorithms/train_dqn.py:95-113) -- as ONE kernel launch and
+// no copy operation: k_gym_call (pb_encode_small.cuh) reads the actions in place from pinned host
+// memory, steps, answers the getters, encodes the observation and writes all of it straight into
+// a pinned block; its last CTA publishes the call's sequence number there and the host waits for
+// that word (a stream query every few thousand polls catches a failed launch).
+namespace {
+// the pinned block, the pinned actions and the arrival counter of pb_step_snapshot_host
+int snap_alloc(pb_engine *e) {
+    const size_t n = (size_t)e->n;
+    const GymCallLayout l = gym_call_layout(n);
+    if (!e->snap_pin) {
+        PB_CUDA(cudaMallocHost(&e->snap_pin, l.total));
+        memset(e->snap_pin, 0, l.off_obs);
+    }
+    if (!e->snap_actions_pin) PB_CUDA(cudaMallocHost(&e->snap_actions_pin, n));
+    if (!e->snap_arrive) {
+        PB_CUDA(cudaMalloc(&e->snap_arrive, sizeof(unsigned int)));
+        PB_CUDA(cudaMemset(e->snap_arrive, 0, sizeof(unsigned int)));
+    }
+    static thread_local int attr_set_for = -1;
+    if (attr_set_for != e->device) {
+        PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        attr_set_for = e->device;
+    }
+    return PB_OK;
+}
+}  // namespace
+
+int pb_snapshot_block(pb_engine *e, void **block_host, uint8_t **actions_host, size_t *offsets) {
+    if (!e || !block_host || !actions_host || !offsets)
+        return fail(PB_ERR_INVALID_ARG, "pb_snapshot_block: null argument");
+    if (e->n > PB_SNAPSHOT_MAX_ENVS)
+        return fail(PB_ERR_INVALID_ARG, "pb_snapshot_block: engines of up to 1024 envs");
+    DeviceGuard g(e->device);
+    const int rc = snap_alloc(e);
+    if (rc != PB_OK) return rc;
+    const GymCallLayout l = gym_call_layout((size_t)e->n);
+    *block_host = e->snap_pin;
+    *actions_host = e->snap_actions_pin;
+    offsets[0] = l.off_info;
+    offsets[1] = l.off_reward;
+    offsets[2] = l.off_done;
+    offsets[3] = l.off_mask;
+    offsets[4] = l.off_obs;
+    offsets[5] = l.total;
+    return PB_OK;
+}
+
 int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_reset,
                           int32_t *reward_host, uint8_t *done_host, int32_t *info_host,
                           uint8_t *mask_host, float *obs_host, void *stream) {
@@ -1158,42 +1209,41 @@ int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_re
     DeviceGuard g(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->n;
-    // block layout: bad u64 | info int32[n][8] | reward int32[n] | done u8[n] | mask u8[n][5] | pad | obs
-    const size_t off_bad = 0, off_info = 8, off_reward = off_info + 32 * n, off_done = off_reward + 4 * n;
-    const size_t off_mask = off_done + n, small = (off_mask + 5 * n + 15) & ~(size_t)15;
-    const size_t total = small + sizeof(float) * OBS_FLOATS * n;
-    if (!e->snap_dev) PB_CUDA(cudaMalloc(&e->snap_dev, total));
-    if (!e->snap_pin) PB_CUDA(cudaMallocHost(&e->snap_pin, total));
-    if (!e->snap_actions_pin) PB_CUDA(cudaMallocHost(&e->snap_actions_pin, n));
-    unsigned char *d = e->snap_dev, *h = e->snap_pin;
-    if (actions_host) {
-        // the previous call synchronised the stream: the pinned actions are free to overwrite
-        memcpy(e->snap_actions_pin, actions_host, n);
-        k_step<<<grid_for(e->n), STEP_THREADS, 0, s>>>(
-            e->st, e->st, rng_params(e), e->snap_actions_pin,
-            reinterpret_cast<int32_t *>(d + off_reward), d + off_done, nullptr, auto_reset, e->bad_action, nullptr, 0ull, 0ll, e->n,
-            trace_slot(e, PB_TRACE_STEP));
-        PB_CUDA(cudaGetLastError());
-    }
-    k_snapshot<<<grid_for(e->n), STEP_THREADS, 0, s>>>(
-        e->st, reinterpret_cast<int32_t *>(d + off_info), d + off_mask, e->bad_action,
-        reinterpret_cast<unsigned long long *>(d + off_bad));
+    const GymCallLayout l = gym_call_layout(n);
+    const int rc = snap_alloc(e);
+    if (rc != PB_OK) return rc;
+    unsigned char *h = e->snap_pin;
+    // the previous call waited for its kernel: the pinned actions and the block are free.
+    // Pointers INTO the engine's own pinned buffers (pb_snapshot_block) mean "in place": no copy.
+    if (actions_host && actions_host != e->snap_actions_pin) memcpy(e->snap_actions_pin, actions_host, n);
+    const unsigned long long seq = ++e->snap_seq;
+    k_gym_call<<<(unsigned)n, SMALL_THREADS, SMALL_SMEM, s>>>(
+        e->st, rng_params(e), actions_host ? e->snap_actions_pin : nullptr, auto_reset,
+        e->bad_action, h, obs_host ? 1 : 0, e->snap_arrive, seq,
+        trace_slot(e, actions_host ? PB_TRACE_STEP : PB_TRACE_ENCODE));
     PB_CUDA(cudaGetLastError());
-    if (obs_host) {
-        int rc = launch_encode(e, reinterpret_cast<float *>(d + small), OBS_FLOATS, 0, e->n, s);
-        if (rc != PB_OK) return rc;
+    volatile unsigned long long *seq_word = reinterpret_cast<volatile unsigned long long *>(h + l.off_seq);
+    for (unsigned int polls = 1; *seq_word != seq; polls++) {
+        // a failed launch never publishes: ask the stream now and then
+        if ((polls & 0xfff) == 0) {
+            const cudaError_t q = cudaStreamQuery(s);
+            if (q != cudaSuccess && q != cudaErrorNotReady) PB_CUDA(q);
+        }
+        cpu_relax();
     }
-    PB_CUDA(cudaMemcpyAsync(h, d, obs_host ? total : small, cudaMemcpyDeviceToHost, s));
-    PB_CUDA(cudaStreamSynchronize(s));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    auto out = [&](void *dst, size_t off, size_t bytes) {
+        if (dst && dst != h + off) memcpy(dst, h + off, bytes);
+    };
     if (actions_host) {
-        memcpy(reward_host, h + off_reward, 4 * n);
-        memcpy(done_host, h + off_done, n);
+        out(reward_host, l.off_reward, 4 * n);
+        out(done_host, l.off_done, n);
     }
-    if (info_host) memcpy(info_host, h + off_info, 32 * n);
-    if (mask_host) memcpy(mask_host, h + off_mask, 5 * n);
-    if (obs_host) memcpy(obs_host, h + small, sizeof(float) * OBS_FLOATS * n);
+    out(info_host, l.off_info, 32 * n);
+    out(mask_host, l.off_mask, 5 * n);
+    out(obs_host, l.off_obs, sizeof(float) * OBS_FLOATS * n);
     unsigned long long bad;
-    memcpy(&bad, h + off_bad, sizeof(bad));
+    memcpy(&bad, h + l.off_bad, sizeof(bad));
     if (bad != ~0ull) return fail(PB_ERR_INVALID_ACTION, "Invalid action");
     return PB_OK;
 }
@@ -1355,3 +1405,4 @@ int pb_trace_end(pb_engine *e, pb_trace_record *out_host, int64_t max_records, i
 #include "pb_rollout_abi.inl"
 #include "pb_replay_abi.inl"
 #include "pb_qnet_abi.inl"
+#include "pb_optim_abi.inl"

@@ -77,6 +77,7 @@ class BatchedPacmanGym:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self._dev_index = int(dev.index)
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
         self.seed = int(seed)
@@ -117,7 +118,12 @@ class BatchedPacmanGym:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # the raw handle of torch's current stream on the engine's device (the private accessor is
+        # ~10x cheaper than building a torch.cuda.Stream object per call; same handle)
+        try:
+            return C.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
+        except AttributeError:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _new(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -572,12 +578,24 @@ class BatchedPacmanGym:
         `obs` float32 [N, 17, 28, 31] (if want_obs)."""
         b = getattr(self, "_snap_bufs", None)
         if b is None:
+            # numpy views of the engine's own pinned block (pb_snapshot_block): the kernel reads the
+            # actions from, and writes every answer into, this memory -- no host-side copies
             n = self.num_envs
+            blk, act, offs = C.c_void_p(), C.c_void_p(), (C.c_size_t * 6)()
+            check(self._L.pb_snapshot_block(self._h, C.byref(blk), C.byref(act), offs))
+
+            def view(addr, shape, dtype):
+                nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                return np.frombuffer((C.c_char * nbytes).from_address(addr), dtype).reshape(shape)
+
             b = self._snap_bufs = {
-                "reward": np.zeros(n, np.int32), "done": np.zeros(n, np.bool_),
-                "info": np.zeros((n, 8), np.int32), "mask": np.zeros((n, NUM_ACTIONS), np.bool_),
-                "obs": np.zeros((n,) + OBS_SHAPE, np.float32), "actions": np.zeros(n, np.uint8)}
-            self._snap_ptrs = {k: v.ctypes.data_as(C.c_void_p) for k, v in b.items()}
+                "info": view(blk.value + offs[0], (n, 8), np.int32),
+                "reward": view(blk.value + offs[1], (n,), np.int32),
+                "done": view(blk.value + offs[2], (n,), np.bool_),
+                "mask": view(blk.value + offs[3], (n, NUM_ACTIONS), np.bool_),
+                "obs": view(blk.value + offs[4], (n,) + OBS_SHAPE, np.float32),
+                "actions": view(act.value, (n,), np.uint8)}
+            self._snap_ptrs = {k: C.c_void_p(v.ctypes.data) for k, v in b.items()}
         p = self._snap_ptrs
         aptr = None
         if actions is not None:

@@ -128,7 +128,7 @@ class PacmanGym(_SingleEnvSurface):
     # The reference's loop asks an env several questions between two mutations (`is_done()`,
     # `obs_numpy()`, `action_mask()`, `score()` ...: src/replay_buffer.py:107-137,
     # src/algorithms/train_dqn.py:95-113).  `step()` brings everything back with the step's own
-    # synchronisation (pb_step_snapshot_host: k_step, k_snapshot, k_encode_obs, one copy), and the
+    # launch (pb_step_snapshot_host: k_gym_call steps, answers and encodes into pinned memory), and the
     # getters answer from that snapshot until the env changes again.
     def _snapshot(self) -> dict:
         if self._snap is None:
@@ -149,7 +149,7 @@ class PacmanGym(_SingleEnvSurface):
         if not 0 <= int(action) <= 255:
             raise OverflowError("out of range integral type conversion attempted")
         self._snap = None
-        self._snap = snap = self._batch.step_snapshot(np.array([int(action)], np.uint8), want_obs=True)
+        self._snap = snap = self._batch.step_snapshot((int(action),), want_obs=True)
         return int(snap["reward"][0]), bool(snap["done"][0])
 
     def score(self) -> int:  # env.rs:269-271

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NUM_ACTIONS, OBS_SHAPE, check
+from ._lib import NUM_ACTIONS, OBS_SHAPE, check, raw_stream
 from .engine import BatchedPacmanGym
 from .gym import PacmanGym
 
@@ -90,7 +90,7 @@ class BatchedMCTS:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return raw_stream(self.device)
 
     def _mask_u8(self, mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if mask is None:

@@ -61,7 +61,7 @@ class _BiasPoolSiLU(torch.autograd.Function):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         _lib.check(_lib.load().pb_bias_pool_silu_fwd(
             p(x), p(bias.contiguous()), n, h, w, c, int(pool), p(z), p(y), p(idx), dev.index,
-            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            _lib.raw_stream(dev)))
         if need_bwd:
             ctx.save_for_backward(z, idx) if pool else ctx.save_for_backward(z)
             ctx.pool, ctx.in_shape = pool, (n, c, h, w)
@@ -83,7 +83,7 @@ class _BiasPoolSiLU(torch.autograd.Function):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         _lib.check(_lib.load().pb_bias_pool_silu_bwd(
             p(dy), p(z), p(idx), n, h, w, c, int(ctx.pool), p(dx), p(db), dev.index,
-            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            _lib.raw_stream(dev)))
         return dx, db, None
 
 
@@ -113,7 +113,7 @@ def qnet_head(x: torch.Tensor, conv_bias: torch.Tensor, lin: nn.Linear, out: nn.
     head = (p(x), n, h * w, p(conv_bias), p(lin.weight), p(lin.bias),
             p(value.weight if value is not None else None), p(value.bias if value is not None else None),
             p(out.weight), p(out.bias), out.out_features, int(value is not None), p(q))
-    tail = (x.device.index, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    tail = (x.device.index, _lib.raw_stream(x.device))
     if greedy_mask is None:
         _lib.check(_lib.load().pb_qnet_head_fwd(*head, *tail))
         return q
@@ -149,7 +149,7 @@ class _QNetHead(torch.autograd.Function):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         _lib.check(_lib.load().pb_qnet_head_fwd_train(
             p(x), n, h * w, p(conv_bias), p(w1), p(b1), p(wv), p(bv), p(wa), p(ba), n_out, int(dueling),
-            p(q), p(pre), p(idx), p(u), dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            p(q), p(pre), p(idx), p(u), dev.index, _lib.raw_stream(dev)))
         ctx.save_for_backward(pre, idx, u, w1, wv, wa)
         ctx.shape = (n, c, h, w)
         return q
@@ -175,7 +175,7 @@ class _QNetHead(torch.autograd.Function):
         _lib.check(L.pb_qnet_head_bwd(
             p(dq.contiguous()), p(pre), p(idx), p(u), p(w1), p(wv), p(wa), n, h * w, n_out, int(dueling),
             p(dx), p(dcb), p(dw1), p(db1), p(dwv), p(dbv), p(dwa), p(dba), p(scratch), dev.index,
-            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            _lib.raw_stream(dev)))
         return dx, dcb, dw1, db1, dwv, dbv, dwa, dba
 
 
@@ -228,7 +228,7 @@ def obs_to_padded_nhwc(obs: torch.Tensor, channels: int = 32) -> torch.Tensor:
         zero = _ZERO_I64[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
     _lib.check(_lib.load().pb_replay_slot_obs(
         C.c_void_p(obs.data_ptr()), n, 1, C.c_void_p(zero.data_ptr()), C.c_void_p(out.data_ptr()), channels,
-        dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        dev.index, _lib.raw_stream(dev)))
     return out
 
 
@@ -493,7 +493,7 @@ class NetV2(nn.Module):
             _lib.check(_lib.load().pb_qnet_head_policy_value(
                 p(x5), n, x5.shape[2] * x5.shape[3], p(last.bias), p(lin.weight), p(lin.bias), p(out.weight),
                 p(out.bias), rows, p(m), float(value_scale), p(raw), p(value), p(policy), dev.index,
-                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                _lib.raw_stream(dev)))
             return value, policy
         pred = self(obs)
         return (pred[:, -1] * value_scale,

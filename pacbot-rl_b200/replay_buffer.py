@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NUM_ACTIONS, OBS_SHAPE, check
+from ._lib import NUM_ACTIONS, OBS_SHAPE, check, raw_stream
 from .engine import BatchedPacmanGym
 from .policies import EpsilonGreedy, MaxQPolicy, Policy
 
@@ -206,7 +206,7 @@ class ReplayBuffer:
                 C.c_void_p(self._done.data_ptr()), C.c_void_p(self._next_mask.data_ptr()))
 
     def _stream(self) -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return raw_stream(self.device)
 
     @torch.no_grad()
     def _select(self, last_obs: torch.Tensor) -> torch.Tensor:

@@ -985,3 +985,61 @@ def test_qnetv2_fused_blocks_match_the_plain_network(pb):
         assert not getattr(portable_copy(fused), "_fused_blocks", False)
     finally:
         torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+@pytest.mark.parametrize("max_norm", [10.0, 0.05])
+def test_clip_adam_matches_clip_grad_norm_and_torch_adam(pb, max_norm):
+    """optim.ClipAdam (pb_clip_adam: two launches) against the reference's pair
+    `clip_grad_norm_(params, max_norm)` + `torch.optim.Adam.step()` (train_dqn.py:133,200-206) on
+    QNetV2's own parameter list in channels-last layout, 25 steps of random gradients of very
+    different scales (clipping active and inactive): returned norm, weights and both moments
+    within float32 rounding (rtol 1e-5); also inside a replayed CUDA graph."""
+    import torch
+
+    from pacbot_rl_b200 import models
+    from pacbot_rl_b200.optim import ClipAdam
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net_a = models.QNetV2(pb.OBS_SHAPE, 5).to(dev).use_channels_last()
+    net_b = models.QNetV2(pb.OBS_SHAPE, 5).to(dev).use_channels_last()
+    net_b.load_state_dict(net_a.state_dict())
+    pa, pbs = list(net_a.parameters()), list(net_b.parameters())
+    ours = ClipAdam(pa, lr=3e-4)
+    ref = torch.optim.Adam(pbs, lr=3e-4)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    for step in range(25):
+        scale = 10.0 ** ((step % 5) - 3)
+        for x, y in zip(pa, pbs):
+            g = torch.randn(x.shape, device=dev, generator=gen) * scale
+            x.grad = torch.empty_like(x).copy_(g)          # the parameter's own layout
+            y.grad = torch.empty_like(y).copy_(g)
+        n_ref = torch.nn.utils.clip_grad_norm_(pbs, max_norm=max_norm)
+        ref.step()
+        n_ours = ours.clip_and_step(max_norm)
+        torch.testing.assert_close(n_ours, n_ref, rtol=1e-5, atol=0)
+        for x, y in zip(pa, pbs):
+            torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-7)
+    assert int(ours.step_count) == 25
+    off = 0
+    for x, y in zip(pa, pbs):
+        st = ref.state[y]
+        k = x.numel()
+        m = torch.as_strided(ours.exp_avg[off:off + k], x.shape, x.stride())
+        v = torch.as_strided(ours.exp_avg_sq[off:off + k], x.shape, x.stride())
+        torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+        off += k
+    # graph replay: fixed gradient addresses, device-resident step counter
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ours.clip_and_step(max_norm)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    w_before = pa[0].detach().clone()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(ours.step_count) == 28 and not torch.equal(pa[0], w_before)

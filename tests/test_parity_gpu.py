@@ -544,3 +544,53 @@ def test_config2_2m_envs_sampled_slices_vs_oracle(pb, oracle):
             if t in (8, 11):
                 assert_obs_equal(ob.obs(), env.obs_range(f, per, stage).cpu().numpy(), ctx)
     assert episodes > 0
+
+
+def test_small_batch_encoder_matches_persistent_and_oracle(pb, oracle):
+    """k_obs_small (one CTA per env: launches of up to 512 envs, pb_encode_small.cuh) against the
+    persistent k_encode_obs (the 2 048-env launch) and the oracle, on fuzzed states and a few steps
+    on: ranges of 1 / 31 / 33 / 512 envs at odd offsets, bit for bit."""
+    torch = torch_mod()
+    n = 2048
+    rng = np.random.default_rng(321)
+    tape = rng.integers(0, 2**32, size=(n, 120), dtype=np.uint32)
+    st = fuzz_states(rng, pb, n)
+    ob, env = make_pair(pb, oracle, n, st["cfg_flags"], tape, auto_reset=False)
+    env.set_state(st)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    for t in range(5):
+        full = env.obs()                                   # persistent kernel
+        assert_obs_equal(ob.obs(), full.cpu().numpy(), f"persistent, step {t}", ob.export_state())
+        for first, count in ((0, 1), (7, 31), (100, 33), (1536, 512), (2047, 1), (1000, 257)):
+            part = torch.full((count,) + pb.OBS_SHAPE, -3.0, device="cuda:0")
+            env.obs_range(first, count, part)              # one CTA per env
+            assert torch.equal(part.view(torch.int32), full[first:first + count].view(torch.int32)), (t, first, count)
+        a = random_valid_actions(rng, ob.action_mask(), p_invalid_move=0.2)
+        compare_step(ob, env, a, t, False, check_obs=False)
+
+
+def test_gym_call_kernel_vs_oracle_on_fuzzed_states(pb, oracle):
+    """k_gym_call (pb_step_snapshot_host: step + getters + observation of the per-env drop-in in
+    one launch, written straight to pinned host memory) against the oracle on fuzzed states:
+    reward, done, score / lives / is_done / remaining_pellets, mask, observation bits and the full
+    state, every step, with and without auto reset."""
+    n = 1024
+    for auto_reset in (False, True):
+        rng = np.random.default_rng(77 + auto_reset)
+        tape = rng.integers(0, 2**32, size=(n, 400), dtype=np.uint32)
+        st = fuzz_states(rng, pb, n)
+        ob, env = make_pair(pb, oracle, n, st["cfg_flags"], tape, auto_reset=auto_reset)
+        env.set_state(st)
+        ob.import_state(gpu_to_oracle_state(oracle, st))
+        for t in range(10):
+            a = random_valid_actions(rng, ob.action_mask(), p_invalid_move=0.2)
+            r_o, d_o = ob.step(a, auto_reset=auto_reset)
+            snap = env.step_snapshot(a, want_obs=True)
+            assert np.array_equal(snap["reward"], r_o) and np.array_equal(snap["done"], d_o.astype(bool)), t
+            so = ob.export_state()
+            assert_states_equal(so, env.get_state(), f"gym call, step {t}")
+            assert np.array_equal(snap["info"][:, 0], so["curr_score"]), t
+            assert np.array_equal(snap["info"][:, 1], so["curr_lives"]), t
+            assert np.array_equal(snap["info"][:, 4], so["num_pellets"]), t
+            assert np.array_equal(snap["mask"], ob.action_mask().astype(bool)), t
+            assert_obs_equal(ob.obs(), snap["obs"], f"gym call, step {t}", so)
