@@ -466,6 +466,22 @@ int pb_qnet_head_bwd(const float *dq_dev, const float *p_dev, const uint8_t *idx
                      float *scratch_dev, int device, void *stream);
 int64_t pb_qnet_head_bwd_scratch_floats(int64_t n);
 
+/* ---- the arithmetic of a DQN iteration around the network (src/algorithms/train_dqn.py:167-206) */
+/* Double-DQN target (:167-183): target[b] = reward[b] * reward_scale + (done[b] ? 0 : gamma *
+ * Q_target(s')[b][argmax_a masked Q_online(s')[b][a]]); masked-out actions count as -inf, ties go
+ * to the first maximum (torch.argmax).  q_*_dev float32 [n][num_actions], mask_dev / done_dev
+ * uint8 (bool), reward_dev float32 [n]; same float32 operations as the reference expressions. */
+int pb_dqn_target(const float *q_target_dev, const float *q_online_dev, const uint8_t *mask_dev,
+                  const float *reward_dev, const uint8_t *done_dev, double gamma, double reward_scale,
+                  float *target_out_dev, int64_t n, int64_t num_actions, int device, void *stream);
+/* Loss (:193-197): out4[0] = mean_b (Q[b][a_b] - target[b])^2; dq_out [n][num_actions] = its
+ * gradient with respect to the Q table (2 / n * (Q[b][a_b] - target[b]) at a_b, 0 elsewhere);
+ * the logged statistics out4[1] = stat_scale * mean_b max_a Q[b][a], out4[2] = stat_scale *
+ * mean(target), out4[3] = 1.0 if the loss is finite (the reference's error_if_nonfinite tripwire,
+ * :200-204).  One CTA, sums in a fixed order. */
+int pb_dqn_loss(const float *all_q_dev, const int64_t *actions_dev, const float *target_dev, int64_t n,
+                int64_t num_actions, double stat_scale, float *out4_dev, float *dq_out_dev, int device,
+                void *stream);
 /* ---- end of a DQN iteration (src/algorithms/train_dqn.py:200-206) -----------------------------
  * torch.nn.utils.clip_grad_norm_(parameters, max_norm) followed by torch.optim.Adam.step()
  * (default Adam: no weight decay, no amsgrad) over `count` <= 32 float32 tensors, two launches.

@@ -117,6 +117,8 @@ SIGNATURES = {
     "pb_qnet_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp,
                          _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "pb_qnet_head_bwd_scratch_floats": (_i64, [_i64]),
+    "pb_dqn_target": (_int, [_vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _i64, _i64, _int, _vp]),
+    "pb_dqn_loss": (_int, [_vp, _vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _int, _vp]),
     "pb_clip_adam": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double,
                      C.c_double, C.c_double, _vp, _int, _vp]),
     "pb_replay_advance": (_int, [_vp, _vp, _i64, _int, _vp]),

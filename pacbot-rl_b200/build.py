@@ -22,7 +22,7 @@ HEADERS = [
     os.path.join(CSRC, "pb_rollout_abi.inl"),
     os.path.join(CSRC, "pb_replay_abi.inl"),
     os.path.join(CSRC, "pb_qnet_abi.inl"),
-    os.path.join(CSRC, "pb_optim_abi.inl"),
+    os.path.join(CSRC, "pb_dqn_abi.inl"),
     os.path.join(os.path.dirname(HERE), "include", "pacbot_b200.h"),
 ]
 NVCC_FLAGS = [

@@ -1,7 +1,16 @@
-// pb_optim_abi.inl -- pb_clip_adam: the end of a DQN iteration (reference:
-// /root/reference/src/algorithms/train_dqn.py:200-206, `clip_grad_norm_(parameters, max_norm)` then
-// `Adam.step()`) as TWO launches over the network's parameter list; included at the end of
-// pb_kernels.cu.
+// pb_dqn_abi.inl -- the arithmetic of a DQN iteration around the network (reference:
+// /root/reference/src/algorithms/train_dqn.py:167-206); included at the end of pb_kernels.cu.
+//
+//   pb_dqn_target   the double-DQN target of :167-183 from the two next-state Q tables: ONE launch
+//                   (torch: bitwise_not, 2 x masked_fill, argmax, gather, zeros_like, 2 x mul,
+//                   where, add).  Same float32 operations in the same order: bit-identical.
+//   pb_dqn_loss     Q(s)[a], the MSE loss of :193-197, its gradient with respect to the Q table
+//                   (2 / B * (Q(s)[a] - target) at the taken action, 0 elsewhere) and the
+//                   iteration's logged statistics (mean max Q, mean target, finite-loss flag) in
+//                   ONE single-CTA launch with fixed-order sums (torch: gather, mse_loss, amax,
+//                   2 x mean, isfinite, and backward mse_loss_backward, zeros, scatter).
+//   pb_clip_adam    `clip_grad_norm_(parameters, max_norm)` then `Adam.step()` (:200-206) as TWO
+//                   launches over the network's parameter list:
 //
 // torch runs this tail as ~8 launches (foreach norm, stack, norm, add, reciprocal, clamp, foreach
 // mul, the fused multi-tensor Adam and its step counters): ~0.1 ms of a 2.1 ms iteration for
@@ -111,6 +120,69 @@ k_clip_adam(OptTensors tl, float *__restrict__ exp_avg, float *__restrict__ exp_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// double-DQN target (train_dqn.py:167-183) and loss (:193-197)
+// ---------------------------------------------------------------------------------------------
+constexpr int DQN_MAX_ACTIONS = 8;
+
+__global__ void __launch_bounds__(256)
+k_dqn_target(const float *__restrict__ q_target, const float *__restrict__ q_online,
+             const uint8_t *__restrict__ mask, const float *__restrict__ reward,
+             const uint8_t *__restrict__ done, float gamma, float reward_scale,
+             float *__restrict__ target, long long n, int na) {
+    const long long b = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (b >= n) return;
+    const float ninf = -INFINITY;
+    // next_actions = online_next_q.masked_fill(~mask, -inf).argmax(1): first maximum, NaN wins
+    int best = 0;
+    float best_v = 0.0f;
+    for (int a = 0; a < na; a++) {
+        const float v = mask[b * na + a] ? q_online[b * na + a] : ninf;
+        if (a == 0 || v > best_v || (v != v && best_v == best_v)) {
+            best = a;
+            best_v = v;
+        }
+    }
+    const float ret = mask[b * na + best] ? q_target[b * na + best] : ninf;
+    const float discounted = done[b] ? 0.0f : __fmul_rn(gamma, ret);
+    target[b] = __fadd_rn(__fmul_rn(reward[b], reward_scale), discounted);
+}
+
+// out[0] = mean((Q[b][a_b] - target[b])^2), out[1] = stat_scale * mean_b max_a Q[b][a],
+// out[2] = stat_scale * mean(target), out[3] = 1 if the loss is finite else 0;
+// dq[b][a] = 2 / n * (Q[b][a_b] - target[b]) for a == a_b, else 0
+__global__ void __launch_bounds__(OPT_THREADS)
+k_dqn_loss(const float *__restrict__ all_q, const long long *__restrict__ actions,
+           const float *__restrict__ target, long long n, int na, float stat_scale,
+           float *__restrict__ out, float *__restrict__ dq) {
+    __shared__ float red[OPT_THREADS / 32];
+    float sq = 0.0f, mx = 0.0f, tg = 0.0f;
+    const float norm = 2.0f / (float)n;
+    for (long long b = threadIdx.x; b < n; b += OPT_THREADS) {
+        const int act = (int)actions[b];
+        const float t = target[b];
+        float best = all_q[b * na], pred = 0.0f;
+        for (int a = 0; a < na; a++) {
+            const float q = all_q[b * na + a];
+            best = (q > best || q != q) ? q : best;
+            pred = a == act ? q : pred;
+        }
+        const float d = pred - t;
+        for (int a = 0; a < na; a++) dq[b * na + a] = a == act ? norm * d : 0.0f;
+        sq = fmaf(d, d, sq);
+        mx += best;
+        tg += t;
+    }
+    const float s_sq = block_sum(sq, red), s_mx = block_sum(mx, red), s_tg = block_sum(tg, red);
+    if (threadIdx.x == 0) {
+        const float loss = s_sq / (float)n;
+        out[0] = loss;
+        out[1] = stat_scale * (s_mx / (float)n);
+        out[2] = stat_scale * (s_tg / (float)n);
+        out[3] = (loss == loss && fabsf(loss) != INFINITY) ? 1.0f : 0.0f;
+    }
+}
+
 }  // namespace pb
 
 extern "C" {
@@ -143,6 +215,36 @@ int pb_clip_adam(int count, float *const *params_dev, const float *const *grads_
     k_clip_adam<<<grid, OPT_THREADS, 0, s>>>(tl, exp_avg_dev, exp_avg_sq_dev, partials_dev,
                                             reinterpret_cast<const long long *>(step_dev), (float)max_norm,
                                             lr, beta1, beta2, (float)eps, grad_norm_out_dev);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_dqn_target(const float *q_target_dev, const float *q_online_dev, const uint8_t *mask_dev,
+                  const float *reward_dev, const uint8_t *done_dev, double gamma, double reward_scale,
+                  float *target_out_dev, int64_t n, int64_t num_actions, int device, void *stream) {
+    using namespace pb;
+    if (!q_target_dev || !q_online_dev || !mask_dev || !reward_dev || !done_dev || !target_out_dev || n <= 0 ||
+        num_actions <= 0 || num_actions > DQN_MAX_ACTIONS)
+        return fail(PB_ERR_INVALID_ARG, "pb_dqn_target: bad arguments (1..8 actions)");
+    DeviceGuard g(device);
+    k_dqn_target<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        q_target_dev, q_online_dev, mask_dev, reward_dev, done_dev, (float)gamma, (float)reward_scale,
+        target_out_dev, n, (int)num_actions);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int pb_dqn_loss(const float *all_q_dev, const int64_t *actions_dev, const float *target_dev, int64_t n,
+                int64_t num_actions, double stat_scale, float *out4_dev, float *dq_out_dev, int device,
+                void *stream) {
+    using namespace pb;
+    if (!all_q_dev || !actions_dev || !target_dev || !out4_dev || !dq_out_dev || n <= 0 || num_actions <= 0 ||
+        num_actions > DQN_MAX_ACTIONS)
+        return fail(PB_ERR_INVALID_ARG, "pb_dqn_loss: bad arguments (1..8 actions)");
+    DeviceGuard g(device);
+    k_dqn_loss<<<1, OPT_THREADS, 0, (cudaStream_t)stream>>>(
+        all_q_dev, reinterpret_cast<const long long *>(actions_dev), target_dev, n, (int)num_actions,
+        (float)stat_scale, out4_dev, dq_out_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

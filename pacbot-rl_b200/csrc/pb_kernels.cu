@@ -1405,4 +1405,4 @@ int pb_trace_end(pb_engine *e, pb_trace_record *out_host, int64_t max_records, i
 #include "pb_rollout_abi.inl"
 #include "pb_replay_abi.inl"
 #include "pb_qnet_abi.inl"
-#include "pb_optim_abi.inl"
+#include "pb_dqn_abi.inl"

@@ -2,7 +2,7 @@
 
 Reference: /root/reference/src/algorithms/train_dqn.py:133 (`torch.optim.Adam(q_net.parameters(),
 lr)`) and :200-206 (`clip_grad_norm_(..., max_norm)` then `optimizer.step()`).  `ClipAdam` does
-both in two launches (`pb_clip_adam`, csrc/pb_optim_abi.inl) instead of torch's ~8; same
+both in two launches (`pb_clip_adam`, csrc/pb_dqn_abi.inl) instead of torch's ~8; same
 hyper-parameters and defaults as `torch.optim.Adam` (betas (0.9, 0.999), eps 1e-8, no weight decay,
 no amsgrad), results within float32 rounding of the torch pair (tests/test_dqn_gpu.py)."""
 from __future__ import annotations

@@ -39,7 +39,7 @@ import ctypes as C
 import torch
 import torch.nn.functional as F
 
-from . import models
+from . import _lib, models
 from ._lib import check
 from .engine import BatchedPacmanGym
 from .optim import ClipAdam
@@ -99,26 +99,83 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
+def _fusable(*tensors: torch.Tensor) -> bool:
+    """CUDA, contiguous, and float32 where floating: what pb_dqn_target / pb_dqn_loss take."""
+    return all(t.is_cuda and t.is_contiguous() and (not t.is_floating_point() or t.dtype == torch.float32)
+               for t in tensors)
+
+
 def dqn_targets(batch: ReplayBatch, q_net, target_q_net, discount_factor: float,
                 reward_scale: float) -> torch.Tensor:
     """Double-DQN target (train_dqn.py:167-183): r * reward_scale + gamma * Q_target(s')[argmax_a
     masked Q_online(s')], 0 where the episode ended.  A finished transition has an all-False next
-    mask: every Q is -inf there, exactly as in the reference, and the done mask zeroes it."""
+    mask: every Q is -inf there, exactly as in the reference, and the done mask zeroes it.
+    On the GPU the arithmetic after the two forwards is ONE launch (pb_dqn_target: the same float32
+    operations in the same order, bit-identical to the expressions below)."""
     with torch.no_grad():
         masks = batch.next_action_masks
-        next_q = target_q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
-        online_next_q = q_net(batch.next_obs).masked_fill(~masks, -torch.inf)
+        q_t, q_o = target_q_net(batch.next_obs), q_net(batch.next_obs)
+        if (_fusable(q_t, q_o, masks, batch.rewards, batch.done) and masks.dtype == torch.bool
+                and batch.done.dtype == torch.bool and q_t.shape[1] <= 8):
+            out = torch.empty(q_t.shape[0], dtype=torch.float32, device=q_t.device)
+            p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+            check(_lib.load().pb_dqn_target(
+                p(q_t), p(q_o), p(masks), p(batch.rewards), p(batch.done), float(discount_factor),
+                float(reward_scale), p(out), q_t.shape[0], q_t.shape[1], q_t.device.index,
+                _lib.raw_stream(q_t.device)))
+            return out
+        next_q = q_t.masked_fill(~masks, -torch.inf)
+        online_next_q = q_o.masked_fill(~masks, -torch.inf)
         next_actions = online_next_q.argmax(dim=1)
         returns = next_q.gather(1, next_actions.unsqueeze(1)).squeeze(1)
         discounted = torch.where(batch.done, torch.zeros_like(returns), discount_factor * returns)
         return batch.rewards * reward_scale + discounted
 
 
+class _QLoss(torch.autograd.Function):
+    """mse_loss(Q[range(B), actions], target) of train_dqn.py:193-197 with its gradient and the
+    iteration's logged statistics from one launch (pb_dqn_loss)."""
+
+    @staticmethod
+    def forward(ctx, all_q, actions, target, stat_scale):
+        out = torch.empty(4, dtype=torch.float32, device=all_q.device)
+        dq = torch.empty_like(all_q)
+        p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+        check(_lib.load().pb_dqn_loss(
+            p(all_q), p(actions), p(target), all_q.shape[0], all_q.shape[1], float(stat_scale), p(out),
+            p(dq), all_q.device.index, _lib.raw_stream(all_q.device)))
+        ctx.save_for_backward(dq)
+        loss, stats = out[0], out[1:]
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        (dq,) = ctx.saved_tensors
+        return dq * grad_loss, None, None, None
+
+
+def dqn_loss_stats(batch: ReplayBatch, q_net, target_q: torch.Tensor, stat_scale: float = 1.0):
+    """MSE between Q(s)[a] and the target (train_dqn.py:193-197) -> (loss, all Q-values, stats)
+    with stats = [stat_scale * mean_b max_a Q, stat_scale * mean(target), isfinite(loss)], the
+    quantities train_dqn.py:208-216 logs."""
+    all_q = q_net(batch.obs)
+    if (_fusable(all_q, batch.actions, target_q) and batch.actions.dtype == torch.int64
+            and all_q.shape[1] <= 8):
+        loss, stats = _QLoss.apply(all_q, batch.actions, target_q, stat_scale)
+        return loss, all_q, stats
+    predicted = all_q.gather(1, batch.actions.unsqueeze(1)).squeeze(1)
+    loss = F.mse_loss(predicted, target_q)
+    with torch.no_grad():
+        stats = torch.stack([all_q.detach().amax(dim=1).mean() * stat_scale, target_q.mean() * stat_scale,
+                             torch.isfinite(loss.detach()).to(all_q.dtype)])
+    return loss, all_q, stats
+
+
 def dqn_loss(batch: ReplayBatch, q_net, target_q: torch.Tensor):
     """MSE between Q(s)[a] and the target (train_dqn.py:193-197) -> (loss, all Q-values)."""
-    all_q = q_net(batch.obs)
-    predicted = all_q.gather(1, batch.actions.unsqueeze(1)).squeeze(1)
-    return F.mse_loss(predicted, target_q), all_q
+    loss, all_q, _ = dqn_loss_stats(batch, q_net, target_q)
+    return loss, all_q
 
 
 EVAL_FIELDS = ("score", "steps", "cleared", "pellets_start", "pellets_end", "finished")
@@ -328,7 +385,7 @@ class DQNTrainer:
         # accumulation launches and the zero fill per iteration); inside the captured graph the
         # gradients come from the graph's private pool, i.e. the same addresses at every replay
         self.optimizer.zero_grad(set_to_none=True)
-        loss, all_q = dqn_loss(batch, self.q_net, target_q)
+        loss, _all_q, stats = dqn_loss_stats(batch, self.q_net, target_q, 1.0 / cfg.reward_scale)
         loss.backward()
         if self.world > 1:
             self._allreduce_grads()
@@ -337,10 +394,8 @@ class DQNTrainer:
         else:
             grad_norm = torch.nn.utils.clip_grad_norm_(self.params, max_norm=cfg.grad_clip_norm)
             self.optimizer.step()
-        with torch.no_grad():
-            self._acc += torch.stack([
-                loss.detach(), grad_norm.detach(), all_q.detach().amax(dim=1).mean() / cfg.reward_scale,
-                target_q.mean() / cfg.reward_scale, torch.isfinite(loss.detach()).float()])
+        with torch.no_grad():   # loss, grad norm, avg predicted value, avg target, finite flag
+            self._acc += torch.cat([torch.stack([loss.detach(), grad_norm.detach()]), stats])
         # collect experience (train_dqn.py:263-265); epsilon was set by the host wrapper
         for _ in range(cfg.experience_steps):
             self.replay.generate_experience_step(count_on_host=False)

