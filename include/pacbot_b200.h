@@ -489,7 +489,7 @@ int pb_dqn_loss(const float *all_q_dev, const int64_t *actions_dev, const float 
  * a parameter and its gradient share one memory layout (storage order is what is paired).
  * exp_avg_dev / exp_avg_sq_dev: float32 [sum sizes], the moments in tensor order (zero at start);
  * step_dev: int64 [1] device step counter, advanced by the call (zero at start);
- * partials_dev: float32 [count * 8] scratch; grad_norm_out_dev: float32 [1], the total norm BEFORE
+ * partials_dev: float32 [count * 8 + 2] scratch; grad_norm_out_dev: float32 [1], the total norm BEFORE
  * clipping, what clip_grad_norm_ returns (may be NULL).  The gradients are read, not rewritten.
  * The hyper-parameters are doubles, as torch takes them (1 - beta is rounded to float32 once). */
 int pb_clip_adam(int count, float *const *params_dev, const float *const *grads_dev,

@@ -16,7 +16,8 @@
 // mul, the fused multi-tensor Adam and its step counters): ~0.1 ms of a 2.1 ms iteration for
 // 156 934 parameters, all of it launch and dependency latency.  Here:
 //   k_grad_sqnorm   one CTA row per tensor: partial sums of g^2 (fixed order: deterministic);
-//                   CTA (0, 0) also advances the device-resident step counter
+//                   CTA (0, 0) also advances the device-resident step counter and derives the
+//                   step's bias corrections (double arithmetic, once)
 //   k_clip_adam     every CTA adds the partials up in the same order, derives the clip
 //                   coefficient min(1, max_norm / (norm + 1e-6)) (torch/nn/utils/clip_grad.py) and
 //                   applies Adam to its slice with the clipped gradient g * coef:
@@ -58,8 +59,11 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     return t;
 }
 
+// partials: float32 [count * OPT_ROW] sums of squares, followed by 2 floats written by CTA (0, 0):
+// the step size lr / (1 - beta1^t) and sqrt(1 - beta2^t) of THIS step (double arithmetic, once)
 __global__ void __launch_bounds__(OPT_THREADS)
-k_grad_sqnorm(OptTensors tl, float *__restrict__ partials, long long *step) {
+k_grad_sqnorm(OptTensors tl, float *__restrict__ partials, long long *step, double lr, double beta1,
+              double beta2) {
     __shared__ float red[OPT_THREADS / 32];
     const int t = blockIdx.y;
     const float *g = tl.g[t];
@@ -73,16 +77,30 @@ k_grad_sqnorm(OptTensors tl, float *__restrict__ partials, long long *step) {
     const float s = block_sum(acc, red);
     if (threadIdx.x == 0) {
         partials[t * OPT_ROW + blockIdx.x] = s;
-        if (blockIdx.x == 0 && blockIdx.y == 0) *step += 1;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            const long long now = *step + 1;
+            *step = now;
+            const double bc1 = 1.0 - pow(beta1, (double)now), bc2 = 1.0 - pow(beta2, (double)now);
+            partials[tl.count * OPT_ROW] = (float)(lr / bc1);
+            partials[tl.count * OPT_ROW + 1] = (float)sqrt(bc2);
+        }
     }
 }
 
+// grid (columns, count): CTA (x, t) owns elements x * 1024 .. of tensor t in steps of
+// gridDim.x * 1024, four independent elements per thread and step (the loads of a step are all
+// requested before the first use: the kernel is latency bound, 157 K parameters in all)
+constexpr int ADAM_PER_THREAD = 4;
 __global__ void __launch_bounds__(OPT_THREADS)
 k_clip_adam(OptTensors tl, float *__restrict__ exp_avg, float *__restrict__ exp_avg_sq,
-            const float *__restrict__ partials, const long long *__restrict__ step, float max_norm,
-            double lr, double beta1_d, double beta2_d, float eps, float *__restrict__ grad_norm_out) {
+            const float *__restrict__ partials, float max_norm, double beta1_d, double beta2_d,
+            float eps, float *__restrict__ grad_norm_out) {
+    const int t = blockIdx.y;
+    const long long size = tl.start[t + 1] - tl.start[t];
+    constexpr int CHUNK = OPT_THREADS * ADAM_PER_THREAD;
+    if ((long long)blockIdx.x * CHUNK >= size) return;     // whole CTA: no barrier is skipped
     __shared__ float red[OPT_THREADS / 32];
-    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    __shared__ float s_coef;
     const int nparts = tl.count * OPT_ROW;
     const float mine = threadIdx.x < nparts ? partials[threadIdx.x] : 0.0f;   // nparts <= 256
     const float total = block_sum(mine, red);
@@ -90,33 +108,40 @@ k_clip_adam(OptTensors tl, float *__restrict__ exp_avg, float *__restrict__ exp_
         const float norm = sqrtf(total);
         const float coef = max_norm / (norm + 1e-6f);
         s_coef = coef < 1.0f ? coef : 1.0f;
-        const double t = (double)*step;
-        const double bc1 = 1.0 - pow(beta1_d, t), bc2 = 1.0 - pow(beta2_d, t);
-        s_step_size = (float)(lr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
         if (blockIdx.x == 0 && blockIdx.y == 0 && grad_norm_out) *grad_norm_out = norm;
     }
     __syncthreads();
-    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    const int t = blockIdx.y;
+    const float coef = s_coef, step_size = partials[nparts], bc2_sqrt = partials[nparts + 1];
     float *p = tl.p[t];
     const float *g = tl.g[t];
-    const long long size = tl.start[t + 1] - tl.start[t];
     float *m = exp_avg + tl.start[t], *v = exp_avg_sq + tl.start[t];
     // the hyper-parameters are doubles like torch's; 1 - beta is rounded to float32 once, from the
     // double difference (1.0f - 0.999f is 1.3e-5 away from float(1 - 0.999))
     const float w = (float)(1.0 - beta1_d), beta2 = (float)beta2_d, one_minus_beta2 = (float)(1.0 - beta2_d);
-    for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < size;
-         i += (long long)OPT_ROW * OPT_THREADS) {
-        const float gi = g[i] * coef;
-        const float m0 = m[i];
-        // ATen lerp: start + weight * (end - start) for weight < 0.5
-        const float m1 = w < 0.5f ? m0 + w * (gi - m0) : gi - (gi - m0) * (1.0f - w);
-        const float v1 = beta2 * v[i] + one_minus_beta2 * gi * gi;
-        m[i] = m1;
-        v[i] = v1;
-        const float denom = sqrtf(v1) / bc2_sqrt + eps;
-        p[i] -= step_size * m1 / denom;
+    for (long long base = (long long)blockIdx.x * CHUNK; base < size; base += (long long)gridDim.x * CHUNK) {
+        float gi[ADAM_PER_THREAD], m0[ADAM_PER_THREAD], v0[ADAM_PER_THREAD], p0[ADAM_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < ADAM_PER_THREAD; k++) {
+            const long long i = base + k * OPT_THREADS + threadIdx.x;
+            const bool in = i < size;
+            gi[k] = in ? g[i] : 0.0f;
+            m0[k] = in ? m[i] : 0.0f;
+            v0[k] = in ? v[i] : 0.0f;
+            p0[k] = in ? p[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < ADAM_PER_THREAD; k++) {
+            const long long i = base + k * OPT_THREADS + threadIdx.x;
+            if (i >= size) continue;
+            const float gc = gi[k] * coef;
+            // ATen lerp: start + weight * (end - start) for weight < 0.5
+            const float m1 = w < 0.5f ? m0[k] + w * (gc - m0[k]) : gc - (gc - m0[k]) * (1.0f - w);
+            const float v1 = beta2 * v0[k] + one_minus_beta2 * gc * gc;
+            m[i] = m1;
+            v[i] = v1;
+            const float denom = sqrtf(v1) / bc2_sqrt + eps;
+            p[i] = p0[k] - step_size * m1 / denom;
+        }
     }
 }
 
@@ -210,11 +235,17 @@ int pb_clip_adam(int count, float *const *params_dev, const float *const *grads_
     DeviceGuard g(device);
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 grid(OPT_ROW, (unsigned)count);
-    k_grad_sqnorm<<<grid, OPT_THREADS, 0, s>>>(tl, partials_dev, reinterpret_cast<long long *>(step_dev));
+    k_grad_sqnorm<<<grid, OPT_THREADS, 0, s>>>(tl, partials_dev, reinterpret_cast<long long *>(step_dev), lr,
+                                              beta1, beta2);
     PB_CUDA(cudaGetLastError());
-    k_clip_adam<<<grid, OPT_THREADS, 0, s>>>(tl, exp_avg_dev, exp_avg_sq_dev, partials_dev,
-                                            reinterpret_cast<const long long *>(step_dev), (float)max_norm,
-                                            lr, beta1, beta2, (float)eps, grad_norm_out_dev);
+    long long largest = 0;
+    for (int t = 0; t < count; t++) largest = sizes[t] > largest ? sizes[t] : largest;
+    constexpr long long chunk = OPT_THREADS * ADAM_PER_THREAD;
+    long long cols = (largest + chunk - 1) / chunk;
+    if (cols > 256) cols = 256;
+    k_clip_adam<<<dim3((unsigned)cols, (unsigned)count), OPT_THREADS, 0, s>>>(
+        tl, exp_avg_dev, exp_avg_sq_dev, partials_dev, (float)max_norm, beta1, beta2, (float)eps,
+        grad_norm_out_dev);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -6,7 +6,7 @@
 // (32 envs per experience step, 1 env per evaluation step), the MCTS collector (one leaf per tree)
 // and the per-env drop-in (gym.py, ONE env) only ever launch small batches, so they get:
 //
-//   k_obs_small   PacmanGym::obs (env.rs:410-500) for <= SMALL_ENC_MAX envs: one 256-thread CTA
+//   k_obs_small   PacmanGym::obs (env.rs:410-500) for <= SMALL_ENC_MAX envs: one 512-thread CTA
 //                 per env assembles the whole 59 024 B observation in shared memory (base values
 //                 with 128-bit stores, then the <= 29 single cells of cell_role(), the SAME
 //                 per-lane roles as the persistent kernel) and copies it out with coalesced
@@ -25,17 +25,26 @@
 
 namespace pb {
 
-constexpr int SMALL_THREADS = 256;
+// threads per CTA (= per env); -DPB_OBS_SMALL_THREADS / -DPB_GYM_CALL_THREADS for A/B builds
+#ifndef PB_OBS_SMALL_THREADS
+#define PB_OBS_SMALL_THREADS 512
+#endif
+#ifndef PB_GYM_CALL_THREADS
+#define PB_GYM_CALL_THREADS 512
+#endif
+constexpr int OBS_SMALL_THREADS = PB_OBS_SMALL_THREADS;
+constexpr int GYM_CALL_THREADS = PB_GYM_CALL_THREADS;
 constexpr int SMALL_IMG_BYTES = OBS_FLOATS * 4;                      // 59 024: all 17 channels
 constexpr int SMALL_SMEM = SMALL_IMG_BYTES + 32 * 4;                 // + the pellet words
 static_assert(SMALL_IMG_BYTES % 16 == 0, "the image is copied out as float4");
-// launches of up to this many envs go to k_obs_small (three 59 KB CTAs fit an SM: 444 resident
-// CTAs, so up to about one wave); larger ones to the persistent k_encode_obs
-constexpr long long SMALL_ENC_MAX = 512;
+// launches of up to this many envs go to k_obs_small, larger ones to the persistent k_encode_obs
+// (tools/small_encode_latency.py: 128 envs 8.2 vs 10.3 us per launch, 512 envs 14.4 vs 10.7 us)
+constexpr long long SMALL_ENC_MAX = 256;
 
-// One env's observation into `img` (shared memory, OBS_FLOATS floats), by all SMALL_THREADS
-// threads of the CTA; `words` (shared, 32 words) receives the pellet bitboard.  Ends with a
+// One env's observation into `img` (shared memory, OBS_FLOATS floats), by all THREADS threads of
+// the CTA; `words` (shared, 32 words) receives the pellet bitboard.  Ends with a
 // __syncthreads(): the image is complete and visible to the whole CTA on return.
+template <int THREADS>
 __device__ __forceinline__ void build_obs_image(const StateView &st, long long env, float *img,
                                                 uint32_t *words) {
     const int t = threadIdx.x, lane = t & 31;
@@ -46,7 +55,7 @@ __device__ __forceinline__ void build_obs_image(const StateView &st, long long e
     // every warp evaluates the roles (register work); warp 0 does the stores after the fill
     const CellRole role = cell_role(s, words[lane], lane);
     float4 *img4 = reinterpret_cast<float4 *>(img);
-    for (int j = t; j < OBS_CH * CH_VEC; j += SMALL_THREADS) {
+    for (int j = t; j < OBS_CH * CH_VEC; j += THREADS) {
         const int ch = j / CH_VEC, q = j - ch * CH_VEC;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ch == 0) {                      // walls (env.rs:426), cell c = col * ROWS + (30 - row)
@@ -74,16 +83,18 @@ __device__ __forceinline__ void build_obs_image(const StateView &st, long long e
     __syncthreads();
 }
 
+template <int THREADS>
 __device__ __forceinline__ void copy_obs_image(const float *img, float *dst) {
     const float4 *src4 = reinterpret_cast<const float4 *>(img);
     float4 *dst4 = reinterpret_cast<float4 *>(dst);
-    for (int j = threadIdx.x; j < OBS_CH * CH_VEC; j += SMALL_THREADS) dst4[j] = src4[j];
+#pragma unroll 4
+    for (int j = threadIdx.x; j < OBS_CH * CH_VEC; j += THREADS) dst4[j] = src4[j];
 }
 
 // Same contract as k_encode_obs for envs [env_first, env_first + gridDim.x): out + k * env_stride,
 // optional ring-slot indirection read from device memory (CUDA-graph replays while the ring
 // advances), optional device-timeline record.
-__global__ void __launch_bounds__(SMALL_THREADS)
+__global__ void __launch_bounds__(OBS_SMALL_THREADS)
 k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
             const long long *__restrict__ slot_index, long long slot_stride,
             TraceRec *__restrict__ trace) {
@@ -97,8 +108,8 @@ k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long lo
     }
     if (slot_index) out += *slot_index * slot_stride;
     const long long k = blockIdx.x;
-    build_obs_image(st, env_first + k, img, words);
-    copy_obs_image(img, out + k * env_stride);
+    build_obs_image<OBS_SMALL_THREADS>(st, env_first + k, img, words);
+    copy_obs_image<OBS_SMALL_THREADS>(img, out + k * env_stride);
     if (trace && threadIdx.x == 0) stamp_max(&trace->end, global_timer_ns());
 }
 
@@ -125,7 +136,7 @@ __host__ __device__ inline GymCallLayout gym_call_layout(size_t n) {
 // no step, only the answers.  `blk` is the caller's pinned block (GymCallLayout); `arrive` a
 // device counter that is zero between launches; `seq` the number to publish when the whole block
 // is in host memory.
-__global__ void __launch_bounds__(SMALL_THREADS)
+__global__ void __launch_bounds__(GYM_CALL_THREADS, 1)
 k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int auto_reset,
            unsigned long long *bad_action, unsigned char *__restrict__ blk, int want_obs,
            unsigned int *arrive, unsigned long long seq, TraceRec *__restrict__ trace) {
@@ -177,8 +188,8 @@ k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int 
     }
     __syncthreads();   // thread 0's state (global memory) is what the CTA encodes
     if (want_obs) {
-        build_obs_image(st, i, img, words);
-        copy_obs_image(img, reinterpret_cast<float *>(blk + l.off_obs) + i * (long long)OBS_FLOATS);
+        build_obs_image<GYM_CALL_THREADS>(st, i, img, words);
+        copy_obs_image<GYM_CALL_THREADS>(img, reinterpret_cast<float *>(blk + l.off_obs) + i * (long long)OBS_FLOATS);
     }
     // The CTA's stores to host memory (all threads', made visible to thread 0 by the barrier; the
     // fence is cumulative) are performed before thread 0 counts the CTA in; the last CTA hands the

@@ -498,6 +498,13 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        // the kernel in front of a small encode is k_step, which runs under the largest carve-out
+        // (see pb_create): ask for the same one, so that the SMs are not reconfigured in between.
+        // PB_SMALL_CARVEOUT=0 leaves the driver's choice (A/B runs).
+        const char *cv = getenv("PB_SMALL_CARVEOUT");
+        if (!(cv && cv[0] == '0'))
+            PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         attr_set_for = e->device;
     }
     // Small batches (the DQN loop's 32 envs, an evaluation env, the leaves of a few hundred MCTS
@@ -510,7 +517,7 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     }();
     if (count <= small_max) {
         TraceRec *trace = trace_slot(e, PB_TRACE_ENCODE);
-        k_obs_small<<<(unsigned)count, SMALL_THREADS, SMALL_SMEM, s>>>(
+        k_obs_small<<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, s>>>(
             e->st, out_dev, stride, first, slot_index, slot_stride, trace);
         PB_CUDA(cudaGetLastError());
         return PB_OK;
@@ -1217,7 +1224,7 @@ int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_re
     // Pointers INTO the engine's own pinned buffers (pb_snapshot_block) mean "in place": no copy.
     if (actions_host && actions_host != e->snap_actions_pin) memcpy(e->snap_actions_pin, actions_host, n);
     const unsigned long long seq = ++e->snap_seq;
-    k_gym_call<<<(unsigned)n, SMALL_THREADS, SMALL_SMEM, s>>>(
+    k_gym_call<<<(unsigned)n, GYM_CALL_THREADS, SMALL_SMEM, s>>>(
         e->st, rng_params(e), actions_host ? e->snap_actions_pin : nullptr, auto_reset,
         e->bad_action, h, obs_host ? 1 : 0, e->snap_arrive, seq,
         trace_slot(e, actions_host ? PB_TRACE_STEP : PB_TRACE_ENCODE));

@@ -51,7 +51,7 @@ class ClipAdam:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._partials = torch.zeros(8 * len(self.params), dtype=torch.float32, device=dev)
+        self._partials = torch.zeros(8 * len(self.params) + 2, dtype=torch.float32, device=dev)
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
         k = len(self.params)
         self._sizes = (C.c_int64 * k)(*[p.numel() for p in self.params])

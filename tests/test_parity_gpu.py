@@ -547,9 +547,9 @@ def test_config2_2m_envs_sampled_slices_vs_oracle(pb, oracle):
 
 
 def test_small_batch_encoder_matches_persistent_and_oracle(pb, oracle):
-    """k_obs_small (one CTA per env: launches of up to 512 envs, pb_encode_small.cuh) against the
+    """k_obs_small (one CTA per env: launches of up to 256 envs, pb_encode_small.cuh) against the
     persistent k_encode_obs (the 2 048-env launch) and the oracle, on fuzzed states and a few steps
-    on: ranges of 1 / 31 / 33 / 512 envs at odd offsets, bit for bit."""
+    on: ranges of 1 / 31 / 33 / 129 / 256 envs at odd offsets, bit for bit."""
     torch = torch_mod()
     n = 2048
     rng = np.random.default_rng(321)
@@ -561,7 +561,7 @@ def test_small_batch_encoder_matches_persistent_and_oracle(pb, oracle):
     for t in range(5):
         full = env.obs()                                   # persistent kernel
         assert_obs_equal(ob.obs(), full.cpu().numpy(), f"persistent, step {t}", ob.export_state())
-        for first, count in ((0, 1), (7, 31), (100, 33), (1536, 512), (2047, 1), (1000, 257)):
+        for first, count in ((0, 1), (7, 31), (100, 33), (1536, 256), (2047, 1), (1000, 129)):
             part = torch.full((count,) + pb.OBS_SHAPE, -3.0, device="cuda:0")
             env.obs_range(first, count, part)              # one CTA per env
             assert torch.equal(part.view(torch.int32), full[first:first + count].view(torch.int32)), (t, first, count)
