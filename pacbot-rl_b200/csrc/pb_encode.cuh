@@ -218,6 +218,16 @@ __device__ __forceinline__ bool warp_arrived(unsigned int v) {
 // offset of (channel, cell) inside the private image (channel 0 is not part of it)
 __device__ __forceinline__ int img_off(int ch, int cell) { return (ch - 1) * CH_FLOATS + cell; }
 
+// The two fill values of an env's observation: a plain pellet's channel-1 value (env.rs:427-441:
+// (points + LAST_REWARD if this is the last pellet) as f32 / 200.0, IEEE-rounded compile-time
+// constants) and channel 15, ticks per step / update period (env.rs:484, one IEEE division).
+__device__ __forceinline__ float obs_pellet_value(const EnvR &s) {
+    return s.num_pellets == 1 ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f : (float)PELLET_POINTS / 200.0f;
+}
+__device__ __forceinline__ float obs_speed_value(const EnvR &s) {
+    return __fdiv_rn((float)s.tps, (float)s.period);
+}
+
 // The single cells of one env's observation as per-lane roles: pure register work, branch free.
 // Called by all 32 lanes of a warp; lane l < PEL_WORDS holds word l of the observation-ordered
 // pellet bitboard in F.  Every lane ends up with at most ONE store into the image of channels
@@ -290,11 +300,10 @@ __device__ __forceinline__ CellRole cell_role(const EnvR &s, const uint32_t F, c
     // env.rs:427-441: (points + LAST_REWARD if this is the last pellet) as f32 / 200.0; the
     // four possible quotients are IEEE-rounded compile-time constants
     const bool last_pellet = s.num_pellets == 1;
-    const float pv = last_pellet ? (float)(PELLET_POINTS + LAST_REWARD) / 200.0f
-                                 : (float)PELLET_POINTS / 200.0f;
+    const float pv = obs_pellet_value(s);
     const float sv = last_pellet ? (float)(SUPER_PELLET_POINTS + LAST_REWARD) / 200.0f
                                  : (float)SUPER_PELLET_POINTS / 200.0f;
-    const float sp = __fdiv_rn((float)s.tps, (float)s.period);      // env.rs:484
+    const float sp = obs_speed_value(s);
     const float timer_v = gfr > 0 ? c_tab.fright_q[gfr & 0xff] : c_tab.mode_q[s.mode_steps & 0xff];
     // one store per lane
     bool do_store, unpatch;

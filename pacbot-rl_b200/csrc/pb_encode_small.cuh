@@ -35,46 +35,53 @@ namespace pb {
 constexpr int OBS_SMALL_THREADS = PB_OBS_SMALL_THREADS;
 constexpr int GYM_CALL_THREADS = PB_GYM_CALL_THREADS;
 constexpr int SMALL_IMG_BYTES = OBS_FLOATS * 4;                      // 59 024: all 17 channels
-constexpr int SMALL_SMEM = SMALL_IMG_BYTES + 32 * 4;                 // + the pellet words
+constexpr int SMALL_SMEM = SMALL_IMG_BYTES + 64 * 4;                 // + pellet words, wall rows
 static_assert(SMALL_IMG_BYTES % 16 == 0, "the image is copied out as float4");
 // launches of up to this many envs go to k_obs_small, larger ones to the persistent k_encode_obs
 // (tools/small_encode_latency.py: 128 envs 8.2 vs 10.3 us per launch, 512 envs 14.4 vs 10.7 us)
 constexpr long long SMALL_ENC_MAX = 256;
 
 // One env's observation into `img` (shared memory, OBS_FLOATS floats), by all THREADS threads of
-// the CTA; `words` (shared, 32 words) receives the pellet bitboard.  Ends with a
+// the CTA; `words` (shared, 64 words) receives the pellet bitboard (0..27) and the wall rows
+// (32..62: a per-lane row index into __constant__ memory would be serialised address by address,
+// ncu: short-scoreboard stalls; shared memory serves 32 different rows at once).  Ends with a
 // __syncthreads(): the image is complete and visible to the whole CTA on return.
 template <int THREADS>
 __device__ __forceinline__ void build_obs_image(const StateView &st, long long env, float *img,
                                                 uint32_t *words) {
     const int t = threadIdx.x, lane = t & 31;
     if (t < 32) words[t] = (t < PEL_WORDS) ? st.pel[(long long)t * st.npad + env] : 0u;
+    else if (t < 64) words[t] = c_tab.walls[t - 32];
     EnvR s;
     load_env(st, env, s);
     __syncthreads();
-    // every warp evaluates the roles (register work); warp 0 does the stores after the fill
-    const CellRole role = cell_role(s, words[lane], lane);
+    // warp 0 evaluates the single-cell roles (a few hundred instructions of register work) and
+    // stores them after the fill; every thread needs the two fill values only
+    CellRole role{};
+    if (t < 32) role = cell_role(s, words[lane], lane);
+    const float pv = obs_pellet_value(s), sp = obs_speed_value(s);
+    const uint32_t *walls = words + 32;
     float4 *img4 = reinterpret_cast<float4 *>(img);
     for (int j = t; j < OBS_CH * CH_VEC; j += THREADS) {
-        const int ch = j / CH_VEC, q = j - ch * CH_VEC;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch == 0) {                      // walls (env.rs:426), cell c = col * ROWS + (30 - row)
+        if (j < CH_VEC) {                   // ch 0: walls (env.rs:426), cell c = col * ROWS + (30 - row)
             float w[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int c = 4 * q + u;
+                const int c = 4 * j + u;
                 const int col = c / ROWS, row = ROWS - 1 - (c % ROWS);
-                w[u] = ((c_tab.walls[row] >> col) & 1u) ? 1.0f : 0.0f;
+                w[u] = ((walls[row] >> col) & 1u) ? 1.0f : 0.0f;
             }
             v = make_float4(w[0], w[1], w[2], w[3]);
-        } else if (ch == 1) {               // pellet values: one nibble of the bitboard
+        } else if (j < 2 * CH_VEC) {        // ch 1: pellet values, one nibble of the bitboard
+            const int q = j - CH_VEC;
             const uint32_t nib = words[q >> 3] >> (4 * (q & 7));
-            v.x = (nib & 1u) ? role.pv : 0.0f;
-            v.y = (nib & 2u) ? role.pv : 0.0f;
-            v.z = (nib & 4u) ? role.pv : 0.0f;
-            v.w = (nib & 8u) ? role.pv : 0.0f;
-        } else if (ch == 15) {              // ticks per step / update period (env.rs:484)
-            v = make_float4(role.sp, role.sp, role.sp, role.sp);
+            v.x = (nib & 1u) ? pv : 0.0f;
+            v.y = (nib & 2u) ? pv : 0.0f;
+            v.z = (nib & 4u) ? pv : 0.0f;
+            v.w = (nib & 8u) ? pv : 0.0f;
+        } else if (j >= 15 * CH_VEC && j < 16 * CH_VEC) {   // ch 15: ticks per step / update period (env.rs:484)
+            v = make_float4(sp, sp, sp, sp);
         }
         img4[j] = v;
     }
