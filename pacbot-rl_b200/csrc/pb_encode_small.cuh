@@ -48,10 +48,13 @@ constexpr long long SMALL_ENC_MAX = 256;
 // __syncthreads(): the image is complete and visible to the whole CTA on return.
 template <int THREADS>
 __device__ __forceinline__ void build_obs_image(const StateView &st, long long env, float *img,
-                                                uint32_t *words) {
+                                                uint32_t *words, bool have_pellet_words = false) {
     const int t = threadIdx.x, lane = t & 31;
-    if (t < 32) words[t] = (t < PEL_WORDS) ? st.pel[(long long)t * st.npad + env] : 0u;
-    else if (t < 64) words[t] = c_tab.walls[t - 32];
+    if (t < 32) {
+        if (!have_pellet_words) words[t] = (t < PEL_WORDS) ? st.pel[(long long)t * st.npad + env] : 0u;
+    } else if (t < 64) {
+        words[t] = c_tab.walls[t - 32];
+    }
     EnvR s;
     load_env(st, env, s);
     __syncthreads();
@@ -156,12 +159,17 @@ k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int 
         stamp_min(&trace->begin, t);
         stamp_min(&trace->ready, t);
     }
-    load_walls(s_walls);
+    // the env's pellet words go to shared memory first: the step reads them at every tick (and
+    // eating writes them), and a single stepping thread hides no global-memory round trip
     const long long i = blockIdx.x;
+    if (threadIdx.x < 32)
+        words[threadIdx.x] = threadIdx.x < PEL_WORDS ? st.pel[(long long)threadIdx.x * st.npad + i] : 0u;
+    load_walls(s_walls);   // ends with a __syncthreads()
     const GymCallLayout l = gym_call_layout((size_t)st.n);
     if (threadIdx.x == 0) {
         EnvR s;
         load_env(st, i, s);
+        const PelRef pel{words, 1};
         int32_t *reward = reinterpret_cast<int32_t *>(blk + l.off_reward);
         uint8_t *done_out = blk + l.off_done;
         if (actions) {
@@ -171,7 +179,6 @@ k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int 
                 reward[i] = 0;
                 done_out[i] = 0;
             } else {
-                const PelRef pel{st.pel + i, st.npad};
                 const RngCtx rng = make_rng(rp, i);
                 int rew;
                 bool done;
@@ -186,16 +193,17 @@ k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int 
         o[0] = s.score;
         o[1] = s.lives;
         o[2] = is_done(s);
-        o[3] = first_ai_done(st, i, s);
+        o[3] = first_ai_done(pel, s);
         o[4] = s.num_pellets;
         o[5] = s.tps;
         o[6] = s.level;
         o[7] = (int)s.ticks;
         write_mask(blk + l.off_mask, i, action_mask_bits(s, s_walls));          // env.rs:293-302
     }
-    __syncthreads();   // thread 0's state (global memory) is what the CTA encodes
+    __syncthreads();   // thread 0's state (global memory) and pellet words (shared) are what the CTA encodes
+    if (actions && threadIdx.x < PEL_WORDS) st.pel[(long long)threadIdx.x * st.npad + i] = words[threadIdx.x];
     if (want_obs) {
-        build_obs_image<GYM_CALL_THREADS>(st, i, img, words);
+        build_obs_image<GYM_CALL_THREADS>(st, i, img, words, true);
         copy_obs_image<GYM_CALL_THREADS>(img, reinterpret_cast<float *>(blk + l.off_obs) + i * (long long)OBS_FLOATS);
     }
     // The CTA's stores to host memory (all threads', made visible to thread 0 by the barrier; the

@@ -189,16 +189,19 @@ __global__ void __launch_bounds__(STEP_THREADS) k_mask(StateView st, uint8_t *__
     write_mask(out, i, action_mask_bits(s, s_walls));
 }
 
-__device__ __forceinline__ bool first_ai_done(const StateView &st, long long i, const EnvR &s) {
+__device__ __forceinline__ bool first_ai_done(const PelRef &pel, const EnvR &s) {
     // env.rs:281-285: all four super pellets gone and no ghost frightened
     bool any = false;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int b = fbit(k < 2 ? 3 : 23, (k & 1) ? 26 : 1);
-        any |= (st.pel[(long long)(b >> 5) * st.npad + i] >> (b & 31)) & 1u;
+        any |= (pel.get(b >> 5) >> (b & 31)) & 1u;
     }
     return !any && s.g[0].fright == 0 && s.g[1].fright == 0 && s.g[2].fright == 0 &&
            s.g[3].fright == 0;
+}
+__device__ __forceinline__ bool first_ai_done(const StateView &st, long long i, const EnvR &s) {
+    return first_ai_done(PelRef{st.pel + i, st.npad}, s);
 }
 
 __global__ void __launch_bounds__(STEP_THREADS)

@@ -234,9 +234,17 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
               const uint8_t *__restrict__ active, uint8_t *__restrict__ leaf_kind_out,
               uint8_t *__restrict__ leaf_mask_out) {
     __shared__ uint32_t s_walls[32];
+    // the simulation's pellet words live in shared memory while the tree is walked: every tick
+    // of every simulated env step reads (and eating writes) them, and with one tree per warp
+    // nothing hides a global-memory round trip per access.  Word w of the tree owned by lane l
+    // sits at s_pel[w * 32 + l] (a lane only ever touches its own column: no synchronisation);
+    // the 28 loads that bring them in are requested together.
+    __shared__ uint32_t s_pel[PEL_WORDS * MCTS_THREADS];
     load_walls(s_walls);
+    const int lane = threadIdx.x;
     const long long i = mcts_tree_of_thread(v);
-    if (i >= v.n) return;
+    const bool owner = i < v.n;
+    if (!owner) return;
     EnvR s;
     load_env(root, i, s);
     int kind = MCTS_INACTIVE;
@@ -245,9 +253,12 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
             atomicOr(v.error, MCTS_ERR_ROOT_DONE);
         } else {
             // env.clone(): the simulation steps slot i of the `sim` engine
-            for (int w = 0; w < PEL_WORDS; w++)
-                sim.pel[(long long)w * sim.npad + i] = root.pel[(long long)w * root.npad + i];
-            const PelRef pel{sim.pel + i, sim.npad};
+            uint32_t words[PEL_WORDS];
+#pragma unroll
+            for (int w = 0; w < PEL_WORDS; w++) words[w] = root.pel[(long long)w * root.npad + i];
+#pragma unroll
+            for (int w = 0; w < PEL_WORDS; w++) s_pel[w * MCTS_THREADS + lane] = words[w];
+            const PelRef pel{s_pel + lane, MCTS_THREADS};
             RngCtx rng;
             rng.seed = sim_seed(seed, *v.epoch);
             rng.gid = (uint64_t)(gid_base + i);
@@ -285,6 +296,9 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
             }
             v.traj_len[i] = len;
             store_env(sim, i, s);
+#pragma unroll
+            for (int w = 0; w < PEL_WORDS; w++)
+                sim.pel[(long long)w * sim.npad + i] = s_pel[w * MCTS_THREADS + lane];
         }
     }
     v.leaf_kind[i] = (uint8_t)kind;
