@@ -1218,6 +1218,13 @@ int pb_step_snapshot_host(pb_engine *e, const uint8_t *actions_host, int auto_re
         return fail(PB_ERR_INVALID_ARG, "pb_step_snapshot_host: a step needs reward / done outputs");
     DeviceGuard g(e->device);
     cudaStream_t s = (cudaStream_t)stream;
+    // the call waits for its kernel on the host: inside a stream capture the kernel would only be
+    // recorded and the wait below would never end
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return fail(PB_ERR_INVALID_ARG, "pb_step_snapshot_host: the stream is being captured (a host round trip cannot be part of a CUDA graph)");
+    }
     const size_t n = (size_t)e->n;
     const GymCallLayout l = gym_call_layout(n);
     const int rc = snap_alloc(e);

@@ -289,3 +289,21 @@ def test_pacman_gym_snapshot_follows_every_mutation(pb):
     assert np.array_equal(ctx.root_obs_numpy(), ctx.env.obs_numpy())
     ctx.reset()
     assert np.array_equal(ctx.root_obs_numpy(), ctx.env.obs_numpy())
+
+
+def test_step_snapshot_refuses_a_capturing_stream(pb):
+    """pb_step_snapshot_host waits on the host for a word its kernel publishes: on a stream that
+    is being captured the kernel would only be recorded, so the call must refuse instead of
+    waiting forever."""
+    import torch
+
+    b = pb.BatchedPacmanGym(4, False, False, device="cuda:0", seed=2)
+    b.reset()
+    before = b.step_snapshot(np.zeros(4, np.uint8))["info"].copy()     # buffers exist, path works
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        with pytest.raises(ValueError, match="captured"):
+            b.step_snapshot(None, want_obs=False)
+    torch.cuda.synchronize()
+    again = b.step_snapshot(None, want_obs=False)["info"]              # and still works afterwards
+    assert np.array_equal(again, before)
