@@ -872,7 +872,7 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
         return model.policy_value(obs, mask, 100.0)
 
     cfg = alphazero.AlphaZeroConfig(tree_size, 1000, 0.99, num_envs)
-    col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=seed)
+    col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=seed, leaf_layout="nhwc32")
     if graph:
         col.enable_cuda_graph()
     finished: list = []
@@ -889,7 +889,7 @@ def mcts_throughput(dev, seed: int, num_envs: int, tree_size: int, steps: int, g
     out = {"sims_per_sec": steps * num_envs / dt, "env_steps_per_sec": items / dt,
            "search_iterations": steps, "ms_per_iteration": 1e3 * dt / steps, "cuda_graph": graph,
            "config": f"{num_envs} trees x tree_size {tree_size}, NetV2 fp32 evaluator (cuDNN convolutions, NHWC, fused block tails and head) on "
-                     "device-resident leaf observations, Dirichlet root noise, max_episode_length 1000"}
+                     "device-resident leaf observations written channels-last by the encoder, Dirichlet root noise, max_episode_length 1000"}
     if cpu_steps:
         import ctypes as C
 

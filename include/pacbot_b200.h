@@ -152,6 +152,12 @@ int pb_step(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8
  * written at out_dev + i * env_stride_floats (stride >= PB_OBS_FLOATS and a multiple of 4 floats;
  * 0 means dense).  out_dev must be 16-byte aligned. */
 int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void *stream);
+/* obs() of envs [first, first+count) in the layout the networks' first convolution takes:
+ * channels-last, zero-padded to 32 channels -- float32 [count][28][31][32] (a torch tensor of
+ * shape [count, 32, 28, 31] in channels_last memory format), channels 17..31 zero.  Same values
+ * as pb_encode_obs followed by a layout change (src/models.py:70-77 consumes it), one launch, one
+ * CTA per env.  out_dev must be 16-byte aligned. */
+int pb_encode_obs_nhwc32(pb_engine *e, int64_t first, int64_t count, float *out_dev, void *stream);
 
 /* Same for envs [first, first + count) only; env first + k is written at out_dev + k * stride.
  * Lets a caller stream a large env population through a smaller observation ring. */

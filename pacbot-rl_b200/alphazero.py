@@ -77,14 +77,16 @@ class BatchedExperienceCollector:
     and only gets involved when an episode ended."""
 
     def __init__(self, evaluator: Callable, config: AlphaZeroConfig, *, device=None, seed: int = 0,
-                 env_id_base: int = 0, noise_fn: Optional[Callable] = None) -> None:
+                 env_id_base: int = 0, noise_fn: Optional[Callable] = None,
+                 leaf_layout: str = "nchw") -> None:
         self.config = config
         P, L = config.num_parallel_envs, config.max_episode_length
         # PacmanGym::new(true, false) + reset (alphazero.rs:72-73)
         self.env = BatchedPacmanGym(P, True, False, device=device, seed=seed, env_id_base=env_id_base)
         self.env.reset()
         self.device = self.env.device
-        self.mcts = BatchedMCTS(self.env, evaluator, config.tree_size, noise_fn=noise_fn)
+        self.mcts = BatchedMCTS(self.env, evaluator, config.tree_size, noise_fn=noise_fn,
+                                leaf_layout=leaf_layout)
         self.mcts.reset_root()  # MCTSContext::new -> reset_root
         dev = self.device
         self.remaining = torch.full((P,), config.tree_size - 1, dtype=torch.int32, device=dev)

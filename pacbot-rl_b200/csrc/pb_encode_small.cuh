@@ -101,9 +101,29 @@ __device__ __forceinline__ void copy_obs_image(const float *img, float *dst) {
     for (int j = threadIdx.x; j < OBS_CH * CH_VEC; j += THREADS) dst4[j] = src4[j];
 }
 
+// The image as a channels-last observation zero-padded to 32 channels (float32 [28][31][32] per
+// env = [cell][channel], what the networks' first convolution takes: models.obs_to_padded_nhwc):
+// one float4 of four consecutive channels per thread and step, coalesced 128-bit stores.
+constexpr int NHWC_CH = 32;
+constexpr int NHWC_FLOATS = CH_FLOATS * NHWC_CH;                      // 27 776 per env
+template <int THREADS>
+__device__ __forceinline__ void copy_obs_image_nhwc32(const float *img, float *dst) {
+    float4 *dst4 = reinterpret_cast<float4 *>(dst);
+    for (int j = threadIdx.x; j < CH_FLOATS * (NHWC_CH / 4); j += THREADS) {
+        const int cell = j >> 3, c = (j & 7) * 4;
+        float4 v;
+        v.x = c + 0 < OBS_CH ? img[(c + 0) * CH_FLOATS + cell] : 0.0f;
+        v.y = c + 1 < OBS_CH ? img[(c + 1) * CH_FLOATS + cell] : 0.0f;
+        v.z = c + 2 < OBS_CH ? img[(c + 2) * CH_FLOATS + cell] : 0.0f;
+        v.w = c + 3 < OBS_CH ? img[(c + 3) * CH_FLOATS + cell] : 0.0f;
+        dst4[j] = v;
+    }
+}
+
 // Same contract as k_encode_obs for envs [env_first, env_first + gridDim.x): out + k * env_stride,
 // optional ring-slot indirection read from device memory (CUDA-graph replays while the ring
-// advances), optional device-timeline record.
+// advances), optional device-timeline record.  NHWC32: the padded channels-last form instead.
+template <bool NHWC32>
 __global__ void __launch_bounds__(OBS_SMALL_THREADS)
 k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
             const long long *__restrict__ slot_index, long long slot_stride,
@@ -119,7 +139,8 @@ k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long lo
     if (slot_index) out += *slot_index * slot_stride;
     const long long k = blockIdx.x;
     build_obs_image<OBS_SMALL_THREADS>(st, env_first + k, img, words);
-    copy_obs_image<OBS_SMALL_THREADS>(img, out + k * env_stride);
+    if (NHWC32) copy_obs_image_nhwc32<OBS_SMALL_THREADS>(img, out + k * env_stride);
+    else copy_obs_image<OBS_SMALL_THREADS>(img, out + k * env_stride);
     if (trace && threadIdx.x == 0) stamp_max(&trace->end, global_timer_ns());
 }
 

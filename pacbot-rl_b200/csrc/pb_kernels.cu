@@ -492,23 +492,35 @@ void rows_to_flat(const uint32_t rows[PB_ROWS], uint32_t *f) {
             }
 }
 
-int launch_encode(pb_engine *e, float *out_dev, long long stride, long long first,
-                  long long count, cudaStream_t s, const long long *slot_index = nullptr,
-                  long long slot_stride = 0) {
-    if (count <= 0) return PB_OK;
+int encode_attrs(pb_engine *e) {
     static thread_local int attr_set_for = -1;
     if (attr_set_for != e->device) {
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
-        PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_obs_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_obs_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         // the kernel in front of a small encode is k_step, which runs under the largest carve-out
         // (see pb_create): ask for the same one, so that the SMs are not reconfigured in between.
         // PB_SMALL_CARVEOUT=0 leaves the driver's choice (A/B runs).
         const char *cv = getenv("PB_SMALL_CARVEOUT");
-        if (!(cv && cv[0] == '0'))
-            PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributePreferredSharedMemoryCarveout,
+        if (!(cv && cv[0] == '0')) {
+            PB_CUDA(cudaFuncSetAttribute(k_obs_small<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
+            PB_CUDA(cudaFuncSetAttribute(k_obs_small<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        }
         attr_set_for = e->device;
+    }
+    return PB_OK;
+}
+
+int launch_encode(pb_engine *e, float *out_dev, long long stride, long long first,
+                  long long count, cudaStream_t s, const long long *slot_index = nullptr,
+                  long long slot_stride = 0) {
+    if (count <= 0) return PB_OK;
+    {
+        const int rc = encode_attrs(e);
+        if (rc != PB_OK) return rc;
     }
     // Small batches (the DQN loop's 32 envs, an evaluation env, the leaves of a few hundred MCTS
     // trees): one CTA per env instead of the persistent kernel, whose prologue alone costs more
@@ -520,7 +532,7 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
     }();
     if (count <= small_max) {
         TraceRec *trace = trace_slot(e, PB_TRACE_ENCODE);
-        k_obs_small<<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, s>>>(
+        k_obs_small<false><<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, s>>>(
             e->st, out_dev, stride, first, slot_index, slot_stride, trace);
         PB_CUDA(cudaGetLastError());
         return PB_OK;
@@ -829,6 +841,20 @@ int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_d
 int pb_encode_obs(pb_engine *e, float *out_dev, int64_t env_stride_floats, void *stream) {
     if (!e) return fail(PB_ERR_INVALID_ARG, "pb_encode_obs: null engine");
     return pb_encode_obs_range(e, 0, e->n, out_dev, env_stride_floats, stream);
+}
+
+int pb_encode_obs_nhwc32(pb_engine *e, int64_t first, int64_t count, float *out_dev, void *stream) {
+    if (!e || !out_dev || first < 0 || count < 0 || first + count > e->n ||
+        (reinterpret_cast<uintptr_t>(out_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG, "pb_encode_obs_nhwc32: bad arguments (out must be 16-byte aligned)");
+    if (count == 0) return PB_OK;
+    DeviceGuard g(e->device);
+    const int rc = encode_attrs(e);
+    if (rc != PB_OK) return rc;
+    k_obs_small<true><<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, (cudaStream_t)stream>>>(
+        e->st, out_dev, (long long)NHWC_FLOATS, first, nullptr, 0ll, trace_slot(e, PB_TRACE_ENCODE));
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
 }
 
 int pb_encode_obs_ring(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,

@@ -407,6 +407,25 @@ class BatchedPacmanGym:
                                           OBS_FLOATS, self._stream()))
         return out
 
+    def obs_nhwc32(self, out: Optional[torch.Tensor] = None, first: int = 0,
+                   count: Optional[int] = None) -> torch.Tensor:
+        """obs() of envs [first, first+count) as the networks take it: float32 [count, 32, 28, 31]
+        in channels_last memory format, channels 17..31 zero (pb_encode_obs_nhwc32: the encoder
+        writes this layout itself -- no layout-conversion launch between it and the first
+        convolution).  `out`: a tensor of that shape and memory format to fill."""
+        if count is None:
+            count = self.num_envs - first
+        shape = (count, 32) + OBS_SHAPE[1:]
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device,
+                              memory_format=torch.channels_last)
+        elif (out.dtype != torch.float32 or out.device != self.device or tuple(out.shape) != shape
+              or not out.is_contiguous(memory_format=torch.channels_last)):
+            raise ValueError(f"out: expected a channels_last float32 tensor of shape {shape} on {self.device}")
+        check(self._L.pb_encode_obs_nhwc32(self._h, first, count, C.c_void_p(out.data_ptr()),
+                                           self._stream()))
+        return out
+
     def obs_ring(self, ring: torch.Tensor, slot_index: torch.Tensor) -> None:
         """obs() of all envs into ring[slot_index] where `slot_index` is a 1-element int64 DEVICE
         tensor read at kernel time (CUDA-graph friendly).  ring: float32 [R, N, 17, 28, 31]."""

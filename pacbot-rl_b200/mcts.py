@@ -49,9 +49,17 @@ class BatchedMCTS:
 
     def __init__(self, env: BatchedPacmanGym, evaluator: Callable, max_nodes: int, *,
                  noise_fn: Optional[Callable] = None, noise_mix: float = NOISE_MIX,
-                 dirichlet_alpha: float = DIRICHLET_ALPHA) -> None:
+                 dirichlet_alpha: float = DIRICHLET_ALPHA, leaf_layout: str = "nchw") -> None:
+        if leaf_layout not in ("nchw", "nhwc32"):
+            raise ValueError("leaf_layout: 'nchw' or 'nhwc32'")
         self.env = env
         self.evaluator = evaluator
+        # "nchw": the evaluator gets leaf observations as the reference's evaluator does, float32
+        # [n, 17, 28, 31].  "nhwc32": channels-last and zero-padded to 32 channels ([n, 32, 28, 31]
+        # in channels_last memory format), written that way by the encoder itself -- what
+        # NetV2.policy_value / QNetV2 feed their first convolution, without the layout-conversion
+        # launch in between.  The observations of fresh roots (reset_root) stay "nchw".
+        self.leaf_layout = leaf_layout
         self.max_nodes = int(max_nodes)
         self.noise_mix = float(noise_mix)
         self.dirichlet_alpha = float(dirichlet_alpha)
@@ -69,7 +77,11 @@ class BatchedMCTS:
         check(self._L.pb_mcts_create(C.byref(self._h), env._h, self.sim._h, self.max_nodes))
         dev = self.device
         self._obs = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev)
-        self._leaf_obs = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev)
+        if leaf_layout == "nhwc32":
+            self._leaf_obs = torch.empty((n, 32) + OBS_SHAPE[1:], dtype=torch.float32, device=dev,
+                                         memory_format=torch.channels_last)
+        else:
+            self._leaf_obs = torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev)
         self._graph = None
         self._leaf_kind = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._leaf_mask = torch.zeros((n, NUM_ACTIONS), dtype=torch.uint8, device=dev)
@@ -166,7 +178,10 @@ class BatchedMCTS:
         a = self._mask_u8(active)
         check(self._L.pb_mcts_select(self._h, self._p(a), self._p(self._leaf_kind),
                                      self._p(self._leaf_mask), self._stream()))
-        leaf_obs = self.sim.obs(out=self._leaf_obs)
+        if self.leaf_layout == "nhwc32":
+            leaf_obs = self.sim.obs_nhwc32(out=self._leaf_obs)
+        else:
+            leaf_obs = self.sim.obs(out=self._leaf_obs)
         value, policy = self._evaluate(leaf_obs, self._leaf_mask.view(torch.bool))
         check(self._L.pb_mcts_backprop(self._h, self._p(value), self._p(policy), self._stream()))
 

@@ -138,7 +138,9 @@ class AlphaZeroTrainer:
             self.model_evaluator,
             AlphaZeroConfig(args.tree_size, args.max_episode_length, args.discount_factor,
                             args.num_parallel_envs),
-            device=self.device, seed=args.seed, env_id_base=self.rank * args.num_parallel_envs)
+            device=self.device, seed=args.seed, env_id_base=self.rank * args.num_parallel_envs,
+            # NetV2.policy_value takes the padded channels-last batch as the encoder writes it
+            leaf_layout="nhwc32" if getattr(self.model, "_fused_blocks", False) else "nchw")
         self.buffer = ExperienceBuffer(args.experience_buffer_size, args.batch_size, self.device, args.seed)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.learning_rate)
         self.num_exp_steps_needed = self.buffer.capacity  # start by filling the buffer (:149)

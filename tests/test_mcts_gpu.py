@@ -339,3 +339,52 @@ def test_alphazero_trainer_short_run(pb, tmp_path):
     obs, mask, value, dist = tr.buffer.sample(32)
     assert obs.shape == (32, 17, 28, 31) and torch.isfinite(obs).all()
     assert (dist[~mask] == 0).all() and torch.allclose(dist.sum(1), torch.ones(32, device="cuda:0"), atol=1e-5)
+
+
+def test_nhwc32_leaf_layout_gives_the_same_search(pb):
+    """BatchedMCTS(leaf_layout="nhwc32"): the encoder writes leaf observations channels-last and
+    zero-padded to 32 channels (pb_encode_obs_nhwc32) and NetV2.policy_value takes them as they
+    are.  (1) That tensor is bit for bit what the layout-conversion launch makes of obs();
+    (2) two collectors that differ only in the leaf layout build identical trees and experience."""
+    from pacbot_rl_b200 import alphazero, models
+
+    dev = torch.device("cuda:0")
+    env = pb.BatchedPacmanGym(300, True, True, device=dev, seed=4)
+    env.reset()
+    for k in range(7):
+        env.step_random(call_idx=k)
+    direct = env.obs_nhwc32()
+    via = models.obs_to_padded_nhwc(env.obs())
+    assert direct.shape == via.shape == (300, 32, 28, 31) and direct.stride() == via.stride()
+    assert torch.equal(direct.view(torch.int32), via.view(torch.int32))
+    part = torch.full((40, 32, 28, 31), -1.0, device=dev).contiguous(memory_format=torch.channels_last)
+    env.obs_nhwc32(out=part, first=211, count=40)
+    assert torch.equal(part, via[211:251])
+    with pytest.raises(ValueError):
+        env.obs_nhwc32(out=torch.empty((300, 32, 28, 31), device=dev))     # not channels_last
+
+    torch.manual_seed(0)
+    model = models.NetV2((17, 28, 31), 6).to(dev).use_fused_blocks().eval()
+    with torch.no_grad():                    # the final layer starts at zero: make the outputs vary
+        for p in model.network[17].parameters():
+            p.normal_(0.0, 0.3)
+
+    @torch.no_grad()
+    def evaluator(obs, mask):
+        return model.policy_value(obs, mask, 100.0)
+
+    cfg = alphazero.AlphaZeroConfig(8, 6, 0.99, 48)     # episodes are cut after 6 env steps: hand-outs within 100 iterations
+    cols = [alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=9, leaf_layout=layout)
+            for layout in ("nchw", "nhwc32")]
+    batches = []
+    for col in cols:
+        finished = []
+        for _ in range(100):
+            col.generate_experience_step(finished)
+        col.mcts.check()
+        assert finished
+        batches.append((col.mcts.node_count().cpu(), col.mcts.root_visits().cpu(), col.mcts.value().cpu(),
+                        torch.cat([f[1] for f in finished]).cpu(), torch.cat([f[3] for f in finished]).cpu()))
+    assert len(batches[0][3]) > 0
+    for a, b in zip(*batches):
+        assert torch.equal(a, b)

@@ -16,7 +16,8 @@ def evaluator(obs, mask):
     return model.policy_value(obs, mask, 100.0)
 
 def make():
-    return alphazero.BatchedExperienceCollector(evaluator, alphazero.AlphaZeroConfig(100, 1000, 0.99, P), device=dev)
+    return alphazero.BatchedExperienceCollector(evaluator, alphazero.AlphaZeroConfig(100, 1000, 0.99, P), device=dev,
+                                                leaf_layout="nhwc32")
 
 def wall(col, steps=300):
     fin = []
