@@ -199,7 +199,14 @@ class EpisodeEvaluator:
         self.phase1_policy, self.use_graph = phase1_policy, use_graph
         self.env = BatchedPacmanGym(self.n, False, False, device=device, seed=seed, env_id_base=env_id_base)
         n = self.n
-        self.obs = torch.empty((n, 17, 28, 31), dtype=torch.float32, device=device)
+        # a fused QNetV2 takes the observation channels-last and padded to 32 channels: the encoder
+        # writes it that way itself (pb_encode_obs_nhwc32), one launch less per evaluation step
+        self._nhwc = bool(getattr(getattr(policy, "q_net", None), "_fused_blocks", False))
+        if self._nhwc:
+            self.obs = torch.empty((n, 32, 28, 31), dtype=torch.float32, device=device,
+                                   memory_format=torch.channels_last)
+        else:
+            self.obs = torch.empty((n, 17, 28, 31), dtype=torch.float32, device=device)
         self.mask = torch.zeros((n, 5), dtype=torch.bool, device=device)
         # per-env bookkeeping, updated by ONE kernel per step (pb_eval_track): rows 0 score,
         # 1 steps, 2 lives, 3 pellets_end, 4 finished (done within max_steps), 5 alive, 6 steps left
@@ -216,7 +223,10 @@ class EpisodeEvaluator:
         """reset_env(gym) + pellets_start (train_dqn.py:95-97)."""
         reset_env(self.env, self.phase1_policy)
         self.pellets_start.copy_(self.env.remaining_pellets())
-        self.env.obs(out=self.obs)
+        if self._nhwc:
+            self.env.obs_nhwc32(out=self.obs)
+        else:
+            self.env.obs(out=self.obs)
         self.env.action_mask(out=self.mask)
         t = self.track
         t.zero_()
@@ -233,7 +243,11 @@ class EpisodeEvaluator:
         env = self.env
         pol = self.policy
         actions = pol.actions_u8(self.obs, self.mask) if hasattr(pol, "actions_u8") else pol(self.obs, self.mask)
-        _, done = env.step_obs(actions, self.obs, mask_out=self.mask)
+        if self._nhwc:
+            _, done = env.step(actions, check_actions=False, mask_out=self.mask)
+            env.obs_nhwc32(out=self.obs)
+        else:
+            _, done = env.step_obs(actions, self.obs, mask_out=self.mask)
         check(env._L.pb_eval_track(env._h, C.c_void_p(done.data_ptr()), C.c_void_p(self.track.data_ptr()),
                                    env._stream()))
 

@@ -1043,3 +1043,34 @@ def test_clip_adam_matches_clip_grad_norm_and_torch_adam(pb, max_norm):
         graph.replay()
     torch.cuda.synchronize()
     assert int(ours.step_count) == 28 and not torch.equal(pa[0], w_before)
+
+
+def test_evaluator_channels_last_observations_give_the_same_episodes(pb):
+    """EpisodeEvaluator hands a fused QNetV2 its observations channels-last and padded to 32
+    channels straight from the encoder (pb_encode_obs_nhwc32).  The same network behind a policy
+    object that hides what it is gets the channel-major observation and converts it itself: the
+    bits that reach the first convolution are the same, so every episode must be identical."""
+    import torch
+
+    from pacbot_rl_b200 import models, train_dqn
+    from pacbot_rl_b200.policies import MaxQPolicy
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = models.QNetV2(pb.OBS_SHAPE, 5).to(dev).use_fused_blocks().eval()
+    with torch.no_grad():
+        for head in (net.value_head, net.advantage_head):
+            for p in head.parameters():
+                p.normal_(0.0, 0.5)
+
+    class Opaque:                        # no `q_net` attribute: the evaluator keeps channel-major buffers
+        def actions_u8(self, obs, mask):
+            assert tuple(obs.shape[1:]) == (17, 28, 31)
+            return net.greedy_actions(obs, mask)
+
+    direct = train_dqn.run_eval_episodes(MaxQPolicy(net), dev, 24, 150, seed=5, env_id_base=40)
+    via = train_dqn.run_eval_episodes(Opaque(), dev, 24, 150, seed=5, env_id_base=40)
+    assert set(direct) == set(via)
+    for k in direct:
+        assert torch.equal(direct[k], via[k]), k
+    assert int(direct["steps"].max()) > 20
