@@ -4,7 +4,6 @@ object, driven as src/replay_buffer.py:107-137 does).  Run on a GPU box:
 Prints wall-clock microseconds per call for the layers of the path: the raw C-ABI call
 (pb_step_snapshot_host = one k_gym_call launch + the wait for its sequence word), the engine
 method around it, the gym method around that, and the whole reference call pattern."""
-import ctypes as C
 import json
 import os
 import sys
