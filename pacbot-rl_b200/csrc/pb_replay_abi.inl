@@ -82,14 +82,19 @@ k_replay_sample(const uint8_t *__restrict__ ring_valid, long long total, int bat
         if (ring_valid[j]) list[w++] = (int)j;
     const int m = s_scan[SAMPLE_THREADS - 1];
     const unsigned long long call = (unsigned long long)*call_dev;
-    for (int j = tid; j < batch; j += SAMPLE_THREADS) raw[j] = replay_raw(seed, call, (uint32_t)j);
+    // the draws, and (when there are enough candidates) the partner index of every position, are
+    // computed by all threads; only the dependent chain of swaps is left to one thread
+    for (int j = tid; j < batch; j += SAMPLE_THREADS) {
+        const uint32_t u = replay_raw(seed, call, (uint32_t)j);
+        raw[j] = (m >= batch) ? (uint32_t)j + below(u, (uint32_t)(m - j)) : u;
+    }
     __syncthreads();
     if (tid == 0) {
         if (num_valid_out) *num_valid_out = m;
         if (m >= batch) {
             // partial Fisher-Yates: position j takes a uniformly chosen element of list[j..m)
             for (int j = 0; j < batch; j++) {
-                const int r = j + (int)below(raw[j], (uint32_t)(m - j));
+                const int r = (int)raw[j];
                 const int a = list[j], b = list[r];
                 list[r] = a;
                 list[j] = b;
