@@ -170,6 +170,13 @@ int pb_encode_obs_range(pb_engine *e, int64_t first, int64_t count, float *out_d
  * ring advances (src/replay_buffer.py's deque append, done in place). */
 int pb_encode_obs_ring(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,
                        const int64_t *slot_index_dev, void *stream);
+/* pb_encode_obs_ring that ALSO hands the same observations out in the networks' input layout
+ * (channels-last, zero-padded to 32 channels: nhwc_out_dev float32 [n][28][31][32], see
+ * pb_encode_obs_nhwc32), from the same launch (one CTA per env): the replay ring of
+ * src/replay_buffer.py keeps the channel-major observation, the policy's next forward
+ * (src/replay_buffer.py:107-112) reads its input without a layout conversion in between. */
+int pb_encode_obs_ring_nhwc32(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,
+                              const int64_t *slot_index_dev, float *nhwc_out_dev, void *stream);
 
 /* pb_step followed by pb_encode_obs of the resulting states, back to back on `stream`. */
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,

@@ -122,12 +122,14 @@ __device__ __forceinline__ void copy_obs_image_nhwc32(const float *img, float *d
 
 // Same contract as k_encode_obs for envs [env_first, env_first + gridDim.x): out + k * env_stride,
 // optional ring-slot indirection read from device memory (CUDA-graph replays while the ring
-// advances), optional device-timeline record.  NHWC32: the padded channels-last form instead.
-template <bool NHWC32>
+// advances), optional device-timeline record.  `out_nhwc` (may be given instead of, or together
+// with, `out`): the padded channels-last form of the same observations, env k at
+// out_nhwc + k * NHWC_FLOATS -- the replay ring keeps the channel-major observation while the
+// policy's next forward gets its input layout from the same launch.
 __global__ void __launch_bounds__(OBS_SMALL_THREADS)
 k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long long env_first,
             const long long *__restrict__ slot_index, long long slot_stride,
-            TraceRec *__restrict__ trace) {
+            float *__restrict__ out_nhwc, TraceRec *__restrict__ trace) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *img = reinterpret_cast<float *>(smem_raw);
     uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw + SMALL_IMG_BYTES);
@@ -136,11 +138,13 @@ k_obs_small(StateView st, float *__restrict__ out, long long env_stride, long lo
         stamp_min(&trace->begin, t);
         stamp_min(&trace->ready, t);
     }
-    if (slot_index) out += *slot_index * slot_stride;
     const long long k = blockIdx.x;
     build_obs_image<OBS_SMALL_THREADS>(st, env_first + k, img, words);
-    if (NHWC32) copy_obs_image_nhwc32<OBS_SMALL_THREADS>(img, out + k * env_stride);
-    else copy_obs_image<OBS_SMALL_THREADS>(img, out + k * env_stride);
+    if (out) {
+        if (slot_index) out += *slot_index * slot_stride;
+        copy_obs_image<OBS_SMALL_THREADS>(img, out + k * env_stride);
+    }
+    if (out_nhwc) copy_obs_image_nhwc32<OBS_SMALL_THREADS>(img, out_nhwc + k * (long long)NHWC_FLOATS);
     if (trace && threadIdx.x == 0) stamp_max(&trace->end, global_timer_ns());
 }
 

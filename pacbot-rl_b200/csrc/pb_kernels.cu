@@ -496,27 +496,25 @@ int encode_attrs(pb_engine *e) {
     static thread_local int attr_set_for = -1;
     if (attr_set_for != e->device) {
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
-        PB_CUDA(cudaFuncSetAttribute(k_obs_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
-        PB_CUDA(cudaFuncSetAttribute(k_obs_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         // the kernel in front of a small encode is k_step, which runs under the largest carve-out
         // (see pb_create): ask for the same one, so that the SMs are not reconfigured in between.
         // PB_SMALL_CARVEOUT=0 leaves the driver's choice (A/B runs).
         const char *cv = getenv("PB_SMALL_CARVEOUT");
-        if (!(cv && cv[0] == '0')) {
-            PB_CUDA(cudaFuncSetAttribute(k_obs_small<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        if (!(cv && cv[0] == '0'))
+            PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
-            PB_CUDA(cudaFuncSetAttribute(k_obs_small<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
-        }
         attr_set_for = e->device;
     }
     return PB_OK;
 }
 
+// `nhwc_out` (small launches only, see pb_encode_obs_ring_nhwc32): the same observations also in
+// the padded channels-last layout, from the same launch
 int launch_encode(pb_engine *e, float *out_dev, long long stride, long long first,
                   long long count, cudaStream_t s, const long long *slot_index = nullptr,
-                  long long slot_stride = 0) {
+                  long long slot_stride = 0, float *nhwc_out = nullptr) {
     if (count <= 0) return PB_OK;
     {
         const int rc = encode_attrs(e);
@@ -530,10 +528,10 @@ int launch_encode(pb_engine *e, float *out_dev, long long stride, long long firs
         const char *v = getenv("PB_SMALL_ENC_MAX");
         return v ? atoll(v) : (long long)SMALL_ENC_MAX;
     }();
-    if (count <= small_max) {
+    if (count <= small_max || nhwc_out) {
         TraceRec *trace = trace_slot(e, PB_TRACE_ENCODE);
-        k_obs_small<false><<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, s>>>(
-            e->st, out_dev, stride, first, slot_index, slot_stride, trace);
+        k_obs_small<<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, s>>>(
+            e->st, out_dev, stride, first, slot_index, slot_stride, nhwc_out, trace);
         PB_CUDA(cudaGetLastError());
         return PB_OK;
     }
@@ -851,8 +849,8 @@ int pb_encode_obs_nhwc32(pb_engine *e, int64_t first, int64_t count, float *out_
     DeviceGuard g(e->device);
     const int rc = encode_attrs(e);
     if (rc != PB_OK) return rc;
-    k_obs_small<true><<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, (cudaStream_t)stream>>>(
-        e->st, out_dev, (long long)NHWC_FLOATS, first, nullptr, 0ll, trace_slot(e, PB_TRACE_ENCODE));
+    k_obs_small<<<(unsigned)count, OBS_SMALL_THREADS, SMALL_SMEM, (cudaStream_t)stream>>>(
+        e->st, nullptr, 0ll, first, nullptr, 0ll, out_dev, trace_slot(e, PB_TRACE_ENCODE));
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -865,6 +863,18 @@ int pb_encode_obs_ring(pb_engine *e, float *ring_dev, int64_t slot_stride_floats
     DeviceGuard g(e->device);
     return launch_encode(e, ring_dev, OBS_FLOATS, 0, e->n, (cudaStream_t)stream,
                          reinterpret_cast<const long long *>(slot_index_dev), slot_stride_floats);
+}
+
+int pb_encode_obs_ring_nhwc32(pb_engine *e, float *ring_dev, int64_t slot_stride_floats,
+                              const int64_t *slot_index_dev, float *nhwc_out_dev, void *stream) {
+    if (!e || !ring_dev || !slot_index_dev || !nhwc_out_dev || (slot_stride_floats & 3) ||
+        slot_stride_floats < (int64_t)OBS_FLOATS * e->n || (reinterpret_cast<uintptr_t>(ring_dev) & 15) ||
+        (reinterpret_cast<uintptr_t>(nhwc_out_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG, "pb_encode_obs_ring_nhwc32: bad arguments");
+    DeviceGuard g(e->device);
+    return launch_encode(e, ring_dev, OBS_FLOATS, 0, e->n, (cudaStream_t)stream,
+                         reinterpret_cast<const long long *>(slot_index_dev), slot_stride_floats,
+                         nhwc_out_dev);
 }
 
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,

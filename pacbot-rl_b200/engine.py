@@ -426,14 +426,27 @@ class BatchedPacmanGym:
                                            self._stream()))
         return out
 
-    def obs_ring(self, ring: torch.Tensor, slot_index: torch.Tensor) -> None:
+    def obs_ring(self, ring: torch.Tensor, slot_index: torch.Tensor,
+                 nhwc32_out: Optional[torch.Tensor] = None) -> None:
         """obs() of all envs into ring[slot_index] where `slot_index` is a 1-element int64 DEVICE
-        tensor read at kernel time (CUDA-graph friendly).  ring: float32 [R, N, 17, 28, 31]."""
+        tensor read at kernel time (CUDA-graph friendly).  ring: float32 [R, N, 17, 28, 31].
+        `nhwc32_out` (float32 [N, 32, 28, 31], channels_last): the same observations also in the
+        networks' input layout, from the same launch (pb_encode_obs_ring_nhwc32)."""
         if (ring.dtype != torch.float32 or ring.device != self.device or not ring.is_contiguous()
                 or tuple(ring.shape[1:]) != (self.num_envs,) + OBS_SHAPE):
             raise ValueError("ring: expected contiguous float32 [R, N, 17, 28, 31] on the engine device")
         if slot_index.dtype != torch.int64 or slot_index.device != self.device or slot_index.numel() != 1:
             raise ValueError("slot_index: expected a 1-element int64 tensor on the engine device")
+        if nhwc32_out is not None:
+            shape = (self.num_envs, 32) + OBS_SHAPE[1:]
+            if (nhwc32_out.dtype != torch.float32 or nhwc32_out.device != self.device
+                    or tuple(nhwc32_out.shape) != shape
+                    or not nhwc32_out.is_contiguous(memory_format=torch.channels_last)):
+                raise ValueError(f"nhwc32_out: expected a channels_last float32 tensor of shape {shape}")
+            check(self._L.pb_encode_obs_ring_nhwc32(
+                self._h, C.c_void_p(ring.data_ptr()), self.num_envs * OBS_FLOATS,
+                C.c_void_p(slot_index.data_ptr()), C.c_void_p(nhwc32_out.data_ptr()), self._stream()))
+            return
         check(self._L.pb_encode_obs_ring(self._h, C.c_void_p(ring.data_ptr()),
                                          self.num_envs * OBS_FLOATS,
                                          C.c_void_p(slot_index.data_ptr()), self._stream()))

@@ -147,6 +147,10 @@ class ReplayBuffer:
         # per-step scratch (fixed addresses: CUDA-graph capture)
         self._last_obs = (_channels_last_empty((n,) + self._batch_shape, dev) if self.channels_last
                           else torch.empty((n,) + OBS_SHAPE, dtype=torch.float32, device=dev))
+        # True once `_last_obs` holds the observation of ring slot t (written by the encoder of the
+        # step before); anything that rewrites the current slot behind the buffer's back has to
+        # call invalidate_last_obs()
+        self._last_obs_fresh = False
         self._act = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._reward = torch.zeros(n, dtype=torch.int32, device=dev)
         self._done_step = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -182,6 +186,11 @@ class ReplayBuffer:
     @property
     def capacity(self) -> int:
         return self._slots * self.num_envs
+
+    def invalidate_last_obs(self) -> None:
+        """The current ring slot was rewritten from outside (tests that plant env states): the
+        next step re-derives the policy's input from the slot."""
+        self._last_obs_fresh = False
 
     def fill(self, min_valid: int = 1) -> None:
         """Generate experience until the ring has wrapped once (the reference's `fill()` loops until
@@ -233,8 +242,14 @@ class ReplayBuffer:
         `count_on_host=False` is for CUDA-graph replay: the caller advances `_t` itself."""
         r, n = self._ring, self.num_envs
         L, stream, dev = self._L, self._stream(), self.device.index
-        check(L.pb_replay_slot_obs(C.c_void_p(self._obs.data_ptr()), n, r, C.c_void_p(self._t_dev.data_ptr()),
-                                   C.c_void_p(self._last_obs.data_ptr()), self._cl_arg, dev, stream))
+        # the policy's input: ring slot t in the network's layout.  With the padded channels-last
+        # layout the encoder of the PREVIOUS step has already written it next to the ring slot
+        # (one launch, pb_encode_obs_ring_nhwc32); otherwise, and for the first step, it is a
+        # transposing copy of the slot.
+        dual = self._cl_arg == PADDED_CHANNELS
+        if not (dual and self._last_obs_fresh):
+            check(L.pb_replay_slot_obs(C.c_void_p(self._obs.data_ptr()), n, r, C.c_void_p(self._t_dev.data_ptr()),
+                                       C.c_void_p(self._last_obs.data_ptr()), self._cl_arg, dev, stream))
         actions = self._select(self._last_obs)
         if self.phase1_policy is not None:
             old = self.phase1_policy(self._last_obs, self._mask).to(torch.uint8)
@@ -242,7 +257,11 @@ class ReplayBuffer:
         # step + auto reset, then the observation of the resulting state straight into slot t+1
         self.envs.step(actions, check_actions=False, mask_out=self._mask, reward_out=self._reward,
                        done_out=self._done_step)
-        self.envs.obs_ring(self._obs, self._nxt_dev)
+        if dual:
+            self.envs.obs_ring(self._obs, self._nxt_dev, nhwc32_out=self._last_obs)
+            self._last_obs_fresh = True
+        else:
+            self.envs.obs_ring(self._obs, self._nxt_dev)
         a_p, r_p, d_p, m_p = self._slot_ptrs()
         phase = C.c_void_p(self._in_phase1.data_ptr()) if self.phase1_policy is not None else None
         check(L.pb_replay_record(n, r, C.c_void_p(self._t_dev.data_ptr()), C.c_void_p(actions.data_ptr()),

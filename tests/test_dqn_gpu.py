@@ -396,11 +396,16 @@ def test_replay_record_collate_and_slot_obs_match_plain_indexing(pb, channels_la
         assert x.shape[1] == buf.obs_channels and not bool(x[:, 17:].any())
         return x[:, :17]
 
+    dual = channels_last and pad                 # the encoder writes the policy's next input itself
     for t in range(r + 30):                      # wrap the ring
         before = buf._obs[t % r].clone()
+        if dual and t > 0:                       # what the policy is about to see == ring slot t
+            assert torch.equal(real(buf._last_obs), before), t
         buf.generate_experience_step()
-        # last_obs handed to the policy == the ring slot of step t
-        assert torch.equal(real(buf._last_obs), before), t
+        if dual:     # pb_encode_obs_ring_nhwc32: slot t + 1 and its channels-last twin, one launch
+            assert torch.equal(real(buf._last_obs), buf._obs[(t + 1) % r]), t
+        else:        # last_obs handed to the policy == the ring slot of step t
+            assert torch.equal(real(buf._last_obs), before), t
         assert buf._last_obs.is_contiguous(
             memory_format=torch.channels_last if channels_last else torch.contiguous_format)
         # what k_replay_record appended == the step's own outputs
