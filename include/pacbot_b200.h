@@ -600,6 +600,15 @@ int pb_mcts_collect_act(pb_mcts *m, pb_engine *snap, int max_episode_length, int
                         int32_t *remaining_dev, int32_t *ep_len_dev, uint8_t *ep_mask_dev,
                         float *ep_dist_dev, float *ep_value_dev, uint8_t *status_dev,
                         uint32_t *flags_dev, void *stream);
+/* pb_mcts_backprop + pb_mcts_collect_act + pb_mcts_root_noise_dirichlet (for the trees that
+ * collect_act re-rooted, mcts.rs:160-163) as ONE launch: the tail of a collector step
+ * (alphazero.rs:141-195) after the evaluator.  A tree's three stages only touch that tree's own
+ * nodes, env and counters, so the results are those of the three separate calls. */
+int pb_mcts_backprop_collect(pb_mcts *m, const float *value_dev, const float *policy_dev, pb_engine *snap,
+                             int max_episode_length, int tree_size, int32_t *remaining_dev,
+                             int32_t *ep_len_dev, uint8_t *ep_mask_dev, float *ep_dist_dev,
+                             float *ep_value_dev, uint8_t *status_dev, uint32_t *flags_dev, float alpha,
+                             float mix, void *stream);
 /* Per-tree getters (mcts.rs:173-243) */
 #define PB_MCTS_Q_BEST_ACTION 0         /* int32 [n]: most visited valid child, ties -> last */
 #define PB_MCTS_Q_ACTION_DISTRIBUTION 1 /* float32 [n][5]: child visits / (root visits - 1) */

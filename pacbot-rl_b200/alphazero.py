@@ -101,6 +101,9 @@ class BatchedExperienceCollector:
         self._status = torch.zeros(P, dtype=torch.uint8, device=dev)
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._graph = None
+        # backprop + env steps + built-in root noise as one launch (pb_mcts_backprop_collect);
+        # False: the three separate launches (what runs with an injected noise_fn anyway)
+        self.fused_tail = True
         self._pending: list = []   # finished episodes not handed out yet
         self._out_count = 0
         self.search_iterations = 0
@@ -109,6 +112,16 @@ class BatchedExperienceCollector:
     def _device_step(self) -> None:
         cfg = self.config
         p = BatchedMCTS._p
+        m = self.mcts
+        if self.fused_tail and m.noise_fn is None and m._graph is None:
+            # built-in root noise: everything after the evaluator -- backprop, the env steps that
+            # became due, the noise on the re-rooted trees -- is ONE launch
+            value, policy = m.select_and_evaluate()
+            check(m._L.pb_mcts_backprop_collect(
+                m._h, p(value), p(policy), self.snap._h, cfg.max_episode_length, cfg.tree_size,
+                p(self.remaining), p(self.ep_len), p(self.ep_mask), p(self.ep_dist), p(self.ep_value),
+                p(self._status), p(self._flags), m.dirichlet_alpha, m.noise_mix, m._stream()))
+            return
         self.mcts.search_iteration()
         check(self.mcts._L.pb_mcts_collect_act(
             self.mcts._h, self.snap._h, cfg.max_episode_length, cfg.tree_size, p(self.remaining),

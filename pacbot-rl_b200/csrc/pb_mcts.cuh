@@ -167,13 +167,11 @@ __device__ __forceinline__ float noise_gamma(float a, uint64_t key, uint32_t &ct
     return d * boost;   // (the mean; 64 rejections in a row do not happen)
 }
 
-__global__ void __launch_bounds__(MCTS_THREADS)
-k_mcts_root_noise_dirichlet(MctsView v, StateView root, const uint8_t *__restrict__ mask, float alpha,
-                            float keep, float mix, unsigned long long seed, long long gid_base) {
-    __shared__ uint32_t s_walls[32];
-    load_walls(s_walls);
-    const long long i = mcts_tree_of_thread(v);
-    if (i >= v.n || (mask && !mask[i])) return;
+// add_root_policy_noise with the built-in Dirichlet draw, for tree i (one thread)
+__device__ __forceinline__ void mcts_dirichlet_noise_tree(const MctsView &v, const StateView &root,
+                                                          const uint32_t *s_walls, long long i, float alpha,
+                                                          float keep, float mix, unsigned long long seed,
+                                                          long long gid_base) {
     EnvR s;
     load_env(root, i, s);
     const uint32_t m = action_mask_bits(s, s_walls);
@@ -196,6 +194,16 @@ k_mcts_root_noise_dirichlet(MctsView v, StateView root, const uint8_t *__restric
         nd->prior[a] = __fadd_rn(__fmul_rn(keep, nd->prior[a]), __fmul_rn(mix, noise));
         k++;
     }
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_root_noise_dirichlet(MctsView v, StateView root, const uint8_t *__restrict__ mask, float alpha,
+                            float keep, float mix, unsigned long long seed, long long gid_base) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = mcts_tree_of_thread(v);
+    if (i >= v.n || (mask && !mask[i])) return;
+    mcts_dirichlet_noise_tree(v, root, s_walls, i, alpha, keep, mix, seed, gid_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -309,11 +317,10 @@ k_mcts_select(MctsView v, StateView root, StateView sim, uint64_t seed, long lon
 // ---------------------------------------------------------------------------------------------
 // backprop_trajectory (mcts.rs:325-381), iterative: expand the leaf, then walk the path upwards
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MCTS_THREADS)
-k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__restrict__ policy) {
-    const long long i = mcts_tree_of_thread(v);
-    if (i == 0) *v.epoch += 1ull;  // one search iteration done (select of the next one sees it)
-    if (i >= v.n) return;
+// backprop_trajectory for tree i (one thread): expand the leaf, then walk the path upwards
+__device__ __forceinline__ void mcts_backprop_tree(const MctsView &v, long long i,
+                                                   const float *__restrict__ value,
+                                                   const float *__restrict__ policy) {
     const int kind = v.leaf_kind[i];
     if (kind == MCTS_INACTIVE) return;
     v.leaf_kind[i] = MCTS_INACTIVE;  // a trajectory is consumed exactly once
@@ -360,6 +367,14 @@ k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__rest
     // child == path[0] == root
     nodes[child].visit += 1u;
     nodes[child].total = __fadd_rn(nodes[child].total, __fmul_rn(MCTS_DISCOUNT, subsequent));
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_backprop(MctsView v, const float *__restrict__ value, const float *__restrict__ policy) {
+    const long long i = mcts_tree_of_thread(v);
+    if (i == 0) *v.epoch += 1ull;  // one search iteration done (select of the next one sees it)
+    if (i >= v.n) return;
+    mcts_backprop_tree(v, i, value, policy);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,21 +462,17 @@ k_mcts_take_action(MctsView v, StateView root, RngParams rp, const uint8_t *__re
 // ---------------------------------------------------------------------------------------------
 enum { MCTS_ST_TRUNCATED_BIT = 8 };  // or-ed into the take_action status when the episode is cut
 
-__global__ void __launch_bounds__(MCTS_THREADS)
-k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int max_len,
-                   int tree_size, int32_t *__restrict__ remaining, int32_t *__restrict__ ep_len,
-                   uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
-                   float *__restrict__ ep_value, uint8_t *__restrict__ status,
-                   unsigned int *__restrict__ host_flags) {
-    __shared__ uint32_t s_walls[32];
-    load_walls(s_walls);
-    const long long i = mcts_tree_of_thread(v);
-    if (i >= v.n) return;
+// the env-step half of generate_experience_step for tree i (one thread); returns the status byte
+__device__ __forceinline__ int mcts_collect_act_tree(
+    const MctsView &v, const StateView &root, const RngParams &rp, const StateView &snap,
+    const uint32_t *s_walls, long long i, int max_len, int tree_size, int32_t *__restrict__ remaining,
+    int32_t *__restrict__ ep_len, uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
+    float *__restrict__ ep_value, uint8_t *__restrict__ status, unsigned int *__restrict__ host_flags) {
     const int left = remaining[i] - 1;  // alphazero.rs:142
     remaining[i] = left;
     if (left != 0) {
         status[i] = MCTS_ST_UNTOUCHED;
-        return;
+        return MCTS_ST_UNTOUCHED;
     }
     const int t = ep_len[i];
     const long long slot = i * max_len + t;
@@ -507,6 +518,47 @@ k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int
     }
     status[i] = (uint8_t)st;
     if (flags) atomicOr(host_flags, flags);
+    return st;
+}
+
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int max_len,
+                   int tree_size, int32_t *__restrict__ remaining, int32_t *__restrict__ ep_len,
+                   uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
+                   float *__restrict__ ep_value, uint8_t *__restrict__ status,
+                   unsigned int *__restrict__ host_flags) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = mcts_tree_of_thread(v);
+    if (i >= v.n) return;
+    mcts_collect_act_tree(v, root, rp, snap, s_walls, i, max_len, tree_size, remaining, ep_len, ep_mask,
+                          ep_dist, ep_value, status, host_flags);
+}
+
+// One search iteration's tail for the collector, ONE launch instead of three (plus the two torch
+// kernels that derived the noise mask from the status bytes): backprop of the evaluated leaf, the
+// env step that became due (experience record, take_action, next budget) and, for a tree that
+// take_action re-rooted, the Dirichlet noise on its new root (mcts.rs:160-163).  A tree's three
+// stages only touch that tree's own nodes, env and counters, so running them back to back in the
+// tree's thread is the order the separate launches give.
+__global__ void __launch_bounds__(MCTS_THREADS)
+k_mcts_backprop_collect(MctsView v, const float *__restrict__ value, const float *__restrict__ policy,
+                        StateView root, RngParams rp, StateView snap, int max_len, int tree_size,
+                        int32_t *__restrict__ remaining, int32_t *__restrict__ ep_len,
+                        uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
+                        float *__restrict__ ep_value, uint8_t *__restrict__ status,
+                        unsigned int *__restrict__ host_flags, float alpha, float keep, float mix,
+                        unsigned long long noise_seed, long long gid_base) {
+    __shared__ uint32_t s_walls[32];
+    load_walls(s_walls);
+    const long long i = mcts_tree_of_thread(v);
+    if (i == 0) *v.epoch += 1ull;
+    if (i >= v.n) return;
+    mcts_backprop_tree(v, i, value, policy);
+    const int st = mcts_collect_act_tree(v, root, rp, snap, s_walls, i, max_len, tree_size, remaining, ep_len,
+                                         ep_mask, ep_dist, ep_value, status, host_flags);
+    if ((st & 7) == MCTS_ST_REROOTED)
+        mcts_dirichlet_noise_tree(v, root, s_walls, i, alpha, keep, mix, noise_seed, gid_base);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -178,6 +178,26 @@ int pb_mcts_collect_act(pb_mcts *m, pb_engine *snap, int max_episode_length, int
     return PB_OK;
 }
 
+int pb_mcts_backprop_collect(pb_mcts *m, const float *value_dev, const float *policy_dev, pb_engine *snap,
+                             int max_episode_length, int tree_size, int32_t *remaining_dev,
+                             int32_t *ep_len_dev, uint8_t *ep_mask_dev, float *ep_dist_dev,
+                             float *ep_value_dev, uint8_t *status_dev, uint32_t *flags_dev, float alpha,
+                             float mix, void *stream) {
+    if (!m || !value_dev || !policy_dev || !snap || !remaining_dev || !ep_len_dev || !ep_mask_dev ||
+        !ep_dist_dev || !ep_value_dev || !status_dev || !flags_dev || max_episode_length < 1 ||
+        tree_size < 2 || !(alpha > 0.0f) || snap->device != m->device ||
+        snap->n < m->v.n * (long long)max_episode_length)
+        return fail(PB_ERR_INVALID_ARG,
+                    "pb_mcts_backprop_collect: bad arguments (snap needs n * max_episode_length envs)");
+    DeviceGuard g(m->device);
+    k_mcts_backprop_collect<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
+        m->v, value_dev, policy_dev, m->root->st, rng_params(m->root), snap->st, max_episode_length,
+        tree_size, remaining_dev, ep_len_dev, ep_mask_dev, ep_dist_dev, ep_value_dev, status_dev, flags_dev,
+        alpha, 1.0f - mix, mix, m->root->seed, m->root->gid_base);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 int pb_mcts_query(pb_mcts *m, int what, void *out_dev, void *stream) {
     if (!m || !out_dev || what < 0 || what > MCTS_Q_ROOT_VISITS)
         return fail(PB_ERR_INVALID_ARG, "pb_mcts_query: bad arguments");

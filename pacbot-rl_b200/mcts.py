@@ -175,6 +175,13 @@ class BatchedMCTS:
         if active is None and self._graph is not None:
             self._graph.replay()
             return
+        value, policy = self.select_and_evaluate(active)
+        check(self._L.pb_mcts_backprop(self._h, self._p(value), self._p(policy), self._stream()))
+
+    def select_and_evaluate(self, active: Optional[torch.Tensor] = None):
+        """The first half of a search iteration: select a trajectory per active tree, encode the
+        leaf observations, run the evaluator -> (value [n], policy [n, 5]) for pb_mcts_backprop
+        (or the collector's fused tail, pb_mcts_backprop_collect)."""
         a = self._mask_u8(active)
         check(self._L.pb_mcts_select(self._h, self._p(a), self._p(self._leaf_kind),
                                      self._p(self._leaf_mask), self._stream()))
@@ -182,8 +189,7 @@ class BatchedMCTS:
             leaf_obs = self.sim.obs_nhwc32(out=self._leaf_obs)
         else:
             leaf_obs = self.sim.obs(out=self._leaf_obs)
-        value, policy = self._evaluate(leaf_obs, self._leaf_mask.view(torch.bool))
-        check(self._L.pb_mcts_backprop(self._h, self._p(value), self._p(policy), self._stream()))
+        return self._evaluate(leaf_obs, self._leaf_mask.view(torch.bool))
 
     def enable_cuda_graph(self) -> None:
         """Capture select -> encode -> evaluator -> backprop (all trees active) in ONE CUDA graph;

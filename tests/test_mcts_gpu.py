@@ -388,3 +388,40 @@ def test_nhwc32_leaf_layout_gives_the_same_search(pb):
     assert len(batches[0][3]) > 0
     for a, b in zip(*batches):
         assert torch.equal(a, b)
+
+
+def test_fused_collector_tail_equals_the_three_launches(pb):
+    """pb_mcts_backprop_collect (backprop + env steps + built-in Dirichlet root noise in one
+    launch) against the three separate launches it replaces: two collectors that differ only in
+    `fused_tail`, same seed, 200 steps through several env steps, re-roots, episode ends and
+    resets: tree statistics, priors (noise), budgets, episode records and hand-outs identical."""
+    from pacbot_rl_b200 import alphazero
+
+    dev = torch.device("cuda:0")
+
+    def evaluator(obs, mask):          # deterministic, input dependent, no network
+        flat = obs.reshape(obs.shape[0], -1)
+        value = flat[:, 1000:1400].sum(dim=1) * 0.01 - 0.3
+        m = mask.to(torch.float32)
+        pol = m * (1.0 + flat[:, 2000:2005].abs())
+        return value, pol / pol.sum(dim=1, keepdim=True)
+
+    cfg = alphazero.AlphaZeroConfig(10, 8, 0.99, 96)
+    out = []
+    for fused in (True, False):
+        col = alphazero.BatchedExperienceCollector(evaluator, cfg, device=dev, seed=31, env_id_base=5)
+        col.fused_tail = fused
+        finished = []
+        for _ in range(200):
+            col.generate_experience_step(finished)
+        col.mcts.check()
+        assert finished
+        out.append(dict(
+            nodes=col.mcts.node_count().cpu(), visits=col.mcts.root_visits().cpu(), value=col.mcts.value().cpu(),
+            prior=col.mcts.policy_prior().cpu(), remaining=col.remaining.cpu(), ep_len=col.ep_len.cpu(),
+            ep_value=col.ep_value.cpu(), ep_dist=col.ep_dist.cpu(), state=col.env.get_state().tobytes(),
+            handed=torch.cat([f[1] for f in finished]).cpu(), dist=torch.cat([f[3] for f in finished]).cpu()))
+    a, b = out
+    for k in a:
+        same = a[k] == b[k] if isinstance(a[k], bytes) else torch.equal(a[k], b[k])
+        assert same, k
