@@ -608,7 +608,12 @@ int pb_mcts_backprop_collect(pb_mcts *m, const float *value_dev, const float *po
                              int max_episode_length, int tree_size, int32_t *remaining_dev,
                              int32_t *ep_len_dev, uint8_t *ep_mask_dev, float *ep_dist_dev,
                              float *ep_value_dev, uint8_t *status_dev, uint32_t *flags_dev, float alpha,
-                             float mix, void *stream);
+                             float mix, int publish, void *stream);
+/* publish != 0: the launch also reports to the host without a copy or a stream synchronisation.
+ * Its last CTA takes the accumulated flag word (and clears *flags_dev), and writes
+ * (number of publishing launches so far << 32) | flags to the pinned word handed out by
+ * pb_mcts_step_word; the host polls that word for the count it expects. */
+int pb_mcts_step_word(pb_mcts *m, uint64_t **host_word_out);
 /* Per-tree getters (mcts.rs:173-243) */
 #define PB_MCTS_Q_BEST_ACTION 0         /* int32 [n]: most visited valid child, ties -> last */
 #define PB_MCTS_Q_ACTION_DISTRIBUTION 1 /* float32 [n][5]: child visits / (root visits - 1) */

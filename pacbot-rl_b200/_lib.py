@@ -166,7 +166,8 @@ SIGNATURES = {
     "pb_mcts_take_action": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_mcts_collect_act": (_int, [_vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_mcts_backprop_collect": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 C.c_float, C.c_float, _vp]),
+                                 C.c_float, C.c_float, _int, _vp]),
+    "pb_mcts_step_word": (_int, [_vp, C.POINTER(_vp)]),
     "pb_mcts_query": (_int, [_vp, _int, _vp, _vp]),
     "pb_mcts_check": (_int, [_vp, C.POINTER(_u64), _vp]),
 }

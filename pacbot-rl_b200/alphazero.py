@@ -10,6 +10,7 @@ observations; the observations are produced by the encoder kernel when an episod
 list."""
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -104,6 +105,16 @@ class BatchedExperienceCollector:
         # backprop + env steps + built-in root noise as one launch (pb_mcts_backprop_collect);
         # False: the three separate launches (what runs with an injected noise_fn anyway)
         self.fused_tail = True
+        # the fused tail reports to the host through a pinned word its last CTA publishes
+        # ((launch count << 32) | flags): the per-step flag read is a poll of host memory, not a
+        # copy + stream synchronisation.  None: the flags are read from the device (`.item()`).
+        self._word = None
+        self._word_expected = 0
+        step_word = getattr(self.mcts._L, "pb_mcts_step_word", None)
+        if step_word is not None and noise_fn is None:
+            addr = C.c_void_p()
+            check(step_word(self.mcts._h, C.byref(addr)))
+            self._word = C.c_uint64.from_address(addr.value)
         self._pending: list = []   # finished episodes not handed out yet
         self._out_count = 0
         self.search_iterations = 0
@@ -120,7 +131,8 @@ class BatchedExperienceCollector:
             check(m._L.pb_mcts_backprop_collect(
                 m._h, p(value), p(policy), self.snap._h, cfg.max_episode_length, cfg.tree_size,
                 p(self.remaining), p(self.ep_len), p(self.ep_mask), p(self.ep_dist), p(self.ep_value),
-                p(self._status), p(self._flags), m.dirichlet_alpha, m.noise_mix, m._stream()))
+                p(self._status), p(self._flags), m.dirichlet_alpha, m.noise_mix,
+                1 if self._word is not None else 0, m._stream()))
             return
         self.mcts.search_iteration()
         check(self.mcts._L.pb_mcts_collect_act(
@@ -217,9 +229,35 @@ class BatchedExperienceCollector:
         else:
             self._device_step()
         self.search_iterations += 1
-        if int(self._flags.item()):  # the one host read per step
-            self._flags.zero_()
+        if self._publishing():
+            flags = self._wait_word()             # the one host read per step: a pinned word
+        else:
+            flags = int(self._flags.item())       # ... or a device read
+            if flags:
+                self._flags.zero_()
+        if flags:
             self._finish(finished)
+
+    def _publishing(self) -> bool:
+        m = self.mcts
+        return self._word is not None and self.fused_tail and m.noise_fn is None and m._graph is None
+
+    def _wait_word(self) -> int:
+        """Wait for the step just enqueued to publish its word -> the step's flags."""
+        self._word_expected += 1
+        want, word = self._word_expected, self._word
+        spins = 0
+        while (word.value >> 32) != want:
+            spins += 1
+            if spins % 200_000 == 0:
+                # nothing for a long time: drain the device (surfaces a kernel error) and trust the
+                # count the device reports from here on
+                torch.cuda.synchronize(self.device)
+                got = word.value >> 32
+                if got != want:
+                    self._word_expected = got
+                    break
+        return int(word.value & 0xFFFFFFFF)
 
     def generate_experience(self, materialize_obs: bool = True) -> ExperienceBatch:
         """generate_experience (alphazero.rs:86-92): at least one finished episode."""

@@ -541,6 +541,10 @@ k_mcts_collect_act(MctsView v, StateView root, RngParams rp, StateView snap, int
 // take_action re-rooted, the Dirichlet noise on its new root (mcts.rs:160-163).  A tree's three
 // stages only touch that tree's own nodes, env and counters, so running them back to back in the
 // tree's thread is the order the separate launches give.
+// `host_word` (optional, pinned host memory): the step's report to the host without a copy or a
+// stream synchronisation.  The last CTA to finish takes the flag word accumulated by all trees
+// (and clears it), counts the launch in `launches`, and publishes (launch count << 32) | flags after
+// a system fence; the host polls that word (alphazero.py).  `arrive` is zero between launches.
 __global__ void __launch_bounds__(MCTS_THREADS)
 k_mcts_backprop_collect(MctsView v, const float *__restrict__ value, const float *__restrict__ policy,
                         StateView root, RngParams rp, StateView snap, int max_len, int tree_size,
@@ -548,17 +552,34 @@ k_mcts_backprop_collect(MctsView v, const float *__restrict__ value, const float
                         uint8_t *__restrict__ ep_mask, float *__restrict__ ep_dist,
                         float *__restrict__ ep_value, uint8_t *__restrict__ status,
                         unsigned int *__restrict__ host_flags, float alpha, float keep, float mix,
-                        unsigned long long noise_seed, long long gid_base) {
+                        unsigned long long noise_seed, long long gid_base, unsigned int *arrive,
+                        unsigned long long *launches, unsigned long long *host_word) {
     __shared__ uint32_t s_walls[32];
     load_walls(s_walls);
     const long long i = mcts_tree_of_thread(v);
     if (i == 0) *v.epoch += 1ull;
-    if (i >= v.n) return;
-    mcts_backprop_tree(v, i, value, policy);
-    const int st = mcts_collect_act_tree(v, root, rp, snap, s_walls, i, max_len, tree_size, remaining, ep_len,
-                                         ep_mask, ep_dist, ep_value, status, host_flags);
-    if ((st & 7) == MCTS_ST_REROOTED)
-        mcts_dirichlet_noise_tree(v, root, s_walls, i, alpha, keep, mix, noise_seed, gid_base);
+    if (i < v.n) {
+        mcts_backprop_tree(v, i, value, policy);
+        const int st = mcts_collect_act_tree(v, root, rp, snap, s_walls, i, max_len, tree_size, remaining,
+                                             ep_len, ep_mask, ep_dist, ep_value, status, host_flags);
+        if ((st & 7) == MCTS_ST_REROOTED)
+            mcts_dirichlet_noise_tree(v, root, s_walls, i, alpha, keep, mix, noise_seed, gid_base);
+    }
+    if (!host_word) return;
+    __syncthreads();   // every tree of this CTA has raised its flags
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int before = atomicAdd(arrive, 1u);
+        if (before == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long flags = atomicExch(host_flags, 0u);
+            const unsigned long long seq = *launches + 1ull;
+            *launches = seq;
+            atomicExch(arrive, 0u);
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(host_word) = (seq << 32) | flags;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -6,6 +6,11 @@ struct pb_mcts {
     pb_engine *sim = nullptr;   // borrowed; slot i holds the env clone tree i simulates with
     int device = 0;
     MctsView v{};
+    // pb_mcts_backprop_collect's report to the host: arrival counter and launch counter (device),
+    // the published word (pinned host memory); created on first use
+    unsigned int *arrive = nullptr;
+    unsigned long long *launches = nullptr;
+    unsigned long long *host_word = nullptr;
 };
 
 namespace {
@@ -91,6 +96,9 @@ int pb_mcts_destroy(pb_mcts *m) {
     cudaFree(v.epoch);
     cudaFree(v.noise_calls);
     cudaFree(v.error);
+    cudaFree(m->arrive);
+    cudaFree(m->launches);
+    if (m->host_word) cudaFreeHost(m->host_word);
     delete m;
     return PB_OK;
 }
@@ -178,22 +186,40 @@ int pb_mcts_collect_act(pb_mcts *m, pb_engine *snap, int max_episode_length, int
     return PB_OK;
 }
 
+int pb_mcts_step_word(pb_mcts *m, uint64_t **host_word_out) {
+    if (!m || !host_word_out) return fail(PB_ERR_INVALID_ARG, "pb_mcts_step_word: null argument");
+    DeviceGuard g(m->device);
+    if (!m->host_word) {
+        PB_CUDA(cudaMalloc(&m->arrive, sizeof(unsigned int)));
+        PB_CUDA(cudaMemset(m->arrive, 0, sizeof(unsigned int)));
+        PB_CUDA(cudaMalloc(&m->launches, sizeof(unsigned long long)));
+        PB_CUDA(cudaMemset(m->launches, 0, sizeof(unsigned long long)));
+        PB_CUDA(cudaMallocHost(&m->host_word, sizeof(unsigned long long)));
+        *m->host_word = 0ull;
+    }
+    *host_word_out = reinterpret_cast<uint64_t *>(m->host_word);
+    return PB_OK;
+}
+
 int pb_mcts_backprop_collect(pb_mcts *m, const float *value_dev, const float *policy_dev, pb_engine *snap,
                              int max_episode_length, int tree_size, int32_t *remaining_dev,
                              int32_t *ep_len_dev, uint8_t *ep_mask_dev, float *ep_dist_dev,
                              float *ep_value_dev, uint8_t *status_dev, uint32_t *flags_dev, float alpha,
-                             float mix, void *stream) {
+                             float mix, int publish, void *stream) {
     if (!m || !value_dev || !policy_dev || !snap || !remaining_dev || !ep_len_dev || !ep_mask_dev ||
         !ep_dist_dev || !ep_value_dev || !status_dev || !flags_dev || max_episode_length < 1 ||
         tree_size < 2 || !(alpha > 0.0f) || snap->device != m->device ||
         snap->n < m->v.n * (long long)max_episode_length)
         return fail(PB_ERR_INVALID_ARG,
                     "pb_mcts_backprop_collect: bad arguments (snap needs n * max_episode_length envs)");
+    if (publish && !m->host_word)
+        return fail(PB_ERR_INVALID_ARG, "pb_mcts_backprop_collect: publish needs pb_mcts_step_word first");
     DeviceGuard g(m->device);
     k_mcts_backprop_collect<<<mcts_grid(m->v), MCTS_THREADS, 0, (cudaStream_t)stream>>>(
         m->v, value_dev, policy_dev, m->root->st, rng_params(m->root), snap->st, max_episode_length,
         tree_size, remaining_dev, ep_len_dev, ep_mask_dev, ep_dist_dev, ep_value_dev, status_dev, flags_dev,
-        alpha, 1.0f - mix, mix, m->root->seed, m->root->gid_base);
+        alpha, 1.0f - mix, mix, m->root->seed, m->root->gid_base, m->arrive, m->launches,
+        publish ? m->host_word : nullptr);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -24,7 +24,24 @@
 struct HostDim3 {
     unsigned x, y, z;
 };
-static HostDim3 threadIdx, blockIdx;
+static HostDim3 threadIdx, blockIdx, gridDim;
+// the publishing tail of k_mcts_backprop_collect (last-CTA hand-over to a pinned host word) only
+// has to compile here: the host build never passes a host word, the tail returns before it
+static inline void __syncthreads() {}
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+template <class T>
+static inline T atomicAdd(T *p, T v) {
+    const T old = *p;
+    *p += v;
+    return old;
+}
+template <class T>
+static inline T atomicExch(T *p, T v) {
+    const T old = *p;
+    *p = v;
+    return old;
+}
 static inline unsigned atomicOr(unsigned *p, unsigned v) {
     const unsigned old = *p;
     *p |= v;
@@ -314,6 +331,23 @@ int hm_mcts_collect_act(void *h, void *snap_h, int max_len, int tree_size, int32
     launch(m->v, [&] {
         k_mcts_collect_act(m->v, m->root->st, rng_params(m->root), snap->st, max_len, tree_size,
                            remaining, ep_len, ep_mask, ep_dist, ep_value, status, flags);
+    });
+    return PB_OK;
+}
+
+// pb_mcts_backprop_collect: backprop + env steps + built-in root noise, one "launch" (no host word:
+// the publishing tail is not run here)
+int hm_mcts_backprop_collect(void *h, const float *value, const float *policy, void *snap_h, int max_len,
+                             int tree_size, int32_t *remaining, int32_t *ep_len, uint8_t *ep_mask,
+                             float *ep_dist, float *ep_value, uint8_t *status, uint32_t *flags, float alpha,
+                             float mix) {
+    HMcts *m = static_cast<HMcts *>(h);
+    HEngine *snap = static_cast<HEngine *>(snap_h);
+    if (snap->st.n < m->v.n * (long long)max_len) return PB_ERR_INVALID_ARG;
+    launch(m->v, [&] {
+        k_mcts_backprop_collect(m->v, value, policy, m->root->st, rng_params(m->root), snap->st, max_len,
+                                tree_size, remaining, ep_len, ep_mask, ep_dist, ep_value, status, flags, alpha,
+                                1.0f - mix, mix, m->root->seed, m->root->gid_base, nullptr, nullptr, nullptr);
     });
     return PB_OK;
 }

@@ -47,6 +47,8 @@ def hm(pb):
     L.hm_mcts_check.argtypes = [vp, vp]
     L.hm_mcts_collect_act.restype = C.c_int
     L.hm_mcts_collect_act.argtypes = [vp, vp, C.c_int, C.c_int] + [vp] * 7
+    L.hm_mcts_backprop_collect.restype = C.c_int
+    L.hm_mcts_backprop_collect.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int] + [vp] * 7 + [C.c_float, C.c_float]
     L.hm_engine_copy_envs.restype = C.c_int
     L.hm_engine_copy_envs.argtypes = [vp, vp, vp, vp, i64]
     L.hm_engine_step.restype = i64
@@ -316,6 +318,14 @@ class HostABI:
                             ep_value, status, flags, stream):
         return self._lib.hm_mcts_collect_act(h, snap_h, max_len, tree_size, remaining, ep_len, ep_mask,
                                              ep_dist, ep_value, status, flags)
+
+
+    def pb_mcts_backprop_collect(self, h, value, policy, snap_h, max_len, tree_size, remaining, ep_len,
+                                 ep_mask, ep_dist, ep_value, status, flags, alpha, mix, publish, stream):
+        assert not publish     # the pinned host word is a GPU facility
+        return self._lib.hm_mcts_backprop_collect(h, value, policy, snap_h, max_len, tree_size, remaining,
+                                                  ep_len, ep_mask, ep_dist, ep_value, status, flags,
+                                                  alpha, mix)
 
 
 def _check(rc):   # pacbot-rl_b200/_lib.py::check with the adapter's error text
