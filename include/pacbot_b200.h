@@ -182,6 +182,17 @@ int pb_encode_obs_ring_nhwc32(pb_engine *e, float *ring_dev, int64_t slot_stride
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,
                    uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev,
                    int64_t env_stride_floats, void *stream);
+/* pb_step + the observation of the resulting states for a SMALL engine (the DQN loop's 32 envs, an
+ * evaluation env), one launch, one CTA per env: in pb_step the envs of a small batch share one
+ * warp and their divergent game logic is serialised; here every env steps on a warp of its own
+ * and its CTA then encodes the observation -- channel-major at obs_out_dev + i * env_stride_floats
+ * (+ *slot_index_dev * slot_stride_floats when slot_index_dev is given: the replay ring's slot,
+ * read at kernel time) and / or channels-last padded to 32 channels at nhwc_out_dev (see
+ * pb_encode_obs_nhwc32); either output may be NULL.  Same results as pb_step + pb_encode_obs*. */
+int pb_step_encode_small(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8_t *done_dev,
+                         uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev, int64_t env_stride_floats,
+                         const int64_t *slot_index_dev, int64_t slot_stride_floats, float *nhwc_out_dev,
+                         void *stream);
 
 /* PacmanGym::action_mask (env.rs:293-302): uint8 [n][5]. */
 int pb_action_mask(pb_engine *e, uint8_t *mask_out_dev, void *stream);

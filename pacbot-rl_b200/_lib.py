@@ -96,6 +96,7 @@ SIGNATURES = {
     "pb_encode_obs_ring": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "pb_encode_obs_ring_nhwc32": (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pb_step_encode": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp]),
+    "pb_step_encode_small": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _vp, _vp]),
     "pb_action_mask": (_int, [_vp, _vp, _vp]),
     "pb_query": (_int, [_vp, _int, _vp, _vp]),
     "pb_sample_actions": (_int, [_vp, _vp, _u64, _vp]),

@@ -258,4 +258,65 @@ k_gym_call(StateView st, RngParams rp, const uint8_t *__restrict__ actions, int 
     }
 }
 
+// pb_step + the observation of the resulting state for a small batch, ONE launch, device buffers:
+// what the DQN loop's experience step (32 envs) and an evaluation step (1 env) need.  One CTA per
+// env: thread 0 steps the env on pellet words held in shared memory (in k_step the 32 envs of a
+// small batch share ONE warp and their divergent game logic is executed lane group by lane group:
+// 8 us per 32-env launch; here every env has a warp of its own on its own SM), then the CTA
+// encodes the observation -- channel-major at out + k * env_stride (optionally through the
+// ring-slot indirection) and / or channels-last padded to 32 channels at out_nhwc + k * NHWC_FLOATS.
+// Same results as k_step followed by k_obs_small (tests diff them and the oracle).
+__global__ void __launch_bounds__(GYM_CALL_THREADS, 1)
+k_step_obs_small(StateView st, RngParams rp, const uint8_t *__restrict__ actions,
+                 int32_t *__restrict__ reward, uint8_t *__restrict__ done_out,
+                 uint8_t *__restrict__ mask_out, int auto_reset, unsigned long long *bad_action,
+                 float *__restrict__ out, long long env_stride, const long long *__restrict__ slot_index,
+                 long long slot_stride, float *__restrict__ out_nhwc, TraceRec *__restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *img = reinterpret_cast<float *>(smem_raw);
+    uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw + SMALL_IMG_BYTES);
+    __shared__ uint32_t s_walls[32];
+    if (trace && threadIdx.x == 0) {
+        const unsigned long long t = global_timer_ns();
+        stamp_min(&trace->begin, t);
+        stamp_min(&trace->ready, t);
+    }
+    const long long i = blockIdx.x;
+    if (threadIdx.x < 32)
+        words[threadIdx.x] = threadIdx.x < PEL_WORDS ? st.pel[(long long)threadIdx.x * st.npad + i] : 0u;
+    load_walls(s_walls);   // ends with a __syncthreads()
+    if (threadIdx.x == 0) {
+        EnvR s;
+        load_env(st, i, s);
+        const PelRef pel{words, 1};
+        const int action = actions[i];
+        if (action > 4) {  // env.rs:83-88: "Invalid action" -- env untouched
+            atomicMin(bad_action, (unsigned long long)i);
+            reward[i] = 0;
+            done_out[i] = 0;
+        } else {
+            const RngCtx rng = make_rng(rp, i);
+            int rew;
+            bool done;
+            gym_step(s, pel, c_tab, s_walls, rng, action, rew, done);
+            if (done && auto_reset) gym_reset(s, pel, c_tab, s_walls, rng, true);
+            store_env(st, i, s);
+            reward[i] = rew;
+            done_out[i] = done ? 1 : 0;
+        }
+        if (mask_out) write_mask(mask_out, i, action_mask_bits(s, s_walls));
+    }
+    __syncthreads();   // thread 0's state (global memory) and pellet words (shared) are what the CTA encodes
+    if (threadIdx.x < PEL_WORDS) st.pel[(long long)threadIdx.x * st.npad + i] = words[threadIdx.x];
+    if (out || out_nhwc) {
+        build_obs_image<GYM_CALL_THREADS>(st, i, img, words, true);
+        if (out) {
+            if (slot_index) out += *slot_index * slot_stride;
+            copy_obs_image<GYM_CALL_THREADS>(img, out + i * env_stride);
+        }
+        if (out_nhwc) copy_obs_image_nhwc32<GYM_CALL_THREADS>(img, out_nhwc + i * (long long)NHWC_FLOATS);
+    }
+    if (trace && threadIdx.x == 0) stamp_max(&trace->end, global_timer_ns());
+}
+
 }  // namespace pb

@@ -498,6 +498,7 @@ int encode_attrs(pb_engine *e) {
         PB_CUDA(cudaFuncSetAttribute(k_encode_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         PB_CUDA(cudaFuncSetAttribute(k_gym_call, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(k_step_obs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
         // the kernel in front of a small encode is k_step, which runs under the largest carve-out
         // (see pb_create): ask for the same one, so that the SMs are not reconfigured in between.
         // PB_SMALL_CARVEOUT=0 leaves the driver's choice (A/B runs).
@@ -883,6 +884,29 @@ int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev
     int rc = pb_step(e, actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset, stream);
     if (rc != PB_OK) return rc;
     return pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
+}
+
+int pb_step_encode_small(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev, uint8_t *done_dev,
+                         uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev, int64_t env_stride_floats,
+                         const int64_t *slot_index_dev, int64_t slot_stride_floats, float *nhwc_out_dev,
+                         void *stream) {
+    if (!e || !actions_dev || !reward_dev || !done_dev)
+        return fail(PB_ERR_INVALID_ARG, "pb_step_encode_small: null argument");
+    if (obs_out_dev && ((env_stride_floats & 3) || env_stride_floats < OBS_FLOATS ||
+                        (reinterpret_cast<uintptr_t>(obs_out_dev) & 15) || (slot_stride_floats & 3)))
+        return fail(PB_ERR_INVALID_ARG, "pb_step_encode_small: strides must be multiples of 4 floats (>= 14756), "
+                                        "outputs 16-byte aligned");
+    if (nhwc_out_dev && (reinterpret_cast<uintptr_t>(nhwc_out_dev) & 15))
+        return fail(PB_ERR_INVALID_ARG, "pb_step_encode_small: nhwc_out must be 16-byte aligned");
+    DeviceGuard g(e->device);
+    const int rc = encode_attrs(e);
+    if (rc != PB_OK) return rc;
+    k_step_obs_small<<<(unsigned)e->n, GYM_CALL_THREADS, SMALL_SMEM, (cudaStream_t)stream>>>(
+        e->st, rng_params(e), actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset, e->bad_action,
+        obs_out_dev, env_stride_floats, reinterpret_cast<const long long *>(slot_index_dev),
+        slot_stride_floats, nhwc_out_dev, trace_slot(e, PB_TRACE_STEP));
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
 }
 
 int pb_action_mask(pb_engine *e, uint8_t *mask_out_dev, void *stream) {

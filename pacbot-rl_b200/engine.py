@@ -451,6 +451,51 @@ class BatchedPacmanGym:
                                          self.num_envs * OBS_FLOATS,
                                          C.c_void_p(slot_index.data_ptr()), self._stream()))
 
+    SMALL_BATCH = 256   # up to here a launch is "small": one CTA per env (csrc/pb_encode_small.cuh)
+
+    def step_encode_small(self, actions, *, reward_out: torch.Tensor, done_out: torch.Tensor,
+                          mask_out: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None,
+                          ring: Optional[torch.Tensor] = None, slot_index: Optional[torch.Tensor] = None,
+                          nhwc32_out: Optional[torch.Tensor] = None) -> None:
+        """step() and the observation(s) of the resulting states in ONE launch, one CTA per env
+        (pb_step_encode_small; meant for engines of up to SMALL_BATCH envs: the DQN loop's
+        experience step, an evaluation step).  Observation outputs, any subset: `obs_out` float32
+        [N, 17, 28, 31]; or `ring` [R, N, 17, 28, 31] + `slot_index` (1-element int64 device tensor
+        read at kernel time); `nhwc32_out` [N, 32, 28, 31] channels_last.  No action check here:
+        an action > 4 leaves its env untouched and is reported by check_actions()."""
+        a = self._actions_u8(actions)
+        n = self.num_envs
+        self._check_tensor(reward_out, (n,), torch.int32, "reward_out")
+        done = self._check_tensor(done_out.view(torch.uint8), (n,), torch.uint8, "done_out")
+        mptr = None
+        if mask_out is not None:
+            mptr = C.c_void_p(self._check_tensor(
+                mask_out.view(torch.uint8), (n, NUM_ACTIONS), torch.uint8, "mask_out").data_ptr())
+        optr, stride, sptr, sstride = None, 0, None, 0
+        if ring is not None:
+            if (obs_out is not None or slot_index is None or ring.dtype != torch.float32
+                    or ring.device != self.device or not ring.is_contiguous()
+                    or tuple(ring.shape[1:]) != (n,) + OBS_SHAPE or slot_index.dtype != torch.int64
+                    or slot_index.device != self.device or slot_index.numel() != 1):
+                raise ValueError("ring: contiguous float32 [R, N, 17, 28, 31] + a 1-element int64 slot_index "
+                                 "on the engine device (and no obs_out)")
+            optr, stride = C.c_void_p(ring.data_ptr()), OBS_FLOATS
+            sptr, sstride = C.c_void_p(slot_index.data_ptr()), n * OBS_FLOATS
+        elif obs_out is not None:
+            self._check_tensor(obs_out, (n,) + OBS_SHAPE, torch.float32, "obs_out")
+            optr, stride = C.c_void_p(obs_out.data_ptr()), OBS_FLOATS
+        nptr = None
+        if nhwc32_out is not None:
+            shape = (n, 32) + OBS_SHAPE[1:]
+            if (nhwc32_out.dtype != torch.float32 or nhwc32_out.device != self.device
+                    or tuple(nhwc32_out.shape) != shape
+                    or not nhwc32_out.is_contiguous(memory_format=torch.channels_last)):
+                raise ValueError(f"nhwc32_out: expected a channels_last float32 tensor of shape {shape}")
+            nptr = C.c_void_p(nhwc32_out.data_ptr())
+        check(self._L.pb_step_encode_small(
+            self._h, C.c_void_p(a.data_ptr()), C.c_void_p(reward_out.data_ptr()), C.c_void_p(done.data_ptr()),
+            mptr, int(self.auto_reset), optr, stride, sptr, sstride, nptr, self._stream()))
+
     def step_obs(self, actions, obs_out: torch.Tensor, *, check_actions: bool = False,
                  mask_out: Optional[torch.Tensor] = None):
         """step() then obs() of the resulting states, back to back (one C-ABI call)."""

@@ -255,13 +255,21 @@ class ReplayBuffer:
             old = self.phase1_policy(self._last_obs, self._mask).to(torch.uint8)
             actions = self._act.copy_(torch.where(self._in_phase1, old, actions))
         # step + auto reset, then the observation of the resulting state straight into slot t+1
-        self.envs.step(actions, check_actions=False, mask_out=self._mask, reward_out=self._reward,
-                       done_out=self._done_step)
-        if dual:
-            self.envs.obs_ring(self._obs, self._nxt_dev, nhwc32_out=self._last_obs)
-            self._last_obs_fresh = True
+        if n <= BatchedPacmanGym.SMALL_BATCH:
+            # ... in ONE launch for a small batch (every env steps on a warp of its own, its CTA
+            # encodes), which with the padded channels-last layout also writes the policy's next input
+            self.envs.step_encode_small(actions, reward_out=self._reward, done_out=self._done_step,
+                                        mask_out=self._mask, ring=self._obs, slot_index=self._nxt_dev,
+                                        nhwc32_out=self._last_obs if dual else None)
+            self._last_obs_fresh = dual
         else:
-            self.envs.obs_ring(self._obs, self._nxt_dev)
+            self.envs.step(actions, check_actions=False, mask_out=self._mask, reward_out=self._reward,
+                           done_out=self._done_step)
+            if dual:
+                self.envs.obs_ring(self._obs, self._nxt_dev, nhwc32_out=self._last_obs)
+                self._last_obs_fresh = True
+            else:
+                self.envs.obs_ring(self._obs, self._nxt_dev)
         a_p, r_p, d_p, m_p = self._slot_ptrs()
         phase = C.c_void_p(self._in_phase1.data_ptr()) if self.phase1_policy is not None else None
         check(L.pb_replay_record(n, r, C.c_void_p(self._t_dev.data_ptr()), C.c_void_p(actions.data_ptr()),

@@ -208,6 +208,8 @@ class EpisodeEvaluator:
         else:
             self.obs = torch.empty((n, 17, 28, 31), dtype=torch.float32, device=device)
         self.mask = torch.zeros((n, 5), dtype=torch.bool, device=device)
+        self._reward = torch.zeros(n, dtype=torch.int32, device=device)
+        self._done = torch.zeros(n, dtype=torch.bool, device=device)
         # per-env bookkeeping, updated by ONE kernel per step (pb_eval_track): rows 0 score,
         # 1 steps, 2 lives, 3 pellets_end, 4 finished (done within max_steps), 5 alive, 6 steps left
         self.track = torch.zeros((7, n), dtype=torch.int32, device=device)
@@ -243,7 +245,12 @@ class EpisodeEvaluator:
         env = self.env
         pol = self.policy
         actions = pol.actions_u8(self.obs, self.mask) if hasattr(pol, "actions_u8") else pol(self.obs, self.mask)
-        if self._nhwc:
+        if self.n <= BatchedPacmanGym.SMALL_BATCH:     # step + encode: one launch, one CTA per env
+            done = self._done
+            env.step_encode_small(actions, reward_out=self._reward, done_out=done, mask_out=self.mask,
+                                  obs_out=None if self._nhwc else self.obs,
+                                  nhwc32_out=self.obs if self._nhwc else None)
+        elif self._nhwc:
             _, done = env.step(actions, check_actions=False, mask_out=self.mask)
             env.obs_nhwc32(out=self.obs)
         else:

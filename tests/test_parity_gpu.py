@@ -594,3 +594,57 @@ def test_gym_call_kernel_vs_oracle_on_fuzzed_states(pb, oracle):
             assert np.array_equal(snap["info"][:, 4], so["num_pellets"]), t
             assert np.array_equal(snap["mask"], ob.action_mask().astype(bool)), t
             assert_obs_equal(ob.obs(), snap["obs"], f"gym call, step {t}", so)
+
+
+def test_small_step_encode_kernel_vs_oracle_and_separate_calls(pb, oracle):
+    """k_step_obs_small (pb_step_encode_small: step + observation of a small batch in one launch,
+    one CTA per env) on fuzzed states: reward, done, mask, state and both observation layouts
+    against the oracle and against pb_step + pb_encode_obs on a twin engine, with auto reset,
+    blocked moves and an invalid action (that env untouched, reported by check_actions)."""
+    torch = torch_mod()
+    from pacbot_rl_b200 import models
+
+    n = 200
+    rng = np.random.default_rng(4242)
+    tape = rng.integers(0, 2**32, size=(n, 500), dtype=np.uint32)
+    st = fuzz_states(rng, pb, n)
+    ob, env = make_pair(pb, oracle, n, st["cfg_flags"], tape, auto_reset=True)
+    _, twin = make_pair(pb, oracle, n, st["cfg_flags"], tape, auto_reset=True)
+    for e in (env, twin):
+        e.set_state(st)
+    ob.import_state(gpu_to_oracle_state(oracle, st))
+    reward = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    done = torch.zeros(n, dtype=torch.bool, device="cuda:0")
+    mask = torch.zeros((n, 5), dtype=torch.bool, device="cuda:0")
+    obs = torch.empty((n,) + pb.OBS_SHAPE, device="cuda:0")
+    ring = torch.zeros((3, n) + pb.OBS_SHAPE, device="cuda:0")
+    nhwc = torch.empty((n, 32, 28, 31), device="cuda:0").contiguous(memory_format=torch.channels_last)
+    for t in range(12):
+        a = random_valid_actions(rng, ob.action_mask(), p_invalid_move=0.2)
+        r_o, d_o = ob.step(a, auto_reset=True)
+        a_dev = torch.from_numpy(a).cuda()
+        r_t, d_t = twin.step(a_dev)
+        if t % 2 == 0:
+            env.step_encode_small(a_dev, reward_out=reward, done_out=done, mask_out=mask, obs_out=obs,
+                                  nhwc32_out=nhwc)
+            got = obs
+        else:
+            slot = torch.tensor([t % 3], dtype=torch.int64, device="cuda:0")
+            env.step_encode_small(a_dev, reward_out=reward, done_out=done, mask_out=mask, ring=ring,
+                                  slot_index=slot, nhwc32_out=nhwc)
+            got = ring[t % 3]
+        assert np.array_equal(r_o, reward.cpu().numpy()) and np.array_equal(d_o.astype(bool), done.cpu().numpy()), t
+        assert torch.equal(reward, r_t) and torch.equal(done, d_t), t
+        assert np.array_equal(ob.action_mask().astype(bool), mask.cpu().numpy()), t
+        so = ob.export_state()
+        assert_states_equal(so, env.get_state(), f"small step, step {t}")
+        assert env.get_state().tobytes() == twin.get_state().tobytes()
+        assert_obs_equal(ob.obs(), got.cpu().numpy(), f"small step, step {t}", so)
+        assert torch.equal(nhwc, models.obs_to_padded_nhwc(twin.obs())), t
+    before = env.get_state()
+    bad = np.zeros(n, np.uint8)
+    bad[17] = 9
+    env.step_encode_small(torch.from_numpy(bad).cuda(), reward_out=reward, done_out=done, obs_out=obs)
+    with pytest.raises(ValueError, match="Invalid action"):
+        env.check_actions()
+    assert env.get_state()[17].tobytes() == before[17].tobytes() and int(reward[17]) == 0
