@@ -881,6 +881,10 @@ int pb_encode_obs_ring_nhwc32(pb_engine *e, float *ring_dev, int64_t slot_stride
 int pb_step_encode(pb_engine *e, const uint8_t *actions_dev, int32_t *reward_dev,
                    uint8_t *done_dev, uint8_t *mask_out_dev, int auto_reset, float *obs_out_dev,
                    int64_t env_stride_floats, void *stream) {
+    // a small engine: one launch, every env on a warp of its own (pb_step_encode_small)
+    if (e && actions_dev && reward_dev && done_dev && obs_out_dev && e->n <= SMALL_ENC_MAX)
+        return pb_step_encode_small(e, actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset, obs_out_dev,
+                                    env_stride_floats, nullptr, 0, nullptr, stream);
     int rc = pb_step(e, actions_dev, reward_dev, done_dev, mask_out_dev, auto_reset, stream);
     if (rc != PB_OK) return rc;
     return pb_encode_obs(e, obs_out_dev, env_stride_floats, stream);
