@@ -244,6 +244,9 @@ class BatchedExperienceCollector:
 
     def _wait_word(self) -> int:
         """Wait for the step just enqueued to publish its word -> the step's flags."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("generate_experience_step waits for the device: it cannot run inside a CUDA "
+                               "graph capture (use enable_cuda_graph(), which captures the device part only)")
         self._word_expected += 1
         want, word = self._word_expected, self._word
         spins = 0
