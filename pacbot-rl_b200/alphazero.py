@@ -247,7 +247,7 @@ class BatchedExperienceCollector:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("generate_experience_step waits for the device: it cannot run inside a CUDA "
                                "graph capture (use enable_cuda_graph(), which captures the device part only)")
-        self._word_expected += 1
+        self._word_expected = (self._word_expected + 1) & 0xFFFFFFFF    # the word carries 32 bits of it
         want, word = self._word_expected, self._word
         spins = 0
         while (word.value >> 32) != want:
